@@ -1,0 +1,204 @@
+/*
+ * rsp.h -- thin C ABI of librsp.so: the B200-native per-frame phased-array chain
+ *          DBF -> pulse compression -> MTD -> GOCA-CFAR -> monopulse (+ host clustering).
+ *
+ * Drop-in boundary for the reference's MATLAB hot path (all paths under
+ * /root/reference/Simulation/):
+ *
+ *   fun_process_single_frame.m:13
+ *       final_targets = fun_process_single_frame(targets, config, cfar_params,
+ *                                                cluster_params, precomputed_data, frame_idx)
+ *   process_stage2_mtd.m:1
+ *       [MTD_results, PC_results] = process_stage2_mtd(iq_data, angle, config)
+ *
+ * A MEX gateway (mex/ in this repo) or the ctypes binding (rsp_b200/_abi.py) unpacks the
+ * MATLAB structs into the POD structs below and calls these entry points.  Plain pointers
+ * and sizes only; no exceptions cross this boundary; every function returns an rsp_status
+ * (0 = OK, negative = error, text via rsp_last_error).
+ *
+ * Index conventions: detection indices (v_idx, r_idx, pair_idx) are 1-based exactly like the
+ * reference's all_raw_detections rows [v, r, pair, amp] (fun_process_single_frame.m:220).
+ *
+ * Layouts (complex64 = interleaved {float re, im}; complex128 likewise with doubles):
+ *   RSP_LAYOUT_PCN      raw[p][c][n]   device-native: range sample fastest, then channel, then pulse
+ *   RSP_LAYOUT_MATLAB   MATLAB [P,N,C] column-major, i.e. raw[c][n][p] (pulse fastest), the
+ *                       in-memory order of raw_iq_data_noise (fun_process_single_frame.m:81)
+ *   range-Doppler map   rdm[b][g][v]   Doppler fastest == MATLAB rdm_13beam(v,g,b) byte order
+ *                       (fun_process_single_frame.m:131-136)
+ *   pulse compression   pc[b][g][p]    == MATLAB pc_results_13beam(p,g,b) byte order (:101-127)
+ *
+ * The context is not thread-safe: one context per host thread / CUDA stream.
+ */
+#ifndef RSP_H_
+#define RSP_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSP_ABI_VERSION 1
+#define RSP_MAX_CHANNELS 32
+#define RSP_MAX_BEAMS 16
+
+typedef enum {
+    RSP_OK = 0,
+    RSP_ERR_INVALID_ARG = -1,
+    RSP_ERR_UNSUPPORTED = -2,     /* shape outside what the kernels implement */
+    RSP_ERR_CUDA = -3,            /* CUDA runtime failure, text in rsp_last_error */
+    RSP_ERR_NO_DEVICE = -4,       /* no CUDA device: there is NO CPU fallback */
+    RSP_ERR_OVERFLOW = -5,        /* detection list exceeded max_detections (never truncated silently) */
+    RSP_ERR_NOT_READY = -6        /* constants not uploaded / stage not run yet */
+} rsp_status;
+
+typedef enum { RSP_LAYOUT_PCN = 0, RSP_LAYOUT_MATLAB = 1 } rsp_layout;
+typedef enum { RSP_MEM_HOST = 0, RSP_MEM_DEVICE = 1 } rsp_mem;
+typedef enum { RSP_C64 = 0, RSP_C128 = 1 } rsp_dtype;
+
+typedef struct { float re, im; } rsp_c64;
+typedef struct { double re, im; } rsp_c128;
+
+/* Shape + detector parameters.  Field sources:
+ *   config.Sig_Config.{channel_num, beam_num, prtNum, point_PRT, point_prt_segments}
+ *       (fun_process_single_frame.m:17,47,92,175; main_simulate_echoes_with_array_v8_3.m:71-84)
+ *   precomputed_data.{seg_start_*, N_gate_*, fir_delay}      (fun_process_single_frame.m:25,30-36)
+ *   cfar_params.{T_CFAR, guardCells_*, refCells_*}           (fun_process_single_frame.m:177-179)
+ */
+typedef struct {
+    int32_t abi_version;          /* RSP_ABI_VERSION */
+    int32_t n_channels;           /* C */
+    int32_t n_beams;              /* B */
+    int32_t n_pulses;             /* P (prtNum) */
+    int32_t n_samples;            /* N (point_PRT) */
+    int32_t seg_start[3];         /* 1-based first sample of the narrow / medium / long segment */
+    int32_t n_gates[3];           /* gates kept from each segment (sum = G) */
+    int32_t fir_delay;            /* circshift of the narrow FIR output */
+    float   t_cfar;
+    int32_t guard_r, guard_v, ref_r, ref_v;
+    int32_t max_detections;       /* capacity of the per-CPI detection list */
+    int32_t monopulse_complex;    /* 0: amplitude ratio (fun_process_single_frame.m:282-285),
+                                     1: complex ratio, real part (main_plot_snr_vs_angle_error.m:454-461) */
+    int32_t device;               /* CUDA device ordinal */
+} rsp_params;
+
+/* Filters, windows, axes and calibration tables: precomputed_data
+ * (main_simulate_echoes_with_array_v8_3.m:121-183), all double precision as MATLAB holds them.
+ * The matched filters are passed as TIME-DOMAIN taps (precomputed_data.MF_medium_win /
+ * MF_long_win, v8_3:146,148); the library builds its own block spectra from them. */
+typedef struct {
+    const rsp_c128* dbf_weights;  /* [B][C] row-major = DBF_coeffs_data_C (used conjugated, fsf:95) */
+    const double*   fir;          /* MF_narrow taps */
+    int32_t         n_fir;
+    const rsp_c128* mf_medium;    /* time-domain matched filter, medium pulse */
+    int32_t         n_mf_medium;
+    const rsp_c128* mf_long;      /* time-domain matched filter, long pulse */
+    int32_t         n_mf_long;
+    const double*   mtd_win;      /* [P] MTD_win */
+    const double*   range_axis;   /* [G] */
+    const double*   velocity_axis;/* [P] */
+    double          delta_r, delta_v;
+    const double*   beam_angles_deg; /* [B] */
+    const double*   k_slopes;     /* [B-1] k_slopes_LUT */
+} rsp_constants;
+
+/* One CFAR detection after S9 (fun_process_single_frame.m:220 and :293-297). */
+typedef struct {
+    int32_t v_idx, r_idx, pair_idx;   /* 1-based */
+    float   power;                    /* S(v,r) = |rdm_A| + |rdm_B| */
+    double  range, velocity, angle;
+} rsp_detection;
+
+/* One clustered target (fun_process_single_frame.m:340-350, :393-406). */
+typedef struct { double range, velocity, angle, power; } rsp_target;
+
+typedef struct {
+    double max_range_sep, max_vel_sep, max_angle_sep;   /* cluster_params, fsf:328,381 */
+} rsp_cluster_params;
+
+typedef struct rsp_ctx rsp_ctx;
+
+/* ---- lifecycle ---- */
+int rsp_abi_version(void);
+int rsp_device_count(void);
+int rsp_create(const rsp_params* params, rsp_ctx** out);
+void rsp_destroy(rsp_ctx* ctx);
+const char* rsp_last_error(const rsp_ctx* ctx);          /* ctx may be NULL: last create() error */
+int rsp_upload_constants(rsp_ctx* ctx, const rsp_constants* k);
+int rsp_set_stream(rsp_ctx* ctx, void* cuda_stream);      /* cudaStream_t; NULL = context's own stream */
+int rsp_synchronize(rsp_ctx* ctx);
+
+/* ---- the hot path: S5 -> S9 on one CPI (fun_process_single_frame.m:90-146) ----
+ * raw: C*N*P complex samples in `layout`/`dtype`, in host or device memory.
+ * rdm_out: optional (may be NULL) destination for the complex64 range-Doppler map [B][G][P]
+ *          in `rdm_mem` space; NULL keeps it in the context (rsp_get_rdm).
+ * dets: host array of capacity det_cap; *n_dets receives the count.  The list is returned in the
+ *       reference's order (pair ascending, then range, then Doppler: MATLAB find, fsf:215-221). */
+int rsp_process_cpi(rsp_ctx* ctx, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem raw_mem,
+                    void* rdm_out, rsp_mem rdm_mem,
+                    rsp_detection* dets, int32_t det_cap, int32_t* n_dets);
+
+/* ---- device-resident CPI stream (throughput path; no host<->device traffic, asynchronous) ----
+ * Processes n_cpi cubes: cube i is read from raw_dev + (i % raw_pool) * C*N*P complex64 (RSP_LAYOUT_PCN),
+ * its RDM is written to rdm_dev + (i % rdm_pool) * B*G*P complex64, its detections to slot
+ * (first_slot + i) of the context's device detection ring.  Returns after enqueueing. */
+int rsp_stream_enqueue(rsp_ctx* ctx, const void* raw_dev, int32_t raw_pool, void* rdm_dev, int32_t rdm_pool,
+                       int32_t n_cpi, int32_t first_slot);
+int rsp_stream_slots(const rsp_ctx* ctx);                 /* capacity of the detection ring (CPIs) */
+/* Raw device pointers to the ring: counts[slot] (int32) and records[slot][max_detections] (unsorted). */
+int rsp_stream_device_buffers(rsp_ctx* ctx, void** counts_dev, void** records_dev);
+/* Copy one slot to the host and sort it into the reference order. */
+int rsp_stream_fetch(rsp_ctx* ctx, int32_t slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets);
+/* Sort an unsorted record list (e.g. gathered from another rank) into the reference order. */
+int rsp_sort_detections(rsp_detection* dets, int32_t n);
+
+/* ---- intermediates of the last rsp_process_cpi (parity / process_stage2_mtd outputs) ---- */
+int rsp_get_beam(rsp_ctx* ctx, rsp_c64* dst_host);        /* [P][B][N]  iq_data_13beam, fsf:92-97 */
+int rsp_get_pc(rsp_ctx* ctx, rsp_c64* dst_host);          /* [P][B][G]  device-native order */
+int rsp_get_rdm(rsp_ctx* ctx, rsp_c64* dst_host);         /* [B][G][P]  rdm_13beam */
+int rsp_get_amp(rsp_ctx* ctx, float* dst_host);           /* [B][G][P]  |rdm| */
+
+/* ---- S10 + S11 on the host (fun_process_single_frame.m:302-407), order-dependent BFS ---- */
+int rsp_cluster(const rsp_detection* dets, int32_t n_dets, const rsp_cluster_params* cp,
+                rsp_target* stage1, int32_t* n_stage1,      /* capacity n_dets each; stage1 may be NULL */
+                rsp_target* final_targets, int32_t* n_final);
+
+/* ---- S5 -> S11: the whole fun_process_single_frame after echo synthesis ---- */
+int rsp_process_frame(rsp_ctx* ctx, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem raw_mem,
+                      const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap, int32_t* n_final);
+
+/* ---- process_stage2_mtd.m:1 on an already beamformed + range-gated cube ----
+ * iq: MATLAB [P,G,B] column-major complex (dtype), host memory.  Outputs MATLAB-ordered [P,G,B]
+ * complex128: mtd_out = Doppler map, pc_out = pulse-compressed cube.  See DESIGN.md for the
+ * semantics specified by this repo (the callee fun_MTD_produce is not shipped by the reference). */
+int rsp_stage2_mtd(rsp_ctx* ctx, const void* iq, rsp_dtype dtype, rsp_c128* mtd_out, rsp_c128* pc_out);
+
+/* ---- introspection ---- */
+typedef struct {
+    int32_t n_gates_total;        /* G */
+    int32_t fft_len_medium, fft_len_long, blocks_medium, blocks_long;
+    int32_t kernels_per_cpi;      /* launches rsp_process_cpi / rsp_stream_enqueue issue per CPI */
+    int64_t algorithmic_bytes_per_cpi;   /* 8*P*N*C + 8*B*P*G */
+    int64_t launches_total;       /* kernels launched by this context so far */
+} rsp_info;
+int rsp_get_info(const rsp_ctx* ctx, rsp_info* info);
+
+/* ---- per-kernel device timing (bench.py's roofline leg) ----
+ * While enabled, every kernel of subsequently enqueued CPIs is bracketed by CUDA events on the
+ * context's stream.  rsp_get_kernel_times synchronises, returns for each kernel class its name,
+ * accumulated device milliseconds and launch count, and clears the accumulators. */
+#define RSP_MAX_KERNEL_CLASSES 8
+typedef struct {
+    int32_t n;
+    const char* name[RSP_MAX_KERNEL_CLASSES];
+    double total_ms[RSP_MAX_KERNEL_CLASSES];
+    int64_t launches[RSP_MAX_KERNEL_CLASSES];
+} rsp_kernel_times;
+int rsp_set_profiling(rsp_ctx* ctx, int enable);
+int rsp_get_kernel_times(rsp_ctx* ctx, rsp_kernel_times* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSP_H_ */

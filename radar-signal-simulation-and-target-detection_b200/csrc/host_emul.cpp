@@ -1,0 +1,125 @@
+// host_emul.cpp -- g++-built (no GPU) emulation of the kernel phases in rsp_phases.cuh.
+// TEST INFRASTRUCTURE: lets tests/test_host_emulation.py check the exact per-thread code of the
+// CUDA kernels against NumPy on a machine without a GPU.  Barriers become loops over tid.
+#include <cstring>
+#include <vector>
+#include "rsp_plan.hpp"
+
+using namespace rsp;
+
+template <int R1> static void run_pc_block(const PcBlockArgs& a, cf* s) {
+    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_load_pass1<R1>(a, s, t);
+    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_pass2<R1>(a, s, t);
+    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_mid<R1>(a, s, t);
+    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_ipass2<R1>(a, s, t);
+    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_ipass1_store<R1>(a, s, t);
+}
+
+extern "C" {
+
+int emul_small_dft(int R, int sign, float* v) {
+    cf* c = reinterpret_cast<cf*>(v);
+    if (sign < 0) {
+        switch (R) {
+            case 2: SmallDft<2, -1>::run(c); return 0;
+            case 4: SmallDft<4, -1>::run(c); return 0;
+            case 8: SmallDft<8, -1>::run(c); return 0;
+            case 16: SmallDft<16, -1>::run(c); return 0;
+        }
+    } else {
+        switch (R) {
+            case 2: SmallDft<2, +1>::run(c); return 0;
+            case 4: SmallDft<4, +1>::run(c); return 0;
+            case 8: SmallDft<8, +1>::run(c); return 0;
+            case 16: SmallDft<16, +1>::run(c); return 0;
+        }
+    }
+    return -1;
+}
+
+// One segment of one line through the overlap-save blocks.  L == 0 -> library's own choice.
+int emul_pc_segment(const float* line, int N, int seg_start0, int gate0, int ngates, const double* taps_ri,
+                    int ntaps, int L, float* out_line, int* L_used, int* nblk_used) {
+    if (L == 0) L = choose_pc_len(ntaps, ngates);
+    std::vector<zc> taps(ntaps);
+    for (int i = 0; i < ntaps; ++i) taps[i] = zc(taps_ri[2 * i], taps_ri[2 * i + 1]);
+    PcPlan pl;
+    if (!make_pc_plan(pl, L, taps.data(), ntaps, seg_start0, gate0, ngates)) return -1;
+    std::vector<cf> smem((size_t)rsp_pad16(L) + 16);
+    for (int blk = 0; blk < pl.nblk; ++blk) {
+        PcBlockArgs a;
+        a.line = reinterpret_cast<const cf*>(line);
+        a.out_line = reinterpret_cast<cf*>(out_line);
+        a.tw1 = pl.tw1.data();
+        a.tw2 = pl.tw2.data();
+        a.H = pl.H.data();
+        a.N = N;
+        a.seg_start0 = seg_start0;
+        a.taps = ntaps;
+        a.g0 = gate0 + blk * pl.valid;
+        a.g_end = gate0 + ngates;
+        switch (pl.R1) {
+            case 4: run_pc_block<4>(a, smem.data()); break;
+            case 8: run_pc_block<8>(a, smem.data()); break;
+            case 16: run_pc_block<16>(a, smem.data()); break;
+            default: return -2;
+        }
+    }
+    if (L_used) *L_used = L;
+    if (nblk_used) *nblk_used = pl.nblk;
+    return 0;
+}
+
+int emul_pc_narrow(const float* line, int N, int seg_start0, const float* fir, int nfir, int fir_delay, int ngates,
+                   float* out_line) {
+    cf* o = reinterpret_cast<cf*>(out_line);
+    for (int g = 0; g < ngates; ++g)
+        o[g] = pc_narrow_gate(reinterpret_cast<const cf*>(line), N, seg_start0, fir, nfir, fir_delay, g);
+    return 0;
+}
+
+// Doppler FFT of a [P][TG] tile (pulse-major, as it is read from the pc cube), window applied here.
+int emul_mtd_tile(const float* x, int P, int TG, const float* win, float* out /* [TG][P] */, int* radices_out) {
+    DopplerPlan dp;
+    if (!make_doppler_plan(dp, P)) return -1;
+    const cf* xi = reinterpret_cast<const cf*>(x);
+    std::vector<cf> s((size_t)P * (TG + 1));
+    for (int p = 0; p < P; ++p)
+        for (int gl = 0; gl < TG; ++gl) {
+            const float w = win[p] * ((p & 1) ? -1.f : 1.f);
+            s[(size_t)dp.perm[p] * (TG + 1) + gl] = cscale(xi[(size_t)p * TG + gl], w);
+        }
+    for (int pass = dp.plan.nrad - 1; pass >= 0; --pass)
+        for (int t = 0; t < RSP_MTD_THREADS; ++t)
+            mtd_dit_pass<-1>(s.data(), dp.plan, pass, dp.tw.data(), TG, t, RSP_MTD_THREADS);
+    cf* o = reinterpret_cast<cf*>(out);
+    for (int gl = 0; gl < TG; ++gl)
+        for (int row = 0; row < P; ++row) o[(size_t)gl * P + row] = s[(size_t)row * (TG + 1) + gl];
+    if (radices_out)
+        for (int i = 0; i < 4; ++i) radices_out[i] = i < dp.plan.nrad ? dp.plan.radices[i] : 0;
+    return 0;
+}
+
+// CFAR over a full sum map S[G][P] (one pair) using the tile routine on tiles of TG gates.
+int emul_cfar_map(const float* S, int G, int P, int guard_r, int guard_v, int ref_r, int ref_v, float t_cfar, int TG,
+                  unsigned char* det /* [G][P] */) {
+    CfarParams c;
+    c.P = P; c.G = G; c.guard_r = guard_r; c.guard_v = guard_v; c.ref_r = ref_r; c.ref_v = ref_v; c.t_cfar = t_cfar;
+    const int mR = guard_r + ref_r, mV = guard_v + ref_v;
+    std::memset(det, 0, (size_t)G * P);
+    for (int g_first = mR; g_first < G - mR; g_first += TG) {
+        const float* tile = S + (size_t)(g_first - mR) * P;      // rows g_first-mR ...
+        for (int gl = 0; gl < TG && g_first + gl < G - mR; ++gl)
+            for (int v = mV; v < P - mV; ++v) {
+                float cut;
+                if (cfar_cut(tile, P, c, gl, v, &cut)) det[(size_t)(g_first + gl) * P + v] = 1;
+            }
+    }
+    return 0;
+}
+
+double emul_spline5_peak(const double* y, int os) { return rsp_spline5_peak(y, os); }
+
+int emul_digit_reverse(int f, int L, const int* radices, int nrad) { return rsp_digit_reverse(f, L, radices, nrad); }
+
+}  // extern "C"

@@ -1,0 +1,640 @@
+// rsp_api.cu -- the C ABI of include/rsp.h: context, constant upload, per-CPI launch sequence.
+// There is no CPU fallback: without a CUDA device rsp_create fails with RSP_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rsp.h"
+#include "rsp_kernels.cuh"
+#include "rsp_plan.hpp"
+
+using namespace rsp;
+
+static thread_local std::string g_create_error;
+
+struct rsp_ctx {
+    rsp_params prm{};
+    int C = 0, B = 0, P = 0, N = 0, G = 0;
+    int ldb = 0, ldg = 0;                 // row pitches (complex elements) of beam / pc
+    bool have_constants = false;
+    bool ran = false;
+    bool rdm_in_ctx = false;
+    bool own_stream = true;
+    bool pow2_doppler = false;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // device buffers
+    float2* d_raw = nullptr;              // PCN complex64 staging for host / converted input
+    void* d_stage = nullptr;              // raw staging for dtype/layout conversion
+    size_t stage_bytes = 0;
+    float2* d_beam = nullptr;
+    float2* d_pc = nullptr;
+    float2* d_rdm = nullptr;
+    float* d_amp = nullptr;
+    float2* d_aux = nullptr;              // scratch for stage2 transposes
+    // constants
+    float2* d_W = nullptr;
+    float* d_fir = nullptr;
+    int n_fir = 0;
+    PcPlan med, lng;
+    float2 *d_med_tw1 = nullptr, *d_med_H = nullptr, *d_lng_tw1 = nullptr, *d_lng_H = nullptr, *d_tw2 = nullptr;
+    DopplerPlan dop;
+    float2* d_dop_tw = nullptr;
+    int dop_tw_count = 0;
+    int* d_dop_perm = nullptr;
+    float* d_win = nullptr;
+    double *d_range_axis = nullptr, *d_vel_axis = nullptr, *d_beam_angles = nullptr, *d_k_slopes = nullptr;
+    double delta_r = 0, delta_v = 0;
+    // detection ring
+    int slots = 0;
+    int* d_counts = nullptr;
+    rsp_detection* d_recs = nullptr;
+    int* h_count = nullptr;               // pinned
+    rsp_detection* h_recs = nullptr;      // pinned [max_detections]
+    int mtd_tg = 32;
+    size_t mtd_smem = 0, cfar_smem = 0;
+    // per-kernel event timing (rsp_set_profiling)
+    bool profiling = false;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC_MEDIUM, K_PC_LONG, K_MTD, K_CFAR, K_NCLASS };
+static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft_medium", "pc_fft_long", "mtd", "cfar"};
+
+static cudaEvent_t take_event(rsp_ctx* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+// RAII bracket: records an event before and after one launch when profiling is on
+struct Timed {
+    rsp_ctx* c; int cls; cudaEvent_t a = nullptr;
+    Timed(rsp_ctx* c_, int cls_) : c(c_), cls(cls_) {
+        if (c->profiling) { a = take_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~Timed() {
+        c->launches++;
+        if (c->profiling) { cudaEvent_t b = take_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({cls, a, b}); }
+    }
+};
+
+static int fail(rsp_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(ctx, RSP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T> static cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+template <typename T> static cudaError_t upload(T** dptr, const std::vector<T>& h) {
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    cudaError_t e = dev_alloc(dptr, h.size() ? h.size() : 1);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+template <typename KernelT> static cudaError_t opt_in_smem(KernelT kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" {
+
+int rsp_abi_version(void) { return RSP_ABI_VERSION; }
+
+int rsp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* rsp_last_error(const rsp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void rsp_destroy(rsp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_beam); cudaFree(c->d_pc); cudaFree(c->d_rdm);
+    cudaFree(c->d_amp); cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_fir);
+    cudaFree(c->d_med_tw1); cudaFree(c->d_med_H); cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_H); cudaFree(c->d_tw2);
+    cudaFree(c->d_dop_tw); cudaFree(c->d_dop_perm); cudaFree(c->d_win);
+    cudaFree(c->d_range_axis); cudaFree(c->d_vel_axis); cudaFree(c->d_beam_angles); cudaFree(c->d_k_slopes);
+    cudaFree(c->d_counts); cudaFree(c->d_recs);
+    if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->h_recs) cudaFreeHost(c->h_recs);
+    for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rsp_create(const rsp_params* p, rsp_ctx** out) {
+    if (!p || !out) return fail(nullptr, RSP_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (p->abi_version != RSP_ABI_VERSION)
+        return fail(nullptr, RSP_ERR_INVALID_ARG, "abi_version %d != %d", p->abi_version, RSP_ABI_VERSION);
+    if (p->n_channels < 1 || p->n_channels > RSP_MAX_CHANNELS || p->n_beams < 2 || p->n_beams > RSP_MAX_BEAMS)
+        return fail(nullptr, RSP_ERR_UNSUPPORTED, "need 1..%d channels and 2..%d beams", RSP_MAX_CHANNELS, RSP_MAX_BEAMS);
+    if (p->n_pulses < 2 || p->n_pulses > 4096 || p->n_samples < 64)
+        return fail(nullptr, RSP_ERR_UNSUPPORTED, "need 2..4096 pulses and >= 64 samples");
+    const int G = p->n_gates[0] + p->n_gates[1] + p->n_gates[2];
+    if (p->n_gates[0] < 0 || p->n_gates[1] < 0 || p->n_gates[2] < 0 || G < 1)
+        return fail(nullptr, RSP_ERR_INVALID_ARG, "bad gate counts");
+    for (int i = 0; i < 3; ++i)
+        if (p->seg_start[i] < 1 || p->seg_start[i] > p->n_samples)
+            return fail(nullptr, RSP_ERR_INVALID_ARG, "seg_start[%d] out of range", i);
+    if (p->guard_r < 0 || p->guard_v < 0 || p->ref_r < 1 || p->ref_v < 1 || p->guard_r + p->ref_r < 2 ||
+        p->guard_v + p->ref_v < 2 || p->guard_r + p->ref_r > 64)
+        return fail(nullptr, RSP_ERR_UNSUPPORTED, "CFAR windows: need ref >= 1, 2 <= guard+ref (<= 64 in range)");
+    if (p->max_detections < 1) return fail(nullptr, RSP_ERR_INVALID_ARG, "max_detections < 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(nullptr, RSP_ERR_NO_DEVICE, "no CUDA device visible; librsp has no CPU fallback");
+    }
+    if (p->device < 0 || p->device >= ndev) return fail(nullptr, RSP_ERR_INVALID_ARG, "device %d of %d", p->device, ndev);
+
+    rsp_ctx* c = new rsp_ctx();
+    c->prm = *p;
+    c->C = p->n_channels; c->B = p->n_beams; c->P = p->n_pulses; c->N = p->n_samples; c->G = G;
+    c->ldb = (c->N + 3) & ~3;
+    c->ldg = (c->G + 3) & ~3;
+    c->pow2_doppler = (c->P & (c->P - 1)) == 0;
+#define CUC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            fail(nullptr, RSP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));           \
+            rsp_destroy(c);                                                                         \
+            return RSP_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+    CUC(cudaSetDevice(p->device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t PBG = (size_t)c->P * c->B * c->G;
+    CUC(dev_alloc(&c->d_raw, (size_t)c->P * c->C * c->N));
+    CUC(dev_alloc(&c->d_beam, (size_t)c->P * c->B * c->ldb));
+    CUC(dev_alloc(&c->d_pc, (size_t)c->P * c->B * c->ldg));
+    CUC(dev_alloc(&c->d_rdm, PBG));
+    CUC(dev_alloc(&c->d_amp, PBG));
+    CUC(cudaMemset(c->d_beam, 0, (size_t)c->P * c->B * c->ldb * sizeof(float2)));
+    CUC(cudaMemset(c->d_pc, 0, (size_t)c->P * c->B * c->ldg * sizeof(float2)));
+    const char* es = getenv("RSP_STREAM_SLOTS");
+    c->slots = es ? std::max(1, atoi(es)) : 128;
+    CUC(dev_alloc(&c->d_counts, (size_t)c->slots));
+    CUC(dev_alloc(&c->d_recs, (size_t)c->slots * p->max_detections));
+    CUC(cudaMemset(c->d_counts, 0, (size_t)c->slots * sizeof(int)));
+    CUC(cudaMallocHost(reinterpret_cast<void**>(&c->h_count), sizeof(int)));
+    CUC(cudaMallocHost(reinterpret_cast<void**>(&c->h_recs), (size_t)p->max_detections * sizeof(rsp_detection)));
+#undef CUC
+    *out = c;
+    return RSP_OK;
+}
+
+int rsp_set_stream(rsp_ctx* c, void* s) {
+    if (!c) return RSP_ERR_INVALID_ARG;
+    if (s == nullptr) return RSP_OK;
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = reinterpret_cast<cudaStream_t>(s);
+    c->own_stream = false;
+    return RSP_OK;
+}
+
+int rsp_synchronize(rsp_ctx* c) {
+    if (!c) return RSP_ERR_INVALID_ARG;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RSP_OK;
+}
+
+int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
+    if (!c || !k) return RSP_ERR_INVALID_ARG;
+    if (!k->dbf_weights || !k->fir || !k->mf_medium || !k->mf_long || !k->mtd_win || !k->range_axis ||
+        !k->velocity_axis || !k->beam_angles_deg || !k->k_slopes)
+        return fail(c, RSP_ERR_INVALID_ARG, "null table in rsp_constants");
+    if (k->n_fir < 1 || k->n_fir > 256) return fail(c, RSP_ERR_UNSUPPORTED, "n_fir must be 1..256");
+    CU(c, cudaSetDevice(c->prm.device));
+    const int C = c->C, B = c->B, P = c->P, G = c->G;
+    // conj(W) laid out [c][b]
+    std::vector<float2> W((size_t)C * B);
+    for (int b = 0; b < B; ++b)
+        for (int ch = 0; ch < C; ++ch) {
+            const rsp_c128 w = k->dbf_weights[(size_t)b * C + ch];
+            W[(size_t)ch * B + b] = make_float2((float)w.re, (float)-w.im);
+        }
+    CU(c, upload(&c->d_W, W));
+    std::vector<float> fir(k->n_fir);
+    for (int i = 0; i < k->n_fir; ++i) fir[i] = (float)k->fir[i];
+    CU(c, upload(&c->d_fir, fir));
+    c->n_fir = k->n_fir;
+
+    // pulse-compression block plans
+    const int g1 = c->prm.n_gates[0], g2 = c->prm.n_gates[1], g3 = c->prm.n_gates[2];
+    auto plan_seg = [&](PcPlan& pl, const rsp_c128* taps, int nt, int seg_start1, int gate0, int ng,
+                        const char* env) -> int {
+        if (ng == 0) { pl = PcPlan(); return RSP_OK; }
+        if (nt < 1 || nt > 4096) return fail(c, RSP_ERR_UNSUPPORTED, "matched filter length %d not in 1..4096", nt);
+        std::vector<zc> t(nt);
+        for (int i = 0; i < nt; ++i) t[i] = zc(taps[i].re, taps[i].im);
+        int L = choose_pc_len(nt, ng);
+        const char* e = getenv(env);
+        if (e && atoi(e) > 0) L = atoi(e);
+        if (!make_pc_plan(pl, L, t.data(), nt, seg_start1 - 1, gate0, ng))
+            return fail(c, RSP_ERR_UNSUPPORTED, "no block plan for %d taps (L=%d)", nt, L);
+        return RSP_OK;
+    };
+    int rc = plan_seg(c->med, k->mf_medium, k->n_mf_medium, c->prm.seg_start[1], g1, g2, "RSP_PC_LEN_MEDIUM");
+    if (rc) return rc;
+    rc = plan_seg(c->lng, k->mf_long, k->n_mf_long, c->prm.seg_start[2], g1 + g2, g3, "RSP_PC_LEN_LONG");
+    if (rc) return rc;
+    if (c->med.L) { CU(c, upload(&c->d_med_tw1, c->med.tw1)); CU(c, upload(&c->d_med_H, c->med.H)); }
+    if (c->lng.L) { CU(c, upload(&c->d_lng_tw1, c->lng.tw1)); CU(c, upload(&c->d_lng_H, c->lng.H)); }
+    CU(c, upload(&c->d_tw2, make_twiddles(256, 16)));
+    for (int L : {1024, 2048, 4096}) {
+        const size_t sm = ((size_t)rsp_pad16(L) + 16) * sizeof(float2);
+        if (L == 1024) CU(c, opt_in_smem(pc_fft_kernel<4>, sm));
+        if (L == 2048) CU(c, opt_in_smem(pc_fft_kernel<8>, sm));
+        if (L == 4096) CU(c, opt_in_smem(pc_fft_kernel<16>, sm));
+    }
+
+    // Doppler plan
+    std::vector<float> win(P);
+    if (c->pow2_doppler) {
+        if (!make_doppler_plan(c->dop, P)) return fail(c, RSP_ERR_UNSUPPORTED, "no Doppler plan for P=%d", P);
+        for (int p = 0; p < P; ++p) win[p] = (float)(k->mtd_win[p] * ((p & 1) ? -1.0 : 1.0));
+        CU(c, upload(&c->d_dop_tw, c->dop.tw));
+        CU(c, upload(&c->d_dop_perm, c->dop.perm));
+        c->dop_tw_count = (int)c->dop.tw.size();
+        c->mtd_tg = 32;
+        c->mtd_smem = ((size_t)P * 33 + c->dop_tw_count) * sizeof(float2) + (size_t)P * (sizeof(float) + sizeof(int));
+        CU(c, opt_in_smem(mtd_kernel<32>, c->mtd_smem));
+    } else {
+        c->dop.plan.P = P;
+        c->dop.plan.nrad = 0;
+        std::vector<float2> tw(P);
+        for (int m = 0; m < P; ++m) {
+            const double ang = -2.0 * kPi * (double)m / (double)P;
+            tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        for (int p = 0; p < P; ++p) win[p] = (float)k->mtd_win[p];
+        CU(c, upload(&c->d_dop_tw, tw));
+        c->dop_tw_count = P;
+        const int tgs[3] = {32, 16, 8};
+        c->mtd_tg = 0;
+        for (int tg : tgs) {
+            const size_t sm = ((size_t)2 * P * (tg + 1) + P) * sizeof(float2);
+            if (sm <= 200 * 1024) { c->mtd_tg = tg; c->mtd_smem = sm; break; }
+        }
+        if (!c->mtd_tg) return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
+        if (c->mtd_tg == 32) CU(c, opt_in_smem(mtd_dft_kernel<32>, c->mtd_smem));
+        if (c->mtd_tg == 16) CU(c, opt_in_smem(mtd_dft_kernel<16>, c->mtd_smem));
+        if (c->mtd_tg == 8) CU(c, opt_in_smem(mtd_dft_kernel<8>, c->mtd_smem));
+    }
+    CU(c, upload(&c->d_win, win));
+    c->cfar_smem = (size_t)(32 + 2 * (c->prm.guard_r + c->prm.ref_r)) * P * sizeof(float);
+    if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
+    CU(c, opt_in_smem(cfar_kernel<32>, c->cfar_smem));
+
+    CU(c, upload(&c->d_range_axis, std::vector<double>(k->range_axis, k->range_axis + G)));
+    CU(c, upload(&c->d_vel_axis, std::vector<double>(k->velocity_axis, k->velocity_axis + P)));
+    CU(c, upload(&c->d_beam_angles, std::vector<double>(k->beam_angles_deg, k->beam_angles_deg + B)));
+    CU(c, upload(&c->d_k_slopes, std::vector<double>(k->k_slopes, k->k_slopes + (B - 1))));
+    c->delta_r = k->delta_r;
+    c->delta_v = k->delta_v;
+    c->have_constants = true;
+    return RSP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// launch sequence for one CPI (device-resident PCN complex64 input)
+// ------------------------------------------------------------------------------------------
+template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw) {
+    constexpr int SPT = NB <= 8 ? 4 : 2;
+    Timed t(c, K_DBF);
+    dim3 grid((c->N + 256 * SPT - 1) / (256 * SPT), c->P);
+    dbf_kernel<NB, SPT><<<grid, 256, 0, c->stream>>>(raw, c->d_beam, c->d_W, c->C, c->N, c->ldb);
+}
+
+static int launch_dbf_any(rsp_ctx* c, const float2* raw) {
+    switch (c->B) {
+#define CASE(n) case n: launch_dbf<n>(c, raw); break;
+        CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+        CASE(15) CASE(16)
+#undef CASE
+        default: return fail(c, RSP_ERR_UNSUPPORTED, "n_beams %d", c->B);
+    }
+    return RSP_OK;
+}
+
+static void launch_pc_seg(rsp_ctx* c, const PcPlan& pl, const float2* tw1, const float2* H, int cls) {
+    if (!pl.L) return;
+    Timed t(c, cls);
+    PcKernelArgs a;
+    a.beam = c->d_beam; a.pc = c->d_pc; a.tw1 = tw1; a.tw2 = c->d_tw2; a.H = H;
+    a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg; a.B = c->B;
+    a.seg_start0 = pl.seg_start0; a.taps = pl.taps; a.gate0 = pl.gate0; a.g_end = pl.gate0 + pl.ngates; a.valid = pl.valid;
+    dim3 grid(pl.nblk, c->B, c->P);
+    const size_t sm = ((size_t)rsp_pad16(pl.L) + 16) * sizeof(float2);
+    if (pl.R1 == 4) pc_fft_kernel<4><<<grid, RSP_PC_THREADS, sm, c->stream>>>(a);
+    else if (pl.R1 == 8) pc_fft_kernel<8><<<grid, RSP_PC_THREADS, sm, c->stream>>>(a);
+    else pc_fft_kernel<16><<<grid, RSP_PC_THREADS, sm, c->stream>>>(a);
+}
+
+static void launch_pc(rsp_ctx* c) {
+    if (c->prm.n_gates[0] > 0) {
+        dim3 grid(c->B, c->P);
+        Timed t(c, K_PC_NARROW);
+        pc_narrow_kernel<<<grid, 256, 0, c->stream>>>(c->d_beam, c->d_pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
+                                                      c->ldb, c->ldg, c->B, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
+    }
+    launch_pc_seg(c, c->med, c->d_med_tw1, c->d_med_H, K_PC_MEDIUM);
+    launch_pc_seg(c, c->lng, c->d_lng_tw1, c->d_lng_H, K_PC_LONG);
+}
+
+static void launch_mtd(rsp_ctx* c, float2* rdm) {
+    MtdArgs a;
+    a.pc = c->d_pc; a.rdm = rdm; a.amp = c->d_amp; a.win = c->d_win; a.tw = c->d_dop_tw; a.perm = c->d_dop_perm;
+    a.plan = c->dop.plan; a.tw_count = c->dop_tw_count; a.B = c->B; a.G = c->G; a.ldg = c->ldg;
+    const int tg = c->mtd_tg;
+    dim3 grid((c->G + tg - 1) / tg, c->B);
+    Timed t(c, K_MTD);
+    if (c->pow2_doppler) mtd_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
+    else if (tg == 32) mtd_dft_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
+    else if (tg == 16) mtd_dft_kernel<16><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
+    else mtd_dft_kernel<8><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
+}
+
+static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
+    CfarArgs a;
+    a.amp = c->d_amp; a.rdm = rdm;
+    a.c.P = c->P; a.c.G = c->G; a.c.guard_r = c->prm.guard_r; a.c.guard_v = c->prm.guard_v;
+    a.c.ref_r = c->prm.ref_r; a.c.ref_v = c->prm.ref_v; a.c.t_cfar = c->prm.t_cfar;
+    a.count = c->d_counts + slot;
+    a.recs = c->d_recs + (size_t)slot * c->prm.max_detections;
+    a.cap = c->prm.max_detections;
+    a.range_axis = c->d_range_axis; a.vel_axis = c->d_vel_axis; a.beam_angles = c->d_beam_angles; a.k_slopes = c->d_k_slopes;
+    a.delta_r = c->delta_r; a.delta_v = c->delta_v; a.complex_mode = c->prm.monopulse_complex;
+    const int mR = c->prm.guard_r + c->prm.ref_r, mV = c->prm.guard_v + c->prm.ref_v;
+    const int ncut = c->G - 2 * mR;
+    if (ncut <= 0 || c->P - 2 * mV <= 0) return;       // nothing is testable (fsf:192-193 ranges empty)
+    dim3 grid((ncut + 31) / 32, c->B - 1);
+    Timed t(c, K_CFAR);
+    cfar_kernel<32><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
+}
+
+static int kernels_per_cpi(const rsp_ctx* c) {
+    int n = 1 /*dbf*/ + (c->prm.n_gates[0] > 0) + (c->med.L > 0) + (c->lng.L > 0) + 1 /*mtd*/;
+    const int mR = c->prm.guard_r + c->prm.ref_r, mV = c->prm.guard_v + c->prm.ref_v;
+    if (c->G - 2 * mR > 0 && c->P - 2 * mV > 0) n += 1;
+    return n;
+}
+
+// enqueue S5..S9 for one device-resident PCN cube
+static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot) {
+    cudaMemsetAsync(c->d_counts + slot, 0, sizeof(int), c->stream);
+    int rc = launch_dbf_any(c, raw);
+    if (rc) return rc;
+    launch_pc(c);
+    launch_mtd(c, rdm);
+    launch_cfar(c, rdm, slot);
+    CU(c, cudaGetLastError());
+    return RSP_OK;
+}
+
+static bool det_less(const rsp_detection& a, const rsp_detection& b) {
+    if (a.pair_idx != b.pair_idx) return a.pair_idx < b.pair_idx;
+    if (a.r_idx != b.r_idx) return a.r_idx < b.r_idx;
+    return a.v_idx < b.v_idx;
+}
+
+// bring the input cube to device PCN complex64; returns the device pointer to use
+static int stage_input(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem mem, const float2** out) {
+    const size_t n = (size_t)c->P * c->C * c->N;
+    const size_t esz = dtype == RSP_C64 ? sizeof(float2) : sizeof(double2);
+    if (layout == RSP_LAYOUT_PCN && dtype == RSP_C64) {
+        if (mem == RSP_MEM_DEVICE) { *out = static_cast<const float2*>(raw); return RSP_OK; }
+        CU(c, cudaMemcpyAsync(c->d_raw, raw, n * esz, cudaMemcpyHostToDevice, c->stream));
+        *out = c->d_raw;
+        return RSP_OK;
+    }
+    const void* src = raw;
+    if (mem == RSP_MEM_HOST) {
+        if (c->stage_bytes < n * esz) {
+            if (c->d_stage) cudaFree(c->d_stage);
+            c->d_stage = nullptr;
+            CU(c, cudaMalloc(&c->d_stage, n * esz));
+            c->stage_bytes = n * esz;
+        }
+        CU(c, cudaMemcpyAsync(c->d_stage, raw, n * esz, cudaMemcpyHostToDevice, c->stream));
+        src = c->d_stage;
+    }
+    Timed t(c, K_CONVERT);
+    if (layout == RSP_LAYOUT_PCN) {
+        c128_to_c64_kernel<<<1184, 256, 0, c->stream>>>(static_cast<const double2*>(src), c->d_raw, n);
+    } else {
+        dim3 grid((c->P + 31) / 32, (c->N + 31) / 32, c->C), blk(32, 8);
+        if (dtype == RSP_C64)
+            matlab_to_pcn_kernel<float2><<<grid, blk, 0, c->stream>>>(static_cast<const float2*>(src), c->d_raw, c->P, c->N, c->C);
+        else
+            matlab_to_pcn_kernel<double2><<<grid, blk, 0, c->stream>>>(static_cast<const double2*>(src), c->d_raw, c->P, c->N, c->C);
+    }
+    CU(c, cudaGetLastError());
+    *out = c->d_raw;
+    return RSP_OK;
+}
+
+static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+    CU(c, cudaMemcpyAsync(c->h_count, c->d_counts + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const int n = *c->h_count;
+    if (n_dets) *n_dets = n;
+    if (n > c->prm.max_detections)
+        return fail(c, RSP_ERR_OVERFLOW, "%d detections exceed max_detections=%d", n, c->prm.max_detections);
+    if (n > det_cap) return fail(c, RSP_ERR_OVERFLOW, "%d detections exceed the caller's capacity %d", n, det_cap);
+    if (n > 0) {
+        CU(c, cudaMemcpyAsync(c->h_recs, c->d_recs + (size_t)slot * c->prm.max_detections, (size_t)n * sizeof(rsp_detection),
+                              cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        std::sort(c->h_recs, c->h_recs + n, det_less);
+        std::memcpy(dets, c->h_recs, (size_t)n * sizeof(rsp_detection));
+    }
+    return RSP_OK;
+}
+
+extern "C" {
+
+int rsp_process_cpi(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem raw_mem, void* rdm_out,
+                    rsp_mem rdm_mem, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+    if (!c || !raw || !n_dets || (det_cap > 0 && !dets)) return fail(c, RSP_ERR_INVALID_ARG, "null argument");
+    if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
+    CU(c, cudaSetDevice(c->prm.device));
+    const float2* d_in = nullptr;
+    int rc = stage_input(c, raw, layout, dtype, raw_mem, &d_in);
+    if (rc) return rc;
+    float2* rdm = (rdm_out && rdm_mem == RSP_MEM_DEVICE) ? static_cast<float2*>(rdm_out) : c->d_rdm;
+    rc = enqueue_chain(c, d_in, rdm, 0);
+    if (rc) return rc;
+    if (rdm_out && rdm_mem == RSP_MEM_HOST)
+        CU(c, cudaMemcpyAsync(rdm_out, c->d_rdm, (size_t)c->P * c->B * c->G * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    c->ran = true;
+    c->rdm_in_ctx = (rdm == c->d_rdm);
+    return fetch_slot(c, 0, dets, det_cap, n_dets);
+}
+
+int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* rdm_dev, int32_t rdm_pool, int32_t n_cpi,
+                       int32_t first_slot) {
+    if (!c || !raw_dev || raw_pool < 1 || n_cpi < 0) return fail(c, RSP_ERR_INVALID_ARG, "bad stream arguments");
+    if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
+    if (first_slot < 0 || first_slot + n_cpi > c->slots)
+        return fail(c, RSP_ERR_INVALID_ARG, "slots [%d,%d) exceed the ring of %d", first_slot, first_slot + n_cpi, c->slots);
+    CU(c, cudaSetDevice(c->prm.device));
+    const size_t in_elems = (size_t)c->P * c->C * c->N, out_elems = (size_t)c->P * c->B * c->G;
+    for (int i = 0; i < n_cpi; ++i) {
+        const float2* in = static_cast<const float2*>(raw_dev) + (size_t)(i % raw_pool) * in_elems;
+        float2* rdm = (rdm_dev && rdm_pool > 0) ? static_cast<float2*>(rdm_dev) + (size_t)(i % rdm_pool) * out_elems : c->d_rdm;
+        int rc = enqueue_chain(c, in, rdm, first_slot + i);
+        if (rc) return rc;
+    }
+    return RSP_OK;
+}
+
+int rsp_stream_slots(const rsp_ctx* c) { return c ? c->slots : 0; }
+
+int rsp_stream_device_buffers(rsp_ctx* c, void** counts_dev, void** records_dev) {
+    if (!c) return RSP_ERR_INVALID_ARG;
+    if (counts_dev) *counts_dev = c->d_counts;
+    if (records_dev) *records_dev = c->d_recs;
+    return RSP_OK;
+}
+
+int rsp_stream_fetch(rsp_ctx* c, int32_t slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+    if (!c || slot < 0 || slot >= c->slots || !n_dets) return fail(c, RSP_ERR_INVALID_ARG, "bad slot");
+    CU(c, cudaSetDevice(c->prm.device));
+    return fetch_slot(c, slot, dets, det_cap, n_dets);
+}
+
+int rsp_sort_detections(rsp_detection* dets, int32_t n) {
+    if (n < 0 || (n > 0 && !dets)) return RSP_ERR_INVALID_ARG;
+    std::sort(dets, dets + n, det_less);
+    return RSP_OK;
+}
+
+static int copy_out(rsp_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst) return RSP_ERR_INVALID_ARG;
+    if (!c->ran) return fail(c, RSP_ERR_NOT_READY, "no CPI has been processed into the context buffers");
+    CU(c, cudaSetDevice(c->prm.device));
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RSP_OK;
+}
+
+int rsp_get_beam(rsp_ctx* c, rsp_c64* dst) {
+    if (!c || !dst) return RSP_ERR_INVALID_ARG;
+    if (!c->ran) return fail(c, RSP_ERR_NOT_READY, "no CPI processed");
+    CU(c, cudaSetDevice(c->prm.device));
+    CU(c, cudaMemcpy2DAsync(dst, (size_t)c->N * sizeof(float2), c->d_beam, (size_t)c->ldb * sizeof(float2),
+                            (size_t)c->N * sizeof(float2), (size_t)c->P * c->B, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RSP_OK;
+}
+
+int rsp_get_pc(rsp_ctx* c, rsp_c64* dst) {
+    if (!c || !dst) return RSP_ERR_INVALID_ARG;
+    if (!c->ran) return fail(c, RSP_ERR_NOT_READY, "no CPI processed");
+    CU(c, cudaSetDevice(c->prm.device));
+    CU(c, cudaMemcpy2DAsync(dst, (size_t)c->G * sizeof(float2), c->d_pc, (size_t)c->ldg * sizeof(float2),
+                            (size_t)c->G * sizeof(float2), (size_t)c->P * c->B, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RSP_OK;
+}
+
+int rsp_get_rdm(rsp_ctx* c, rsp_c64* dst) {
+    if (c && c->ran && !c->rdm_in_ctx) return fail(c, RSP_ERR_NOT_READY, "the last CPI wrote its RDM to a caller buffer");
+    return copy_out(c, dst, c ? c->d_rdm : nullptr, c ? (size_t)c->P * c->B * c->G * sizeof(float2) : 0);
+}
+
+int rsp_get_amp(rsp_ctx* c, float* dst) {
+    return copy_out(c, dst, c ? c->d_amp : nullptr, c ? (size_t)c->P * c->B * c->G * sizeof(float) : 0);
+}
+
+int rsp_process_frame(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem raw_mem,
+                      const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap, int32_t* n_final) {
+    if (!c || !cp || !n_final) return fail(c, RSP_ERR_INVALID_ARG, "null argument");
+    std::vector<rsp_detection> dets((size_t)c->prm.max_detections);
+    int32_t n = 0;
+    int rc = rsp_process_cpi(c, raw, layout, dtype, raw_mem, nullptr, RSP_MEM_DEVICE, dets.data(), (int32_t)dets.size(), &n);
+    if (rc) return rc;
+    std::vector<rsp_target> fin((size_t)std::max(n, 1));
+    int32_t nf = 0, n1 = 0;
+    rc = rsp_cluster(dets.data(), n, cp, nullptr, &n1, fin.data(), &nf);
+    if (rc) return fail(c, rc, "clustering failed");
+    *n_final = nf;
+    if (nf > cap) return fail(c, RSP_ERR_OVERFLOW, "%d targets exceed the caller's capacity %d", nf, cap);
+    if (nf > 0 && !final_targets) return fail(c, RSP_ERR_INVALID_ARG, "null output");
+    std::memcpy(final_targets, fin.data(), (size_t)nf * sizeof(rsp_target));
+    return RSP_OK;
+}
+
+int rsp_stage2_mtd(rsp_ctx* c, const void* iq, rsp_dtype dtype, rsp_c128* mtd_out, rsp_c128* pc_out) {
+    (void)iq; (void)dtype; (void)mtd_out; (void)pc_out;
+    return fail(c, RSP_ERR_UNSUPPORTED, "rsp_stage2_mtd: not implemented yet (SURVEY.md section 8(f) rank 3)");
+}
+
+int rsp_set_profiling(rsp_ctx* c, int enable) {
+    if (!c) return RSP_ERR_INVALID_ARG;
+    c->profiling = enable != 0;
+    return RSP_OK;
+}
+
+int rsp_get_kernel_times(rsp_ctx* c, rsp_kernel_times* out) {
+    if (!c || !out) return RSP_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->prm.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::memset(out, 0, sizeof *out);
+    out->n = K_NCLASS;
+    for (int i = 0; i < K_NCLASS; ++i) out->name[i] = kKernelNames[i];
+    for (auto& sp : c->spans) {
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, sp.a, sp.b));
+        out->total_ms[sp.cls] += ms;
+        out->launches[sp.cls] += 1;
+        c->event_pool.push_back(sp.a);
+        c->event_pool.push_back(sp.b);
+    }
+    c->spans.clear();
+    return RSP_OK;
+}
+
+int rsp_get_info(const rsp_ctx* c, rsp_info* info) {
+    if (!c || !info) return RSP_ERR_INVALID_ARG;
+    info->n_gates_total = c->G;
+    info->fft_len_medium = c->med.L; info->fft_len_long = c->lng.L;
+    info->blocks_medium = c->med.nblk; info->blocks_long = c->lng.nblk;
+    info->kernels_per_cpi = c->have_constants ? kernels_per_cpi(c) : 0;
+    info->algorithmic_bytes_per_cpi = 8LL * c->P * c->N * c->C + 8LL * c->B * c->P * c->G;
+    info->launches_total = c->launches;
+    return RSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's per-frame interface on top of the C ABI (include/rsp.h).
+
+    final_targets = fun_process_single_frame(targets, config, cfar_params, cluster_params,
+                                             precomputed_data, frame_idx)        # fun_process_single_frame.m:13
+
+keeps the reference's argument names, meaning and "[] when nothing is detected" behaviour.  All of
+S5..S9 (DBF, pulse compression, MTD, CFAR, monopulse) runs in librsp.so's CUDA kernels; S10/S11
+(clustering, order-dependent BFS over a few hundred detections) runs in the library's host C++.
+Nothing in this module computes the chain on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import DETECTION_DTYPE, TARGET_DTYPE
+
+
+def _as_c128(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.complex128))
+
+
+def _as_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _field(obj, name):
+    return obj[name] if isinstance(obj, dict) else getattr(obj, name)
+
+
+def _ptr_of(x):
+    """(pointer, is_device) of a numpy array or a torch tensor."""
+    if hasattr(x, "data_ptr"):                       # torch tensor
+        return C.c_void_p(x.data_ptr()), bool(x.is_cuda)
+    return C.c_void_p(x.ctypes.data), False
+
+
+class RadarChain:
+    """One librsp context: shapes + constants resident on one GPU, one CUDA stream."""
+
+    def __init__(self, config, cfar_params, precomputed_data, device: int = 0, max_detections: int = 8192,
+                 monopulse_complex: bool = False):
+        self._lib = _abi.load()
+        self._ctx = C.c_void_p()
+        sc = _field(config, "Sig_Config")
+        pd = precomputed_data
+        self.C, self.B = int(_field(sc, "channel_num")), int(_field(sc, "beam_num"))
+        self.P, self.N = int(_field(sc, "prtNum")), int(_field(sc, "point_PRT"))
+        gates = [int(_field(pd, "N_gate_narrow")), int(_field(pd, "N_gate_medium")), int(_field(pd, "N_gate_long"))]
+        self.G = sum(gates)
+        if int(_field(pd, "N_total_gate")) != self.G:
+            raise ValueError("N_total_gate does not equal the sum of the three gate counts")
+        self.max_detections = int(max_detections)
+        p = _abi.rsp_params()
+        p.abi_version = _abi.RSP_ABI_VERSION
+        p.n_channels, p.n_beams, p.n_pulses, p.n_samples = self.C, self.B, self.P, self.N
+        p.seg_start[:] = [int(_field(pd, "seg_start_narrow")), int(_field(pd, "seg_start_medium")),
+                          int(_field(pd, "seg_start_long"))]
+        p.n_gates[:] = gates
+        p.fir_delay = int(_field(pd, "fir_delay"))
+        p.t_cfar = float(_field(cfar_params, "T_CFAR"))
+        p.guard_r, p.guard_v = int(_field(cfar_params, "guardCells_R")), int(_field(cfar_params, "guardCells_V"))
+        p.ref_r, p.ref_v = int(_field(cfar_params, "refCells_R")), int(_field(cfar_params, "refCells_V"))
+        p.max_detections = self.max_detections
+        p.monopulse_complex = int(bool(monopulse_complex))
+        p.device = int(device)
+        _abi.check(self._lib.rsp_create(C.byref(p), C.byref(self._ctx)))
+        self._upload(pd)
+
+    # -- set-up -------------------------------------------------------------------------------
+    def _upload(self, pd):
+        W = _as_c128(_field(pd, "DBF_coeffs_data_C"))
+        if W.shape != (self.B, self.C):
+            raise ValueError(f"DBF_coeffs_data_C must be [{self.B},{self.C}], got {W.shape}")
+        fir = _as_f64(_field(pd, "MF_narrow"))
+        try:
+            mf_m, mf_l = _as_c128(_field(pd, "MF_medium_win")), _as_c128(_field(pd, "MF_long_win"))
+        except (KeyError, AttributeError):
+            # only the spectra were supplied (the fields fun_process_single_frame.m:26-27 reads):
+            # the taps are the leading non-zero part of their inverse transform.
+            mf_m = _taps_from_spectrum(_field(pd, "MF_medium_fft"))
+            mf_l = _taps_from_spectrum(_field(pd, "MF_long_fft"))
+        win, ra, va = _as_f64(_field(pd, "MTD_win")).ravel(), _as_f64(_field(pd, "range_axis")).ravel(), \
+            _as_f64(_field(pd, "velocity_axis")).ravel()
+        ang, ks = _as_f64(_field(pd, "beam_angles_deg")).ravel(), _as_f64(_field(pd, "k_slopes_LUT")).ravel()
+        if len(win) != self.P or len(va) != self.P or len(ra) != self.G or len(ang) < self.B or len(ks) < self.B - 1:
+            raise ValueError("precomputed_data table sizes do not match the configuration")
+        k = _abi.rsp_constants()
+        keep = (W, fir, mf_m, mf_l, win, ra, va, ang, ks)        # keep alive during the call
+        k.dbf_weights, k.fir, k.n_fir = W.ctypes.data, fir.ctypes.data, len(fir)
+        k.mf_medium, k.n_mf_medium = mf_m.ctypes.data, len(mf_m)
+        k.mf_long, k.n_mf_long = mf_l.ctypes.data, len(mf_l)
+        k.mtd_win, k.range_axis, k.velocity_axis = win.ctypes.data, ra.ctypes.data, va.ctypes.data
+        k.delta_r, k.delta_v = float(_field(pd, "deltaR")), float(_field(pd, "deltaV"))
+        k.beam_angles_deg, k.k_slopes = ang.ctypes.data, ks.ctypes.data
+        _abi.check(self._lib.rsp_upload_constants(self._ctx, C.byref(k)), self._ctx)
+        del keep
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.rsp_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle: int):
+        _abi.check(self._lib.rsp_set_stream(self._ctx, C.c_void_p(cuda_stream_handle)), self._ctx)
+
+    def synchronize(self):
+        _abi.check(self._lib.rsp_synchronize(self._ctx), self._ctx)
+
+    def info(self) -> dict:
+        i = _abi.rsp_info()
+        _abi.check(self._lib.rsp_get_info(self._ctx, C.byref(i)), self._ctx)
+        return {f: getattr(i, f) for f, _ in i._fields_}
+
+    def set_profiling(self, enable: bool):
+        _abi.check(self._lib.rsp_set_profiling(self._ctx, int(bool(enable))), self._ctx)
+
+    def kernel_times(self) -> dict:
+        """{kernel class: (total device ms, launches)} since the last call (profiling must be on)."""
+        kt = _abi.rsp_kernel_times()
+        _abi.check(self._lib.rsp_get_kernel_times(self._ctx, C.byref(kt)), self._ctx)
+        return {kt.name[i].decode(): (kt.total_ms[i], kt.launches[i]) for i in range(kt.n) if kt.launches[i]}
+
+    # -- S5..S9 ---------------------------------------------------------------------------------
+    def process_cpi(self, raw, layout: str = "pcn", rdm_out=None) -> np.ndarray:
+        """Run DBF -> PC -> MTD -> CFAR -> monopulse on one cube.
+
+        raw: numpy array or torch tensor (host or CUDA), complex64 or complex128;
+             layout "pcn" = raw[p][c][n]; "matlab" = MATLAB [P,N,C] column-major bytes.
+        rdm_out: optional numpy array / CUDA tensor receiving the complex64 map [B][G][P].
+        Returns the detection table (structured array, reference order, 1-based indices)."""
+        n_el = self.P * self.C * self.N
+        ptr, on_dev = _ptr_of(raw)
+        dt = str(raw.dtype).replace("torch.", "")
+        if dt not in ("complex64", "complex128"):
+            raise TypeError(f"raw must be complex64/complex128, got {raw.dtype}")
+        size = raw.numel() if hasattr(raw, "numel") else raw.size
+        if size != n_el:
+            raise ValueError(f"raw has {size} elements, expected P*C*N = {n_el}")
+        if hasattr(raw, "is_contiguous"):
+            if not raw.is_contiguous():
+                raise ValueError("raw must be contiguous")
+        elif not raw.flags["C_CONTIGUOUS"]:
+            raise ValueError("raw must be C-contiguous")
+        lay = {"pcn": _abi.RSP_LAYOUT_PCN, "matlab": _abi.RSP_LAYOUT_MATLAB}[layout]
+        dets = np.zeros(self.max_detections, dtype=DETECTION_DTYPE)
+        n = C.c_int32(0)
+        rptr, rmem = C.c_void_p(), _abi.RSP_MEM_DEVICE
+        if rdm_out is not None:
+            rptr, rdev = _ptr_of(rdm_out)
+            rmem = _abi.RSP_MEM_DEVICE if rdev else _abi.RSP_MEM_HOST
+        _abi.check(self._lib.rsp_process_cpi(
+            self._ctx, ptr, lay, _abi.RSP_C64 if dt == "complex64" else _abi.RSP_C128,
+            _abi.RSP_MEM_DEVICE if on_dev else _abi.RSP_MEM_HOST, rptr, rmem,
+            C.c_void_p(dets.ctypes.data), self.max_detections, C.byref(n)), self._ctx)
+        return dets[:n.value].copy()
+
+    # -- device-resident stream -----------------------------------------------------------------
+    def stream_slots(self) -> int:
+        return int(self._lib.rsp_stream_slots(self._ctx))
+
+    def stream_enqueue(self, raw_dev_ptr: int, raw_pool: int, rdm_dev_ptr: int, rdm_pool: int, n_cpi: int,
+                       first_slot: int = 0):
+        _abi.check(self._lib.rsp_stream_enqueue(self._ctx, C.c_void_p(raw_dev_ptr), raw_pool,
+                                                C.c_void_p(rdm_dev_ptr) if rdm_dev_ptr else C.c_void_p(), rdm_pool,
+                                                n_cpi, first_slot), self._ctx)
+
+    def stream_fetch(self, slot: int) -> np.ndarray:
+        dets = np.zeros(self.max_detections, dtype=DETECTION_DTYPE)
+        n = C.c_int32(0)
+        _abi.check(self._lib.rsp_stream_fetch(self._ctx, slot, C.c_void_p(dets.ctypes.data), self.max_detections,
+                                              C.byref(n)), self._ctx)
+        return dets[:n.value].copy()
+
+    def stream_device_buffers(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _abi.check(self._lib.rsp_stream_device_buffers(self._ctx, C.byref(a), C.byref(b)), self._ctx)
+        return a.value, b.value
+
+    # -- intermediates (parity) -------------------------------------------------------------------
+    def get_beam(self) -> np.ndarray:
+        out = np.empty((self.P, self.B, self.N), np.complex64)
+        _abi.check(self._lib.rsp_get_beam(self._ctx, C.c_void_p(out.ctypes.data)), self._ctx)
+        return out
+
+    def get_pc(self) -> np.ndarray:
+        out = np.empty((self.P, self.B, self.G), np.complex64)
+        _abi.check(self._lib.rsp_get_pc(self._ctx, C.c_void_p(out.ctypes.data)), self._ctx)
+        return out
+
+    def get_rdm(self) -> np.ndarray:
+        out = np.empty((self.B, self.G, self.P), np.complex64)
+        _abi.check(self._lib.rsp_get_rdm(self._ctx, C.c_void_p(out.ctypes.data)), self._ctx)
+        return out
+
+    def get_amp(self) -> np.ndarray:
+        out = np.empty((self.B, self.G, self.P), np.float32)
+        _abi.check(self._lib.rsp_get_amp(self._ctx, C.c_void_p(out.ctypes.data)), self._ctx)
+        return out
+
+
+def _taps_from_spectrum(spec) -> np.ndarray:
+    h = np.fft.ifft(np.asarray(spec, dtype=np.complex128))
+    nz = np.nonzero(np.abs(h) > 1e-9 * np.abs(h).max())[0]
+    return np.ascontiguousarray(h[: int(nz.max()) + 1])
+
+
+def sort_detections(dets: np.ndarray) -> np.ndarray:
+    """Reference order: pair ascending, then range, then Doppler (MATLAB find, fsf:215-221)."""
+    d = np.ascontiguousarray(dets, dtype=DETECTION_DTYPE)
+    _abi.check(_abi.load().rsp_sort_detections(C.c_void_p(d.ctypes.data), len(d)))
+    return d
+
+
+def cluster(dets: np.ndarray, cluster_params):
+    """S10 + S11 (fun_process_single_frame.m:302-407) -> (stage1, final) structured arrays."""
+    lib = _abi.load()
+    d = np.ascontiguousarray(dets, dtype=DETECTION_DTYPE)
+    n = len(d)
+    cp = _abi.rsp_cluster_params(float(_field(cluster_params, "max_range_sep")),
+                                 float(_field(cluster_params, "max_vel_sep")),
+                                 float(_field(cluster_params, "max_angle_sep")))
+    s1 = np.zeros(max(n, 1), dtype=TARGET_DTYPE)
+    fin = np.zeros(max(n, 1), dtype=TARGET_DTYPE)
+    n1, nf = C.c_int32(0), C.c_int32(0)
+    _abi.check(lib.rsp_cluster(C.c_void_p(d.ctypes.data), n, C.byref(cp), C.c_void_p(s1.ctypes.data), C.byref(n1),
+                               C.c_void_p(fin.ctypes.data), C.byref(nf)))
+    return s1[:n1.value].copy(), fin[:nf.value].copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# S4 / S4.1 on the host (inputs of the chain; fun_process_single_frame.m:47-88)
+# ------------------------------------------------------------------------------------------------
+def _matlab_round(x: float) -> int:
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def synthesize_echo(targets: Sequence, config, precomputed_data) -> np.ndarray:
+    """Noise-free echoes raw[p][c][n] (complex128) for a list of targets with fields Range,
+    Velocity, ElevationAngle, SNR_dB (extra fields are ignored), fun_process_single_frame.m:47-77."""
+    sc = _field(config, "Sig_Config")
+    P, N, Cn = int(_field(sc, "prtNum")), int(_field(sc, "point_PRT")), int(_field(sc, "channel_num"))
+    c0, fs, lam, prt = (float(_field(sc, k)) for k in ("c", "fs", "wavelength", "prt"))
+    d_el = float(_field(_field(config, "Array"), "element_spacing"))
+    tx = np.asarray(_field(precomputed_data, "tx_pulse"))
+    p_sig = float(_field(precomputed_data, "P_signal_unscaled"))
+    raw = np.zeros((P, Cn, N), dtype=np.complex128)
+    m = np.arange(P)
+    for t in targets:
+        delay_samples = _matlab_round(2 * float(_field(t, "Range")) / c0 * fs)
+        doppler = np.exp(1j * 2 * np.pi * (2 * float(_field(t, "Velocity")) / lam) * m * prt)
+        amplitude = math.sqrt(10 ** (float(_field(t, "SNR_dB")) / 10) / p_sig)
+        base = np.zeros(N, dtype=np.complex128)
+        if 0 < delay_samples < N:
+            n_echo = min(len(tx), N - delay_samples)
+            base[delay_samples:delay_samples + n_echo] = tx[:n_echo]
+        dphi = 2 * np.pi * d_el * math.sin(math.radians(float(_field(t, "ElevationAngle")))) / lam
+        phasors = np.exp(1j * np.arange(Cn) * dphi)
+        raw += (amplitude * doppler)[:, None, None] * phasors[None, :, None] * base[None, None, :]
+    return raw
+
+
+def add_noise(raw: np.ndarray, rng: np.random.Generator, P_noise_floor: float = 1.0) -> np.ndarray:
+    """fun_process_single_frame.m:81-88 with a NumPy generator in place of MATLAB's randn."""
+    noise = rng.standard_normal(raw.shape) + 1j * rng.standard_normal(raw.shape)
+    return raw + noise * math.sqrt(P_noise_floor / 2)
+
+
+_chain_cache = {}
+
+
+def fun_process_single_frame(targets, config, cfar_params, cluster_params, precomputed_data, frame_idx=1, *,
+                             rng: Optional[np.random.Generator] = None, noise: bool = True,
+                             chain: Optional[RadarChain] = None, device: int = 0) -> List[dict]:
+    """Drop-in for fun_process_single_frame.m:13.  Returns a list of dicts with the reference's
+    fields Range, Velocity, Angle, Power (stage-2 cluster order); ``[]`` when nothing is detected.
+
+    Echo synthesis and noise (S4) are prepared on the host and handed to the device chain as one
+    complex64 cube; ``rng`` seeds the noise (the reference draws from MATLAB's global stream)."""
+    raw = synthesize_echo(targets, config, precomputed_data)
+    if noise:
+        raw = add_noise(raw, rng if rng is not None else np.random.default_rng())
+    raw = np.ascontiguousarray(raw.astype(np.complex64))
+    own = chain is None
+    if own:
+        key = id(precomputed_data)
+        chain = _chain_cache.get(key)
+        if chain is None:
+            chain = RadarChain(config, cfar_params, precomputed_data, device=device)
+            _chain_cache.clear()
+            _chain_cache[key] = chain
+    dets = chain.process_cpi(raw)
+    _, final = cluster(dets, cluster_params)
+    return [dict(Range=float(t["range"]), Velocity=float(t["velocity"]), Angle=float(t["angle"]),
+                 Power=float(t["power"])) for t in final]

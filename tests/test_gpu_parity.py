@@ -1,0 +1,182 @@
+"""GPU parity: the CUDA chain (through the C ABI) against the fp64 oracle on the same seeded cubes.
+
+Every stage boundary is compared (beam cube, pulse-compressed cube, range-Doppler map, amplitude
+map, detection list, per-detection estimates, clustered targets), so a failure names the stage.
+"""
+import numpy as np
+import pytest
+
+import rsp_b200 as rsp
+from conftest import oracle as o
+from parity_utils import RDM_REL_TOL, compare_detections, compare_targets, rel_errors
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_chain(name, **kw):
+    config, cfar_params, cluster_params = rsp.named_config(name)
+    pd = rsp.build_precomputed_data(config)
+    return rsp.RadarChain(config, cfar_params, pd, **kw), config, cfar_params, cluster_params, pd
+
+
+def _oracle_run(name, seed=0, targets=None, complex_ratio=False):
+    cfg, pre, raw = o.make_cube(name, seed, targets)
+    res = o.process_cube(raw.astype(np.complex128), cfg, pre, workers=-1, complex_ratio=complex_ratio)
+    return cfg, pre, raw, res
+
+
+def _check_all(name, chain, cluster_params, cfg, pre, raw, res, stages=True):
+    dets = chain.process_cpi(raw)
+    stats = {}
+    if stages:
+        beam = chain.get_beam()
+        stats["beam"] = rel_errors(beam, res.beam)
+        assert stats["beam"][0] <= 2e-6, stats
+        pc = chain.get_pc()
+        stats["pc"] = rel_errors(pc, res.pc)
+        assert stats["pc"][0] <= 1e-5, stats
+        # per segment too: the narrow piece is ~30 dB below the long one and would hide in the peak norm
+        g1, g2 = pre["N_gate_narrow"], pre["N_gate_medium"]
+        for nm, sl in (("narrow", slice(0, g1)), ("medium", slice(g1, g1 + g2)), ("long", slice(g1 + g2, None))):
+            stats["pc_" + nm] = rel_errors(pc[..., sl], res.pc[..., sl])
+            assert stats["pc_" + nm][0] <= 1e-5, stats
+    rdm = chain.get_rdm()
+    stats["rdm"] = rel_errors(rdm, res.rdm)
+    assert stats["rdm"][0] <= RDM_REL_TOL and stats["rdm"][1] <= RDM_REL_TOL, stats
+    amp = chain.get_amp()
+    assert np.abs(amp - np.abs(res.rdm)).max() <= 1e-5 * np.abs(res.rdm).max()
+    margin = o.cfar_margin(res.S, cfg)
+    stats["det"] = compare_detections(dets, res.raw_detections, margin, res.parameterized, pre)
+    _, final = rsp.cluster(dets, cluster_params)
+    loose = stats["det"]["spline_step_moves"] > 0 or stats["det"]["only_dev"] + stats["det"]["only_ref"] > 0
+    compare_targets(final, res.final_targets, pre, loose=loose)
+    stats["n_final"] = len(final)
+    print(name, stats)
+    return dets, stats
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_chain_matches_oracle(name):
+    chain, config, cfar_params, cluster_params, pd = _device_chain(name)
+    cfg, pre, raw, res = _oracle_run(name)
+    dets, stats = _check_all(name, chain, cluster_params, cfg, pre, raw, res)
+    assert stats["det"]["n_common"] >= 100          # three targets, many cells each
+    chain.close()
+
+
+def test_native_reference_shape_matches_oracle():
+    """The reference's literal configuration: 16 ch x 13 beams x 332 pulses (non power of two) x 5819."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("native")
+    cfg, pre, raw, res = _oracle_run("native")
+    dets, stats = _check_all("native", chain, cluster_params, cfg, pre, raw, res)
+    assert stats["n_final"] == 2
+    chain.close()
+
+
+def test_cfg3_32ch_16beams_matches_oracle():
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg3")
+    cfg, pre, raw, res = _oracle_run("cfg3")
+    _check_all("cfg3", chain, cluster_params, cfg, pre, raw, res, stages=False)
+    chain.close()
+
+
+def test_noise_free_and_empty_scene():
+    """Edge cases: no targets + no noise -> all-zero cube -> no detections -> [] (fsf:229-232,305-308);
+    noise only -> (almost surely) nothing above T = 8."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    zero = np.zeros((chain.P, chain.C, chain.N), np.complex64)
+    dets = chain.process_cpi(zero)
+    assert len(dets) == 0
+    s1, fin = rsp.cluster(dets, cluster_params)
+    assert len(s1) == 0 and len(fin) == 0
+    assert rsp.fun_process_single_frame([], config, cfar_params, cluster_params, pd, 1, noise=False, chain=chain) == []
+    cfg, pre, raw, res = _oracle_run("cfg1", seed=5, targets=[])
+    dets = chain.process_cpi(raw)
+    assert len(dets) == len(res.raw_detections)
+    chain.close()
+
+
+def test_matlab_layout_and_double_input_equal_native_layout():
+    """The MEX path hands over MATLAB [P,N,C] column-major complex double; it must give the same
+    detections as the device-native layout."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    cfg, pre, raw = o.make_cube("cfg1", 1)
+    a = chain.process_cpi(raw)
+    rdm_a = chain.get_rdm()
+    matlab = np.ascontiguousarray(np.transpose(raw, (1, 2, 0)).astype(np.complex128))   # [c][n][p]
+    b = chain.process_cpi(matlab, layout="matlab")
+    assert np.array_equal(chain.get_rdm(), rdm_a)
+    assert np.array_equal(a, b)
+    c = chain.process_cpi(np.ascontiguousarray(raw.astype(np.complex128)))
+    assert np.array_equal(a, c)
+    chain.close()
+
+
+def test_linearity_and_idempotence_at_full_size():
+    """Size-independent properties at BASELINE config 2: the chain up to the RDM is linear
+    (RDM(a*x) == a*RDM(x) for a power of two, bit exact in fp32), and a repeat run is bit identical."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg2")
+    cfg, pre, raw = o.make_cube("cfg2", 2)
+    d1 = chain.process_cpi(raw)
+    r1 = chain.get_rdm()
+    d2 = chain.process_cpi(raw)
+    assert np.array_equal(r1, chain.get_rdm()) and np.array_equal(d1, d2)
+    chain.process_cpi(raw * np.complex64(4.0))
+    assert np.array_equal(chain.get_rdm(), r1 * np.complex64(4.0))
+    chain.close()
+
+
+def test_known_answer_target_cells():
+    """A noise-free point target lands in the expected range gate / Doppler bin in all three
+    pulse-compression segments, and its monopulse angle is the configured elevation."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg2")
+    cfg, pre, _ = o.make_cube("cfg2", None, targets=[])
+    dR = pre["deltaR"]
+    for gate, el in ((150, -5.0), (500, 8.2), (1334, 15.0), (5000, 3.0)):
+        tgt = [o.Target(gate * dR, 0.1 * pre["v_max"], el, 20.0)]
+        raw = o.synthesize_echo(tgt, cfg, pre).astype(np.complex64)
+        chain.process_cpi(raw)
+        amp = chain.get_amp()
+        b, g, v = np.unravel_index(np.argmax(amp), amp.shape)
+        # a target with round-trip delay d samples peaks at 1-based gate d (d-1.5 in the narrow segment)
+        assert abs((g + 1) - gate) <= 2, (gate, g)
+        fd = 2 * tgt[0].Velocity / cfg.wavelength
+        v_expect = (fd * cfg.prt * cfg.prtNum + cfg.prtNum // 2) % cfg.prtNum
+        assert abs(v - v_expect) <= 1, (v, v_expect)
+    chain.close()
+
+
+def test_monopulse_complex_variant():
+    """main_plot_snr_vs_angle_error.m:454-461 uses the complex ratio; same cells, different angle."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1", monopulse_complex=True)
+    cfg, pre, raw, res = _oracle_run("cfg1", seed=3, complex_ratio=True)
+    dets = chain.process_cpi(raw)
+    margin = o.cfar_margin(res.S, cfg)
+    compare_detections(dets, res.raw_detections, margin, res.parameterized, pre, tol_angle=0.02)
+    chain.close()
+
+
+def test_stream_path_equals_single_cpi_path():
+    """The device-resident stream (throughput path) must produce what rsp_process_cpi produces."""
+    import torch
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    cubes = [o.make_cube("cfg1", s)[2] for s in (0, 1, 2)]
+    single = [chain.process_cpi(c) for c in cubes]
+    pool = torch.from_numpy(np.stack(cubes)).cuda()
+    rdm = torch.empty((2, chain.B, chain.G, chain.P), dtype=torch.complex64, device="cuda")
+    chain.stream_enqueue(pool.data_ptr(), 3, rdm.data_ptr(), 2, 6, 0)
+    chain.synchronize()
+    for i in range(6):
+        assert np.array_equal(chain.stream_fetch(i), single[i % 3]), i
+    chain.process_cpi(cubes[2])
+    assert np.array_equal(rdm[1].cpu().numpy(), chain.get_rdm())      # cube 5 -> rdm slot 1
+    chain.close()
+
+
+def test_detection_overflow_is_an_error_not_truncation():
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1", max_detections=8)
+    cfg, pre, raw = o.make_cube("cfg1", 0)
+    with pytest.raises(rsp.RspError) as ei:
+        chain.process_cpi(raw)
+    assert ei.value.code == -5
+    chain.close()

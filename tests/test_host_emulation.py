@@ -1,0 +1,133 @@
+"""CPU checks of the *kernel bodies* (csrc/rsp_phases.cuh) compiled for the host.
+
+The CUDA kernels are written as sequences of host/device "phases"; csrc/host_emul.cpp runs the same
+phases with loops instead of barriers.  Here they are compared with NumPy / the oracle, so the
+butterflies, digit reversal, overlap-save bookkeeping, Doppler plan, CFAR window arithmetic and the
+spline peak search are verified without a GPU.  (The oracle is only the checker.)
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import emul_lib, oracle as o
+
+fp = ctypes.POINTER(ctypes.c_float)
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emul_lib()
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    cfg, pre, raw = o.make_cube("cfg1", 0)
+    beam = o.dbf(raw.astype(np.complex128), pre["DBF_coeffs_data_C"])
+    pc = o.pulse_compress(beam, pre)
+    return cfg, pre, beam, pc
+
+
+@pytest.mark.parametrize("R", [2, 4, 8, 16])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_small_dft(lib, R, sign):
+    rng = np.random.default_rng(R * 7 + sign)
+    x = (rng.standard_normal(R) + 1j * rng.standard_normal(R)).astype(np.complex64)
+    v = x.copy()
+    assert lib.emul_small_dft(R, sign, v.ctypes.data_as(fp)) == 0
+    ref = np.fft.fft(x.astype(np.complex128)) if sign < 0 else np.fft.ifft(x.astype(np.complex128)) * R
+    assert np.abs(v - ref).max() < 5e-6 * np.abs(ref).max()
+
+
+def test_digit_reverse_is_permutation(lib):
+    for L, rad in ((4096, [16, 16, 16]), (2048, [8, 16, 16]), (1024, [4, 16, 16]), (64, [16, 4]), (32, [8, 4])):
+        r = (ctypes.c_int * len(rad))(*rad)
+        pos = [lib.emul_digit_reverse(f, L, r, len(rad)) for f in range(L)]
+        assert sorted(pos) == list(range(L))
+
+
+@pytest.mark.parametrize("seg", ["medium", "long"])
+@pytest.mark.parametrize("L", [0, 1024, 2048, 4096])
+def test_pc_overlap_save_matches_reference_fft_convolution(lib, cfg1, seg, L):
+    cfg, pre, beam, pc = cfg1
+    N, G = cfg.point_PRT, cfg.n_gates
+    g1, g2 = pre["N_gate_narrow"], pre["N_gate_medium"]
+    if seg == "medium":
+        ss, gate0, ng, taps = pre["seg_start_medium"] - 1, g1, g2, pre["MF_medium_win"]
+    else:
+        ss, gate0, ng, taps = pre["seg_start_long"] - 1, g1 + g2, G - g1 - g2, pre["MF_long_win"]
+    if L and L < len(taps):
+        pytest.skip("block shorter than the filter")
+    t = np.ascontiguousarray(np.stack([taps.real, taps.imag], -1))
+    for (p, b) in ((3, 2), (0, 12), (31, 0)):
+        line = np.ascontiguousarray(beam[p, b].astype(np.complex64))
+        out = np.zeros(G, np.complex64)
+        Lu, nb = ctypes.c_int(), ctypes.c_int()
+        rc = lib.emul_pc_segment(line.ctypes.data_as(fp), N, int(ss), int(gate0), int(ng), t.ctypes.data_as(dp),
+                                 len(taps), L, out.ctypes.data_as(fp), ctypes.byref(Lu), ctypes.byref(nb))
+        assert rc == 0
+        ref = pc[p, b, gate0:gate0 + ng]
+        assert np.abs(out[gate0:gate0 + ng] - ref).max() <= 2e-6 * np.abs(ref).max()
+        # the block writer must not touch gates owned by the other segments
+        assert not out[:gate0].any() and not out[gate0 + ng:].any()
+
+
+def test_pc_narrow_fir(lib, cfg1):
+    cfg, pre, beam, pc = cfg1
+    g1 = pre["N_gate_narrow"]
+    fir = pre["MF_narrow"].astype(np.float32)
+    line = np.ascontiguousarray(beam[5, 7].astype(np.complex64))
+    out = np.zeros(g1, np.complex64)
+    lib.emul_pc_narrow(line.ctypes.data_as(fp), cfg.point_PRT, pre["seg_start_narrow"] - 1, fir.ctypes.data_as(fp),
+                       len(fir), pre["fir_delay"], g1, out.ctypes.data_as(fp))
+    ref = pc[5, 7, :g1]
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("P", [32, 64, 128, 256, 512])
+def test_mtd_tile(lib, P):
+    TG = 32
+    rng = np.random.default_rng(P)
+    x = (rng.standard_normal((P, TG)) + 1j * rng.standard_normal((P, TG))).astype(np.complex64)
+    win = np.kaiser(P, 4.5).astype(np.float32)
+    out = np.zeros((TG, P), np.complex64)
+    rad = (ctypes.c_int * 4)()
+    assert lib.emul_mtd_tile(x.ctypes.data_as(fp), P, TG, win.ctypes.data_as(fp), out.ctypes.data_as(fp), rad) == 0
+    ref = np.fft.fftshift(np.fft.fft(x.astype(np.complex128) * win.astype(np.float64)[:, None], axis=0), axes=0).T
+    assert np.abs(out - ref).max() <= 3e-6 * np.abs(ref).max(), list(rad)
+
+
+@pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (150, 48, 3, 4, 2, 3)])
+def test_cfar_tiles_match_oracle(lib, shape):
+    G, P, gR, gV, rR, rV = shape
+    rng = np.random.default_rng(G)
+    S = rng.rayleigh(1.0, (1, G, P))
+    for (g, v) in ((100, P // 2), (40, P // 2 + 3), (G - 20 - 5, P // 2 - 2)):
+        S[0, g, v] += 60.0
+    S = S.astype(np.float32)
+    cfg = o.Config(guardCells_R=gR, guardCells_V=gV, refCells_R=rR, refCells_V=rV, T_CFAR=4.0)
+    det = np.zeros((G, P), np.uint8)
+    lib.emul_cfar_map(S[0].ctypes.data_as(fp), G, P, gR, gV, rR, rV, ctypes.c_float(4.0), 32,
+                      det.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
+    ref = o.cfar_detect(S.astype(np.float64), cfg)
+    margin = o.cfar_margin(S.astype(np.float64), cfg)[0]
+    got = {(int(v) + 1, int(g) + 1) for g, v in zip(*np.nonzero(det))}
+    want = {(int(r[0]), int(r[1])) for r in ref}
+    for (v1, g1) in got ^ want:                      # only near-threshold cells may differ
+        assert margin[g1 - 1, v1 - 1] < 1e-5
+    assert len(want) >= 3
+    # and the vectorised oracle equals the literal scalar loops
+    assert np.array_equal(ref, o.cfar_detect_scalar(S.astype(np.float64), cfg))
+
+
+def test_spline_peak_matches_scipy(lib):
+    lib.emul_spline5_peak.restype = ctypes.c_double
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        y = rng.rayleigh(1.0, 5)
+        y[2] += rng.uniform(0, 5)
+        for os_ in (8, 4):
+            got = lib.emul_spline5_peak(y.ctypes.data_as(dp), os_)
+            assert got == pytest.approx(o._spline_peak(y, os_), abs=1e-12)
