@@ -7,12 +7,17 @@
 
 using namespace rsp;
 
-template <int R1> static void run_pc_block(const PcBlockArgs& a, cf* s) {
-    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_load_pass1<R1>(a, s, t);
-    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_pass2<R1>(a, s, t);
-    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_mid<R1>(a, s, t);
-    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_ipass2<R1>(a, s, t);
-    for (int t = 0; t < RSP_PC_THREADS; ++t) pc_phase_ipass1_store<R1>(a, s, t);
+template <class Cfg> static void run_pc_block(const PcBlockArgs& a, cf* s) {
+    for (int t = 0; t < Cfg::T; ++t) pc_phase_load_pass1<Cfg>(a, s, t);
+    for (int t = 0; t < Cfg::T; ++t) pc_phase_pass2<Cfg>(a, s, t);
+    for (int t = 0; t < Cfg::T; ++t) pc_phase_mid<Cfg>(a, s, t);
+    for (int t = 0; t < Cfg::T; ++t) pc_phase_ipass2<Cfg>(a, s, t);
+    for (int t = 0; t < Cfg::T; ++t) pc_phase_ipass1_store<Cfg>(a, s, t);
+}
+
+template <class Cfg> static void run_mtd_tile(cf* s, const cf* tw) {
+    for (int pass = 0; pass < 3; ++pass)
+        for (int t = 0; t < RSP_MTD_THREADS; ++t) mtd_passes_phase<Cfg>(s, tw, t, pass);
 }
 
 extern "C" {
@@ -45,23 +50,23 @@ int emul_pc_segment(const float* line, int N, int seg_start0, int gate0, int nga
     for (int i = 0; i < ntaps; ++i) taps[i] = zc(taps_ri[2 * i], taps_ri[2 * i + 1]);
     PcPlan pl;
     if (!make_pc_plan(pl, L, taps.data(), ntaps, seg_start0, gate0, ngates)) return -1;
-    std::vector<cf> smem((size_t)rsp_pad16(L) + 16);
+    std::vector<cf> smem((size_t)L + L / 16 + 16);
     for (int blk = 0; blk < pl.nblk; ++blk) {
         PcBlockArgs a;
         a.line = reinterpret_cast<const cf*>(line);
         a.out_line = reinterpret_cast<cf*>(out_line);
         a.tw1 = pl.tw1.data();
         a.tw2 = pl.tw2.data();
-        a.H = pl.H.data();
+        a.Hmid = pl.Hmid.data();
         a.N = N;
         a.seg_start0 = seg_start0;
         a.taps = ntaps;
         a.g0 = gate0 + blk * pl.valid;
         a.g_end = gate0 + ngates;
-        switch (pl.R1) {
-            case 4: run_pc_block<4>(a, smem.data()); break;
-            case 8: run_pc_block<8>(a, smem.data()); break;
-            case 16: run_pc_block<16>(a, smem.data()); break;
+        switch (pl.L) {
+            case 1024: run_pc_block<PcCfg<1024, 16, 16, 4>>(a, smem.data()); break;
+            case 2048: run_pc_block<PcCfg<2048, 8, 16, 16>>(a, smem.data()); break;
+            case 4096: run_pc_block<PcCfg<4096, 16, 16, 16>>(a, smem.data()); break;
             default: return -2;
         }
     }
@@ -81,7 +86,7 @@ int emul_pc_narrow(const float* line, int N, int seg_start0, const float* fir, i
 // Doppler FFT of a [P][TG] tile (pulse-major, as it is read from the pc cube), window applied here.
 int emul_mtd_tile(const float* x, int P, int TG, const float* win, float* out /* [TG][P] */, int* radices_out) {
     DopplerPlan dp;
-    if (!make_doppler_plan(dp, P)) return -1;
+    if (TG != RSP_MTD_TG || !make_doppler_plan(dp, P)) return -1;
     const cf* xi = reinterpret_cast<const cf*>(x);
     std::vector<cf> s((size_t)P * (TG + 1));
     for (int p = 0; p < P; ++p)
@@ -89,30 +94,45 @@ int emul_mtd_tile(const float* x, int P, int TG, const float* win, float* out /*
             const float w = win[p] * ((p & 1) ? -1.f : 1.f);
             s[(size_t)dp.perm[p] * (TG + 1) + gl] = cscale(xi[(size_t)p * TG + gl], w);
         }
-    for (int pass = dp.plan.nrad - 1; pass >= 0; --pass)
-        for (int t = 0; t < RSP_MTD_THREADS; ++t)
-            mtd_dit_pass<-1>(s.data(), dp.plan, pass, dp.tw.data(), TG, t, RSP_MTD_THREADS);
+    switch (P) {
+        case 8: run_mtd_tile<MtdCfg<8, 8, 1, 1>>(s.data(), dp.tw.data()); break;
+        case 16: run_mtd_tile<MtdCfg<16, 16, 1, 1>>(s.data(), dp.tw.data()); break;
+        case 32: run_mtd_tile<MtdCfg<32, 8, 4, 1>>(s.data(), dp.tw.data()); break;
+        case 64: run_mtd_tile<MtdCfg<64, 8, 8, 1>>(s.data(), dp.tw.data()); break;
+        case 128: run_mtd_tile<MtdCfg<128, 16, 8, 1>>(s.data(), dp.tw.data()); break;
+        case 256: run_mtd_tile<MtdCfg<256, 16, 16, 1>>(s.data(), dp.tw.data()); break;
+        case 512: run_mtd_tile<MtdCfg<512, 8, 8, 8>>(s.data(), dp.tw.data()); break;
+        default: return -3;
+    }
     cf* o = reinterpret_cast<cf*>(out);
     for (int gl = 0; gl < TG; ++gl)
         for (int row = 0; row < P; ++row) o[(size_t)gl * P + row] = s[(size_t)row * (TG + 1) + gl];
     if (radices_out)
-        for (int i = 0; i < 4; ++i) radices_out[i] = i < dp.plan.nrad ? dp.plan.radices[i] : 0;
+        for (int i = 0; i < 4; ++i) radices_out[i] = i < 3 ? dp.r[i] : 0;
     return 0;
 }
 
-// CFAR over a full sum map S[G][P] (one pair) using the tile routine on tiles of TG gates.
+// CFAR over a full sum map S[G][P] (one pair) using the two tile phases on tiles of TG gates.
 int emul_cfar_map(const float* S, int G, int P, int guard_r, int guard_v, int ref_r, int ref_v, float t_cfar, int TG,
                   unsigned char* det /* [G][P] */) {
     CfarParams c;
     c.P = P; c.G = G; c.guard_r = guard_r; c.guard_v = guard_v; c.ref_r = ref_r; c.ref_v = ref_v; c.t_cfar = t_cfar;
     const int mR = guard_r + ref_r, mV = guard_v + ref_v;
+    const int rows = TG + 2 * mR;
     std::memset(det, 0, (size_t)G * P);
+    std::vector<float> tile((size_t)rows * P), R5((size_t)cfar_r5_rows(c, TG) * P), D5((size_t)TG * P);
     for (int g_first = mR; g_first < G - mR; g_first += TG) {
-        const float* tile = S + (size_t)(g_first - mR) * P;      // rows g_first-mR ...
+        for (int row = 0; row < rows; ++row)
+            for (int v = 0; v < P; ++v) {
+                const int g = g_first - mR + row;
+                tile[(size_t)row * P + v] = g < G ? S[(size_t)g * P + v] : 0.f;
+            }
+        for (int t = 0; t < RSP_CFAR_THREADS; ++t)
+            cfar_sums_phase(tile.data(), R5.data(), D5.data(), c, TG, t, RSP_CFAR_THREADS);
         for (int gl = 0; gl < TG && g_first + gl < G - mR; ++gl)
             for (int v = mV; v < P - mV; ++v) {
                 float cut;
-                if (cfar_cut(tile, P, c, gl, v, &cut)) det[(size_t)(g_first + gl) * P + v] = 1;
+                if (cfar_decide(tile.data(), R5.data(), D5.data(), c, gl, v, &cut)) det[(size_t)(g_first + gl) * P + v] = 1;
             }
     }
     return 0;

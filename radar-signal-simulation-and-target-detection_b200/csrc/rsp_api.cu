@@ -43,7 +43,8 @@ struct rsp_ctx {
     float* d_fir = nullptr;
     int n_fir = 0;
     PcPlan med, lng;
-    float2 *d_med_tw1 = nullptr, *d_med_H = nullptr, *d_lng_tw1 = nullptr, *d_lng_H = nullptr, *d_tw2 = nullptr;
+    float2 *d_med_tw1 = nullptr, *d_med_tw2 = nullptr, *d_med_H = nullptr;
+    float2 *d_lng_tw1 = nullptr, *d_lng_tw2 = nullptr, *d_lng_H = nullptr;
     DopplerPlan dop;
     float2* d_dop_tw = nullptr;
     int dop_tw_count = 0;
@@ -57,7 +58,7 @@ struct rsp_ctx {
     rsp_detection* d_recs = nullptr;
     int* h_count = nullptr;               // pinned
     rsp_detection* h_recs = nullptr;      // pinned [max_detections]
-    int mtd_tg = 32;
+    int mtd_tg = 32, cfar_tg = 32;
     size_t mtd_smem = 0, cfar_smem = 0;
     // per-kernel event timing (rsp_set_profiling)
     bool profiling = false;
@@ -66,8 +67,8 @@ struct rsp_ctx {
     std::vector<cudaEvent_t> event_pool;
 };
 
-enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC_MEDIUM, K_PC_LONG, K_MTD, K_CFAR, K_NCLASS };
-static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft_medium", "pc_fft_long", "mtd", "cfar"};
+enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC_MEDIUM, K_PC_LONG, K_MTD, K_CFAR, K_REFINE, K_NCLASS };
+static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft_medium", "pc_fft_long", "mtd", "cfar", "refine"};
 
 static cudaEvent_t take_event(rsp_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -119,6 +120,23 @@ template <typename KernelT> static cudaError_t opt_in_smem(KernelT kern, size_t 
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+typedef PcCfg<1024, 16, 16, 4> Pc1024;
+typedef PcCfg<2048, 8, 16, 16> Pc2048;
+typedef PcCfg<4096, 16, 16, 16> Pc4096;
+template <class Cfg> static size_t pc_smem_bytes() {
+    return ((size_t)Cfg::NG * Cfg::SMEM_ELEMS + (Cfg::R2 - 1) * Cfg::SPAN2) * sizeof(float2) + 256 * sizeof(float);
+}
+
+#define RSP_FOR_EACH_POW2_P(X) X(8, 8, 1, 1) X(16, 16, 1, 1) X(32, 8, 4, 1) X(64, 8, 8, 1) X(128, 16, 8, 1) X(256, 16, 16, 1) X(512, 8, 8, 8)
+static cudaError_t mtd_opt_in(int P, size_t bytes) {
+    switch (P) {
+#define X(p, a, b, c) case p: return opt_in_smem(mtd_kernel<MtdCfg<p, a, b, c>>, bytes);
+        RSP_FOR_EACH_POW2_P(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
 extern "C" {
 
 int rsp_abi_version(void) { return RSP_ABI_VERSION; }
@@ -136,7 +154,8 @@ void rsp_destroy(rsp_ctx* c) {
     cudaSetDevice(c->prm.device);
     cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_beam); cudaFree(c->d_pc); cudaFree(c->d_rdm);
     cudaFree(c->d_amp); cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_fir);
-    cudaFree(c->d_med_tw1); cudaFree(c->d_med_H); cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_H); cudaFree(c->d_tw2);
+    cudaFree(c->d_med_tw1); cudaFree(c->d_med_tw2); cudaFree(c->d_med_H);
+    cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_tw2); cudaFree(c->d_lng_H);
     cudaFree(c->d_dop_tw); cudaFree(c->d_dop_perm); cudaFree(c->d_win);
     cudaFree(c->d_range_axis); cudaFree(c->d_vel_axis); cudaFree(c->d_beam_angles); cudaFree(c->d_k_slopes);
     cudaFree(c->d_counts); cudaFree(c->d_recs);
@@ -179,7 +198,6 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     c->C = p->n_channels; c->B = p->n_beams; c->P = p->n_pulses; c->N = p->n_samples; c->G = G;
     c->ldb = (c->N + 3) & ~3;
     c->ldg = (c->G + 3) & ~3;
-    c->pow2_doppler = (c->P & (c->P - 1)) == 0;
 #define CUC(call)                                                                                   \
     do {                                                                                            \
         cudaError_t e__ = (call);                                                                   \
@@ -266,30 +284,23 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     if (rc) return rc;
     rc = plan_seg(c->lng, k->mf_long, k->n_mf_long, c->prm.seg_start[2], g1 + g2, g3, "RSP_PC_LEN_LONG");
     if (rc) return rc;
-    if (c->med.L) { CU(c, upload(&c->d_med_tw1, c->med.tw1)); CU(c, upload(&c->d_med_H, c->med.H)); }
-    if (c->lng.L) { CU(c, upload(&c->d_lng_tw1, c->lng.tw1)); CU(c, upload(&c->d_lng_H, c->lng.H)); }
-    CU(c, upload(&c->d_tw2, make_twiddles(256, 16)));
-    for (int L : {1024, 2048, 4096}) {
-        const size_t sm = ((size_t)rsp_pad16(L) + 16) * sizeof(float2);
-        if (L == 1024) CU(c, opt_in_smem(pc_fft_kernel<4>, sm));
-        if (L == 2048) CU(c, opt_in_smem(pc_fft_kernel<8>, sm));
-        if (L == 4096) CU(c, opt_in_smem(pc_fft_kernel<16>, sm));
-    }
+    if (c->med.L) { CU(c, upload(&c->d_med_tw1, c->med.tw1)); CU(c, upload(&c->d_med_tw2, c->med.tw2)); CU(c, upload(&c->d_med_H, c->med.Hmid)); }
+    if (c->lng.L) { CU(c, upload(&c->d_lng_tw1, c->lng.tw1)); CU(c, upload(&c->d_lng_tw2, c->lng.tw2)); CU(c, upload(&c->d_lng_H, c->lng.Hmid)); }
+    CU(c, opt_in_smem(pc_fft_kernel<Pc1024>, pc_smem_bytes<Pc1024>()));
+    CU(c, opt_in_smem(pc_fft_kernel<Pc2048>, pc_smem_bytes<Pc2048>()));
+    CU(c, opt_in_smem(pc_fft_kernel<Pc4096>, pc_smem_bytes<Pc4096>()));
 
     // Doppler plan
     std::vector<float> win(P);
+    c->pow2_doppler = make_doppler_plan(c->dop, P);
     if (c->pow2_doppler) {
-        if (!make_doppler_plan(c->dop, P)) return fail(c, RSP_ERR_UNSUPPORTED, "no Doppler plan for P=%d", P);
         for (int p = 0; p < P; ++p) win[p] = (float)(k->mtd_win[p] * ((p & 1) ? -1.0 : 1.0));
         CU(c, upload(&c->d_dop_tw, c->dop.tw));
         CU(c, upload(&c->d_dop_perm, c->dop.perm));
-        c->dop_tw_count = (int)c->dop.tw.size();
-        c->mtd_tg = 32;
-        c->mtd_smem = ((size_t)P * 33 + c->dop_tw_count) * sizeof(float2) + (size_t)P * (sizeof(float) + sizeof(int));
-        CU(c, opt_in_smem(mtd_kernel<32>, c->mtd_smem));
+        c->mtd_tg = RSP_MTD_TG;
+        c->mtd_smem = ((size_t)P * (RSP_MTD_TG + 1) + c->dop.tw.size() + 1) * sizeof(float2);
+        CU(c, mtd_opt_in(P, c->mtd_smem));
     } else {
-        c->dop.plan.P = P;
-        c->dop.plan.nrad = 0;
         std::vector<float2> tw(P);
         for (int m = 0; m < P; ++m) {
             const double ang = -2.0 * kPi * (double)m / (double)P;
@@ -297,7 +308,6 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         }
         for (int p = 0; p < P; ++p) win[p] = (float)k->mtd_win[p];
         CU(c, upload(&c->d_dop_tw, tw));
-        c->dop_tw_count = P;
         const int tgs[3] = {32, 16, 8};
         c->mtd_tg = 0;
         for (int tg : tgs) {
@@ -310,9 +320,18 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         if (c->mtd_tg == 8) CU(c, opt_in_smem(mtd_dft_kernel<8>, c->mtd_smem));
     }
     CU(c, upload(&c->d_win, win));
-    c->cfar_smem = (size_t)(32 + 2 * (c->prm.guard_r + c->prm.ref_r)) * P * sizeof(float);
-    if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
-    CU(c, opt_in_smem(cfar_kernel<32>, c->cfar_smem));
+    {   // CFAR tile height: the largest of {64,32,16} whose three shared arrays stay under 80 KB
+        const int mR = c->prm.guard_r + c->prm.ref_r;
+        auto smem_for = [&](int tg) { return (size_t)((tg + 2 * mR) + (tg + mR + c->prm.guard_r + 1) + tg) * P * sizeof(float); };
+        c->cfar_tg = 16;
+        for (int tg : {64, 32, 16})
+            if (smem_for(tg) <= 80 * 1024) { c->cfar_tg = tg; break; }
+        c->cfar_smem = smem_for(c->cfar_tg);
+        if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
+        if (c->cfar_tg == 64) CU(c, opt_in_smem(cfar_kernel<64>, c->cfar_smem));
+        if (c->cfar_tg == 32) CU(c, opt_in_smem(cfar_kernel<32>, c->cfar_smem));
+        if (c->cfar_tg == 16) CU(c, opt_in_smem(cfar_kernel<16>, c->cfar_smem));
+    }
 
     CU(c, upload(&c->d_range_axis, std::vector<double>(k->range_axis, k->range_axis + G)));
     CU(c, upload(&c->d_vel_axis, std::vector<double>(k->velocity_axis, k->velocity_axis + P)));
@@ -330,10 +349,10 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
 // launch sequence for one CPI (device-resident PCN complex64 input)
 // ------------------------------------------------------------------------------------------
 template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw) {
-    constexpr int SPT = NB <= 8 ? 4 : 2;
+    constexpr int SPT = 2, CU_ = 4;
     Timed t(c, K_DBF);
-    dim3 grid((c->N + 256 * SPT - 1) / (256 * SPT), c->P);
-    dbf_kernel<NB, SPT><<<grid, 256, 0, c->stream>>>(raw, c->d_beam, c->d_W, c->C, c->N, c->ldb);
+    dim3 grid((c->N + RSP_DBF_THREADS * SPT - 1) / (RSP_DBF_THREADS * SPT), c->P);
+    dbf_kernel<NB, SPT, CU_><<<grid, RSP_DBF_THREADS, 0, c->stream>>>(raw, c->d_beam, c->d_W, c->C, c->N, c->ldb);
 }
 
 static int launch_dbf_any(rsp_ctx* c, const float2* raw) {
@@ -347,66 +366,93 @@ static int launch_dbf_any(rsp_ctx* c, const float2* raw) {
     return RSP_OK;
 }
 
-static void launch_pc_seg(rsp_ctx* c, const PcPlan& pl, const float2* tw1, const float2* H, int cls) {
+template <class Cfg> static void launch_pc_cfg(rsp_ctx* c, const PcKernelArgs& a) {
+    const int nctas = (a.n_items + Cfg::NG - 1) / Cfg::NG;
+    pc_fft_kernel<Cfg><<<nctas, RSP_PC_THREADS, pc_smem_bytes<Cfg>(), c->stream>>>(a);
+}
+
+static void launch_pc_seg(rsp_ctx* c, const PcPlan& pl, const float2* tw1, const float2* tw2, const float2* H, int cls,
+                          bool with_narrow) {
     if (!pl.L) return;
     Timed t(c, cls);
     PcKernelArgs a;
-    a.beam = c->d_beam; a.pc = c->d_pc; a.tw1 = tw1; a.tw2 = c->d_tw2; a.H = H;
-    a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg; a.B = c->B;
+    a.beam = c->d_beam; a.pc = c->d_pc; a.tw1 = tw1; a.tw2 = tw2; a.Hmid = H;
+    a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
     a.seg_start0 = pl.seg_start0; a.taps = pl.taps; a.gate0 = pl.gate0; a.g_end = pl.gate0 + pl.ngates; a.valid = pl.valid;
-    dim3 grid(pl.nblk, c->B, c->P);
-    const size_t sm = ((size_t)rsp_pad16(pl.L) + 16) * sizeof(float2);
-    if (pl.R1 == 4) pc_fft_kernel<4><<<grid, RSP_PC_THREADS, sm, c->stream>>>(a);
-    else if (pl.R1 == 8) pc_fft_kernel<8><<<grid, RSP_PC_THREADS, sm, c->stream>>>(a);
-    else pc_fft_kernel<16><<<grid, RSP_PC_THREADS, sm, c->stream>>>(a);
+    a.nblk = pl.nblk; a.n_items = c->P * c->B * pl.nblk;
+    a.do_narrow = with_narrow ? 1 : 0;
+    a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
+    a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
+    if (pl.L == 1024) launch_pc_cfg<Pc1024>(c, a);
+    else if (pl.L == 2048) launch_pc_cfg<Pc2048>(c, a);
+    else launch_pc_cfg<Pc4096>(c, a);
 }
 
 static void launch_pc(rsp_ctx* c) {
-    if (c->prm.n_gates[0] > 0) {
-        dim3 grid(c->B, c->P);
+    const bool narrow = c->prm.n_gates[0] > 0;
+    const bool fold = narrow && c->med.L > 0;        // the medium launch computes the narrow gates too
+    if (narrow && !fold) {
         Timed t(c, K_PC_NARROW);
-        pc_narrow_kernel<<<grid, 256, 0, c->stream>>>(c->d_beam, c->d_pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
-                                                      c->ldb, c->ldg, c->B, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
+        pc_narrow_kernel<<<c->P * c->B, 256, 0, c->stream>>>(c->d_beam, c->d_pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
+                                                             c->ldb, c->ldg, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
     }
-    launch_pc_seg(c, c->med, c->d_med_tw1, c->d_med_H, K_PC_MEDIUM);
-    launch_pc_seg(c, c->lng, c->d_lng_tw1, c->d_lng_H, K_PC_LONG);
+    launch_pc_seg(c, c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H, K_PC_MEDIUM, fold);
+    launch_pc_seg(c, c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H, K_PC_LONG, false);
 }
 
 static void launch_mtd(rsp_ctx* c, float2* rdm) {
     MtdArgs a;
     a.pc = c->d_pc; a.rdm = rdm; a.amp = c->d_amp; a.win = c->d_win; a.tw = c->d_dop_tw; a.perm = c->d_dop_perm;
-    a.plan = c->dop.plan; a.tw_count = c->dop_tw_count; a.B = c->B; a.G = c->G; a.ldg = c->ldg;
+    a.P = c->P; a.B = c->B; a.G = c->G; a.ldg = c->ldg;
     const int tg = c->mtd_tg;
     dim3 grid((c->G + tg - 1) / tg, c->B);
     Timed t(c, K_MTD);
-    if (c->pow2_doppler) mtd_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
-    else if (tg == 32) mtd_dft_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
+    if (c->pow2_doppler) {
+        switch (c->P) {
+#define X(p, r0, r1, r2) case p: mtd_kernel<MtdCfg<p, r0, r1, r2>><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a); break;
+            RSP_FOR_EACH_POW2_P(X)
+#undef X
+        }
+    } else if (tg == 32) mtd_dft_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
     else if (tg == 16) mtd_dft_kernel<16><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
     else mtd_dft_kernel<8><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
 }
 
+static bool cfar_testable(const rsp_ctx* c) {
+    const int mR = c->prm.guard_r + c->prm.ref_r, mV = c->prm.guard_v + c->prm.ref_v;
+    return c->G - 2 * mR > 0 && c->P - 2 * mV > 0;      // else fsf:192-193 loop ranges are empty
+}
+
 static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
+    if (!cfar_testable(c)) return;
     CfarArgs a;
-    a.amp = c->d_amp; a.rdm = rdm;
+    a.amp = c->d_amp;
     a.c.P = c->P; a.c.G = c->G; a.c.guard_r = c->prm.guard_r; a.c.guard_v = c->prm.guard_v;
     a.c.ref_r = c->prm.ref_r; a.c.ref_v = c->prm.ref_v; a.c.t_cfar = c->prm.t_cfar;
     a.count = c->d_counts + slot;
     a.recs = c->d_recs + (size_t)slot * c->prm.max_detections;
     a.cap = c->prm.max_detections;
-    a.range_axis = c->d_range_axis; a.vel_axis = c->d_vel_axis; a.beam_angles = c->d_beam_angles; a.k_slopes = c->d_k_slopes;
-    a.delta_r = c->delta_r; a.delta_v = c->delta_v; a.complex_mode = c->prm.monopulse_complex;
-    const int mR = c->prm.guard_r + c->prm.ref_r, mV = c->prm.guard_v + c->prm.ref_v;
-    const int ncut = c->G - 2 * mR;
-    if (ncut <= 0 || c->P - 2 * mV <= 0) return;       // nothing is testable (fsf:192-193 ranges empty)
-    dim3 grid((ncut + 31) / 32, c->B - 1);
-    Timed t(c, K_CFAR);
-    cfar_kernel<32><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
+    const int mR = c->prm.guard_r + c->prm.ref_r;
+    const int ncut = c->G - 2 * mR, tg = c->cfar_tg;
+    dim3 grid((ncut + tg - 1) / tg, c->B - 1);
+    {
+        Timed t(c, K_CFAR);
+        if (tg == 64) cfar_kernel<64><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
+        else if (tg == 32) cfar_kernel<32><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
+        else cfar_kernel<16><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
+    }
+    RefineArgs r;
+    r.amp = c->d_amp; r.rdm = rdm; r.P = c->P; r.G = c->G; r.count = a.count; r.recs = a.recs; r.cap = a.cap;
+    r.range_axis = c->d_range_axis; r.vel_axis = c->d_vel_axis; r.beam_angles = c->d_beam_angles; r.k_slopes = c->d_k_slopes;
+    r.delta_r = c->delta_r; r.delta_v = c->delta_v; r.complex_mode = c->prm.monopulse_complex;
+    Timed t(c, K_REFINE);
+    refine_kernel<<<8, 128, 0, c->stream>>>(r);
 }
 
 static int kernels_per_cpi(const rsp_ctx* c) {
-    int n = 1 /*dbf*/ + (c->prm.n_gates[0] > 0) + (c->med.L > 0) + (c->lng.L > 0) + 1 /*mtd*/;
-    const int mR = c->prm.guard_r + c->prm.ref_r, mV = c->prm.guard_v + c->prm.ref_v;
-    if (c->G - 2 * mR > 0 && c->P - 2 * mV > 0) n += 1;
+    const bool narrow = c->prm.n_gates[0] > 0;
+    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + (c->med.L > 0) + (c->lng.L > 0) + 1 /*mtd*/;
+    if (cfar_testable(c)) n += 2;   // cfar + refine
     return n;
 }
 

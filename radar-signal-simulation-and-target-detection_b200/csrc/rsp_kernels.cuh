@@ -8,7 +8,8 @@
 //   pc_fft_kernel          S6  fun_process_single_frame.m:115-125 (overlap-save blocks)
 //   mtd_kernel             S7  fun_process_single_frame.m:131-136 (power-of-two P)
 //   mtd_dft_kernel         S7  same, any P (the reference's native P = 332)
-//   cfar_kernel            S8 + S9  fun_process_single_frame.m:172-223, 241-298
+//   cfar_kernel            S8  fun_process_single_frame.m:172-223
+//   refine_kernel          S9  fun_process_single_frame.m:241-298
 #pragma once
 #include <cuda_runtime.h>
 #include "rsp.h"
@@ -79,108 +80,146 @@ __global__ void __launch_bounds__(256) pbg_to_bgp_kernel(const float2* __restric
 
 // ------------------------------------------------------------------------------------------
 // S5: digital beamforming.  beam[p][b][n] = sum_c raw[p][c][n] * conj(W[b][c]).
-// One thread owns SPT range samples (strided by 256 so every load is a coalesced 8-byte lane
-// access with no alignment requirement -- the native N = 5819 is odd) and all NB beams in
-// registers; the conjugated weights sit in shared memory and are read as warp broadcasts.
+// One thread owns SPT range samples (strided by the CTA width so every load is a coalesced 8-byte
+// lane access with no alignment requirement -- the native N = 5819 is odd) and all NB beams in
+// registers; the conjugated weights sit in shared memory and are read as warp broadcasts.  The
+// channel loop is software-pipelined CU channels deep (loads of group i+1 are issued before the
+// FMAs of group i) and CTAs are small (128 threads) so that enough bytes are in flight per SM.
 // HBM-bound: reads 8*C bytes, writes 8*B bytes per sample, 8*C*B flops.
 // ------------------------------------------------------------------------------------------
-template <int NB, int SPT>
-__global__ void __launch_bounds__(256) dbf_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
-                                                  const float2* __restrict__ Wc /* [C][NB] conj(W) */, int C, int N,
-                                                  int ldb) {
+#define RSP_DBF_THREADS 128
+template <int NB, int SPT, int CU>
+__global__ void __launch_bounds__(RSP_DBF_THREADS) dbf_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
+                                                              const float2* __restrict__ Wc /* [C][NB] conj(W) */,
+                                                              int C, int N, int ldb) {
     __shared__ float2 sW[RSP_MAX_CHANNELS * NB];
     const int tid = threadIdx.x;
-    for (int i = tid; i < C * NB; i += 256) sW[i] = Wc[i];
+    for (int i = tid; i < C * NB; i += RSP_DBF_THREADS) sW[i] = Wc[i];
     __syncthreads();
     const int p = blockIdx.y;
-    const int n0 = blockIdx.x * (256 * SPT) + tid;
+    const int n0 = blockIdx.x * (RSP_DBF_THREADS * SPT) + tid;
     const float2* rp = raw + (size_t)p * C * N;
     float2 acc[SPT][NB];
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
 #pragma unroll
         for (int b = 0; b < NB; ++b) acc[k][b] = make_float2(0.f, 0.f);
-#pragma unroll 4
-    for (int c = 0; c < C; ++c) {
-        float2 x[SPT];
+    float2 cur[CU][SPT], nxt[CU][SPT];
+    auto load_group = [&](float2 (&dst)[CU][SPT], int c0) {
 #pragma unroll
-        for (int k = 0; k < SPT; ++k) {
-            const int n = n0 + k * 256;
-            x[k] = (n < N) ? __ldcs(rp + (size_t)c * N + n) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const float2 w = sW[c * NB + b];
+        for (int u = 0; u < CU; ++u)
 #pragma unroll
             for (int k = 0; k < SPT; ++k) {
-                acc[k][b].x = fmaf(x[k].x, w.x, fmaf(-x[k].y, w.y, acc[k][b].x));
-                acc[k][b].y = fmaf(x[k].x, w.y, fmaf(x[k].y, w.x, acc[k][b].y));
+                const int n = n0 + k * RSP_DBF_THREADS, c = c0 + u;
+                dst[u][k] = (n < N && c < C) ? __ldcs(rp + (size_t)c * N + n) : make_float2(0.f, 0.f);
+            }
+    };
+    load_group(cur, 0);
+    for (int c0 = 0; c0 < C; c0 += CU) {
+        if (c0 + CU < C) load_group(nxt, c0 + CU);
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            if (c0 + u < C) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float2 w = sW[(c0 + u) * NB + b];
+#pragma unroll
+                    for (int k = 0; k < SPT; ++k) {
+                        acc[k][b].x = fmaf(cur[u][k].x, w.x, fmaf(-cur[u][k].y, w.y, acc[k][b].x));
+                        acc[k][b].y = fmaf(cur[u][k].x, w.y, fmaf(cur[u][k].y, w.x, acc[k][b].y));
+                    }
+                }
             }
         }
+#pragma unroll
+        for (int u = 0; u < CU; ++u)
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) cur[u][k] = nxt[u][k];
     }
 #pragma unroll
     for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int k = 0; k < SPT; ++k) {
-            const int n = n0 + k * 256;
+            const int n = n0 + k * RSP_DBF_THREADS;
             if (n < N) beam[((size_t)p * NB + b) * ldb + n] = acc[k][b];
         }
 }
 
 // ------------------------------------------------------------------------------------------
-// S6: pulse compression
+// S6: pulse compression.  One CTA = Cfg::NG overlap-save blocks (one per group of Cfg::T threads);
+// work item = (line, block).  The medium-segment launch also computes the narrow-pulse FIR gates of
+// its lines (fun_process_single_frame.m:111-112,123).
 // ------------------------------------------------------------------------------------------
 struct PcKernelArgs {
     const float2* beam;
     float2* pc;
     const float2* tw1;
     const float2* tw2;
-    const float2* H;
-    int N, ldb, ldg, B;
+    const float2* Hmid;
+    int N, ldb, ldg;
     int seg_start0, taps, gate0, g_end, valid;
+    int nblk, n_items;
+    // narrow FIR (only when do_narrow)
+    int do_narrow;
+    const float* fir;
+    int nfir, fir_delay, narrow_start0, narrow_gates;
 };
 
-template <int R1>
+template <class Cfg>
 __global__ void __launch_bounds__(RSP_PC_THREADS) pc_fft_kernel(const PcKernelArgs k) {
     extern __shared__ float2 pc_smem[];
-    const int tid = threadIdx.x;
-    const size_t line = (size_t)blockIdx.z * k.B + blockIdx.y;
+    float2* stw2 = pc_smem + Cfg::NG * Cfg::SMEM_ELEMS;
+    constexpr int NTW2 = (Cfg::R2 - 1) * Cfg::SPAN2;
+    float* sfir = reinterpret_cast<float*>(stw2 + NTW2);
+    for (int i = threadIdx.x; i < NTW2; i += RSP_PC_THREADS) stw2[i] = k.tw2[i];
+    if (k.do_narrow)
+        for (int i = threadIdx.x; i < k.nfir; i += RSP_PC_THREADS) sfir[i] = k.fir[i];
+    const int grp = threadIdx.x / Cfg::T, t = threadIdx.x - grp * Cfg::T;
+    const int item = blockIdx.x * Cfg::NG + grp;
+    const bool active = item < k.n_items;
+    const int line = active ? item / k.nblk : 0, blk = active ? item - line * k.nblk : 0;
+    float2* s = pc_smem + grp * Cfg::SMEM_ELEMS;
     PcBlockArgs a;
-    a.line = k.beam + line * k.ldb;
-    a.out_line = k.pc + line * k.ldg;
+    a.line = k.beam + (size_t)line * k.ldb;
+    a.out_line = k.pc + (size_t)line * k.ldg;
     a.tw1 = k.tw1;
-    a.tw2 = k.tw2;
-    a.H = k.H;
+    a.tw2 = stw2;
+    a.Hmid = k.Hmid;
     a.N = k.N;
     a.seg_start0 = k.seg_start0;
     a.taps = k.taps;
-    a.g0 = k.gate0 + blockIdx.x * k.valid;
+    a.g0 = k.gate0 + blk * k.valid;
     a.g_end = k.g_end;
-    pc_phase_load_pass1<R1>(a, pc_smem, tid);
+    if (active) pc_phase_load_pass1<Cfg>(a, s, t);
     __syncthreads();
-    pc_phase_pass2<R1>(a, pc_smem, tid);
+    if (active) pc_phase_pass2<Cfg>(a, s, t);
     __syncthreads();
-    pc_phase_mid<R1>(a, pc_smem, tid);
+    if (active) pc_phase_mid<Cfg>(a, s, t);
     __syncthreads();
-    pc_phase_ipass2<R1>(a, pc_smem, tid);
+    if (active) pc_phase_ipass2<Cfg>(a, s, t);
     __syncthreads();
-    pc_phase_ipass1_store<R1>(a, pc_smem, tid);
+    if (active) {
+        pc_phase_ipass1_store<Cfg>(a, s, t);
+        if (k.do_narrow && blk == 0)
+            for (int g = t; g < k.narrow_gates; g += Cfg::T)
+                a.out_line[g] = pc_narrow_gate(a.line, k.N, k.narrow_start0, sfir, k.nfir, k.fir_delay, g);
+    }
 }
 
 __global__ void __launch_bounds__(256) pc_narrow_kernel(const float2* __restrict__ beam, float2* __restrict__ pc,
                                                         const float* __restrict__ fir, int nfir, int fir_delay, int N,
-                                                        int ldb, int ldg, int B, int seg_start0, int ngates) {
+                                                        int ldb, int ldg, int seg_start0, int ngates) {
     __shared__ float sfir[256];
     for (int i = threadIdx.x; i < nfir; i += 256) sfir[i] = fir[i];
     __syncthreads();
-    const size_t line = (size_t)blockIdx.y * B + blockIdx.x;
+    const size_t line = blockIdx.x;
     const float2* y = beam + line * ldb;
     for (int g = threadIdx.x; g < ngates; g += 256)
         pc[line * ldg + g] = pc_narrow_gate(y, N, seg_start0, sfir, nfir, fir_delay, g);
 }
 
 // ------------------------------------------------------------------------------------------
-// S7: MTD.  Tile = TG gates x P pulses of one beam.  The corner turn happens here: rows of the
+// S7: MTD.  Tile = 32 gates x P pulses of one beam.  The corner turn happens here: rows of the
 // pc cube (range-contiguous) are read coalesced, the FFT runs along the strided pulse dimension
 // with lanes spread over gates (bank-conflict free for any stride), and the Doppler lines leave
 // transposed, contiguous in Doppler, exactly MATLAB's rdm_13beam(v,g,b) byte order.
@@ -192,43 +231,38 @@ struct MtdArgs {
     const float* win;      // [P]; (-1)^p folded in for the power-of-two kernel
     const float2* tw;      // pow2: per-pass twiddles; dft: e^{-2 pi i m/P}, m < P
     const int* perm;       // pow2 only
-    MtdPlan plan;
-    int tw_count;
+    int P;
     int B, G, ldg;
 };
 
-template <int TG>
+template <class Cfg>
 __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
+    constexpr int P = Cfg::P, TG = RSP_MTD_TG;
     extern __shared__ float2 mtd_smem[];
-    const int P = k.plan.P;
-    float2* tile = mtd_smem;
-    float2* stw = tile + (size_t)P * (TG + 1);
-    float* swin = reinterpret_cast<float*>(stw + k.tw_count);
-    int* sperm = reinterpret_cast<int*>(swin + P);
-    const int tid = threadIdx.x;
-    for (int i = tid; i < k.tw_count; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
-    for (int i = tid; i < P; i += RSP_MTD_THREADS) {
-        swin[i] = k.win[i];
-        sperm[i] = k.perm[i];
-    }
-    __syncthreads();
+    float2* tile = mtd_smem;                       // [P][TG + 1]
+    float2* stw = mtd_smem + P * (TG + 1);         // [Cfg::TW_COUNT]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < Cfg::TW_COUNT; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
     const int g0 = blockIdx.x * TG, b = blockIdx.y;
-    for (int e = tid; e < P * TG; e += RSP_MTD_THREADS) {
-        const int p = e / TG, gl = e - p * TG, g = g0 + gl;
+    const int g = g0 + lane;
+    const bool gate_ok = g < k.G;
+#pragma unroll 8
+    for (int p = w; p < P; p += RSP_MTD_THREADS / 32) {
         float2 x = make_float2(0.f, 0.f);
-        if (g < k.G) x = k.pc[((size_t)p * k.B + b) * k.ldg + g];
-        tile[sperm[p] * (TG + 1) + gl] = cscale(x, swin[p]);
+        if (gate_ok) x = k.pc[((size_t)p * k.B + b) * k.ldg + g];
+        tile[k.perm[p] * (TG + 1) + lane] = cscale(x, k.win[p]);
     }
     __syncthreads();
-    for (int pass = k.plan.nrad - 1; pass >= 0; --pass) {
-        mtd_dit_pass<-1>(tile, k.plan, pass, stw, TG, tid, RSP_MTD_THREADS);
-        __syncthreads();
-    }
+    if (Cfg::R2 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 0); __syncthreads(); }
+    if (Cfg::R1 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 1); __syncthreads(); }
+    mtd_passes_phase<Cfg>(tile, stw, tid, 2);
+    __syncthreads();
+    // transposed read-out: consecutive threads take consecutive Doppler rows of one gate
     for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {
-        const int gl = e / P, row = e - gl * P, g = g0 + gl;
-        if (g < k.G) {
+        const int gl = e / P, row = e - gl * P;          // P is a compile-time power of two
+        if (g0 + gl < k.G) {
             const float2 v = tile[row * (TG + 1) + gl];
-            const size_t o = ((size_t)b * k.G + g) * P + row;
+            const size_t o = ((size_t)b * k.G + g0 + gl) * P + row;
             __stcs(k.rdm + o, v);
             k.amp[o] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
         }
@@ -238,7 +272,7 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
 template <int TG>
 __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs k) {
     extern __shared__ float2 mtd_smem[];
-    const int P = k.plan.P;
+    const int P = k.P;
     float2* xin = mtd_smem;
     float2* xout = xin + (size_t)P * (TG + 1);
     float2* stw = xout + (size_t)P * (TG + 1);
@@ -282,15 +316,77 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs 
 }
 
 // ------------------------------------------------------------------------------------------
-// S8 + S9: GOCA-CFAR on S = |rdm_b| + |rdm_{b+1}|, then per detection the spline refinement and
-// the monopulse angle, fused into the compaction (one atomic per detection; detections are rare).
+// S8: GOCA-CFAR on S = |rdm_b| + |rdm_{b+1}| (lean kernel: window sums in shared memory, one
+// compare per cell, compaction with one atomic per detection -- detections are rare).
+// S9: refine_kernel, one thread per detection: spline peak search + monopulse angle.
 // ------------------------------------------------------------------------------------------
 struct CfarArgs {
     const float* amp;            // [B][G][P]
-    const float2* rdm;           // [B][G][P]
     CfarParams c;
     int* count;                  // detection counter of this CPI slot
     rsp_detection* recs;         // records of this CPI slot
+    int cap;
+};
+
+template <int TG>
+__global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k) {
+    extern __shared__ float cfar_smem[];
+    const int P = k.c.P, G = k.c.G;
+    const int mR = k.c.guard_r + k.c.ref_r, mV = k.c.guard_v + k.c.ref_v;
+    const int rows = TG + 2 * mR;
+    float* S = cfar_smem;
+    float* R5 = S + rows * P;
+    float* D5 = R5 + cfar_r5_rows(k.c, TG) * P;
+    const int pair = blockIdx.y;
+    const int g_first = mR + blockIdx.x * TG;
+    const int tid = threadIdx.x;
+    const float* A = k.amp + (size_t)pair * G * P;
+    const float* Bm = A + (size_t)G * P;
+    const size_t base = (size_t)(g_first - mR) * P;
+    const int n_valid = min(rows, G - (g_first - mR)) * P;        // rows that exist in the map
+    const int n_el = rows * P;
+    if ((P & 3) == 0) {
+        const float4* A4 = reinterpret_cast<const float4*>(A + base);
+        const float4* B4 = reinterpret_cast<const float4*>(Bm + base);
+        float4* S4 = reinterpret_cast<float4*>(S);
+        for (int e = tid; e < n_el / 4; e += RSP_CFAR_THREADS) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * e < n_valid) {
+                const float4 a = A4[e], b = B4[e];
+                s = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            }
+            S4[e] = s;
+        }
+    } else {
+        for (int e = tid; e < n_el; e += RSP_CFAR_THREADS) S[e] = e < n_valid ? A[base + e] + Bm[base + e] : 0.f;
+    }
+    __syncthreads();
+    cfar_sums_phase(S, R5, D5, k.c, TG, tid, RSP_CFAR_THREADS);
+    __syncthreads();
+    const int nv = P - 2 * mV;                       // CUT columns [mV, P - mV)
+    for (int e = tid; e < TG * nv; e += RSP_CFAR_THREADS) {
+        const int gl = e / nv, v = mV + (e - gl * nv), g = g_first + gl;
+        if (g >= G - mR) break;
+        float cut;
+        if (!cfar_decide(S, R5, D5, k.c, gl, v, &cut)) continue;
+        const int slot = atomicAdd(k.count, 1);
+        if (slot >= k.cap) continue;        // overflow is reported by the host from the count
+        rsp_detection d;
+        d.v_idx = v + 1;
+        d.r_idx = g + 1;
+        d.pair_idx = pair + 1;
+        d.power = cut;
+        d.range = 0.0; d.velocity = 0.0; d.angle = 0.0;
+        k.recs[slot] = d;
+    }
+}
+
+struct RefineArgs {
+    const float* amp;            // [B][G][P]
+    const float2* rdm;           // [B][G][P]
+    int P, G;
+    const int* count;
+    rsp_detection* recs;
     int cap;
     const double* range_axis;
     const double* vel_axis;
@@ -300,62 +396,40 @@ struct CfarArgs {
     int complex_mode;
 };
 
-template <int TG>
-__global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k) {
-    extern __shared__ float cfar_smem[];
-    const int P = k.c.P, G = k.c.G;
-    const int mR = k.c.guard_r + k.c.ref_r, mV = k.c.guard_v + k.c.ref_v;
-    const int rows = TG + 2 * mR;
-    const int pair = blockIdx.y;
-    const int g_first = mR + blockIdx.x * TG;
-    const int tid = threadIdx.x;
-    const float* A = k.amp + (size_t)pair * G * P;
-    const float* Bm = A + (size_t)G * P;
-    const size_t base = (size_t)(g_first - mR) * P;
-    const int n_el = rows * P;
-    for (int e = tid; e < n_el; e += RSP_CFAR_THREADS) {
-        const int row = e / P;
-        float s = 0.f;
-        if (g_first - mR + row < G) s = A[base + e] + Bm[base + e];
-        cfar_smem[e] = s;
-    }
-    __syncthreads();
-    for (int e = tid; e < TG * P; e += RSP_CFAR_THREADS) {
-        const int gl = e / P, v = e - gl * P, g = g_first + gl;
-        if (g >= G - mR || v < mV || v >= P - mV) continue;
-        float cut;
-        if (!cfar_cut(cfar_smem, P, k.c, gl, v, &cut)) continue;
-        const int slot = atomicAdd(k.count, 1);
-        if (slot >= k.cap) continue;        // overflow is reported by the host from the count
+// fun_process_single_frame.m:241-298 for every record written by cfar_kernel
+__global__ void __launch_bounds__(128) refine_kernel(const RefineArgs k) {
+    const int n = min(*k.count, k.cap);
+    const int P = k.P, G = k.G;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        rsp_detection d = k.recs[i];
+        const int v = d.v_idx - 1, g = d.r_idx - 1, pair = d.pair_idx - 1;
+        const float* A = k.amp + (size_t)pair * G * P;
+        const float* Bm = A + (size_t)G * P;
         double yr[5], yv[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            yr[i] = (double)cfar_smem[(gl + mR - 2 + i) * P + v];
-            yv[i] = (double)cfar_smem[(gl + mR) * P + v - 2 + i];
+        for (int j = 0; j < 5; ++j) {
+            const size_t orr = (size_t)(g - 2 + j) * P + v, ov = (size_t)g * P + v - 2 + j;
+            yr[j] = (double)(A[orr] + Bm[orr]);          // the fp32 sum map S, as cfar_kernel formed it
+            yv[j] = (double)(A[ov] + Bm[ov]);
         }
         const double r_off = rsp_spline5_peak(yr, 8) - 2.0;          // fsf:237 rInterpTimes = 8
         const double v_off = rsp_spline5_peak(yv, 4) - 2.0;          // vInterpTimes = 4
-        rsp_detection d;
-        d.v_idx = v + 1;
-        d.r_idx = g + 1;
-        d.pair_idx = pair + 1;
-        d.power = cut;
         d.range = k.range_axis[g] + r_off * k.delta_r;               // fsf:262
         d.velocity = k.vel_axis[v] + v_off * k.delta_v;              // fsf:278
-        const size_t o = ((size_t)pair * G + g) * P + v;
+        const size_t o = (size_t)g * P + v;
         double ratio;
         const double eps = 2.220446049250313e-16;
         if (k.complex_mode) {                                        // mc:454-461
-            const float2 a = k.rdm[o], bb = k.rdm[o + (size_t)G * P];
+            const float2 a = k.rdm[(size_t)pair * G * P + o], bb = k.rdm[(size_t)(pair + 1) * G * P + o];
             const double nr = (double)a.x - (double)bb.x, ni = (double)a.y - (double)bb.y;
             const double dr = (double)a.x + (double)bb.x + eps, di = (double)a.y + (double)bb.y;
             ratio = (nr * dr + ni * di) / (dr * dr + di * di);
         } else {                                                     // fsf:282-285
-            const double sa = (double)A[(size_t)g * P + v], sb = (double)Bm[(size_t)g * P + v];
+            const double sa = (double)A[o], sb = (double)Bm[o];
             ratio = (sa - sb) / (sa + sb + eps);
         }
         d.angle = 0.5 * (k.beam_angles[pair] + k.beam_angles[pair + 1]) + k.k_slopes[pair] * ratio;   // fsf:286-290
-        k.recs[slot] = d;
+        k.recs[i] = d;
     }
 }
 

@@ -45,18 +45,29 @@ inline std::vector<cf> make_twiddles(int Ls, int r) {   // [(k-1)*span + j] = e^
     return t;
 }
 
-// Pulse-compression block plan: L = R1*256, radices (R1,16,16).
+// Pulse-compression block plan: L = R1*R2*R3 (see PcCfg in rsp_phases.cuh).
 struct PcPlan {
-    int L = 0, R1 = 0, taps = 0, valid = 0, nblk = 0;
+    int L = 0, R1 = 0, R2 = 0, R3 = 0, T = 0, taps = 0, valid = 0, nblk = 0;
     int seg_start0 = 0, gate0 = 0, ngates = 0;
-    std::vector<cf> tw1, tw2, H;
+    std::vector<cf> tw1, tw2, Hmid;
 };
 
+inline bool pc_radices(int L, int* r) {
+    switch (L) {
+        case 1024: r[0] = 16; r[1] = 16; r[2] = 4; return true;
+        case 2048: r[0] = 8; r[1] = 16; r[2] = 16; return true;
+        case 4096: r[0] = 16; r[1] = 16; r[2] = 16; return true;
+    }
+    return false;
+}
+
 inline bool make_pc_plan(PcPlan& pl, int L, const zc* taps, int ntaps, int seg_start0, int gate0, int ngates) {
-    if (L != 1024 && L != 2048 && L != 4096) return false;
+    int r[3];
+    if (!pc_radices(L, r)) return false;
     if (ntaps < 1 || ntaps > L) return false;
     pl.L = L;
-    pl.R1 = L / 256;
+    pl.R1 = r[0]; pl.R2 = r[1]; pl.R3 = r[2];
+    pl.T = L / 16;
     pl.taps = ntaps;
     pl.valid = L - (ntaps - 1);
     pl.seg_start0 = seg_start0;
@@ -64,28 +75,31 @@ inline bool make_pc_plan(PcPlan& pl, int L, const zc* taps, int ntaps, int seg_s
     pl.ngates = ngates;
     pl.nblk = (ngates + pl.valid - 1) / pl.valid;
     pl.tw1 = make_twiddles(L, pl.R1);
-    pl.tw2 = make_twiddles(256, 16);
+    pl.tw2 = make_twiddles(L / pl.R1, pl.R2);
     std::vector<zc> h((size_t)L, zc(0, 0));
     for (int i = 0; i < ntaps; ++i) h[i] = taps[i];
     host_fft(h);
-    const int radices[3] = {pl.R1, 16, 16};
-    pl.H.assign((size_t)L, make_float2(0, 0));
+    std::vector<cf> Hdr((size_t)L);
     for (int f = 0; f < L; ++f) {
-        const int pos = rsp_digit_reverse(f, L, radices, 3);
-        pl.H[pos] = make_float2((float)(h[f].real() / L), (float)(h[f].imag() / L));
+        const int pos = rsp_digit_reverse(f, L, r, 3);
+        Hdr[pos] = make_float2((float)(h[f].real() / L), (float)(h[f].imag() / L));
     }
+    // Hmid[(i*R3 + k)*T + t] = Hdr[R3*(t + T*i) + k]: coalesced over the threads of a group
+    const int nb3 = 16 / pl.R3;
+    pl.Hmid.assign((size_t)L, make_float2(0, 0));
+    for (int i = 0; i < nb3; ++i)
+        for (int k = 0; k < pl.R3; ++k)
+            for (int t = 0; t < pl.T; ++t) pl.Hmid[(size_t)(i * pl.R3 + k) * pl.T + t] = Hdr[(size_t)pl.R3 * (t + pl.T * i) + k];
     return true;
 }
 
-// Cost model used to pick the block length: pass 1 costs ~L*log2(R1), passes 2/3
-// run on max(L/16, 256) thread slots of 16 points each.
+// Cost model used to pick the block length: every pass keeps all threads busy, so the work is
+// proportional to the points transformed; longer blocks waste less on the (taps-1) overlap.
 inline double pc_plan_cost(int L, int ntaps, int ngates) {
     const int valid = L - (ntaps - 1);
     if (valid < 1) return 1e300;
     const int nblk = (ngates + valid - 1) / valid;
-    const double l2r1 = std::log2((double)L / 256.0);
-    const double slots = (double)(L > 4096 ? L : 4096);
-    return nblk * (L * l2r1 + 2.0 * slots * 4.0);
+    return (double)nblk * L;
 }
 
 inline int choose_pc_len(int ntaps, int ngates) {
@@ -94,43 +108,50 @@ inline int choose_pc_len(int ntaps, int ngates) {
     double bc = 1e300;
     for (int i = 0; i < 3; ++i) {
         const double c = pc_plan_cost(cands[i], ntaps, ngates);
-        if (c < bc) { bc = c; best = cands[i]; }
+        if (c <= bc) { bc = c; best = cands[i]; }   // ties: the longer block
     }
     return best;
 }
 
-// Doppler plan for power-of-two P (2 <= P <= 4096).
+// Doppler plan for power-of-two P: radices (R0,R1,R2) in DIF order, fixed per P so that the kernel
+// template (MtdCfg) and the host tables agree.
+inline bool mtd_radices(int P, int* r) {
+    switch (P) {
+        case 2: r[0] = 2; r[1] = 1; r[2] = 1; return true;
+        case 4: r[0] = 4; r[1] = 1; r[2] = 1; return true;
+        case 8: r[0] = 8; r[1] = 1; r[2] = 1; return true;
+        case 16: r[0] = 16; r[1] = 1; r[2] = 1; return true;
+        case 32: r[0] = 8; r[1] = 4; r[2] = 1; return true;
+        case 64: r[0] = 8; r[1] = 8; r[2] = 1; return true;
+        case 128: r[0] = 16; r[1] = 8; r[2] = 1; return true;
+        case 256: r[0] = 16; r[1] = 16; r[2] = 1; return true;
+        case 512: r[0] = 8; r[1] = 8; r[2] = 8; return true;
+    }
+    return false;
+}
+
 struct DopplerPlan {
-    MtdPlan plan;
-    std::vector<cf> tw;        // all passes concatenated
+    int P = 0, r[3] = {1, 1, 1};
+    std::vector<cf> tw;        // passes concatenated at the MtdCfg offsets
     std::vector<int> perm;     // perm[p] = position of input pulse p
 };
 
 inline bool make_doppler_plan(DopplerPlan& dp, int P) {
-    if (P < 2 || (P & (P - 1))) return false;
-    int lg = 0;
-    while ((1 << lg) < P) ++lg;
-    MtdPlan& pl = dp.plan;
-    pl.P = P;
-    pl.nrad = 0;
-    int rem = lg;
-    while (rem > 0) {
-        int step = rem >= 4 ? 4 : rem;
-        if (rem > 4 && rem < 8 && rem - step < 2 && rem - step > 0) step = rem - 2;   // avoid a trailing radix-2
-        if (pl.nrad >= 4) return false;
-        pl.radices[pl.nrad++] = 1 << step;
-        rem -= step;
-    }
+    if (!mtd_radices(P, dp.r)) return false;
+    dp.P = P;
     dp.tw.clear();
     int Ls = P;
-    for (int s = 0; s < pl.nrad; ++s) {
-        pl.tw_off[s] = (int)dp.tw.size();
-        std::vector<cf> t = make_twiddles(Ls, pl.radices[s]);
-        dp.tw.insert(dp.tw.end(), t.begin(), t.end());
-        Ls /= pl.radices[s];
+    for (int s = 0; s < 3; ++s) {
+        if (dp.r[s] > 1) {
+            std::vector<cf> t = make_twiddles(Ls, dp.r[s]);
+            dp.tw.insert(dp.tw.end(), t.begin(), t.end());
+        }
+        Ls /= dp.r[s];
     }
+    int nrad = 0, rad[3];
+    for (int s = 0; s < 3; ++s) if (dp.r[s] > 1) rad[nrad++] = dp.r[s];
     dp.perm.resize(P);
-    for (int p = 0; p < P; ++p) dp.perm[p] = rsp_digit_reverse(p, P, pl.radices, pl.nrad);
+    for (int p = 0; p < P; ++p) dp.perm[p] = rsp_digit_reverse(p, P, rad, nrad);
     return true;
 }
 

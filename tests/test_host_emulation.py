@@ -42,7 +42,7 @@ def test_small_dft(lib, R, sign):
 
 
 def test_digit_reverse_is_permutation(lib):
-    for L, rad in ((4096, [16, 16, 16]), (2048, [8, 16, 16]), (1024, [4, 16, 16]), (64, [16, 4]), (32, [8, 4])):
+    for L, rad in ((4096, [16, 16, 16]), (2048, [8, 16, 16]), (1024, [4, 16, 16]), (64, [8, 8]), (32, [8, 4])):
         r = (ctypes.c_int * len(rad))(*rad)
         pos = [lib.emul_digit_reverse(f, L, r, len(rad)) for f in range(L)]
         assert sorted(pos) == list(range(L))
@@ -86,7 +86,7 @@ def test_pc_narrow_fir(lib, cfg1):
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("P", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("P", [8, 16, 32, 64, 128, 256, 512])
 def test_mtd_tile(lib, P):
     TG = 32
     rng = np.random.default_rng(P)
@@ -99,8 +99,9 @@ def test_mtd_tile(lib, P):
     assert np.abs(out - ref).max() <= 3e-6 * np.abs(ref).max(), list(rad)
 
 
+@pytest.mark.parametrize("tg", [16, 32, 64])
 @pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (150, 48, 3, 4, 2, 3)])
-def test_cfar_tiles_match_oracle(lib, shape):
+def test_cfar_tiles_match_oracle(lib, shape, tg):
     G, P, gR, gV, rR, rV = shape
     rng = np.random.default_rng(G)
     S = rng.rayleigh(1.0, (1, G, P))
@@ -109,7 +110,7 @@ def test_cfar_tiles_match_oracle(lib, shape):
     S = S.astype(np.float32)
     cfg = o.Config(guardCells_R=gR, guardCells_V=gV, refCells_R=rR, refCells_V=rV, T_CFAR=4.0)
     det = np.zeros((G, P), np.uint8)
-    lib.emul_cfar_map(S[0].ctypes.data_as(fp), G, P, gR, gV, rR, rV, ctypes.c_float(4.0), 32,
+    lib.emul_cfar_map(S[0].ctypes.data_as(fp), G, P, gR, gV, rR, rV, ctypes.c_float(4.0), tg,
                       det.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
     ref = o.cfar_detect(S.astype(np.float64), cfg)
     margin = o.cfar_margin(S.astype(np.float64), cfg)[0]
