@@ -15,8 +15,11 @@ template <class Cfg> static void run_pc_block(const PcBlockArgs& a, cf* s) {
     for (int t = 0; t < Cfg::T; ++t) pc_phase_ipass1_store<Cfg>(a, s, t);
 }
 
-template <class Cfg> static void run_mtd_tile(cf* s, const cf* tw) {
-    for (int pass = 0; pass < 3; ++pass)
+template <class Cfg> static void run_mtd_tile(cf* s, const cf* tw, const cf* src, size_t pstride, const int* iperm,
+                                              const float* win) {
+    for (int t = 0; t < RSP_MTD_THREADS; ++t)
+        mtd_first_pass_t<MtdInner<Cfg>::R, Cfg::P>(s, src, pstride, iperm, win, true, t);
+    for (int pass = MtdInner<Cfg>::PASS + 1; pass < 3; ++pass)
         for (int t = 0; t < RSP_MTD_THREADS; ++t) mtd_passes_phase<Cfg>(s, tw, t, pass);
 }
 
@@ -78,8 +81,14 @@ int emul_pc_segment(const float* line, int N, int seg_start0, int gate0, int nga
 int emul_pc_narrow(const float* line, int N, int seg_start0, const float* fir, int nfir, int fir_delay, int ngates,
                    float* out_line) {
     cf* o = reinterpret_cast<cf*>(out_line);
-    for (int g = 0; g < ngates; ++g)
-        o[g] = pc_narrow_gate(reinterpret_cast<const cf*>(line), N, seg_start0, fir, nfir, fir_delay, g);
+    const cf* y = reinterpret_cast<const cf*>(line);
+    for (int g = 0; g < ngates; ++g) {
+        o[g] = pc_narrow_gate(y, N, seg_start0, fir, nfir, fir_delay, g);
+        if (ngates + fir_delay <= N - seg_start0) {           // the shared-memory variant must agree exactly
+            const cf alt = pc_narrow_gate_smem(y + seg_start0, fir, nfir, fir_delay, g);
+            if (alt.x != o[g].x || alt.y != o[g].y) return -1;
+        }
+    }
     return 0;
 }
 
@@ -89,19 +98,13 @@ int emul_mtd_tile(const float* x, int P, int TG, const float* win, float* out /*
     if (TG != RSP_MTD_TG || !make_doppler_plan(dp, P)) return -1;
     const cf* xi = reinterpret_cast<const cf*>(x);
     std::vector<cf> s((size_t)P * (TG + 1));
-    for (int p = 0; p < P; ++p)
-        for (int gl = 0; gl < TG; ++gl) {
-            const float w = win[p] * ((p & 1) ? -1.f : 1.f);
-            s[(size_t)dp.perm[p] * (TG + 1) + gl] = cscale(xi[(size_t)p * TG + gl], w);
-        }
+    std::vector<float> w(P);
+    for (int p = 0; p < P; ++p) w[p] = win[p] * ((p & 1) ? -1.f : 1.f);
+    const int* ip = dp.iperm.data();
     switch (P) {
-        case 8: run_mtd_tile<MtdCfg<8, 8, 1, 1>>(s.data(), dp.tw.data()); break;
-        case 16: run_mtd_tile<MtdCfg<16, 16, 1, 1>>(s.data(), dp.tw.data()); break;
-        case 32: run_mtd_tile<MtdCfg<32, 8, 4, 1>>(s.data(), dp.tw.data()); break;
-        case 64: run_mtd_tile<MtdCfg<64, 8, 8, 1>>(s.data(), dp.tw.data()); break;
-        case 128: run_mtd_tile<MtdCfg<128, 16, 8, 1>>(s.data(), dp.tw.data()); break;
-        case 256: run_mtd_tile<MtdCfg<256, 16, 16, 1>>(s.data(), dp.tw.data()); break;
-        case 512: run_mtd_tile<MtdCfg<512, 8, 8, 8>>(s.data(), dp.tw.data()); break;
+#define X(p, a, b, c) case p: run_mtd_tile<MtdCfg<p, a, b, c>>(s.data(), dp.tw.data(), xi, (size_t)TG, ip, w.data()); break;
+        X(8, 8, 1, 1) X(16, 16, 1, 1) X(32, 8, 4, 1) X(64, 8, 8, 1) X(128, 16, 8, 1) X(256, 16, 16, 1) X(512, 8, 8, 8)
+#undef X
         default: return -3;
     }
     cf* o = reinterpret_cast<cf*>(out);
@@ -133,6 +136,42 @@ int emul_cfar_map(const float* S, int G, int P, int guard_r, int guard_v, int re
             for (int v = mV; v < P - mV; ++v) {
                 float cut;
                 if (cfar_decide(tile.data(), R5.data(), D5.data(), c, gl, v, &cut)) det[(size_t)(g_first + gl) * P + v] = 1;
+            }
+    }
+    return 0;
+}
+
+// Vectorised CFAR (P % 4 == 0): padded tile + quad phases, as cfar4_kernel runs them.
+int emul_cfar4_map(const float* S, int G, int P, int guard_r, int guard_v, int ref_r, int ref_v, float t_cfar, int TG,
+                   int use_template, unsigned char* det /* [G][P] */) {
+    if (P % 4) return -1;
+    CfarParams c;
+    c.P = P; c.G = G; c.guard_r = guard_r; c.guard_v = guard_v; c.ref_r = ref_r; c.ref_v = ref_v; c.t_cfar = t_cfar;
+    const Cfar4Geom g = cfar4_geom(c, TG);
+    const int mR = guard_r + ref_r, mV = guard_v + ref_v;
+    std::memset(det, 0, (size_t)G * P);
+    std::vector<float> tile((size_t)g.rows * g.PP, 0.f), R5((size_t)g.r5_rows * P);
+    for (int g_first = mR; g_first < G - mR; g_first += TG) {
+        std::fill(tile.begin(), tile.end(), 0.f);
+        for (int row = 0; row < g.rows; ++row) {
+            const int gg = g_first - mR + row;
+            if (gg < G)
+                for (int v = 0; v < P; ++v) tile[(size_t)row * g.PP + 4 + v] = S[(size_t)gg * P + v];
+        }
+        for (int t = 0; t < RSP_CFAR_THREADS; ++t) {
+            if (use_template && ref_r == 5) cfar4_r5_phase<5>(tile.data(), R5.data(), c, g, t, RSP_CFAR_THREADS);
+            else cfar4_r5_phase<0>(tile.data(), R5.data(), c, g, t, RSP_CFAR_THREADS);
+        }
+        const int c_lo = mV / 4, c_hi = (P - mV - 1) / 4;
+        for (int gl = 0; gl < TG && g_first + gl < G - mR; ++gl)
+            for (int c4 = c_lo; c4 <= c_hi; ++c4) {
+                float cut[4];
+                unsigned m;
+                if (use_template && ref_r == 5 && ref_v == 5) m = cfar4_decide_quad<5, 5>(tile.data(), R5.data(), c, g, gl, c4, cut);
+                else if (use_template && ref_r == 5 && ref_v == 4) m = cfar4_decide_quad<5, 4>(tile.data(), R5.data(), c, g, gl, c4, cut);
+                else m = cfar4_decide_quad<0, 0>(tile.data(), R5.data(), c, g, gl, c4, cut);
+                for (int j = 0; j < 4; ++j)
+                    if (m & (1u << j)) det[(size_t)(g_first + gl) * P + 4 * c4 + j] = 1;
             }
     }
     return 0;

@@ -58,7 +58,8 @@ struct rsp_ctx {
     rsp_detection* d_recs = nullptr;
     int* h_count = nullptr;               // pinned
     rsp_detection* h_recs = nullptr;      // pinned [max_detections]
-    int mtd_tg = 32, cfar_tg = 32;
+    int mtd_tg = 32, cfar_tg = 32, cfar_variant = 0;
+    bool cfar_vec = false;
     size_t mtd_smem = 0, cfar_smem = 0;
     // per-kernel event timing (rsp_set_profiling)
     bool profiling = false;
@@ -126,6 +127,10 @@ typedef PcCfg<4096, 16, 16, 16> Pc4096;
 template <class Cfg> static size_t pc_smem_bytes() {
     return ((size_t)Cfg::NG * Cfg::SMEM_ELEMS + (Cfg::R2 - 1) * Cfg::SPAN2) * sizeof(float2) + 256 * sizeof(float);
 }
+template <class A, class B> static size_t pc_smem_pair() { return std::max(pc_smem_bytes<A>(), pc_smem_bytes<B>()); }
+// X(long plan, medium plan)
+#define RSP_FOR_EACH_PC_PAIR(X) X(Pc1024, Pc1024) X(Pc2048, Pc1024) X(Pc4096, Pc1024) X(Pc1024, Pc2048) X(Pc2048, Pc2048) \
+    X(Pc4096, Pc2048) X(Pc1024, Pc4096) X(Pc2048, Pc4096) X(Pc4096, Pc4096)
 
 #define RSP_FOR_EACH_POW2_P(X) X(8, 8, 1, 1) X(16, 16, 1, 1) X(32, 8, 4, 1) X(64, 8, 8, 1) X(128, 16, 8, 1) X(256, 16, 16, 1) X(512, 8, 8, 8)
 static cudaError_t mtd_opt_in(int P, size_t bytes) {
@@ -286,9 +291,9 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     if (rc) return rc;
     if (c->med.L) { CU(c, upload(&c->d_med_tw1, c->med.tw1)); CU(c, upload(&c->d_med_tw2, c->med.tw2)); CU(c, upload(&c->d_med_H, c->med.Hmid)); }
     if (c->lng.L) { CU(c, upload(&c->d_lng_tw1, c->lng.tw1)); CU(c, upload(&c->d_lng_tw2, c->lng.tw2)); CU(c, upload(&c->d_lng_H, c->lng.Hmid)); }
-    CU(c, opt_in_smem(pc_fft_kernel<Pc1024>, pc_smem_bytes<Pc1024>()));
-    CU(c, opt_in_smem(pc_fft_kernel<Pc2048>, pc_smem_bytes<Pc2048>()));
-    CU(c, opt_in_smem(pc_fft_kernel<Pc4096>, pc_smem_bytes<Pc4096>()));
+#define X(A, B) CU(c, opt_in_smem(pc_fft_kernel<A, B>, pc_smem_pair<A, B>()));
+    RSP_FOR_EACH_PC_PAIR(X)
+#undef X
 
     // Doppler plan
     std::vector<float> win(P);
@@ -296,7 +301,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     if (c->pow2_doppler) {
         for (int p = 0; p < P; ++p) win[p] = (float)(k->mtd_win[p] * ((p & 1) ? -1.0 : 1.0));
         CU(c, upload(&c->d_dop_tw, c->dop.tw));
-        CU(c, upload(&c->d_dop_perm, c->dop.perm));
+        CU(c, upload(&c->d_dop_perm, c->dop.iperm));
         c->mtd_tg = RSP_MTD_TG;
         c->mtd_smem = ((size_t)P * (RSP_MTD_TG + 1) + c->dop.tw.size() + 1) * sizeof(float2);
         CU(c, mtd_opt_in(P, c->mtd_smem));
@@ -320,17 +325,31 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         if (c->mtd_tg == 8) CU(c, opt_in_smem(mtd_dft_kernel<8>, c->mtd_smem));
     }
     CU(c, upload(&c->d_win, win));
-    {   // CFAR tile height: the largest of {64,32,16} whose three shared arrays stay under 80 KB
+    {   // CFAR tile height: the largest of {64,32,16} whose shared arrays stay under 80 KB
         const int mR = c->prm.guard_r + c->prm.ref_r;
-        auto smem_for = [&](int tg) { return (size_t)((tg + 2 * mR) + (tg + mR + c->prm.guard_r + 1) + tg) * P * sizeof(float); };
+        c->cfar_vec = (P % 4) == 0;
+        auto smem_for = [&](int tg) {
+            const size_t r5 = (size_t)(tg + mR + c->prm.guard_r + 1) * P;
+            return c->cfar_vec ? ((size_t)(tg + 2 * mR) * (P + 8) + r5) * sizeof(float)
+                               : ((size_t)(tg + 2 * mR) * P + r5 + (size_t)tg * P) * sizeof(float);
+        };
         c->cfar_tg = 16;
         for (int tg : {64, 32, 16})
             if (smem_for(tg) <= 80 * 1024) { c->cfar_tg = tg; break; }
         c->cfar_smem = smem_for(c->cfar_tg);
         if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
-        if (c->cfar_tg == 64) CU(c, opt_in_smem(cfar_kernel<64>, c->cfar_smem));
-        if (c->cfar_tg == 32) CU(c, opt_in_smem(cfar_kernel<32>, c->cfar_smem));
-        if (c->cfar_tg == 16) CU(c, opt_in_smem(cfar_kernel<16>, c->cfar_smem));
+        const int rr = c->prm.ref_r, rv = c->prm.ref_v;
+        c->cfar_variant = (rr == 5 && rv == 5) ? 1 : (rr == 5 && rv == 4) ? 2 : 0;
+#define RSP_CFAR_DISPATCH(TGV, ACTION)                                                      \
+        if (!c->cfar_vec) { ACTION(cfar_kernel<TGV>) }                                          \
+        else if (c->cfar_variant == 1) { ACTION((cfar4_kernel<TGV, 5, 5>)) }                    \
+        else if (c->cfar_variant == 2) { ACTION((cfar4_kernel<TGV, 5, 4>)) }                    \
+        else { ACTION((cfar4_kernel<TGV, 0, 0>)) }
+#define OPTIN(K) CU(c, opt_in_smem(K, c->cfar_smem));
+        if (c->cfar_tg == 64) { RSP_CFAR_DISPATCH(64, OPTIN) }
+        else if (c->cfar_tg == 32) { RSP_CFAR_DISPATCH(32, OPTIN) }
+        else { RSP_CFAR_DISPATCH(16, OPTIN) }
+#undef OPTIN
     }
 
     CU(c, upload(&c->d_range_axis, std::vector<double>(k->range_axis, k->range_axis + G)));
@@ -366,38 +385,38 @@ static int launch_dbf_any(rsp_ctx* c, const float2* raw) {
     return RSP_OK;
 }
 
-template <class Cfg> static void launch_pc_cfg(rsp_ctx* c, const PcKernelArgs& a) {
-    const int nctas = (a.n_items + Cfg::NG - 1) / Cfg::NG;
-    pc_fft_kernel<Cfg><<<nctas, RSP_PC_THREADS, pc_smem_bytes<Cfg>(), c->stream>>>(a);
+static void fill_seg(const rsp_ctx* c, PcSegArgs& sg, const PcPlan& pl, const float2* tw1, const float2* tw2, const float2* H) {
+    sg.tw1 = tw1; sg.tw2 = tw2; sg.Hmid = H;
+    sg.seg_start0 = pl.seg_start0; sg.taps = pl.taps; sg.gate0 = pl.gate0; sg.g_end = pl.gate0 + pl.ngates; sg.valid = pl.valid;
+    sg.nblk = pl.nblk;
+    sg.n_items = pl.L ? c->P * c->B * pl.nblk : 0;
+    const int ng = pl.L ? RSP_PC_THREADS / pl.T : 1;
+    sg.n_ctas = (sg.n_items + ng - 1) / ng;
 }
 
-static void launch_pc_seg(rsp_ctx* c, const PcPlan& pl, const float2* tw1, const float2* tw2, const float2* H, int cls,
-                          bool with_narrow) {
-    if (!pl.L) return;
-    Timed t(c, cls);
-    PcKernelArgs a;
-    a.beam = c->d_beam; a.pc = c->d_pc; a.tw1 = tw1; a.tw2 = tw2; a.Hmid = H;
-    a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
-    a.seg_start0 = pl.seg_start0; a.taps = pl.taps; a.gate0 = pl.gate0; a.g_end = pl.gate0 + pl.ngates; a.valid = pl.valid;
-    a.nblk = pl.nblk; a.n_items = c->P * c->B * pl.nblk;
-    a.do_narrow = with_narrow ? 1 : 0;
-    a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
-    a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
-    if (pl.L == 1024) launch_pc_cfg<Pc1024>(c, a);
-    else if (pl.L == 2048) launch_pc_cfg<Pc2048>(c, a);
-    else launch_pc_cfg<Pc4096>(c, a);
-}
-
+// One launch covers the long segment (role 0), the medium segment and the narrow FIR (role 1).
 static void launch_pc(rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
-    const bool fold = narrow && c->med.L > 0;        // the medium launch computes the narrow gates too
+    const bool fold = narrow && c->med.L > 0;        // the medium groups compute the narrow gates too
     if (narrow && !fold) {
         Timed t(c, K_PC_NARROW);
         pc_narrow_kernel<<<c->P * c->B, 256, 0, c->stream>>>(c->d_beam, c->d_pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
                                                              c->ldb, c->ldg, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
     }
-    launch_pc_seg(c, c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H, K_PC_MEDIUM, fold);
-    launch_pc_seg(c, c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H, K_PC_LONG, false);
+    if (!c->med.L && !c->lng.L) return;
+    PcKernelArgs a;
+    a.beam = c->d_beam; a.pc = c->d_pc; a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
+    fill_seg(c, a.seg[0], c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H);
+    fill_seg(c, a.seg[1], c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H);
+    a.do_narrow = fold ? 1 : 0;
+    a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
+    a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
+    const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
+    const int la = c->lng.L ? c->lng.L : 1024, lb = c->med.L ? c->med.L : 1024;
+    Timed t(c, K_PC_LONG);
+#define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->stream>>>(a);
+    RSP_FOR_EACH_PC_PAIR(X)
+#undef X
 }
 
 static void launch_mtd(rsp_ctx* c, float2* rdm) {
@@ -437,9 +456,11 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
     dim3 grid((ncut + tg - 1) / tg, c->B - 1);
     {
         Timed t(c, K_CFAR);
-        if (tg == 64) cfar_kernel<64><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
-        else if (tg == 32) cfar_kernel<32><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
-        else cfar_kernel<16><<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
+#define LAUNCH(K) K<<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
+        if (tg == 64) { RSP_CFAR_DISPATCH(64, LAUNCH) }
+        else if (tg == 32) { RSP_CFAR_DISPATCH(32, LAUNCH) }
+        else { RSP_CFAR_DISPATCH(16, LAUNCH) }
+#undef LAUNCH
     }
     RefineArgs r;
     r.amp = c->d_amp; r.rdm = rdm; r.P = c->P; r.G = c->G; r.count = a.count; r.recs = a.recs; r.cap = a.cap;
@@ -451,7 +472,7 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
 
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
-    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + (c->med.L > 0) + (c->lng.L > 0) + 1 /*mtd*/;
+    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + 1 /*mtd*/;
     if (cfar_testable(c)) n += 2;   // cfar + refine
     return n;
 }

@@ -150,46 +150,49 @@ __global__ void __launch_bounds__(RSP_DBF_THREADS) dbf_kernel(const float2* __re
 // work item = (line, block).  The medium-segment launch also computes the narrow-pulse FIR gates of
 // its lines (fun_process_single_frame.m:111-112,123).
 // ------------------------------------------------------------------------------------------
-struct PcKernelArgs {
-    const float2* beam;
-    float2* pc;
+struct PcSegArgs {
     const float2* tw1;
     const float2* tw2;
     const float2* Hmid;
-    int N, ldb, ldg;
     int seg_start0, taps, gate0, g_end, valid;
-    int nblk, n_items;
-    // narrow FIR (only when do_narrow)
+    int nblk, n_items, n_ctas;
+};
+
+struct PcKernelArgs {
+    const float2* beam;
+    float2* pc;
+    int N, ldb, ldg;
+    PcSegArgs seg[2];            // role 0 = CTAs [0, seg[0].n_ctas), role 1 = the rest
+    // narrow FIR, computed by the role-1 (medium) groups for block 0 of their line when do_narrow
     int do_narrow;
     const float* fir;
     int nfir, fir_delay, narrow_start0, narrow_gates;
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(RSP_PC_THREADS) pc_fft_kernel(const PcKernelArgs k) {
-    extern __shared__ float2 pc_smem[];
-    float2* stw2 = pc_smem + Cfg::NG * Cfg::SMEM_ELEMS;
+__device__ __forceinline__ void pc_role(const PcKernelArgs& k, const PcSegArgs& sg, int cta, float2* smem, bool narrow) {
     constexpr int NTW2 = (Cfg::R2 - 1) * Cfg::SPAN2;
+    float2* stw2 = smem + Cfg::NG * Cfg::SMEM_ELEMS;
     float* sfir = reinterpret_cast<float*>(stw2 + NTW2);
-    for (int i = threadIdx.x; i < NTW2; i += RSP_PC_THREADS) stw2[i] = k.tw2[i];
-    if (k.do_narrow)
+    for (int i = threadIdx.x; i < NTW2; i += RSP_PC_THREADS) stw2[i] = sg.tw2[i];
+    if (narrow)
         for (int i = threadIdx.x; i < k.nfir; i += RSP_PC_THREADS) sfir[i] = k.fir[i];
     const int grp = threadIdx.x / Cfg::T, t = threadIdx.x - grp * Cfg::T;
-    const int item = blockIdx.x * Cfg::NG + grp;
-    const bool active = item < k.n_items;
-    const int line = active ? item / k.nblk : 0, blk = active ? item - line * k.nblk : 0;
-    float2* s = pc_smem + grp * Cfg::SMEM_ELEMS;
+    const int item = cta * Cfg::NG + grp;
+    const bool active = item < sg.n_items;
+    const int line = active ? item / sg.nblk : 0, blk = active ? item - line * sg.nblk : 0;
+    float2* s = smem + grp * Cfg::SMEM_ELEMS;
     PcBlockArgs a;
     a.line = k.beam + (size_t)line * k.ldb;
     a.out_line = k.pc + (size_t)line * k.ldg;
-    a.tw1 = k.tw1;
+    a.tw1 = sg.tw1;
     a.tw2 = stw2;
-    a.Hmid = k.Hmid;
+    a.Hmid = sg.Hmid;
     a.N = k.N;
-    a.seg_start0 = k.seg_start0;
-    a.taps = k.taps;
-    a.g0 = k.gate0 + blk * k.valid;
-    a.g_end = k.g_end;
+    a.seg_start0 = sg.seg_start0;
+    a.taps = sg.taps;
+    a.g0 = sg.gate0 + blk * sg.valid;
+    a.g_end = sg.g_end;
     if (active) pc_phase_load_pass1<Cfg>(a, s, t);
     __syncthreads();
     if (active) pc_phase_pass2<Cfg>(a, s, t);
@@ -198,12 +201,32 @@ __global__ void __launch_bounds__(RSP_PC_THREADS) pc_fft_kernel(const PcKernelAr
     __syncthreads();
     if (active) pc_phase_ipass2<Cfg>(a, s, t);
     __syncthreads();
-    if (active) {
-        pc_phase_ipass1_store<Cfg>(a, s, t);
-        if (k.do_narrow && blk == 0)
+    if (active) pc_phase_ipass1_store<Cfg>(a, s, t);
+    if (narrow) {                                   // uniform over the CTA
+        const int need = k.narrow_gates + k.fir_delay;
+        const bool fast = need <= k.N - k.narrow_start0 && need <= Cfg::SMEM_ELEMS;
+        __syncthreads();
+        if (active && blk == 0) {
+            if (fast) {
+                for (int i = t; i < need; i += Cfg::T) s[i] = a.line[k.narrow_start0 + i];
+            }
+        }
+        __syncthreads();
+        if (active && blk == 0) {
             for (int g = t; g < k.narrow_gates; g += Cfg::T)
-                a.out_line[g] = pc_narrow_gate(a.line, k.N, k.narrow_start0, sfir, k.nfir, k.fir_delay, g);
+                a.out_line[g] = fast ? pc_narrow_gate_smem(s, sfir, k.nfir, k.fir_delay, g)
+                                     : pc_narrow_gate(a.line, k.N, k.narrow_start0, sfir, k.nfir, k.fir_delay, g);
+        }
     }
+}
+
+// CfgA = block plan of role 0 (the long segment), CfgB = role 1 (the medium segment + narrow FIR).
+// The short role-1 CTAs have the highest block indices, so they fill the tail of the long ones.
+template <class CfgA, class CfgB>
+__global__ void __launch_bounds__(RSP_PC_THREADS, 3) pc_fft_kernel(const PcKernelArgs k) {
+    extern __shared__ float2 pc_smem[];
+    if ((int)blockIdx.x < k.seg[0].n_ctas) pc_role<CfgA>(k, k.seg[0], blockIdx.x, pc_smem, false);
+    else pc_role<CfgB>(k, k.seg[1], blockIdx.x - k.seg[0].n_ctas, pc_smem, k.do_narrow != 0);
 }
 
 __global__ void __launch_bounds__(256) pc_narrow_kernel(const float2* __restrict__ beam, float2* __restrict__ pc,
@@ -230,7 +253,7 @@ struct MtdArgs {
     float* amp;
     const float* win;      // [P]; (-1)^p folded in for the power-of-two kernel
     const float2* tw;      // pow2: per-pass twiddles; dft: e^{-2 pi i m/P}, m < P
-    const int* perm;       // pow2 only
+    const int* perm;       // pow2 only: iperm[pos] = pulse stored at position pos
     int P;
     int B, G, ldg;
 };
@@ -241,23 +264,17 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
     extern __shared__ float2 mtd_smem[];
     float2* tile = mtd_smem;                       // [P][TG + 1]
     float2* stw = mtd_smem + P * (TG + 1);         // [Cfg::TW_COUNT]
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < Cfg::TW_COUNT; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
     const int g0 = blockIdx.x * TG, b = blockIdx.y;
-    const int g = g0 + lane;
-    const bool gate_ok = g < k.G;
-#pragma unroll 8
-    for (int p = w; p < P; p += RSP_MTD_THREADS / 32) {
-        float2 x = make_float2(0.f, 0.f);
-        if (gate_ok) x = k.pc[((size_t)p * k.B + b) * k.ldg + g];
-        tile[k.perm[p] * (TG + 1) + lane] = cscale(x, k.win[p]);
-    }
+    // innermost pass straight from global memory (k.perm holds the INVERSE permutation here)
+    mtd_first_pass_t<MtdInner<Cfg>::R, P>(tile, k.pc + (size_t)b * k.ldg + g0, (size_t)k.B * k.ldg, k.perm, k.win,
+                                          g0 + lane < k.G, tid);
     __syncthreads();
-    if (Cfg::R2 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 0); __syncthreads(); }
-    if (Cfg::R1 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 1); __syncthreads(); }
-    mtd_passes_phase<Cfg>(tile, stw, tid, 2);
-    __syncthreads();
+    if (MtdInner<Cfg>::PASS < 1 && Cfg::R1 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 1); __syncthreads(); }
+    if (MtdInner<Cfg>::PASS < 2) { mtd_passes_phase<Cfg>(tile, stw, tid, 2); __syncthreads(); }
     // transposed read-out: consecutive threads take consecutive Doppler rows of one gate
+#pragma unroll 4
     for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {
         const int gl = e / P, row = e - gl * P;          // P is a compile-time power of two
         if (g0 + gl < k.G) {
@@ -378,6 +395,60 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k
         d.power = cut;
         d.range = 0.0; d.velocity = 0.0; d.angle = 0.0;
         k.recs[slot] = d;
+    }
+}
+
+// Vectorised variant for P % 4 == 0 (see cfar4_* in rsp_phases.cuh); RR/RV = compile-time reference
+// window lengths (0 = run time).
+template <int TG, int RR, int RV>
+__global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar4_kernel(const CfarArgs k) {
+    extern __shared__ float cfar_smem[];
+    const Cfar4Geom g = cfar4_geom(k.c, TG);
+    const int P = k.c.P, G = k.c.G;
+    const int mR = k.c.guard_r + k.c.ref_r, mV = k.c.guard_v + k.c.ref_v;
+    float* S = cfar_smem;                       // [rows][PP]
+    float* R5 = S + g.rows * g.PP;              // [r5_rows][P]
+    const int pair = blockIdx.y;
+    const int g_first = mR + blockIdx.x * TG;
+    const int tid = threadIdx.x;
+    const float4* A4 = reinterpret_cast<const float4*>(k.amp + ((size_t)pair * G + (g_first - mR)) * P);
+    const float4* B4 = A4 + (size_t)G * g.P4;
+    float4* S4 = reinterpret_cast<float4*>(S);
+    const int pp4 = g.PP / 4;
+    const int rows_valid = min(g.rows, G - (g_first - mR));
+    for (int idx = tid; idx < g.rows * pp4; idx += RSP_CFAR_THREADS) {       // zero halo + rows beyond the map
+        const int row = idx / pp4, c = idx - row * pp4;
+        if (c == 0 || c == pp4 - 1 || row >= rows_valid) S4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int idx = tid; idx < rows_valid * g.P4; idx += RSP_CFAR_THREADS) {
+        int row, c4;
+        cfar4_split(g, idx, row, c4);
+        const float4 a = A4[idx], b = B4[idx];
+        S4[row * pp4 + 1 + c4] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    __syncthreads();
+    cfar4_r5_phase<RR>(S, R5, k.c, g, tid, RSP_CFAR_THREADS);
+    __syncthreads();
+    const int c_lo = mV / 4, nq = (P - mV - 1) / 4 - c_lo + 1;            // quads holding at least one CUT
+    const int gl_end = min(TG, G - mR - g_first);
+    for (int idx = tid; idx < gl_end * nq; idx += RSP_CFAR_THREADS) {
+        const int gl = idx / nq, c4 = c_lo + (idx - gl * nq);
+        float cut[4];
+        unsigned m = cfar4_decide_quad<RR, RV>(S, R5, k.c, g, gl, c4, cut);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const int slot = atomicAdd(k.count, 1);
+            if (slot < k.cap) {
+                rsp_detection d;
+                d.v_idx = 4 * c4 + j + 1;
+                d.r_idx = g_first + gl + 1;
+                d.pair_idx = pair + 1;
+                d.power = cut[j];
+                d.range = 0.0; d.velocity = 0.0; d.angle = 0.0;
+                k.recs[slot] = d;
+            }
+        }
     }
 }
 

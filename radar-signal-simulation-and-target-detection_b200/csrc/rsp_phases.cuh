@@ -50,30 +50,76 @@ struct PcBlockArgs {
     int g_end;           // one past the last gate this segment owns
 };
 
+// Padded shared-memory addressing: pad16(base + off) == pad16(base) + off + (off >> 4) whenever
+// (base & 15) + (off & 15) < 16, which holds for every access below (strides are multiples of 16, or
+// base & 15 < 4 with strides of 4).  So each thread computes one padded base per butterfly and all
+// other addresses are compile-time immediates.
+#define RSP_POFF(off) ((off) + ((off) >> 4))
+
 template <class Cfg> RSP_HD void pc_phase_load_pass1(const PcBlockArgs& a, cf* s, int t) {
     const int s0 = a.seg_start0 + a.g0 - (a.taps - 1);
+    const bool interior = s0 >= a.seg_start0 && s0 + Cfg::L <= a.N;      // uniform over the group
 #pragma unroll
     for (int i = 0; i < Cfg::NB1; ++i) {
         const int q = t + i * Cfg::T;
         cf v[Cfg::R1];
+        if (interior) {
+            const cf* src = a.line + s0 + q;
 #pragma unroll
-        for (int m = 0; m < Cfg::R1; ++m) {
-            const int idx = s0 + q + m * Cfg::SPAN1;
-            v[m] = (idx >= a.seg_start0 && idx < a.N) ? a.line[idx] : make_float2(0.f, 0.f);
+            for (int m = 0; m < Cfg::R1; ++m) v[m] = src[m * Cfg::SPAN1];
+        } else {
+#pragma unroll
+            for (int m = 0; m < Cfg::R1; ++m) {
+                const int idx = s0 + q + m * Cfg::SPAN1;
+                v[m] = (idx >= a.seg_start0 && idx < a.N) ? a.line[idx] : make_float2(0.f, 0.f);
+            }
         }
         SmallDft<Cfg::R1, -1>::run(v);
-        s[rsp_pad16(q)] = v[0];
+        cf* sb = s + rsp_pad16(q);
+        const cf* tw = a.tw1 + q;
+        sb[0] = v[0];
 #pragma unroll
         for (int k = 1; k < Cfg::R1; ++k) {
-            const cf w = a.tw1[(k - 1) * Cfg::SPAN1 + q];
-            s[rsp_pad16(q + k * Cfg::SPAN1)] = mul_tw<-1>(v[k], w.x, w.y);
+            const cf w = tw[(k - 1) * Cfg::SPAN1];
+            sb[RSP_POFF(k * Cfg::SPAN1)] = mul_tw<-1>(v[k], w.x, w.y);
         }
+    }
+}
+
+// one radix-R2 DIF / DIT butterfly of pass 2 (sub-transform length LS2, stride SPAN2)
+template <class Cfg, int SIGN, bool DIF> RSP_HD void pc_pass2_butterfly(cf* s, const cf* tw2, int q) {
+    constexpr int R = Cfg::R2, SPAN = Cfg::SPAN2;
+    const int blk = q / SPAN, j = q - blk * SPAN;
+    cf* sb = s + rsp_pad16(blk * Cfg::LS2 + j);
+    const cf* tw = tw2 + j;
+    cf v[R];
+    if (DIF) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = sb[RSP_POFF(m * SPAN)];
+        SmallDft<R, SIGN>::run(v);
+        sb[0] = v[0];
+#pragma unroll
+        for (int k = 1; k < R; ++k) {
+            const cf w = tw[(k - 1) * SPAN];
+            sb[RSP_POFF(k * SPAN)] = mul_tw<SIGN>(v[k], w.x, w.y);
+        }
+    } else {
+        v[0] = sb[0];
+#pragma unroll
+        for (int k = 1; k < R; ++k) {
+            const cf w = tw[(k - 1) * SPAN];
+            const cf x = sb[RSP_POFF(k * SPAN)];
+            v[k] = mul_tw<SIGN>(x, w.x, w.y);
+        }
+        SmallDft<R, SIGN>::run(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) sb[RSP_POFF(m * SPAN)] = v[m];
     }
 }
 
 template <class Cfg> RSP_HD void pc_phase_pass2(const PcBlockArgs& a, cf* s, int t) {
 #pragma unroll
-    for (int i = 0; i < Cfg::NB2; ++i) dif_butterfly<Cfg::R2, -1>(s, Cfg::LS2, t + i * Cfg::T, a.tw2, PadAddr());
+    for (int i = 0; i < Cfg::NB2; ++i) pc_pass2_butterfly<Cfg, -1, true>(s, a.tw2, t + i * Cfg::T);
 }
 
 // last forward pass (Ls = R3, no twiddles) . H . first inverse pass, all in registers
@@ -81,43 +127,63 @@ template <class Cfg> RSP_HD void pc_phase_mid(const PcBlockArgs& a, cf* s, int t
 #pragma unroll
     for (int i = 0; i < Cfg::NB3; ++i) {
         const int q = t + i * Cfg::T;
+        cf* sb = s + rsp_pad16(Cfg::R3 * q);
+        const cf* h = a.Hmid + (i * Cfg::R3) * Cfg::T + t;
         cf v[Cfg::R3];
 #pragma unroll
-        for (int m = 0; m < Cfg::R3; ++m) v[m] = s[rsp_pad16(Cfg::R3 * q + m)];
+        for (int m = 0; m < Cfg::R3; ++m) v[m] = sb[m];
         SmallDft<Cfg::R3, -1>::run(v);
 #pragma unroll
-        for (int k = 0; k < Cfg::R3; ++k) v[k] = cmul(v[k], a.Hmid[(i * Cfg::R3 + k) * Cfg::T + t]);
+        for (int k = 0; k < Cfg::R3; ++k) v[k] = cmul(v[k], h[k * Cfg::T]);
         SmallDft<Cfg::R3, +1>::run(v);
 #pragma unroll
-        for (int m = 0; m < Cfg::R3; ++m) s[rsp_pad16(Cfg::R3 * q + m)] = v[m];
+        for (int m = 0; m < Cfg::R3; ++m) sb[m] = v[m];
     }
 }
 
 template <class Cfg> RSP_HD void pc_phase_ipass2(const PcBlockArgs& a, cf* s, int t) {
 #pragma unroll
-    for (int i = 0; i < Cfg::NB2; ++i) dit_butterfly<Cfg::R2, +1>(s, Cfg::LS2, t + i * Cfg::T, a.tw2, PadAddr());
+    for (int i = 0; i < Cfg::NB2; ++i) pc_pass2_butterfly<Cfg, +1, false>(s, a.tw2, t + i * Cfg::T);
 }
 
 template <class Cfg> RSP_HD void pc_phase_ipass1_store(const PcBlockArgs& a, const cf* s, int t) {
+    // every output of the block is wanted when the block lies inside the segment's gate range
+    const bool full = a.g0 + Cfg::L - (a.taps - 1) <= a.g_end;
 #pragma unroll
     for (int i = 0; i < Cfg::NB1; ++i) {
         const int q = t + i * Cfg::T;
+        const cf* sb = s + rsp_pad16(q);
+        const cf* tw = a.tw1 + q;
         cf v[Cfg::R1];
-        v[0] = s[rsp_pad16(q)];
+        v[0] = sb[0];
 #pragma unroll
         for (int k = 1; k < Cfg::R1; ++k) {
-            const cf w = a.tw1[(k - 1) * Cfg::SPAN1 + q];
-            const cf x = s[rsp_pad16(q + k * Cfg::SPAN1)];
+            const cf w = tw[(k - 1) * Cfg::SPAN1];
+            const cf x = sb[RSP_POFF(k * Cfg::SPAN1)];
             v[k] = mul_tw<+1>(x, w.x, w.y);
         }
         SmallDft<Cfg::R1, +1>::run(v);
+        cf* dst = a.out_line + a.g0 + q - (a.taps - 1);
 #pragma unroll
         for (int m = 0; m < Cfg::R1; ++m) {
             const int io = q + m * Cfg::SPAN1;
-            const int g = a.g0 + io - (a.taps - 1);
-            if (io >= a.taps - 1 && g < a.g_end) a.out_line[g] = v[m];
+            if (io >= a.taps - 1 && (full || a.g0 + io - (a.taps - 1) < a.g_end)) dst[m * Cfg::SPAN1] = v[m];
         }
     }
+}
+
+// Narrow-pulse FIR from a shared-memory copy of the line head: ys[i] = y[seg_start0 + i].
+// Valid when ngates + fir_delay <= Lseg (no circshift wrap), which the kernel checks.
+RSP_HD cf pc_narrow_gate_smem(const cf* ys, const float* fir, int nfir, int fir_delay, int g) {
+    const int ui = g + fir_delay;
+    const int kmax = ui + 1 < nfir ? ui + 1 : nfir;
+    cf acc = make_float2(0.f, 0.f);
+    for (int k = 0; k < kmax; ++k) {
+        const cf x = ys[ui - k];
+        acc.x += fir[k] * x.x;
+        acc.y += fir[k] * x.y;
+    }
+    return acc;
 }
 
 // Narrow-pulse FIR + circshift (fun_process_single_frame.m:111-112,123):
@@ -171,6 +237,33 @@ template <int R, int LS, int P> RSP_HD void mtd_dit_pass_t(cf* s, const cf* tw, 
     for (int q = tid / RSP_MTD_TG; q < NBF; q += RSP_MTD_THREADS / RSP_MTD_TG)
         dit_butterfly<(R > 1 ? R : 2), -1>(s, LS, q, tw, addr);
 }
+
+// Innermost DIT pass straight from global memory: butterfly q takes the pulses iperm[q*R + k]
+// (Ls = R, stride 1, no twiddles), so the digit-reversed placement costs nothing.
+//   src = pc + b*ldg + g0 (pulse stride = pstride elements); gate_ok masks gates beyond G.
+template <int R, int P>
+RSP_HD void mtd_first_pass_t(cf* s, const cf* src, size_t pstride, const int* iperm, const float* win, bool gate_ok,
+                             int tid) {
+    constexpr int NBF = P / R;
+    const int gl = tid & (RSP_MTD_TG - 1);
+#pragma unroll
+    for (int q = tid / RSP_MTD_TG; q < NBF; q += RSP_MTD_THREADS / RSP_MTD_TG) {
+        cf v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int p = iperm[q * R + k];
+            v[k] = gate_ok ? cscale(src[(size_t)p * pstride + gl], win[p]) : make_float2(0.f, 0.f);
+        }
+        SmallDft<R, -1>::run(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) s[(q * R + m) * (RSP_MTD_TG + 1) + gl] = v[m];
+    }
+}
+
+template <class Cfg> struct MtdInner {     // radix of the innermost non-trivial pass and its index
+    static constexpr int PASS = Cfg::R2 > 1 ? 0 : (Cfg::R1 > 1 ? 1 : 2);
+    static constexpr int R = Cfg::R2 > 1 ? Cfg::R2 : (Cfg::R1 > 1 ? Cfg::R1 : Cfg::R0);
+};
 
 template <class Cfg> RSP_HD void mtd_passes_phase(cf* s, const cf* tw, int tid, int pass) {
     // pass 0 = innermost (radix R2, Ls = R2), 1 = middle (R1, Ls = R1*R2), 2 = outermost (R0, Ls = P)
@@ -227,4 +320,109 @@ RSP_HD int cfar_decide(const float* S, const float* R5, const float* D5, const C
     const float noise_v = fmaxf(lead_v / (float)c.ref_v, trail_v / (float)c.ref_v);
     *cut_out = cut;
     return cut > c.t_cfar * fmaxf(noise_r, noise_v);
+}
+
+// =============================================================================================
+// CFAR, vectorised variant (P % 4 == 0): every thread works on quads of 4 consecutive Doppler bins.
+//   S tile: rows = gates [g_first - mR, g_first + TG + mR), row pitch PP = P + 8 floats with the data
+//   at column offset 4 (zero halo of 4 on both sides, so the Doppler windows of partially valid
+//   quads never leave the row).  R5 (range window sums) has pitch P.
+//   RR / RV are the compile-time reference-window lengths (0 = use the run-time value).
+// =============================================================================================
+#if !defined(__CUDACC__)
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#endif
+
+struct Cfar4Geom {
+    int P, P4, sh;        // P4 = P/4; sh = log2(P4) when P4 is a power of two, else -1
+    int PP;               // padded row pitch of S (floats) = P + 8
+    int TG, rows, r5_rows;
+};
+
+RSP_HD Cfar4Geom cfar4_geom(const CfarParams& c, int TG) {
+    Cfar4Geom g;
+    g.P = c.P;
+    g.P4 = c.P / 4;
+    g.sh = -1;
+    for (int s = 0; s < 16; ++s)
+        if ((1 << s) == g.P4) g.sh = s;
+    g.PP = c.P + 8;
+    g.TG = TG;
+    g.rows = TG + 2 * (c.guard_r + c.ref_r);
+    g.r5_rows = cfar_r5_rows(c, TG);
+    return g;
+}
+
+RSP_HD void cfar4_split(const Cfar4Geom& g, int idx, int& row, int& c4) {
+    if (g.sh >= 0) { row = idx >> g.sh; c4 = idx & (g.P4 - 1); }
+    else { row = idx / g.P4; c4 = idx - row * g.P4; }
+}
+
+RSP_HD float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+template <int RR>
+RSP_HD void cfar4_r5_phase(const float* S, float* R5, const CfarParams& c, const Cfar4Geom& g, int tid, int nthreads) {
+    const int rr = RR > 0 ? RR : c.ref_r;
+    const int n = g.r5_rows * g.P4;
+    const int pp4 = g.PP / 4;
+    const float4* S4 = reinterpret_cast<const float4*>(S);
+    float4* R4 = reinterpret_cast<float4*>(R5);
+    for (int idx = tid; idx < n; idx += nthreads) {
+        int row, c4;
+        cfar4_split(g, idx, row, c4);
+        float4 acc = S4[row * pp4 + 1 + c4];
+#pragma unroll
+        for (int i = 1; i < rr; ++i) acc = f4add(acc, S4[(row + i) * pp4 + 1 + c4]);
+        R4[idx] = acc;
+    }
+}
+
+// Decision for the quad (gl, c4): returns a 4-bit detection mask, cut[] receives the four S values.
+template <int RR, int RV>
+RSP_HD unsigned cfar4_decide_quad(const float* S, const float* R5, const CfarParams& c, const Cfar4Geom& g, int gl, int c4,
+                                  float cut[4]) {
+    const int rr = RR > 0 ? RR : c.ref_r, rv = RV > 0 ? RV : c.ref_v;
+    const int mR = c.guard_r + c.ref_r, mV = c.guard_v + c.ref_v;
+    const int v0 = 4 * c4;
+    const float* row = S + (gl + mR) * g.PP + 4;             // row[v] = S(gl, v)
+    const float4 cq = *reinterpret_cast<const float4*>(row + v0);
+    const float4 lr = *reinterpret_cast<const float4*>(R5 + gl * g.P + v0);
+    const float4 tr = *reinterpret_cast<const float4*>(R5 + (gl + mR + c.guard_r + 1) * g.P + v0);
+    float lead[4], trail[4];
+    if (RV > 0) {
+        float xl[(RV > 0 ? RV : 1) + 3], xt[(RV > 0 ? RV : 1) + 3];
+#pragma unroll
+        for (int i = 0; i < RV + 3; ++i) {
+            xl[i] = row[v0 - mV + i];
+            xt[i] = row[v0 + c.guard_v + 1 + i];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = xl[j], b = xt[j];
+#pragma unroll
+            for (int i = 1; i < RV; ++i) { a += xl[j + i]; b += xt[j + i]; }
+            lead[j] = a;
+            trail[j] = b;
+        }
+    } else {
+        for (int j = 0; j < 4; ++j) {
+            float a = row[v0 + j - mV], b = row[v0 + j + c.guard_v + 1];
+            for (int i = 1; i < rv; ++i) { a += row[v0 + j - mV + i]; b += row[v0 + j + c.guard_v + 1 + i]; }
+            lead[j] = a;
+            trail[j] = b;
+        }
+    }
+    const float kr = c.t_cfar / (float)rr, kv = c.t_cfar / (float)rv;     // T * mean == (T/ref) * sum
+    const float cu[4] = {cq.x, cq.y, cq.z, cq.w};
+    const float l4[4] = {lr.x, lr.y, lr.z, lr.w}, t4[4] = {tr.x, tr.y, tr.z, tr.w};
+    unsigned mask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int v = v0 + j;
+        const float thr = fmaxf(kr * fmaxf(l4[j], t4[j]), kv * fmaxf(lead[j], trail[j]));
+        cut[j] = cu[j];
+        if (v >= mV && v < c.P - mV && cu[j] > thr) mask |= 1u << j;
+    }
+    return mask;
 }

@@ -134,6 +134,7 @@ struct DopplerPlan {
     int P = 0, r[3] = {1, 1, 1};
     std::vector<cf> tw;        // passes concatenated at the MtdCfg offsets
     std::vector<int> perm;     // perm[p] = position of input pulse p
+    std::vector<int> iperm;    // iperm[pos] = pulse stored at pos
 };
 
 inline bool make_doppler_plan(DopplerPlan& dp, int P) {
@@ -151,7 +152,11 @@ inline bool make_doppler_plan(DopplerPlan& dp, int P) {
     int nrad = 0, rad[3];
     for (int s = 0; s < 3; ++s) if (dp.r[s] > 1) rad[nrad++] = dp.r[s];
     dp.perm.resize(P);
-    for (int p = 0; p < P; ++p) dp.perm[p] = rsp_digit_reverse(p, P, rad, nrad);
+    dp.iperm.resize(P);
+    for (int p = 0; p < P; ++p) {
+        dp.perm[p] = rsp_digit_reverse(p, P, rad, nrad);
+        dp.iperm[dp.perm[p]] = p;
+    }
     return true;
 }
 

@@ -80,8 +80,8 @@ def test_pc_narrow_fir(lib, cfg1):
     fir = pre["MF_narrow"].astype(np.float32)
     line = np.ascontiguousarray(beam[5, 7].astype(np.complex64))
     out = np.zeros(g1, np.complex64)
-    lib.emul_pc_narrow(line.ctypes.data_as(fp), cfg.point_PRT, pre["seg_start_narrow"] - 1, fir.ctypes.data_as(fp),
-                       len(fir), pre["fir_delay"], g1, out.ctypes.data_as(fp))
+    assert 0 == lib.emul_pc_narrow(line.ctypes.data_as(fp), cfg.point_PRT, pre["seg_start_narrow"] - 1,
+                                   fir.ctypes.data_as(fp), len(fir), pre["fir_delay"], g1, out.ctypes.data_as(fp))
     ref = pc[5, 7, :g1]
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
@@ -121,6 +121,30 @@ def test_cfar_tiles_match_oracle(lib, shape, tg):
     assert len(want) >= 3
     # and the vectorised oracle equals the literal scalar loops
     assert np.array_equal(ref, o.cfar_detect_scalar(S.astype(np.float64), cfg))
+
+
+@pytest.mark.parametrize("use_template", [0, 1])
+@pytest.mark.parametrize("tg", [16, 32, 64])
+@pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (150, 48, 3, 4, 2, 3), (120, 332, 10, 10, 5, 5)])
+def test_cfar_vectorised_quads_match_oracle(lib, shape, tg, use_template):
+    G, P, gR, gV, rR, rV = shape
+    rng = np.random.default_rng(G + P)
+    S = rng.rayleigh(1.0, (1, G, P))
+    for (g, v) in ((100, P // 2), (40, P // 2 + 3), (G - gR - rR - 1, P - gV - rV - 1), (gR + rR, gV + rV)):
+        S[0, g, v] += 60.0
+    S = S.astype(np.float32)
+    cfg = o.Config(guardCells_R=gR, guardCells_V=gV, refCells_R=rR, refCells_V=rV, T_CFAR=4.0)
+    det = np.zeros((G, P), np.uint8)
+    rc = lib.emul_cfar4_map(S[0].ctypes.data_as(fp), G, P, gR, gV, rR, rV, ctypes.c_float(4.0), tg, use_template,
+                            det.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
+    assert rc == 0
+    ref = o.cfar_detect(S.astype(np.float64), cfg)
+    margin = o.cfar_margin(S.astype(np.float64), cfg)[0]
+    got = {(int(v) + 1, int(g) + 1) for g, v in zip(*np.nonzero(det))}
+    want = {(int(r[0]), int(r[1])) for r in ref}
+    for (v1, g1) in got ^ want:
+        assert margin[g1 - 1, v1 - 1] < 1e-5
+    assert len(want) >= 4          # including the two corner CUTs
 
 
 def test_spline_peak_matches_scipy(lib):
