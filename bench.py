@@ -216,7 +216,10 @@ def main():
     host_pool = make_pool(rsp, config, pd, pool_n, seed0=1000 * rank)
     pool = torch.from_numpy(host_pool).cuda()
     rdm_ring = torch.empty((rdm_n, B, G, P), dtype=torch.complex64, device="cuda")
-    stream = torch.cuda.current_stream()
+    # everything timed runs on ONE explicit torch stream: the chain's kernels (rsp_set_stream), the
+    # NCCL gather and the CUDA events that bracket the timed region
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     chain.set_stream(stream.cuda_stream)
 
     # detection ring as torch tensors (zero-copy) for the NCCL gather
@@ -253,12 +256,16 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         barrier()
+        wall0 = time.perf_counter()
         ev0.record(stream)
         for _ in range(args.steps):
             step()
         ev1.record(stream)
         barrier()
+        wall_ms = (time.perf_counter() - wall0) * 1e3
     ms = ev0.elapsed_time(ev1)
+    # the device-event time must agree with the host clock around the same (fully synchronised) region
+    assert abs(wall_ms - ms) <= 0.1 * wall_ms + 1.0, f"event time {ms:.2f} ms vs wall {wall_ms:.2f} ms"
     launches = chain.info()["launches_total"] - launches0
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -328,7 +335,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIG_DESC[name], "name": name, "C": C_, "B": B, "P": P, "N": N, "G": G,
                        "cpis_per_step": cps, "input_pool_cpis": pool_n, "rdm_pool": rdm_n,

@@ -126,7 +126,10 @@ int rsp_create(const rsp_params* params, rsp_ctx** out);
 void rsp_destroy(rsp_ctx* ctx);
 const char* rsp_last_error(const rsp_ctx* ctx);          /* ctx may be NULL: last create() error */
 int rsp_upload_constants(rsp_ctx* ctx, const rsp_constants* k);
-int rsp_set_stream(rsp_ctx* ctx, void* cuda_stream);      /* cudaStream_t; NULL = context's own stream */
+/* Run on the caller's stream (a cudaStream_t handle; 0 is the legacy default stream, as PyTorch's
+ * default stream reports).  RSP_STREAM_OWN switches back to the context's own non-blocking stream. */
+#define RSP_STREAM_OWN ((void*)(intptr_t)-1)
+int rsp_set_stream(rsp_ctx* ctx, void* cuda_stream);
 int rsp_synchronize(rsp_ctx* ctx);
 
 /* ---- the hot path: S5 -> S9 on one CPI (fun_process_single_frame.m:90-146) ----

@@ -156,7 +156,7 @@ int emul_cfar4_map(const float* S, int G, int P, int guard_r, int guard_v, int r
         for (int row = 0; row < g.rows; ++row) {
             const int gg = g_first - mR + row;
             if (gg < G)
-                for (int v = 0; v < P; ++v) tile[(size_t)row * g.PP + 4 + v] = S[(size_t)gg * P + v];
+                for (int v = 0; v < P; ++v) tile[(size_t)row * g.PP + RSP_CFAR_HALO + v] = S[(size_t)gg * P + v];
         }
         for (int t = 0; t < RSP_CFAR_THREADS; ++t) {
             if (use_template && ref_r == 5) cfar4_r5_phase<5>(tile.data(), R5.data(), c, g, t, RSP_CFAR_THREADS);
@@ -167,9 +167,11 @@ int emul_cfar4_map(const float* S, int G, int P, int guard_r, int guard_v, int r
             for (int c4 = c_lo; c4 <= c_hi; ++c4) {
                 float cut[4];
                 unsigned m;
-                if (use_template && ref_r == 5 && ref_v == 5) m = cfar4_decide_quad<5, 5>(tile.data(), R5.data(), c, g, gl, c4, cut);
-                else if (use_template && ref_r == 5 && ref_v == 4) m = cfar4_decide_quad<5, 4>(tile.data(), R5.data(), c, g, gl, c4, cut);
-                else m = cfar4_decide_quad<0, 0>(tile.data(), R5.data(), c, g, gl, c4, cut);
+                if (use_template && ref_r == 5 && ref_v == 5 && guard_v == 10)
+                    m = cfar4_decide_quad<5, 5, 10>(tile.data(), R5.data(), c, g, gl, c4, cut);
+                else if (use_template && ref_r == 5 && ref_v == 4 && guard_v == 2)
+                    m = cfar4_decide_quad<5, 4, 2>(tile.data(), R5.data(), c, g, gl, c4, cut);
+                else m = cfar4_decide_quad<0, 0, 0>(tile.data(), R5.data(), c, g, gl, c4, cut);
                 for (int j = 0; j < 4; ++j)
                     if (m & (1u << j)) det[(size_t)(g_first + gl) * P + 4 * c4 + j] = 1;
             }

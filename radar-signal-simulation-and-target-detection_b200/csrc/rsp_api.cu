@@ -33,10 +33,21 @@ struct rsp_ctx {
     float2* d_raw = nullptr;              // PCN complex64 staging for host / converted input
     void* d_stage = nullptr;              // raw staging for dtype/layout conversion
     size_t stage_bytes = 0;
-    float2* d_beam = nullptr;
-    float2* d_pc = nullptr;
+    // A lane = one CUDA stream + its own intermediates.  The single-CPI calls use lane 0; the stream
+    // path deals consecutive CPIs round-robin over n_lanes so that one CPI's memory-bound kernels
+    // and tails overlap another CPI's FP-bound kernels.
+    struct Lane {
+        cudaStream_t s = nullptr;
+        float2* beam = nullptr;
+        float2* pc = nullptr;
+        float* amp = nullptr;
+        cudaEvent_t done = nullptr;
+    };
+    Lane lanes[8];
+    int n_lanes = 1;
+    Lane* cur = nullptr;                  // lane the launch helpers enqueue on
+    cudaEvent_t fork = nullptr;
     float2* d_rdm = nullptr;
-    float* d_amp = nullptr;
     float2* d_aux = nullptr;              // scratch for stage2 transposes
     // constants
     float2* d_W = nullptr;
@@ -55,6 +66,7 @@ struct rsp_ctx {
     // detection ring
     int slots = 0;
     int* d_counts = nullptr;
+    int* d_done = nullptr;                // CFAR completion tickets, one per slot
     rsp_detection* d_recs = nullptr;
     int* h_count = nullptr;               // pinned
     rsp_detection* h_recs = nullptr;      // pinned [max_detections]
@@ -68,8 +80,8 @@ struct rsp_ctx {
     std::vector<cudaEvent_t> event_pool;
 };
 
-enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC_MEDIUM, K_PC_LONG, K_MTD, K_CFAR, K_REFINE, K_NCLASS };
-static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft_medium", "pc_fft_long", "mtd", "cfar", "refine"};
+enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC, K_MTD, K_CFAR, K_NCLASS };
+static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft", "mtd", "cfar_refine"};
 
 static cudaEvent_t take_event(rsp_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -81,11 +93,11 @@ static cudaEvent_t take_event(rsp_ctx* c) {
 struct Timed {
     rsp_ctx* c; int cls; cudaEvent_t a = nullptr;
     Timed(rsp_ctx* c_, int cls_) : c(c_), cls(cls_) {
-        if (c->profiling) { a = take_event(c); cudaEventRecord(a, c->stream); }
+        if (c->profiling) { a = take_event(c); cudaEventRecord(a, c->cur->s); }
     }
     ~Timed() {
         c->launches++;
-        if (c->profiling) { cudaEvent_t b = take_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({cls, a, b}); }
+        if (c->profiling) { cudaEvent_t b = take_event(c); cudaEventRecord(b, c->cur->s); c->spans.push_back({cls, a, b}); }
     }
 };
 
@@ -157,8 +169,15 @@ const char* rsp_last_error(const rsp_ctx* ctx) { return ctx ? ctx->err.c_str() :
 void rsp_destroy(rsp_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->prm.device);
-    cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_beam); cudaFree(c->d_pc); cudaFree(c->d_rdm);
-    cudaFree(c->d_amp); cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_fir);
+    cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_rdm);
+    for (auto& ln : c->lanes) {
+        cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp);
+        if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
+    }
+    if (c->fork) cudaEventDestroy(c->fork);
+    cudaFree(c->d_done);
+    cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_fir);
     cudaFree(c->d_med_tw1); cudaFree(c->d_med_tw2); cudaFree(c->d_med_H);
     cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_tw2); cudaFree(c->d_lng_H);
     cudaFree(c->d_dop_tw); cudaFree(c->d_dop_perm); cudaFree(c->d_win);
@@ -216,17 +235,28 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t PBG = (size_t)c->P * c->B * c->G;
     CUC(dev_alloc(&c->d_raw, (size_t)c->P * c->C * c->N));
-    CUC(dev_alloc(&c->d_beam, (size_t)c->P * c->B * c->ldb));
-    CUC(dev_alloc(&c->d_pc, (size_t)c->P * c->B * c->ldg));
     CUC(dev_alloc(&c->d_rdm, PBG));
-    CUC(dev_alloc(&c->d_amp, PBG));
-    CUC(cudaMemset(c->d_beam, 0, (size_t)c->P * c->B * c->ldb * sizeof(float2)));
-    CUC(cudaMemset(c->d_pc, 0, (size_t)c->P * c->B * c->ldg * sizeof(float2)));
+    const char* el = getenv("RSP_LANES");
+    c->n_lanes = el ? std::min(8, std::max(1, atoi(el))) : 3;
+    CUC(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+    for (int i = 0; i < c->n_lanes; ++i) {
+        rsp_ctx::Lane& ln = c->lanes[i];
+        if (i == 0) ln.s = c->stream; else CUC(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        CUC(dev_alloc(&ln.beam, (size_t)c->P * c->B * c->ldb));
+        CUC(dev_alloc(&ln.pc, (size_t)c->P * c->B * c->ldg));
+        CUC(dev_alloc(&ln.amp, PBG));
+        CUC(cudaMemset(ln.beam, 0, (size_t)c->P * c->B * c->ldb * sizeof(float2)));
+        CUC(cudaMemset(ln.pc, 0, (size_t)c->P * c->B * c->ldg * sizeof(float2)));
+    }
+    c->cur = &c->lanes[0];
     const char* es = getenv("RSP_STREAM_SLOTS");
     c->slots = es ? std::max(1, atoi(es)) : 128;
     CUC(dev_alloc(&c->d_counts, (size_t)c->slots));
     CUC(dev_alloc(&c->d_recs, (size_t)c->slots * p->max_detections));
     CUC(cudaMemset(c->d_counts, 0, (size_t)c->slots * sizeof(int)));
+    CUC(dev_alloc(&c->d_done, (size_t)c->slots));
+    CUC(cudaMemset(c->d_done, 0, (size_t)c->slots * sizeof(int)));
     CUC(cudaMallocHost(reinterpret_cast<void**>(&c->h_count), sizeof(int)));
     CUC(cudaMallocHost(reinterpret_cast<void**>(&c->h_recs), (size_t)p->max_detections * sizeof(rsp_detection)));
 #undef CUC
@@ -236,10 +266,19 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
 
 int rsp_set_stream(rsp_ctx* c, void* s) {
     if (!c) return RSP_ERR_INVALID_ARG;
-    if (s == nullptr) return RSP_OK;
-    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-    c->stream = reinterpret_cast<cudaStream_t>(s);
-    c->own_stream = false;
+    CU(c, cudaSetDevice(c->prm.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (s == RSP_STREAM_OWN) {
+        if (!c->own_stream) {
+            CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            c->own_stream = true;
+        }
+    } else {
+        if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+        c->stream = reinterpret_cast<cudaStream_t>(s);
+        c->own_stream = false;
+    }
+    c->lanes[0].s = c->stream;
     return RSP_OK;
 }
 
@@ -330,21 +369,21 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         c->cfar_vec = (P % 4) == 0;
         auto smem_for = [&](int tg) {
             const size_t r5 = (size_t)(tg + mR + c->prm.guard_r + 1) * P;
-            return c->cfar_vec ? ((size_t)(tg + 2 * mR) * (P + 8) + r5) * sizeof(float)
+            return c->cfar_vec ? ((size_t)(tg + 2 * mR) * (P + 2 * RSP_CFAR_HALO) + r5) * sizeof(float)
                                : ((size_t)(tg + 2 * mR) * P + r5 + (size_t)tg * P) * sizeof(float);
         };
         c->cfar_tg = 16;
         for (int tg : {64, 32, 16})
-            if (smem_for(tg) <= 80 * 1024) { c->cfar_tg = tg; break; }
+            if (smem_for(tg) <= 72 * 1024) { c->cfar_tg = tg; break; }
         c->cfar_smem = smem_for(c->cfar_tg);
         if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
-        const int rr = c->prm.ref_r, rv = c->prm.ref_v;
-        c->cfar_variant = (rr == 5 && rv == 5) ? 1 : (rr == 5 && rv == 4) ? 2 : 0;
+        const int rr = c->prm.ref_r, rv = c->prm.ref_v, gv = c->prm.guard_v;
+        c->cfar_variant = (rr == 5 && rv == 5 && gv == 10) ? 1 : (rr == 5 && rv == 4 && gv == 2) ? 2 : 0;
 #define RSP_CFAR_DISPATCH(TGV, ACTION)                                                      \
         if (!c->cfar_vec) { ACTION(cfar_kernel<TGV>) }                                          \
-        else if (c->cfar_variant == 1) { ACTION((cfar4_kernel<TGV, 5, 5>)) }                    \
-        else if (c->cfar_variant == 2) { ACTION((cfar4_kernel<TGV, 5, 4>)) }                    \
-        else { ACTION((cfar4_kernel<TGV, 0, 0>)) }
+        else if (c->cfar_variant == 1) { ACTION((cfar4_kernel<TGV, 5, 5, 10>)) }                \
+        else if (c->cfar_variant == 2) { ACTION((cfar4_kernel<TGV, 5, 4, 2>)) }                 \
+        else { ACTION((cfar4_kernel<TGV, 0, 0, 0>)) }
 #define OPTIN(K) CU(c, opt_in_smem(K, c->cfar_smem));
         if (c->cfar_tg == 64) { RSP_CFAR_DISPATCH(64, OPTIN) }
         else if (c->cfar_tg == 32) { RSP_CFAR_DISPATCH(32, OPTIN) }
@@ -367,16 +406,16 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
 // ------------------------------------------------------------------------------------------
 // launch sequence for one CPI (device-resident PCN complex64 input)
 // ------------------------------------------------------------------------------------------
-template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw) {
+template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw, int* det_count) {
     constexpr int SPT = 2, CU_ = 4;
     Timed t(c, K_DBF);
     dim3 grid((c->N + RSP_DBF_THREADS * SPT - 1) / (RSP_DBF_THREADS * SPT), c->P);
-    dbf_kernel<NB, SPT, CU_><<<grid, RSP_DBF_THREADS, 0, c->stream>>>(raw, c->d_beam, c->d_W, c->C, c->N, c->ldb);
+    dbf_kernel<NB, SPT, CU_><<<grid, RSP_DBF_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_W, c->C, c->N, c->ldb, det_count);
 }
 
-static int launch_dbf_any(rsp_ctx* c, const float2* raw) {
+static int launch_dbf_any(rsp_ctx* c, const float2* raw, int* det_count) {
     switch (c->B) {
-#define CASE(n) case n: launch_dbf<n>(c, raw); break;
+#define CASE(n) case n: launch_dbf<n>(c, raw, det_count); break;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
         CASE(15) CASE(16)
 #undef CASE
@@ -400,12 +439,12 @@ static void launch_pc(rsp_ctx* c) {
     const bool fold = narrow && c->med.L > 0;        // the medium groups compute the narrow gates too
     if (narrow && !fold) {
         Timed t(c, K_PC_NARROW);
-        pc_narrow_kernel<<<c->P * c->B, 256, 0, c->stream>>>(c->d_beam, c->d_pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
+        pc_narrow_kernel<<<c->P * c->B, 256, 0, c->cur->s>>>(c->cur->beam, c->cur->pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
                                                              c->ldb, c->ldg, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
     }
     if (!c->med.L && !c->lng.L) return;
     PcKernelArgs a;
-    a.beam = c->d_beam; a.pc = c->d_pc; a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
+    a.beam = c->cur->beam; a.pc = c->cur->pc; a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
     fill_seg(c, a.seg[0], c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H);
     fill_seg(c, a.seg[1], c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H);
     a.do_narrow = fold ? 1 : 0;
@@ -413,28 +452,28 @@ static void launch_pc(rsp_ctx* c) {
     a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
     const int la = c->lng.L ? c->lng.L : 1024, lb = c->med.L ? c->med.L : 1024;
-    Timed t(c, K_PC_LONG);
-#define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->stream>>>(a);
+    Timed t(c, K_PC);
+#define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
     RSP_FOR_EACH_PC_PAIR(X)
 #undef X
 }
 
 static void launch_mtd(rsp_ctx* c, float2* rdm) {
     MtdArgs a;
-    a.pc = c->d_pc; a.rdm = rdm; a.amp = c->d_amp; a.win = c->d_win; a.tw = c->d_dop_tw; a.perm = c->d_dop_perm;
+    a.pc = c->cur->pc; a.rdm = rdm; a.amp = c->cur->amp; a.win = c->d_win; a.tw = c->d_dop_tw; a.perm = c->d_dop_perm;
     a.P = c->P; a.B = c->B; a.G = c->G; a.ldg = c->ldg;
     const int tg = c->mtd_tg;
     dim3 grid((c->G + tg - 1) / tg, c->B);
     Timed t(c, K_MTD);
     if (c->pow2_doppler) {
         switch (c->P) {
-#define X(p, r0, r1, r2) case p: mtd_kernel<MtdCfg<p, r0, r1, r2>><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a); break;
+#define X(p, r0, r1, r2) case p: mtd_kernel<MtdCfg<p, r0, r1, r2>><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a); break;
             RSP_FOR_EACH_POW2_P(X)
 #undef X
         }
-    } else if (tg == 32) mtd_dft_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
-    else if (tg == 16) mtd_dft_kernel<16><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
-    else mtd_dft_kernel<8><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->stream>>>(a);
+    } else if (tg == 32) mtd_dft_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
+    else if (tg == 16) mtd_dft_kernel<16><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
+    else mtd_dft_kernel<8><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
 }
 
 static bool cfar_testable(const rsp_ctx* c) {
@@ -445,46 +484,42 @@ static bool cfar_testable(const rsp_ctx* c) {
 static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
     if (!cfar_testable(c)) return;
     CfarArgs a;
-    a.amp = c->d_amp;
+    a.amp = c->cur->amp; a.rdm = rdm;
     a.c.P = c->P; a.c.G = c->G; a.c.guard_r = c->prm.guard_r; a.c.guard_v = c->prm.guard_v;
     a.c.ref_r = c->prm.ref_r; a.c.ref_v = c->prm.ref_v; a.c.t_cfar = c->prm.t_cfar;
     a.count = c->d_counts + slot;
+    a.done = c->d_done + slot;
     a.recs = c->d_recs + (size_t)slot * c->prm.max_detections;
     a.cap = c->prm.max_detections;
+    a.range_axis = c->d_range_axis; a.vel_axis = c->d_vel_axis; a.beam_angles = c->d_beam_angles; a.k_slopes = c->d_k_slopes;
+    a.delta_r = c->delta_r; a.delta_v = c->delta_v; a.complex_mode = c->prm.monopulse_complex;
     const int mR = c->prm.guard_r + c->prm.ref_r;
     const int ncut = c->G - 2 * mR, tg = c->cfar_tg;
     dim3 grid((ncut + tg - 1) / tg, c->B - 1);
-    {
-        Timed t(c, K_CFAR);
-#define LAUNCH(K) K<<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->stream>>>(a);
-        if (tg == 64) { RSP_CFAR_DISPATCH(64, LAUNCH) }
-        else if (tg == 32) { RSP_CFAR_DISPATCH(32, LAUNCH) }
-        else { RSP_CFAR_DISPATCH(16, LAUNCH) }
+    Timed t(c, K_CFAR);
+#define LAUNCH(K) K<<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->cur->s>>>(a);
+    if (tg == 64) { RSP_CFAR_DISPATCH(64, LAUNCH) }
+    else if (tg == 32) { RSP_CFAR_DISPATCH(32, LAUNCH) }
+    else { RSP_CFAR_DISPATCH(16, LAUNCH) }
 #undef LAUNCH
-    }
-    RefineArgs r;
-    r.amp = c->d_amp; r.rdm = rdm; r.P = c->P; r.G = c->G; r.count = a.count; r.recs = a.recs; r.cap = a.cap;
-    r.range_axis = c->d_range_axis; r.vel_axis = c->d_vel_axis; r.beam_angles = c->d_beam_angles; r.k_slopes = c->d_k_slopes;
-    r.delta_r = c->delta_r; r.delta_v = c->delta_v; r.complex_mode = c->prm.monopulse_complex;
-    Timed t(c, K_REFINE);
-    refine_kernel<<<8, 128, 0, c->stream>>>(r);
 }
 
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
     int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + 1 /*mtd*/;
-    if (cfar_testable(c)) n += 2;   // cfar + refine
+    if (cfar_testable(c)) n += 1;   // cfar (+ refine in its last CTA)
     return n;
 }
 
-// enqueue S5..S9 for one device-resident PCN cube
-static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot) {
-    cudaMemsetAsync(c->d_counts + slot, 0, sizeof(int), c->stream);
-    int rc = launch_dbf_any(c, raw);
+// enqueue S5..S9 for one device-resident PCN cube on lane `lane`
+static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, int lane) {
+    c->cur = &c->lanes[lane];
+    int rc = launch_dbf_any(c, raw, c->d_counts + slot);      // dbf_kernel also zeroes the slot's counter
     if (rc) return rc;
     launch_pc(c);
     launch_mtd(c, rdm);
-    launch_cfar(c, rdm, slot);
+    if (cfar_testable(c)) launch_cfar(c, rdm, slot);
+    c->cur = &c->lanes[0];
     CU(c, cudaGetLastError());
     return RSP_OK;
 }
@@ -560,7 +595,7 @@ int rsp_process_cpi(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dt
     int rc = stage_input(c, raw, layout, dtype, raw_mem, &d_in);
     if (rc) return rc;
     float2* rdm = (rdm_out && rdm_mem == RSP_MEM_DEVICE) ? static_cast<float2*>(rdm_out) : c->d_rdm;
-    rc = enqueue_chain(c, d_in, rdm, 0);
+    rc = enqueue_chain(c, d_in, rdm, 0, 0);
     if (rc) return rc;
     if (rdm_out && rdm_mem == RSP_MEM_HOST)
         CU(c, cudaMemcpyAsync(rdm_out, c->d_rdm, (size_t)c->P * c->B * c->G * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
@@ -577,11 +612,20 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
         return fail(c, RSP_ERR_INVALID_ARG, "slots [%d,%d) exceed the ring of %d", first_slot, first_slot + n_cpi, c->slots);
     CU(c, cudaSetDevice(c->prm.device));
     const size_t in_elems = (size_t)c->P * c->C * c->N, out_elems = (size_t)c->P * c->B * c->G;
+    const int nl = std::min(c->n_lanes, std::max(n_cpi, 1));
+    if (nl > 1) {                                    // fork: the extra lanes wait for work already on the caller's stream
+        CU(c, cudaEventRecord(c->fork, c->stream));
+        for (int l = 1; l < nl; ++l) CU(c, cudaStreamWaitEvent(c->lanes[l].s, c->fork, 0));
+    }
     for (int i = 0; i < n_cpi; ++i) {
         const float2* in = static_cast<const float2*>(raw_dev) + (size_t)(i % raw_pool) * in_elems;
         float2* rdm = (rdm_dev && rdm_pool > 0) ? static_cast<float2*>(rdm_dev) + (size_t)(i % rdm_pool) * out_elems : c->d_rdm;
-        int rc = enqueue_chain(c, in, rdm, first_slot + i);
+        int rc = enqueue_chain(c, in, rdm, first_slot + i, i % nl);
         if (rc) return rc;
+    }
+    for (int l = 1; l < nl; ++l) {                   // join
+        CU(c, cudaEventRecord(c->lanes[l].done, c->lanes[l].s));
+        CU(c, cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
     }
     return RSP_OK;
 }
@@ -620,7 +664,7 @@ int rsp_get_beam(rsp_ctx* c, rsp_c64* dst) {
     if (!c || !dst) return RSP_ERR_INVALID_ARG;
     if (!c->ran) return fail(c, RSP_ERR_NOT_READY, "no CPI processed");
     CU(c, cudaSetDevice(c->prm.device));
-    CU(c, cudaMemcpy2DAsync(dst, (size_t)c->N * sizeof(float2), c->d_beam, (size_t)c->ldb * sizeof(float2),
+    CU(c, cudaMemcpy2DAsync(dst, (size_t)c->N * sizeof(float2), c->lanes[0].beam, (size_t)c->ldb * sizeof(float2),
                             (size_t)c->N * sizeof(float2), (size_t)c->P * c->B, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return RSP_OK;
@@ -630,7 +674,7 @@ int rsp_get_pc(rsp_ctx* c, rsp_c64* dst) {
     if (!c || !dst) return RSP_ERR_INVALID_ARG;
     if (!c->ran) return fail(c, RSP_ERR_NOT_READY, "no CPI processed");
     CU(c, cudaSetDevice(c->prm.device));
-    CU(c, cudaMemcpy2DAsync(dst, (size_t)c->G * sizeof(float2), c->d_pc, (size_t)c->ldg * sizeof(float2),
+    CU(c, cudaMemcpy2DAsync(dst, (size_t)c->G * sizeof(float2), c->lanes[0].pc, (size_t)c->ldg * sizeof(float2),
                             (size_t)c->G * sizeof(float2), (size_t)c->P * c->B, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return RSP_OK;
@@ -642,7 +686,7 @@ int rsp_get_rdm(rsp_ctx* c, rsp_c64* dst) {
 }
 
 int rsp_get_amp(rsp_ctx* c, float* dst) {
-    return copy_out(c, dst, c ? c->d_amp : nullptr, c ? (size_t)c->P * c->B * c->G * sizeof(float) : 0);
+    return copy_out(c, dst, c ? c->lanes[0].amp : nullptr, c ? (size_t)c->P * c->B * c->G * sizeof(float) : 0);
 }
 
 int rsp_process_frame(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem raw_mem,

@@ -8,8 +8,8 @@
 //   pc_fft_kernel          S6  fun_process_single_frame.m:115-125 (overlap-save blocks)
 //   mtd_kernel             S7  fun_process_single_frame.m:131-136 (power-of-two P)
 //   mtd_dft_kernel         S7  same, any P (the reference's native P = 332)
-//   cfar_kernel            S8  fun_process_single_frame.m:172-223
-//   refine_kernel          S9  fun_process_single_frame.m:241-298
+//   cfar_kernel/cfar4_kernel  S8  fun_process_single_frame.m:172-223, with S9 (:241-298, refine_record)
+//                             done by the last CTA of the same launch
 #pragma once
 #include <cuda_runtime.h>
 #include "rsp.h"
@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(256) pbg_to_bgp_kernel(const float2* __restric
 template <int NB, int SPT, int CU>
 __global__ void __launch_bounds__(RSP_DBF_THREADS) dbf_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
                                                               const float2* __restrict__ Wc /* [C][NB] conj(W) */,
-                                                              int C, int N, int ldb) {
+                                                              int C, int N, int ldb, int* __restrict__ det_count) {
     __shared__ float2 sW[RSP_MAX_CHANNELS * NB];
     const int tid = threadIdx.x;
+    if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
     for (int i = tid; i < C * NB; i += RSP_DBF_THREADS) sW[i] = Wc[i];
     __syncthreads();
     const int p = blockIdx.y;
@@ -339,14 +340,90 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs 
 // ------------------------------------------------------------------------------------------
 struct CfarArgs {
     const float* amp;            // [B][G][P]
+    const float2* rdm;           // [B][G][P]
     CfarParams c;
-    int* count;                  // detection counter of this CPI slot
+    int* count;                  // detection counter of this CPI slot (zeroed by dbf_kernel)
+    int* done;                   // CTA completion ticket of this slot (self-resetting)
     rsp_detection* recs;         // records of this CPI slot
     int cap;
+    // S9 tables
+    const double* range_axis;
+    const double* vel_axis;
+    const double* beam_angles;
+    const double* k_slopes;
+    double delta_r, delta_v;
+    int complex_mode;
 };
 
+// S9 for record i (fun_process_single_frame.m:241-298): spline peak search on the fp32 sum map the
+// detector used, monopulse ratio from the two beams' amplitudes at the integer cell.
+__device__ __noinline__ void refine_record(const CfarArgs& k, int i) {
+    const int P = k.c.P, G = k.c.G;
+    rsp_detection d = k.recs[i];
+    const int v = d.v_idx - 1, g = d.r_idx - 1, pair = d.pair_idx - 1;
+    const float* A = k.amp + (size_t)pair * G * P;
+    const float* Bm = A + (size_t)G * P;
+    double yr[5], yv[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const size_t orr = (size_t)(g - 2 + j) * P + v, ov = (size_t)g * P + v - 2 + j;
+        yr[j] = (double)(A[orr] + Bm[orr]);
+        yv[j] = (double)(A[ov] + Bm[ov]);
+    }
+    const double r_off = rsp_spline5_peak(yr, 8) - 2.0;          // fsf:237 rInterpTimes = 8
+    const double v_off = rsp_spline5_peak(yv, 4) - 2.0;          // vInterpTimes = 4
+    d.range = k.range_axis[g] + r_off * k.delta_r;               // fsf:262
+    d.velocity = k.vel_axis[v] + v_off * k.delta_v;              // fsf:278
+    const size_t o = (size_t)g * P + v;
+    double ratio;
+    const double eps = 2.220446049250313e-16;
+    if (k.complex_mode) {                                        // mc:454-461
+        const float2 a = k.rdm[(size_t)pair * G * P + o], bb = k.rdm[(size_t)(pair + 1) * G * P + o];
+        const double nr = (double)a.x - (double)bb.x, ni = (double)a.y - (double)bb.y;
+        const double dr = (double)a.x + (double)bb.x + eps, di = (double)a.y + (double)bb.y;
+        ratio = (nr * dr + ni * di) / (dr * dr + di * di);
+    } else {                                                     // fsf:282-285
+        const double sa = (double)A[o], sb = (double)Bm[o];
+        ratio = (sa - sb) / (sa + sb + eps);
+    }
+    d.angle = 0.5 * (k.beam_angles[pair] + k.beam_angles[pair + 1]) + k.k_slopes[pair] * ratio;   // fsf:286-290
+    k.recs[i] = d;
+}
+
+// The last CTA of the grid to finish (ticket counter) refines every record of the CPI: S9 rides in
+// the tail of the CFAR launch instead of costing a launch of its own.
+__device__ __forceinline__ void cfar_finish(const CfarArgs& k) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int total = gridDim.x * gridDim.y;
+        const int ticket = atomicAdd(k.done, 1);
+        s_last = (ticket == total - 1);
+        if (s_last) *k.done = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n = min(*reinterpret_cast<volatile int*>(k.count), k.cap);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) refine_record(k, i);
+}
+
+__device__ __forceinline__ void cfar_emit(const CfarArgs& k, int v, int g, int pair, float power) {
+    const int slot = atomicAdd(k.count, 1);
+    if (slot >= k.cap) return;              // overflow is reported by the host from the count
+    rsp_detection d;
+    d.v_idx = v + 1;
+    d.r_idx = g + 1;
+    d.pair_idx = pair + 1;
+    d.power = power;
+    d.range = 0.0; d.velocity = 0.0; d.angle = 0.0;
+    k.recs[slot] = d;
+}
+
+// generic scalar variant (any P, any window)
 template <int TG>
-__global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k) {
+__global__ void __launch_bounds__(RSP_CFAR_THREADS, 2) cfar_kernel(const CfarArgs k) {
     extern __shared__ float cfar_smem[];
     const int P = k.c.P, G = k.c.G;
     const int mR = k.c.guard_r + k.c.ref_r, mV = k.c.guard_v + k.c.ref_v;
@@ -361,22 +438,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k
     const float* Bm = A + (size_t)G * P;
     const size_t base = (size_t)(g_first - mR) * P;
     const int n_valid = min(rows, G - (g_first - mR)) * P;        // rows that exist in the map
-    const int n_el = rows * P;
-    if ((P & 3) == 0) {
-        const float4* A4 = reinterpret_cast<const float4*>(A + base);
-        const float4* B4 = reinterpret_cast<const float4*>(Bm + base);
-        float4* S4 = reinterpret_cast<float4*>(S);
-        for (int e = tid; e < n_el / 4; e += RSP_CFAR_THREADS) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * e < n_valid) {
-                const float4 a = A4[e], b = B4[e];
-                s = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-            }
-            S4[e] = s;
-        }
-    } else {
-        for (int e = tid; e < n_el; e += RSP_CFAR_THREADS) S[e] = e < n_valid ? A[base + e] + Bm[base + e] : 0.f;
-    }
+    for (int e = tid; e < rows * P; e += RSP_CFAR_THREADS) S[e] = e < n_valid ? A[base + e] + Bm[base + e] : 0.f;
     __syncthreads();
     cfar_sums_phase(S, R5, D5, k.c, TG, tid, RSP_CFAR_THREADS);
     __syncthreads();
@@ -385,23 +447,15 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k
         const int gl = e / nv, v = mV + (e - gl * nv), g = g_first + gl;
         if (g >= G - mR) break;
         float cut;
-        if (!cfar_decide(S, R5, D5, k.c, gl, v, &cut)) continue;
-        const int slot = atomicAdd(k.count, 1);
-        if (slot >= k.cap) continue;        // overflow is reported by the host from the count
-        rsp_detection d;
-        d.v_idx = v + 1;
-        d.r_idx = g + 1;
-        d.pair_idx = pair + 1;
-        d.power = cut;
-        d.range = 0.0; d.velocity = 0.0; d.angle = 0.0;
-        k.recs[slot] = d;
+        if (cfar_decide(S, R5, D5, k.c, gl, v, &cut)) cfar_emit(k, v, g, pair, cut);
     }
+    cfar_finish(k);
 }
 
-// Vectorised variant for P % 4 == 0 (see cfar4_* in rsp_phases.cuh); RR/RV = compile-time reference
-// window lengths (0 = run time).
-template <int TG, int RR, int RV>
-__global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar4_kernel(const CfarArgs k) {
+// Vectorised variant for P % 4 == 0 (see cfar4_* in rsp_phases.cuh); RR/RV/GV = compile-time range
+// reference, Doppler reference and Doppler guard lengths (RR = 0: run time).
+template <int TG, int RR, int RV, int GV>
+__global__ void __launch_bounds__(RSP_CFAR_THREADS, 3) cfar4_kernel(const CfarArgs k) {
     extern __shared__ float cfar_smem[];
     const Cfar4Geom g = cfar4_geom(k.c, TG);
     const int P = k.c.P, G = k.c.G;
@@ -414,17 +468,21 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar4_kernel(const CfarArgs 
     const float4* A4 = reinterpret_cast<const float4*>(k.amp + ((size_t)pair * G + (g_first - mR)) * P);
     const float4* B4 = A4 + (size_t)G * g.P4;
     float4* S4 = reinterpret_cast<float4*>(S);
-    const int pp4 = g.PP / 4;
+    const int pp4 = g.PP / 4, h4 = RSP_CFAR_HALO / 4;
     const int rows_valid = min(g.rows, G - (g_first - mR));
-    for (int idx = tid; idx < g.rows * pp4; idx += RSP_CFAR_THREADS) {       // zero halo + rows beyond the map
-        const int row = idx / pp4, c = idx - row * pp4;
-        if (c == 0 || c == pp4 - 1 || row >= rows_valid) S4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = tid; idx < g.rows * 2 * h4; idx += RSP_CFAR_THREADS) {      // zero the halo columns
+        const int row = idx / (2 * h4), c = idx - row * (2 * h4);
+        S4[row * pp4 + (c < h4 ? c : pp4 - 2 * h4 + c)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int idx = tid; idx < rows_valid * g.P4; idx += RSP_CFAR_THREADS) {
+    for (int idx = tid; idx < g.rows * g.P4; idx += RSP_CFAR_THREADS) {
         int row, c4;
         cfar4_split(g, idx, row, c4);
-        const float4 a = A4[idx], b = B4[idx];
-        S4[row * pp4 + 1 + c4] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows_valid) {
+            const float4 a = A4[idx], b = B4[idx];
+            s = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+        S4[row * pp4 + h4 + c4] = s;
     }
     __syncthreads();
     cfar4_r5_phase<RR>(S, R5, k.c, g, tid, RSP_CFAR_THREADS);
@@ -434,74 +492,14 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar4_kernel(const CfarArgs 
     for (int idx = tid; idx < gl_end * nq; idx += RSP_CFAR_THREADS) {
         const int gl = idx / nq, c4 = c_lo + (idx - gl * nq);
         float cut[4];
-        unsigned m = cfar4_decide_quad<RR, RV>(S, R5, k.c, g, gl, c4, cut);
+        unsigned m = cfar4_decide_quad<RR, RV, GV>(S, R5, k.c, g, gl, c4, cut);
         while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
-            const int slot = atomicAdd(k.count, 1);
-            if (slot < k.cap) {
-                rsp_detection d;
-                d.v_idx = 4 * c4 + j + 1;
-                d.r_idx = g_first + gl + 1;
-                d.pair_idx = pair + 1;
-                d.power = cut[j];
-                d.range = 0.0; d.velocity = 0.0; d.angle = 0.0;
-                k.recs[slot] = d;
-            }
+            cfar_emit(k, 4 * c4 + j, g_first + gl, pair, cut[j]);
         }
     }
-}
-
-struct RefineArgs {
-    const float* amp;            // [B][G][P]
-    const float2* rdm;           // [B][G][P]
-    int P, G;
-    const int* count;
-    rsp_detection* recs;
-    int cap;
-    const double* range_axis;
-    const double* vel_axis;
-    const double* beam_angles;
-    const double* k_slopes;
-    double delta_r, delta_v;
-    int complex_mode;
-};
-
-// fun_process_single_frame.m:241-298 for every record written by cfar_kernel
-__global__ void __launch_bounds__(128) refine_kernel(const RefineArgs k) {
-    const int n = min(*k.count, k.cap);
-    const int P = k.P, G = k.G;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        rsp_detection d = k.recs[i];
-        const int v = d.v_idx - 1, g = d.r_idx - 1, pair = d.pair_idx - 1;
-        const float* A = k.amp + (size_t)pair * G * P;
-        const float* Bm = A + (size_t)G * P;
-        double yr[5], yv[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const size_t orr = (size_t)(g - 2 + j) * P + v, ov = (size_t)g * P + v - 2 + j;
-            yr[j] = (double)(A[orr] + Bm[orr]);          // the fp32 sum map S, as cfar_kernel formed it
-            yv[j] = (double)(A[ov] + Bm[ov]);
-        }
-        const double r_off = rsp_spline5_peak(yr, 8) - 2.0;          // fsf:237 rInterpTimes = 8
-        const double v_off = rsp_spline5_peak(yv, 4) - 2.0;          // vInterpTimes = 4
-        d.range = k.range_axis[g] + r_off * k.delta_r;               // fsf:262
-        d.velocity = k.vel_axis[v] + v_off * k.delta_v;              // fsf:278
-        const size_t o = (size_t)g * P + v;
-        double ratio;
-        const double eps = 2.220446049250313e-16;
-        if (k.complex_mode) {                                        // mc:454-461
-            const float2 a = k.rdm[(size_t)pair * G * P + o], bb = k.rdm[(size_t)(pair + 1) * G * P + o];
-            const double nr = (double)a.x - (double)bb.x, ni = (double)a.y - (double)bb.y;
-            const double dr = (double)a.x + (double)bb.x + eps, di = (double)a.y + (double)bb.y;
-            ratio = (nr * dr + ni * di) / (dr * dr + di * di);
-        } else {                                                     // fsf:282-285
-            const double sa = (double)A[o], sb = (double)Bm[o];
-            ratio = (sa - sb) / (sa + sb + eps);
-        }
-        d.angle = 0.5 * (k.beam_angles[pair] + k.beam_angles[pair + 1]) + k.k_slopes[pair] * ratio;   // fsf:286-290
-        k.recs[i] = d;
-    }
+    cfar_finish(k);
 }
 
 }  // namespace rsp

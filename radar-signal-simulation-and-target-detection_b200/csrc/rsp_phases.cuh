@@ -324,19 +324,20 @@ RSP_HD int cfar_decide(const float* S, const float* R5, const float* D5, const C
 
 // =============================================================================================
 // CFAR, vectorised variant (P % 4 == 0): every thread works on quads of 4 consecutive Doppler bins.
-//   S tile: rows = gates [g_first - mR, g_first + TG + mR), row pitch PP = P + 8 floats with the data
-//   at column offset 4 (zero halo of 4 on both sides, so the Doppler windows of partially valid
-//   quads never leave the row).  R5 (range window sums) has pitch P.
-//   RR / RV are the compile-time reference-window lengths (0 = use the run-time value).
+//   S tile: rows = gates [g_first - mR, g_first + TG + mR), row pitch PP = P + 16 floats with the
+//   data at column offset 8 (zero halo of 8 on both sides, so the aligned Doppler-window loads of
+//   partially valid quads never leave the row).  R5 (range window sums) has pitch P.
+//   RR / RV / GV are compile-time reference / guard lengths (RR = 0: everything at run time).
 // =============================================================================================
 #if !defined(__CUDACC__)
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #endif
+#define RSP_CFAR_HALO 8
 
 struct Cfar4Geom {
     int P, P4, sh;        // P4 = P/4; sh = log2(P4) when P4 is a power of two, else -1
-    int PP;               // padded row pitch of S (floats) = P + 8
+    int PP;               // padded row pitch of S (floats) = P + 2*RSP_CFAR_HALO
     int TG, rows, r5_rows;
 };
 
@@ -347,7 +348,7 @@ RSP_HD Cfar4Geom cfar4_geom(const CfarParams& c, int TG) {
     g.sh = -1;
     for (int s = 0; s < 16; ++s)
         if ((1 << s) == g.P4) g.sh = s;
-    g.PP = c.P + 8;
+    g.PP = c.P + 2 * RSP_CFAR_HALO;
     g.TG = TG;
     g.rows = TG + 2 * (c.guard_r + c.ref_r);
     g.r5_rows = cfar_r5_rows(c, TG);
@@ -366,49 +367,58 @@ RSP_HD void cfar4_r5_phase(const float* S, float* R5, const CfarParams& c, const
     const int rr = RR > 0 ? RR : c.ref_r;
     const int n = g.r5_rows * g.P4;
     const int pp4 = g.PP / 4;
-    const float4* S4 = reinterpret_cast<const float4*>(S);
+    const float4* S4 = reinterpret_cast<const float4*>(S) + RSP_CFAR_HALO / 4;
     float4* R4 = reinterpret_cast<float4*>(R5);
     for (int idx = tid; idx < n; idx += nthreads) {
         int row, c4;
         cfar4_split(g, idx, row, c4);
-        float4 acc = S4[row * pp4 + 1 + c4];
+        float4 acc = S4[row * pp4 + c4];
 #pragma unroll
-        for (int i = 1; i < rr; ++i) acc = f4add(acc, S4[(row + i) * pp4 + 1 + c4]);
+        for (int i = 1; i < rr; ++i) acc = f4add(acc, S4[(row + i) * pp4 + c4]);
         R4[idx] = acc;
     }
 }
 
+// Window sums of 4 consecutive CUTs from aligned float4 loads: out[j] = sum_{i<RV} row[start + j + i],
+// start = v0 + OFF with v0 % 4 == 0 and OFF a compile-time constant (may be negative).
+template <int RV, int OFF> RSP_HD void cfar4_window4(const float* row_v0, float out[4]) {
+    constexpr int LO = ((OFF % 4) + 4) % 4;              // offset of the first element inside its float4
+    constexpr int NV = (LO + RV + 3 + 3) / 4;            // aligned float4s that cover the span
+    float x[4 * NV];
+    const float4* p = reinterpret_cast<const float4*>(row_v0 + (OFF - LO));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 q = p[i];
+        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = x[LO + j];
+#pragma unroll
+        for (int i = 1; i < RV; ++i) a += x[LO + j + i];
+        out[j] = a;
+    }
+}
+
 // Decision for the quad (gl, c4): returns a 4-bit detection mask, cut[] receives the four S values.
-template <int RR, int RV>
+template <int RR, int RV, int GV>
 RSP_HD unsigned cfar4_decide_quad(const float* S, const float* R5, const CfarParams& c, const Cfar4Geom& g, int gl, int c4,
                                   float cut[4]) {
-    const int rr = RR > 0 ? RR : c.ref_r, rv = RV > 0 ? RV : c.ref_v;
-    const int mR = c.guard_r + c.ref_r, mV = c.guard_v + c.ref_v;
+    const int rr = RR > 0 ? RR : c.ref_r, rv = RR > 0 ? RV : c.ref_v, gv = RR > 0 ? GV : c.guard_v;
+    const int mR = c.guard_r + c.ref_r, mV = gv + rv;
     const int v0 = 4 * c4;
-    const float* row = S + (gl + mR) * g.PP + 4;             // row[v] = S(gl, v)
+    const float* row = S + (gl + mR) * g.PP + RSP_CFAR_HALO;             // row[v] = S(gl, v)
     const float4 cq = *reinterpret_cast<const float4*>(row + v0);
     const float4 lr = *reinterpret_cast<const float4*>(R5 + gl * g.P + v0);
     const float4 tr = *reinterpret_cast<const float4*>(R5 + (gl + mR + c.guard_r + 1) * g.P + v0);
     float lead[4], trail[4];
-    if (RV > 0) {
-        float xl[(RV > 0 ? RV : 1) + 3], xt[(RV > 0 ? RV : 1) + 3];
-#pragma unroll
-        for (int i = 0; i < RV + 3; ++i) {
-            xl[i] = row[v0 - mV + i];
-            xt[i] = row[v0 + c.guard_v + 1 + i];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a = xl[j], b = xt[j];
-#pragma unroll
-            for (int i = 1; i < RV; ++i) { a += xl[j + i]; b += xt[j + i]; }
-            lead[j] = a;
-            trail[j] = b;
-        }
+    if (RR > 0) {
+        cfar4_window4<(RR > 0 ? RV : 1), -(GV + RV)>(row + v0, lead);
+        cfar4_window4<(RR > 0 ? RV : 1), GV + 1>(row + v0, trail);
     } else {
         for (int j = 0; j < 4; ++j) {
-            float a = row[v0 + j - mV], b = row[v0 + j + c.guard_v + 1];
-            for (int i = 1; i < rv; ++i) { a += row[v0 + j - mV + i]; b += row[v0 + j + c.guard_v + 1 + i]; }
+            float a = row[v0 + j - mV], b = row[v0 + j + gv + 1];
+            for (int i = 1; i < rv; ++i) { a += row[v0 + j - mV + i]; b += row[v0 + j + gv + 1 + i]; }
             lead[j] = a;
             trail[j] = b;
         }
