@@ -51,6 +51,8 @@ struct rsp_ctx {
     float2* d_aux = nullptr;              // scratch for stage2 transposes
     // constants
     float2* d_W = nullptr;
+    float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
+    int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
     float* d_fir = nullptr;
     int n_fir = 0;
     PcPlan med, lng;
@@ -177,7 +179,7 @@ void rsp_destroy(rsp_ctx* c) {
     }
     if (c->fork) cudaEventDestroy(c->fork);
     cudaFree(c->d_done);
-    cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_fir);
+    cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_Wfrag); cudaFree(c->d_fir);
     cudaFree(c->d_med_tw1); cudaFree(c->d_med_tw2); cudaFree(c->d_med_H);
     cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_tw2); cudaFree(c->d_lng_H);
     cudaFree(c->d_dop_tw); cudaFree(c->d_dop_perm); cudaFree(c->d_win);
@@ -304,6 +306,15 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             W[(size_t)ch * B + b] = make_float2((float)w.re, (float)-w.im);
         }
     CU(c, upload(&c->d_W, W));
+    {   // tensor-core DBF (mma.sync TF32 x3) unless RSP_DBF=ffma
+        const char* e = getenv("RSP_DBF");
+        c->dbf_nt = c->dbf_ks = 0;
+        if (!(e && std::string(e) == "ffma")) {
+            c->dbf_nt = (B + 3) / 4;
+            c->dbf_ks = C <= 16 ? 4 : 8;
+            CU(c, upload(&c->d_Wfrag, make_dbf_fragments(reinterpret_cast<const double*>(k->dbf_weights), B, C, c->dbf_nt, c->dbf_ks)));
+        }
+    }
     std::vector<float> fir(k->n_fir);
     for (int i = 0; i < k->n_fir; ++i) fir[i] = (float)k->fir[i];
     CU(c, upload(&c->d_fir, fir));
@@ -413,7 +424,24 @@ template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw, int* det
     dbf_kernel<NB, SPT, CU_><<<grid, RSP_DBF_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_W, c->C, c->N, c->ldb, det_count);
 }
 
+template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* raw, int* det_count) {
+    Timed t(c, K_DBF);
+    const int per_cta = (RSP_DBF_MMA_THREADS / 32) * 32;
+    dim3 grid((c->N + per_cta - 1) / per_cta, c->P);
+    const bool vec = (c->N % 2 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+    if (vec) dbf_mma_kernel<NT, KS, true><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count);
+    else dbf_mma_kernel<NT, KS, false><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count);
+}
+
 static int launch_dbf_any(rsp_ctx* c, const float2* raw, int* det_count) {
+    if (c->dbf_nt) {
+        const int key = c->dbf_nt * 10 + c->dbf_ks;
+        switch (key) {
+#define CASE(nt, ks) case nt * 10 + ks: launch_dbf_mma<nt, ks>(c, raw, det_count); return RSP_OK;
+            CASE(1, 4) CASE(2, 4) CASE(3, 4) CASE(4, 4) CASE(1, 8) CASE(2, 8) CASE(3, 8) CASE(4, 8)
+#undef CASE
+        }
+    }
     switch (c->B) {
 #define CASE(n) case n: launch_dbf<n>(c, raw, det_count); break;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)

@@ -147,6 +147,122 @@ __global__ void __launch_bounds__(RSP_DBF_THREADS) dbf_kernel(const float2* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// S5 on the tensor cores (C <= 32, B <= 16): the complex contraction as a real GEMM
+//   out[n][2b + {re,im}] = sum_{c,{re,im}} X[n][(c,.)] * Bm[(c,.)][2b + .]      (K = 2C, N = 2B)
+// with mma.sync m16n8k8 TF32 and 3xTF32 error compensation (x = xh + xl, w = wh + wl;
+// xh*wh + xh*wl + xl*wh, fp32 accumulate), which keeps fp32-level accuracy (the <= 1e-4 RDM tolerance
+// rules out plain TF32).  K order inside a k-step of 8 is chosen so that a thread's two A registers of
+// a row are exactly the (re, im) of one float2 load: k = t -> (channel 4s + t, re), k = t + 4 -> (.., im).
+// One warp owns 32 consecutive range samples (two m16 tiles) of one pulse; all its loads are issued
+// up front.  Weight fragments {b0h, b1h, b0l, b1l} are prebuilt on the host, one float4 per
+// (k-step, n-tile, lane), and read from shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+#define RSP_DBF_MMA_THREADS 128
+// VEC = true (N even): fragment row g <-> sample n0 + 2g, row g+8 <-> sample n0 + 2g + 1 (the row order
+// of an MMA tile is free), so a thread's four A registers of a tile are ONE float4 load and its four D
+// registers ONE float4 store: 8 lanes x 16 B = 128 contiguous bytes per channel / beam row.
+// VEC = false (odd N, e.g. the native 5819): rows g, g+8 <-> samples n0 + g, n0 + g + 8, float2 accesses.
+template <int NT, int KS, bool VEC>
+__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_mma_kernel(const float2* __restrict__ raw,
+                                                                      float2* __restrict__ beam,
+                                                                      const float4* __restrict__ Wfrag /* [KS][NT][32] */,
+                                                                      int C, int NB, int N, int ldb,
+                                                                      int* __restrict__ det_count) {
+    __shared__ float4 sW[KS * NT * 32];
+    const int tid = threadIdx.x;
+    if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
+    for (int i = tid; i < KS * NT * 32; i += RSP_DBF_MMA_THREADS) sW[i] = Wfrag[i];
+    const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int p = blockIdx.y;
+    const int n_base = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * 32;      // 32 samples per warp = 2 tiles
+    const float2* rp = raw + (size_t)p * C * N;
+    // x[s][m] = {a0, a2, a1, a3} of tile m, k-step s:  (re, im) of the thread's two rows
+    float4 x[KS][2];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        const int c = 4 * s + t;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C) {
+                if (VEC) {
+                    const int n = n_base + 16 * m + 2 * g;
+                    if (n < N) v = __ldcs(reinterpret_cast<const float4*>(rp + (size_t)c * N + n));
+                } else {
+                    const int n = n_base + 16 * m + g;
+                    if (n < N) { const float2 a = __ldcs(rp + (size_t)c * N + n); v.x = a.x; v.y = a.y; }
+                    if (n + 8 < N) { const float2 a = __ldcs(rp + (size_t)c * N + n + 8); v.z = a.x; v.w = a.y; }
+                }
+            }
+            x[s][m] = v;
+        }
+    }
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const float v[4] = {x[s][m].x, x[s][m].z, x[s][m].y, x[s][m].w};   // a0 (re,row0) a1 (re,row1) a2 (im,row0) a3 (im,row1)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ah[m][i] = to_tf32(v[i]);
+                al[m][i] = to_tf32(v[i] - __uint_as_float(ah[m][i]));
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float4 wf = sW[(s * NT + nt) * 32 + lane];
+            const uint32_t b0h = __float_as_uint(wf.x), b1h = __float_as_uint(wf.y);
+            const uint32_t b0l = __float_as_uint(wf.z), b1l = __float_as_uint(wf.w);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                mma_tf32(acc[m][nt], al[m], b0h, b1h);
+                mma_tf32(acc[m][nt], ah[m], b0l, b1l);
+                mma_tf32(acc[m][nt], ah[m], b0h, b1h);
+            }
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int b = 4 * nt + t;
+        if (b < NB) {
+            float2* row = beam + ((size_t)p * NB + b) * ldb;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (VEC) {
+                    const int n = n_base + 16 * m + 2 * g;
+                    if (n < N)
+                        *reinterpret_cast<float4*>(row + n) = make_float4(acc[m][nt][0], acc[m][nt][1], acc[m][nt][2], acc[m][nt][3]);
+                } else {
+                    const int n = n_base + 16 * m + g;
+                    if (n < N) row[n] = make_float2(acc[m][nt][0], acc[m][nt][1]);
+                    if (n + 8 < N) row[n + 8] = make_float2(acc[m][nt][2], acc[m][nt][3]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // S6: pulse compression.  One CTA = Cfg::NG overlap-save blocks (one per group of Cfg::T threads);
 // work item = (line, block).  The medium-segment launch also computes the narrow-pulse FIR gates of
 // its lines (fun_process_single_frame.m:111-112,123).
@@ -474,6 +590,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, 3) cfar4_kernel(const CfarAr
         const int row = idx / (2 * h4), c = idx - row * (2 * h4);
         S4[row * pp4 + (c < h4 ? c : pp4 - 2 * h4 + c)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll 4
     for (int idx = tid; idx < g.rows * g.P4; idx += RSP_CFAR_THREADS) {
         int row, c4;
         cfar4_split(g, idx, row, c4);

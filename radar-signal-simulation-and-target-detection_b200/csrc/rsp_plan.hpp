@@ -5,6 +5,7 @@
 #include <vector>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include "rsp_phases.cuh"
 
 namespace rsp {
@@ -158,6 +159,36 @@ inline bool make_doppler_plan(DopplerPlan& dp, int P) {
         dp.iperm[dp.perm[p]] = p;
     }
     return true;
+}
+
+// Round-to-nearest (ties away) fp32 -> tf32, like cvt.rna.tf32.f32; result still an fp32 bit pattern.
+inline float host_tf32(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
+// Weight fragments of dbf_mma_kernel: frag[(s*NT + nt)*32 + lane] = {b0h, b1h, b0l, b1l} where, with
+// g = lane >> 2, t = lane & 3, c = 4s + t, b = 4nt + (g >> 1), (wr, wi) = conj(W[b][c]):
+//   output column re (g even): b0 = wr, b1 = -wi;   output column im (g odd): b0 = wi, b1 = wr.
+inline std::vector<float4> make_dbf_fragments(const double* W_ri /* [B][C][2] */, int B, int C, int NT, int KS) {
+    std::vector<float4> f((size_t)KS * NT * 32);
+    for (int s = 0; s < KS; ++s)
+        for (int nt = 0; nt < NT; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3, c = 4 * s + t, b = 4 * nt + (g >> 1);
+                float b0 = 0.f, b1 = 0.f;
+                if (c < C && b < B) {
+                    const float wr = (float)W_ri[((size_t)b * C + c) * 2], wi = (float)-W_ri[((size_t)b * C + c) * 2 + 1];
+                    if ((g & 1) == 0) { b0 = wr; b1 = -wi; } else { b0 = wi; b1 = wr; }
+                }
+                const float b0h = host_tf32(b0), b1h = host_tf32(b1);
+                f[(size_t)(s * NT + nt) * 32 + lane] = make_float4(b0h, b1h, host_tf32(b0 - b0h), host_tf32(b1 - b1h));
+            }
+    return f;
 }
 
 }  // namespace rsp

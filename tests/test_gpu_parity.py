@@ -31,7 +31,7 @@ def _check_all(name, chain, cluster_params, cfg, pre, raw, res, stages=True):
     if stages:
         beam = chain.get_beam()
         stats["beam"] = rel_errors(beam, res.beam)
-        assert stats["beam"][0] <= 2e-6, stats
+        assert stats["beam"][0] <= 5e-6, stats      # 3xTF32 tensor-core contraction, fp32 accumulate
         pc = chain.get_pc()
         stats["pc"] = rel_errors(pc, res.pc)
         assert stats["pc"][0] <= 1e-5, stats
