@@ -172,9 +172,22 @@ int rsp_process_frame(rsp_ctx* ctx, const void* raw, rsp_layout layout, rsp_dtyp
                       const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap, int32_t* n_final);
 
 /* ---- process_stage2_mtd.m:1 on an already beamformed + range-gated cube ----
+ * The context is created with rsp_create (n_gates = the three segment lengths, e.g. 228/723/2453;
+ * n_samples = their sum; the other chain parameters are unused) and configured once with the three
+ * reference pulses (debug_simulated_data_processing_v2.m:309-317), the Doppler window and the width of
+ * the zero-velocity notch (MTD_0v_num, main_test_with_simulated_data.m:124).
  * iq: MATLAB [P,G,B] column-major complex (dtype), host memory.  Outputs MATLAB-ordered [P,G,B]
- * complex128: mtd_out = Doppler map, pc_out = pulse-compressed cube.  See DESIGN.md for the
- * semantics specified by this repo (the callee fun_MTD_produce is not shipped by the reference). */
+ * complex128: mtd_out = Doppler map, pc_out = pulse-compressed cube.  The reference's callee
+ * fun_MTD_produce is not shipped; the semantics are specified by this repo:
+ *   pc(p, g, b)  = sum_k iq(p, g + k, b) * conj(pulse_s(k)),  g and g + k inside segment s;
+ *   mtd(:, g, b) = fftshift(fft(pc(:, g, b) .* win));  rows within +-zero_vel_bins of zero Doppler = 0. */
+typedef struct {
+    const rsp_c128* pulse[3];     /* reference pulse of the narrow / medium / long segment */
+    int32_t         n_pulse[3];
+    const double*   mtd_win;      /* [P], NULL = rectangular */
+    int32_t         zero_vel_bins;/* 0 = no notch */
+} rsp_stage2_config;
+int rsp_stage2_configure(rsp_ctx* ctx, const rsp_stage2_config* cfg);
 int rsp_stage2_mtd(rsp_ctx* ctx, const void* iq, rsp_dtype dtype, rsp_c128* mtd_out, rsp_c128* pc_out);
 
 /* ---- introspection ---- */

@@ -56,6 +56,11 @@ class rsp_info(C.Structure):
                 ("algorithmic_bytes_per_cpi", C.c_int64), ("launches_total", C.c_int64)]
 
 
+class rsp_stage2_config(C.Structure):
+    _fields_ = [("pulse", C.c_void_p * 3), ("n_pulse", C.c_int32 * 3), ("mtd_win", C.c_void_p),
+                ("zero_vel_bins", C.c_int32)]
+
+
 class rsp_kernel_times(C.Structure):
     _fields_ = [("n", C.c_int32), ("name", C.c_char_p * 8), ("total_ms", C.c_double * 8), ("launches", C.c_int64 * 8)]
 
@@ -90,6 +95,7 @@ SYMBOLS = [
                               C.POINTER(C.c_int32)]),
     ("rsp_process_frame", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(rsp_cluster_params), _P, C.c_int32,
                                     C.POINTER(C.c_int32)]),
+    ("rsp_stage2_configure", C.c_int, [_P, C.POINTER(rsp_stage2_config)]),
     ("rsp_stage2_mtd", C.c_int, [_P, _P, C.c_int, _P, _P]),
     ("rsp_get_info", C.c_int, [_P, C.POINTER(rsp_info)]),
     ("rsp_set_profiling", C.c_int, [_P, C.c_int]),

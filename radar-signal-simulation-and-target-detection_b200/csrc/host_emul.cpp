@@ -61,7 +61,8 @@ int emul_pc_segment(const float* line, int N, int seg_start0, int gate0, int nga
         a.tw1 = pl.tw1.data();
         a.tw2 = pl.tw2.data();
         a.Hmid = pl.Hmid.data();
-        a.N = N;
+        a.in_lo = seg_start0;
+        a.in_hi = N;
         a.seg_start0 = seg_start0;
         a.taps = ntaps;
         a.g0 = gate0 + blk * pl.valid;

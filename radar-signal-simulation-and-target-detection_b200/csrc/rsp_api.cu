@@ -56,6 +56,12 @@ struct rsp_ctx {
     float* d_fir = nullptr;
     int n_fir = 0;
     PcPlan med, lng;
+    // stage-2 (process_stage2_mtd) plans: one per gated segment, own tables
+    struct S2Seg { PcPlan pl; float2 *tw1 = nullptr, *tw2 = nullptr, *H = nullptr; int lo = 0, hi = 0; };
+    S2Seg s2[3];
+    bool s2_ready = false;
+    int s2_notch = 0;
+    float* d_s2_win = nullptr;
     float2 *d_med_tw1 = nullptr, *d_med_tw2 = nullptr, *d_med_H = nullptr;
     float2 *d_lng_tw1 = nullptr, *d_lng_tw2 = nullptr, *d_lng_H = nullptr;
     DopplerPlan dop;
@@ -179,6 +185,8 @@ void rsp_destroy(rsp_ctx* c) {
     }
     if (c->fork) cudaEventDestroy(c->fork);
     cudaFree(c->d_done);
+    for (auto& sg : c->s2) { cudaFree(sg.tw1); cudaFree(sg.tw2); cudaFree(sg.H); }
+    cudaFree(c->d_s2_win);
     cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_Wfrag); cudaFree(c->d_fir);
     cudaFree(c->d_med_tw1); cudaFree(c->d_med_tw2); cudaFree(c->d_med_H);
     cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_tw2); cudaFree(c->d_lng_H);
@@ -454,7 +462,7 @@ static int launch_dbf_any(rsp_ctx* c, const float2* raw, int* det_count) {
 
 static void fill_seg(const rsp_ctx* c, PcSegArgs& sg, const PcPlan& pl, const float2* tw1, const float2* tw2, const float2* H) {
     sg.tw1 = tw1; sg.tw2 = tw2; sg.Hmid = H;
-    sg.seg_start0 = pl.seg_start0; sg.taps = pl.taps; sg.gate0 = pl.gate0; sg.g_end = pl.gate0 + pl.ngates; sg.valid = pl.valid;
+    sg.seg_start0 = pl.seg_start0; sg.in_lo = pl.seg_start0; sg.in_hi = c->N; sg.taps = pl.taps; sg.gate0 = pl.gate0; sg.g_end = pl.gate0 + pl.ngates; sg.valid = pl.valid;
     sg.nblk = pl.nblk;
     sg.n_items = pl.L ? c->P * c->B * pl.nblk : 0;
     const int ng = pl.L ? RSP_PC_THREADS / pl.T : 1;
@@ -735,9 +743,146 @@ int rsp_process_frame(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype 
     return RSP_OK;
 }
 
+int rsp_stage2_configure(rsp_ctx* c, const rsp_stage2_config* cfg) {
+    if (!c || !cfg) return RSP_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->prm.device));
+    if (c->N < c->G) return fail(c, RSP_ERR_INVALID_ARG, "stage-2 contexts need n_samples >= sum(n_gates)");
+    int gate0 = 0;
+    for (int s = 0; s < 3; ++s) {
+        rsp_ctx::S2Seg& sg = c->s2[s];
+        const int ng = c->prm.n_gates[s], nt = cfg->n_pulse[s];
+        sg.lo = gate0; sg.hi = gate0 + ng;
+        sg.pl = PcPlan();
+        if (ng > 0) {
+            if (!cfg->pulse[s] || nt < 1 || nt > 4096) return fail(c, RSP_ERR_INVALID_ARG, "stage-2 pulse %d missing or too long", s);
+            std::vector<zc> h(nt);                           // matched filter = conj(fliplr(pulse))
+            for (int i = 0; i < nt; ++i) h[i] = std::conj(zc(cfg->pulse[s][nt - 1 - i].re, cfg->pulse[s][nt - 1 - i].im));
+            const int L = choose_pc_len(nt, ng);
+            // out[g] = sum_k h[k] y[(nt-1) + g - k]  ==  sum_k y[g + k] conj(pulse[k])
+            if (!make_pc_plan(sg.pl, L, h.data(), nt, nt - 1, gate0, ng)) return fail(c, RSP_ERR_UNSUPPORTED, "no block plan for stage-2 segment %d", s);
+            CU(c, upload(&sg.tw1, sg.pl.tw1)); CU(c, upload(&sg.tw2, sg.pl.tw2)); CU(c, upload(&sg.H, sg.pl.Hmid));
+        }
+        gate0 += ng;
+    }
+#define X(A, B) CU(c, opt_in_smem(pc_fft_kernel<A, B>, pc_smem_pair<A, B>()));
+    RSP_FOR_EACH_PC_PAIR(X)
+#undef X
+    const int P = c->P;
+    std::vector<float> win(P);
+    c->pow2_doppler = make_doppler_plan(c->dop, P);
+    for (int p = 0; p < P; ++p) {
+        const double w = cfg->mtd_win ? cfg->mtd_win[p] : 1.0;
+        win[p] = (float)(c->pow2_doppler ? w * ((p & 1) ? -1.0 : 1.0) : w);
+    }
+    CU(c, upload(&c->d_s2_win, win));
+    if (c->pow2_doppler) {
+        CU(c, upload(&c->d_dop_tw, c->dop.tw));
+        CU(c, upload(&c->d_dop_perm, c->dop.iperm));
+        c->mtd_tg = RSP_MTD_TG;
+        c->mtd_smem = ((size_t)P * (RSP_MTD_TG + 1) + c->dop.tw.size() + 1) * sizeof(float2);
+        CU(c, mtd_opt_in(P, c->mtd_smem));
+    } else {
+        std::vector<float2> tw(P);
+        for (int m = 0; m < P; ++m) {
+            const double ang = -2.0 * kPi * (double)m / (double)P;
+            tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        CU(c, upload(&c->d_dop_tw, tw));
+        c->mtd_tg = 0;
+        for (int tg : {32, 16, 8}) {
+            const size_t sm = ((size_t)2 * P * (tg + 1) + P) * sizeof(float2);
+            if (sm <= 200 * 1024) { c->mtd_tg = tg; c->mtd_smem = sm; break; }
+        }
+        if (!c->mtd_tg) return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
+        if (c->mtd_tg == 32) CU(c, opt_in_smem(mtd_dft_kernel<32>, c->mtd_smem));
+        if (c->mtd_tg == 16) CU(c, opt_in_smem(mtd_dft_kernel<16>, c->mtd_smem));
+        if (c->mtd_tg == 8) CU(c, opt_in_smem(mtd_dft_kernel<8>, c->mtd_smem));
+    }
+    c->s2_notch = cfg->zero_vel_bins < 0 ? 0 : cfg->zero_vel_bins;
+    c->s2_ready = true;
+    return RSP_OK;
+}
+
+static void launch_s2_pair(rsp_ctx* c, const rsp_ctx::S2Seg* a0, const rsp_ctx::S2Seg* a1) {
+    PcKernelArgs a;
+    a.beam = c->cur->beam; a.pc = c->cur->pc; a.N = c->G; a.ldb = c->ldb; a.ldg = c->ldg;
+    const rsp_ctx::S2Seg* segs[2] = {a0, a1};
+    int L[2] = {1024, 1024};
+    for (int i = 0; i < 2; ++i) {
+        PcSegArgs& sg = a.seg[i];
+        std::memset(&sg, 0, sizeof sg);
+        sg.nblk = 1;
+        if (segs[i] && segs[i]->pl.L) {
+            fill_seg(c, sg, segs[i]->pl, segs[i]->tw1, segs[i]->tw2, segs[i]->H);
+            sg.in_lo = segs[i]->lo; sg.in_hi = segs[i]->hi;
+            L[i] = segs[i]->pl.L;
+        }
+    }
+    a.do_narrow = 0; a.fir = nullptr; a.nfir = 0; a.fir_delay = 0; a.narrow_start0 = 0; a.narrow_gates = 0;
+    const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
+    if (nctas == 0) return;
+    Timed t(c, K_PC);
+#define X(A, B) if (L[0] == A::L && L[1] == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
+    RSP_FOR_EACH_PC_PAIR(X)
+#undef X
+}
+
 int rsp_stage2_mtd(rsp_ctx* c, const void* iq, rsp_dtype dtype, rsp_c128* mtd_out, rsp_c128* pc_out) {
-    (void)iq; (void)dtype; (void)mtd_out; (void)pc_out;
-    return fail(c, RSP_ERR_UNSUPPORTED, "rsp_stage2_mtd: not implemented yet (SURVEY.md section 8(f) rank 3)");
+    if (!c || !iq || !mtd_out) return fail(c, RSP_ERR_INVALID_ARG, "null argument");
+    if (!c->s2_ready) return fail(c, RSP_ERR_NOT_READY, "rsp_stage2_configure has not been called");
+    CU(c, cudaSetDevice(c->prm.device));
+    const int P = c->P, G = c->G, B = c->B;
+    const size_t n = (size_t)P * G * B;
+    const size_t esz = dtype == RSP_C64 ? sizeof(float2) : sizeof(double2);
+    if (c->stage_bytes < n * esz) {
+        if (c->d_stage) cudaFree(c->d_stage);
+        c->d_stage = nullptr;
+        CU(c, cudaMalloc(&c->d_stage, n * esz));
+        c->stage_bytes = n * esz;
+    }
+    if (!c->d_aux) CU(c, dev_alloc(&c->d_aux, n));
+    c->cur = &c->lanes[0];
+    CU(c, cudaMemcpyAsync(c->d_stage, iq, n * esz, cudaMemcpyHostToDevice, c->stream));
+    {   // MATLAB [P,G,B] -> lines [p][b][g] in the lane's "beam" buffer (pitch ldb)
+        Timed t(c, K_CONVERT);
+        dim3 grid((P + 31) / 32, (G + 31) / 32, B), blk(32, 8);
+        if (dtype == RSP_C64) pgb_to_pbg_kernel<float2><<<grid, blk, 0, c->stream>>>(static_cast<const float2*>(c->d_stage), c->cur->beam, P, G, B, c->ldb);
+        else pgb_to_pbg_kernel<double2><<<grid, blk, 0, c->stream>>>(static_cast<const double2*>(c->d_stage), c->cur->beam, P, G, B, c->ldb);
+    }
+    launch_s2_pair(c, &c->s2[2], &c->s2[1]);      // long + medium
+    launch_s2_pair(c, &c->s2[0], nullptr);        // narrow
+    {   // MTD with the stage-2 window
+        float* keep = c->d_win;
+        c->d_win = c->d_s2_win;
+        launch_mtd(c, c->d_rdm);
+        c->d_win = keep;
+    }
+    if (c->s2_notch > 0) {
+        const int ctr = P / 2;                    // zero Doppler after fftshift
+        const int lo = std::max(0, ctr - c->s2_notch), hi = std::min(P - 1, ctr + c->s2_notch);
+        Timed t(c, K_CONVERT);
+        doppler_notch_kernel<<<592, 256, 0, c->stream>>>(c->d_rdm, (size_t)B * G, P, lo, hi);
+    }
+    std::vector<float2> h(n);
+    auto to_host = [&](const float2* dev, rsp_c128* dst) -> int {
+        CU(c, cudaMemcpyAsync(h.data(), dev, n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < n; ++i) dst[i] = rsp_c128{(double)h[i].x, (double)h[i].y};
+        return RSP_OK;
+    };
+    int rc = to_host(c->d_rdm, mtd_out);          // rdm[b][g][v] is already MATLAB (v,g,b) byte order
+    if (rc) return rc;
+    if (pc_out) {
+        Timed t(c, K_CONVERT);
+        dim3 grid((P + 31) / 32, (G + 31) / 32, B), blk(32, 8);
+        pbg_to_bgp_kernel<<<grid, blk, 0, c->stream>>>(c->cur->pc, c->d_aux, P, G, B, c->ldg);
+        rc = to_host(c->d_aux, pc_out);
+        if (rc) return rc;
+    }
+    CU(c, cudaGetLastError());
+    c->ran = true;
+    c->rdm_in_ctx = true;
+    return RSP_OK;
 }
 
 int rsp_set_profiling(rsp_ctx* c, int enable) {

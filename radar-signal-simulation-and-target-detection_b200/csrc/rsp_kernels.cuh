@@ -271,7 +271,7 @@ struct PcSegArgs {
     const float2* tw1;
     const float2* tw2;
     const float2* Hmid;
-    int seg_start0, taps, gate0, g_end, valid;
+    int seg_start0, in_lo, in_hi, taps, gate0, g_end, valid;
     int nblk, n_items, n_ctas;
 };
 
@@ -305,7 +305,8 @@ __device__ __forceinline__ void pc_role(const PcKernelArgs& k, const PcSegArgs& 
     a.tw1 = sg.tw1;
     a.tw2 = stw2;
     a.Hmid = sg.Hmid;
-    a.N = k.N;
+    a.in_lo = sg.in_lo;
+    a.in_hi = sg.in_hi;
     a.seg_start0 = sg.seg_start0;
     a.taps = sg.taps;
     a.g0 = sg.gate0 + blk * sg.valid;
@@ -446,6 +447,15 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs 
             __stcs(k.rdm + o, v);
             k.amp[o] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
         }
+    }
+}
+
+// zero-Doppler notch of the stage-2 path: rows [lo, hi] of every (beam, gate) line are cleared
+__global__ void __launch_bounds__(256) doppler_notch_kernel(float2* __restrict__ rdm, size_t n_lines, int P, int lo, int hi) {
+    const int w = hi - lo + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines * w; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t line = i / w;
+        rdm[line * P + lo + (int)(i - line * w)] = make_float2(0.f, 0.f);
     }
 }
 

@@ -43,8 +43,8 @@ struct PcBlockArgs {
     const cf* tw1;       // [(R1-1)][L/R1]      e^{-2 pi i jk/L}          (global)
     const cf* tw2;       // [(R2-1)][R3]        e^{-2 pi i jk/(R2 R3)}    (shared copy in the kernel)
     const cf* Hmid;      // [(NB3*R3)][T]: Hmid[(i*R3+k)*T + t] = H_dr[R3*(t + T*i) + k] / L
-    int N;               // samples per line
-    int seg_start0;      // 0-based first sample of the segment (samples before it count as zero)
+    int in_lo, in_hi;    // input samples outside [in_lo, in_hi) count as zero (segment start .. line end)
+    int seg_start0;      // output gate g reads y[seg_start0 + g - k], k < taps
     int taps;            // matched-filter length
     int g0;              // first output gate of this block
     int g_end;           // one past the last gate this segment owns
@@ -58,7 +58,7 @@ struct PcBlockArgs {
 
 template <class Cfg> RSP_HD void pc_phase_load_pass1(const PcBlockArgs& a, cf* s, int t) {
     const int s0 = a.seg_start0 + a.g0 - (a.taps - 1);
-    const bool interior = s0 >= a.seg_start0 && s0 + Cfg::L <= a.N;      // uniform over the group
+    const bool interior = s0 >= a.in_lo && s0 + Cfg::L <= a.in_hi;       // uniform over the group
 #pragma unroll
     for (int i = 0; i < Cfg::NB1; ++i) {
         const int q = t + i * Cfg::T;
@@ -71,7 +71,7 @@ template <class Cfg> RSP_HD void pc_phase_load_pass1(const PcBlockArgs& a, cf* s
 #pragma unroll
             for (int m = 0; m < Cfg::R1; ++m) {
                 const int idx = s0 + q + m * Cfg::SPAN1;
-                v[m] = (idx >= a.seg_start0 && idx < a.N) ? a.line[idx] : make_float2(0.f, 0.f);
+                v[m] = (idx >= a.in_lo && idx < a.in_hi) ? a.line[idx] : make_float2(0.f, 0.f);
             }
         }
         SmallDft<Cfg::R1, -1>::run(v);

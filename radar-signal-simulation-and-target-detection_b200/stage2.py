@@ -1,0 +1,113 @@
+"""Host-side mirror of ``[MTD_results, PC_results] = process_stage2_mtd(iq_data, angle, config)``
+(/root/reference/Simulation/process_stage2_mtd.m:1) over rsp_stage2_configure / rsp_stage2_mtd.
+
+The per-beam callee ``fun_MTD_produce`` (and its three callees) are not shipped by the reference, so the
+arithmetic below is SPECIFIED BY THIS REPO, following the only surviving copy of the
+set-up code (debug_simulated_data_processing_v2.m:259-351) and the config schema of
+main_test_with_simulated_data.m:46-140:
+
+  * reference pulses   pulse1 = sin(2*pi*t1 + pi/2), pulse2/3 = exp(j*2*pi*(0.5*K*t.^2)),
+                       t = -tau/2 : ts : tau/2 - ts                      (debug_..._v2.m:309-317)
+  * per-segment matched filter (segments = config.Sig_Config.point_prt(2:4) gates of iq_data)
+        pc(p, g, b) = sum_k iq(p, g + k, b) * conj(pulse_s(k)),   g, g + k inside segment s
+  * Doppler            mtd(:, g, b) = fftshift(fft(pc(:, g, b) .* win)),  win = ones unless given
+  * zero-velocity notch rows within +-config.cfar.MTD_0v_num of zero Doppler are cleared
+                       (main_test_with_simulated_data.m:106,124); 0 / absent = off
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .frame import _field
+
+
+def reference_pulses(config):
+    """The three reference pulses of debug_simulated_data_processing_v2.m:309-317."""
+    sc = _field(config, "Sig_Config")
+    fs = float(_field(sc, "fs"))
+    ts = 1.0 / fs
+    tao = [float(x) for x in _field(sc, "tao")]
+    Bw = float(_field(sc, "B"))
+    K2, K3 = -Bw / tao[1], Bw / tao[2]
+    out = []
+    for i, tau in enumerate(tao):
+        n = int(round(tau / ts))
+        t = -tau / 2 + ts * np.arange(n)                     # -tau/2 : ts : tau/2 - ts
+        if i == 0:
+            out.append(np.sin(2 * np.pi * t + np.pi / 2).astype(np.complex128))
+        else:
+            out.append(np.exp(1j * 2 * np.pi * (0.5 * (K2 if i == 1 else K3) * t ** 2)))
+    return out
+
+
+class Stage2Chain:
+    def __init__(self, config, device: int = 0, mtd_win=None):
+        self._lib = _abi.load()
+        self._ctx = C.c_void_p()
+        sc = _field(config, "Sig_Config")
+        mtd = config["mtd"] if "mtd" in config else sc
+        self.P = int(_field(sc, "prtNum"))
+        self.B = int(_field(mtd, "beam_num"))
+        pts = [int(x) for x in _field(sc, "point_prt")]
+        self.gates = pts[1:4]
+        self.G = sum(self.gates)
+        p = _abi.rsp_params()
+        p.abi_version = _abi.RSP_ABI_VERSION
+        p.n_channels, p.n_beams, p.n_pulses, p.n_samples = 1, self.B, self.P, max(self.G, 64)
+        p.seg_start[:] = [1, 1, 1]
+        p.n_gates[:] = self.gates
+        p.fir_delay, p.t_cfar = 0, 8.0
+        p.guard_r = p.guard_v = 1
+        p.ref_r = p.ref_v = 1
+        p.max_detections, p.monopulse_complex, p.device = 16, 0, int(device)
+        _abi.check(self._lib.rsp_create(C.byref(p), C.byref(self._ctx)))
+        pulses = [np.ascontiguousarray(x, dtype=np.complex128) for x in reference_pulses(config)]
+        cfg = _abi.rsp_stage2_config()
+        for i in range(3):
+            cfg.pulse[i] = pulses[i].ctypes.data
+            cfg.n_pulse[i] = len(pulses[i])
+        win = None if mtd_win is None else np.ascontiguousarray(mtd_win, dtype=np.float64)
+        cfg.mtd_win = win.ctypes.data if win is not None else None
+        cfar = config["cfar"] if "cfar" in config else {}
+        cfg.zero_vel_bins = int(cfar["MTD_0v_num"]) if "MTD_0v_num" in cfar else 0
+        _abi.check(self._lib.rsp_stage2_configure(self._ctx, C.byref(cfg)), self._ctx)
+
+    def __call__(self, iq_data: np.ndarray):
+        """iq_data[p, g, b] (any strides, complex) -> (MTD_results, PC_results), both [P, G, B] complex128."""
+        if iq_data.shape != (self.P, self.G, self.B):
+            raise ValueError(f"iq_data must be {(self.P, self.G, self.B)}, got {iq_data.shape}")
+        src = np.asfortranarray(iq_data.astype(np.complex128, copy=False))       # MATLAB byte order
+        mtd = np.empty((self.P, self.G, self.B), np.complex128, order="F")
+        pc = np.empty((self.P, self.G, self.B), np.complex128, order="F")
+        _abi.check(self._lib.rsp_stage2_mtd(self._ctx, C.c_void_p(src.ctypes.data), _abi.RSP_C128,
+                                            C.c_void_p(mtd.ctypes.data), C.c_void_p(pc.ctypes.data)), self._ctx)
+        return mtd, pc
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.rsp_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_cache = {}
+
+
+def process_stage2_mtd(iq_data, angle, config, device: int = 0):
+    """Drop-in for process_stage2_mtd.m:1.  ``angle`` is accepted and unused, like the reference
+    (process_stage2_mtd.m:26)."""
+    key = id(config)
+    ch = _cache.get(key)
+    if ch is None:
+        ch = Stage2Chain(config, device=device)
+        _cache.clear()
+        _cache[key] = ch
+    return ch(np.asarray(iq_data))

@@ -142,3 +142,12 @@ def test_host_echo_synthesis_equals_oracle():
     mine = rsp.synthesize_echo([dict(Range=t.Range, Velocity=t.Velocity, ElevationAngle=t.ElevationAngle,
                                      SNR_dB=t.SNR_dB, const_H=1.0) for t in tg], config, pd)
     assert np.allclose(mine, o.synthesize_echo(tg, ocfg, pre), rtol=1e-12, atol=1e-12)
+
+
+def test_mex_gateways_compile_against_the_prototype_shim():
+    """MATLAB/Octave/mex.h are absent here; the gateway sources must at least be valid C++ against the
+    declared subset of the MEX API and against include/rsp.h."""
+    import subprocess
+    for f in ("fun_process_single_frame_mex.cpp", "process_stage2_mtd_mex.cpp"):
+        subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "mex", "mex_shim"),
+                               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "mex"), os.path.join(ROOT, "mex", f)])

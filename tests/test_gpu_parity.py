@@ -180,3 +180,36 @@ def test_detection_overflow_is_an_error_not_truncation():
         chain.process_cpi(raw)
     assert ei.value.code == -5
     chain.close()
+
+
+@pytest.mark.parametrize("P,B", [(64, 4), (332, 2)])
+def test_process_stage2_mtd_matches_its_specification(P, B):
+    """process_stage2_mtd.m:1 on the gated real-data layout [P, 3404, B] (process_stage2_mtd.m:29-30).
+    The reference's callee is not shipped, so the check is against the oracle statement of the semantics
+    this repo specifies: per-segment matched filter, Doppler FFT, zero-velocity notch."""
+    gates = [228, 723, 2453]
+    config = rsp.Struct(Sig_Config=rsp.Struct(fs=25e6, prtNum=P, tao=[0.16e-6, 8e-6, 28e-6], B=20e6,
+                                              point_prt=[sum(gates)] + gates),
+                        mtd=rsp.Struct(beam_num=B), cfar=rsp.Struct(MTD_0v_num=3))
+    pulses = o.stage2_reference_pulses()
+    assert [len(x) for x in pulses] == [4, 200, 700]
+    assert all(np.allclose(a, b) for a, b in zip(pulses, rsp.reference_pulses(config)))
+    rng = np.random.default_rng(P)
+    iq = (rng.standard_normal((P, sum(gates), B)) + 1j * rng.standard_normal((P, sum(gates), B))) * np.sqrt(0.5)
+    dop = np.exp(2j * np.pi * 0.11 * np.arange(P))
+    for g, seg in ((60, 0), (228 + 300, 1), (951 + 1000, 2)):          # an echo in each segment
+        n = len(pulses[seg])
+        end = [228, 951, 3404][seg]
+        L = min(n, end - g)
+        iq[:, g:g + L, 1] += 5.0 * dop[:, None] * pulses[seg][None, :L]
+    mtd, pc = rsp.process_stage2_mtd(iq, None, config)
+    ref_mtd, ref_pc = o.stage2_mtd(iq, gates, pulses, None, 3)
+    assert mtd.shape == pc.shape == (P, sum(gates), B) and mtd.flags["F_CONTIGUOUS"]
+    e_pc, e_mtd = rel_errors(pc, ref_pc), rel_errors(mtd, ref_mtd)
+    assert e_pc[0] <= 1e-5 and e_mtd[0] <= RDM_REL_TOL and e_mtd[1] <= RDM_REL_TOL, (e_pc, e_mtd)
+    ctr = P // 2
+    assert not mtd[ctr - 3: ctr + 4].any() and mtd[ctr + 4].any()
+    # the compressed echoes peak at the gate where the pulse starts
+    for g, seg in ((60, 0), (228 + 300, 1), (951 + 1000, 2)):
+        lo, hi = [0, 228, 951][seg], [228, 951, 3404][seg]
+        assert lo + int(np.argmax(np.abs(pc[0, lo:hi, 1]))) == g
