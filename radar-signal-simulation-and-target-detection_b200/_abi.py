@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "librsp.so")
+# RSP_LIBRARY selects another build of the same ABI (A/B measurements of kernel generations)
+LIB_PATH = os.environ.get("RSP_LIBRARY") or os.path.join(HERE, "lib", "librsp.so")
 
 RSP_ABI_VERSION = 1
 RSP_OK = 0

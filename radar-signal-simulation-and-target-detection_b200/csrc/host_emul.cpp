@@ -18,7 +18,7 @@ template <class Cfg> static void run_pc_block(const PcBlockArgs& a, cf* s) {
 template <class Cfg> static void run_mtd_tile(cf* s, const cf* tw, const cf* src, size_t pstride, const int* iperm,
                                               const float* win) {
     for (int t = 0; t < RSP_MTD_THREADS; ++t)
-        mtd_first_pass_t<MtdInner<Cfg>::R, Cfg::P>(s, src, pstride, iperm, win, true, t);
+        mtd_first_pass_t<Cfg>(s, src, pstride, win, true, t);
     for (int pass = MtdInner<Cfg>::PASS + 1; pass < 3; ++pass)
         for (int t = 0; t < RSP_MTD_THREADS; ++t) mtd_passes_phase<Cfg>(s, tw, t, pass);
 }

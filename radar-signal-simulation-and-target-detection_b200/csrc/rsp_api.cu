@@ -46,6 +46,7 @@ struct rsp_ctx {
     Lane lanes[8];
     int n_lanes = 1;
     Lane* cur = nullptr;                  // lane the launch helpers enqueue on
+    bool discard = false;                 // stream path: drop dead intermediates from L2 (see l2_discard)
     cudaEvent_t fork = nullptr;
     float2* d_rdm = nullptr;
     float2* d_aux = nullptr;              // scratch for stage2 transposes
@@ -53,6 +54,8 @@ struct rsp_ctx {
     float2* d_W = nullptr;
     float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
+    bool dbf_tma = false;                 // TMA-fed persistent variant
+    int dbf_tma_ctas = 0;
     float* d_fir = nullptr;
     int n_fir = 0;
     PcPlan med, lng;
@@ -321,6 +324,21 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             c->dbf_nt = (B + 3) / 4;
             c->dbf_ks = C <= 16 ? 4 : 8;
             CU(c, upload(&c->d_Wfrag, make_dbf_fragments(reinterpret_cast<const double*>(k->dbf_weights), B, C, c->dbf_nt, c->dbf_ks)));
+            c->dbf_tma = e && std::string(e) == "tma";             // RSP_DBF=tma: persistent cp.async.bulk-fed variant
+            if (c->dbf_tma) {
+                const size_t sm = (size_t)RSP_DBF_TMA_STAGES * C * RSP_DBF_TMA_ROWB;
+                int nsm = 148;
+                cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->prm.device);
+                const char* ec = getenv("RSP_DBF_CTAS_PER_SM");
+                const int per_sm = ec ? std::max(1, atoi(ec)) : (sm <= 72 * 1024 ? 2 : 1);
+                c->dbf_tma_ctas = nsm * per_sm;
+                const int key = c->dbf_nt * 10 + c->dbf_ks;
+                switch (key) {
+#define CASE(nt, ks) case nt * 10 + ks: CU(c, opt_in_smem(dbf_tma_kernel<nt, ks>, sm)); break;
+                    CASE(1, 4) CASE(2, 4) CASE(3, 4) CASE(4, 4) CASE(1, 8) CASE(2, 8) CASE(3, 8) CASE(4, 8)
+#undef CASE
+                }
+            }
         }
     }
     std::vector<float> fir(k->n_fir);
@@ -425,11 +443,21 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
 // ------------------------------------------------------------------------------------------
 // launch sequence for one CPI (device-resident PCN complex64 input)
 // ------------------------------------------------------------------------------------------
+static DiscardArgs dead_buf(const rsp_ctx* c, void* p, size_t bytes) {
+    DiscardArgs d;
+    d.ptr = (c->discard && (reinterpret_cast<uintptr_t>(p) & 127) == 0) ? p : nullptr;
+    d.bytes = bytes;
+    return d;
+}
+static DiscardArgs dead_amp(const rsp_ctx* c) { return dead_buf(c, c->cur->amp, (size_t)c->P * c->B * c->G * sizeof(float)); }
+static DiscardArgs dead_beam(const rsp_ctx* c) { return dead_buf(c, c->cur->beam, (size_t)c->P * c->B * c->ldb * sizeof(float2)); }
+static DiscardArgs dead_pc(const rsp_ctx* c) { return dead_buf(c, c->cur->pc, (size_t)c->P * c->B * c->ldg * sizeof(float2)); }
+
 template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw, int* det_count) {
     constexpr int SPT = 2, CU_ = 4;
     Timed t(c, K_DBF);
     dim3 grid((c->N + RSP_DBF_THREADS * SPT - 1) / (RSP_DBF_THREADS * SPT), c->P);
-    dbf_kernel<NB, SPT, CU_><<<grid, RSP_DBF_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_W, c->C, c->N, c->ldb, det_count);
+    dbf_kernel<NB, SPT, CU_><<<grid, RSP_DBF_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_W, c->C, c->N, c->ldb, det_count, dead_amp(c));
 }
 
 template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* raw, int* det_count) {
@@ -437,8 +465,15 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
     const int per_cta = (RSP_DBF_MMA_THREADS / 32) * 32;
     dim3 grid((c->N + per_cta - 1) / per_cta, c->P);
     const bool vec = (c->N % 2 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
-    if (vec) dbf_mma_kernel<NT, KS, true><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count);
-    else dbf_mma_kernel<NT, KS, false><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count);
+    if (vec && c->dbf_tma) {
+        const size_t sm = (size_t)RSP_DBF_TMA_STAGES * c->C * RSP_DBF_TMA_ROWB;
+        const int n_tiles = c->P * ((c->N + RSP_DBF_TMA_TILE - 1) / RSP_DBF_TMA_TILE);
+        const int nctas = std::min(n_tiles, c->dbf_tma_ctas);
+        dbf_tma_kernel<NT, KS><<<nctas, RSP_DBF_TMA_THREADS, sm, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, c->P, det_count, dead_amp(c));
+        return;
+    }
+    if (vec) dbf_mma_kernel<NT, KS, true><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
+    else dbf_mma_kernel<NT, KS, false><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
 }
 
 static int launch_dbf_any(rsp_ctx* c, const float2* raw, int* det_count) {
@@ -498,6 +533,7 @@ static void launch_mtd(rsp_ctx* c, float2* rdm) {
     MtdArgs a;
     a.pc = c->cur->pc; a.rdm = rdm; a.amp = c->cur->amp; a.win = c->d_win; a.tw = c->d_dop_tw; a.perm = c->d_dop_perm;
     a.P = c->P; a.B = c->B; a.G = c->G; a.ldg = c->ldg;
+    a.dead = dead_beam(c);
     const int tg = c->mtd_tg;
     dim3 grid((c->G + tg - 1) / tg, c->B);
     Timed t(c, K_MTD);
@@ -529,6 +565,7 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
     a.cap = c->prm.max_detections;
     a.range_axis = c->d_range_axis; a.vel_axis = c->d_vel_axis; a.beam_angles = c->d_beam_angles; a.k_slopes = c->d_k_slopes;
     a.delta_r = c->delta_r; a.delta_v = c->delta_v; a.complex_mode = c->prm.monopulse_complex;
+    a.dead = dead_pc(c);
     const int mR = c->prm.guard_r + c->prm.ref_r;
     const int ncut = c->G - 2 * mR, tg = c->cfar_tg;
     dim3 grid((ncut + tg - 1) / tg, c->B - 1);
@@ -649,6 +686,7 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
     CU(c, cudaSetDevice(c->prm.device));
     const size_t in_elems = (size_t)c->P * c->C * c->N, out_elems = (size_t)c->P * c->B * c->G;
     const int nl = std::min(c->n_lanes, std::max(n_cpi, 1));
+    { const char* e = getenv("RSP_L2_DISCARD"); c->discard = !(e && atoi(e) == 0); }
     if (nl > 1) {                                    // fork: the extra lanes wait for work already on the caller's stream
         CU(c, cudaEventRecord(c->fork, c->stream));
         for (int l = 1; l < nl; ++l) CU(c, cudaStreamWaitEvent(c->lanes[l].s, c->fork, 0));
@@ -659,6 +697,7 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
         int rc = enqueue_chain(c, in, rdm, first_slot + i, i % nl);
         if (rc) return rc;
     }
+    c->discard = false;
     for (int l = 1; l < nl; ++l) {                   // join
         CU(c, cudaEventRecord(c->lanes[l].done, c->lanes[l].s));
         CU(c, cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));

@@ -23,6 +23,25 @@ namespace rsp {
 __device__ __forceinline__ float2 to_c64(float2 v) { return v; }
 __device__ __forceinline__ float2 to_c64(double2 v) { return make_float2((float)v.x, (float)v.y); }
 
+// Drop dead intermediates from L2 without writing them back: once the consumer kernel of a buffer has
+// finished, its dirty lines would otherwise be evicted to HBM later (measured: 69 MB of the 166 MB of
+// DRAM traffic per CPI at config 2).  discard.global.L2 makes the contents undefined, which is exactly
+// what a dead buffer is.  Used on the stream path only (the single-CPI path keeps its intermediates
+// readable for rsp_get_beam / rsp_get_pc / rsp_get_amp).
+struct DiscardArgs {
+    void* ptr;            // 128-byte aligned, or nullptr
+    size_t bytes;
+};
+__device__ __forceinline__ void l2_discard(const DiscardArgs& d) {
+    if (!d.ptr) return;
+    const size_t lines = d.bytes >> 7;
+    const size_t gthreads = (size_t)gridDim.x * gridDim.y * gridDim.z * blockDim.x * blockDim.y;
+    const size_t gtid = ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (blockDim.x * blockDim.y) +
+                        threadIdx.y * blockDim.x + threadIdx.x;
+    char* base = static_cast<char*>(d.ptr);
+    for (size_t i = gtid; i < lines; i += gthreads) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + (i << 7)) : "memory");
+}
+
 template <typename TIN>
 __global__ void __launch_bounds__(256) matlab_to_pcn_kernel(const TIN* __restrict__ in, float2* __restrict__ out,
                                                             int P, int N, int C) {
@@ -91,9 +110,11 @@ __global__ void __launch_bounds__(256) pbg_to_bgp_kernel(const float2* __restric
 template <int NB, int SPT, int CU>
 __global__ void __launch_bounds__(RSP_DBF_THREADS) dbf_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
                                                               const float2* __restrict__ Wc /* [C][NB] conj(W) */,
-                                                              int C, int N, int ldb, int* __restrict__ det_count) {
+                                                              int C, int N, int ldb, int* __restrict__ det_count,
+                                                              const DiscardArgs dead) {
     __shared__ float2 sW[RSP_MAX_CHANNELS * NB];
     const int tid = threadIdx.x;
+    l2_discard(dead);
     if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
     for (int i = tid; i < C * NB; i += RSP_DBF_THREADS) sW[i] = Wc[i];
     __syncthreads();
@@ -178,9 +199,10 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_mma_kernel(const floa
                                                                       float2* __restrict__ beam,
                                                                       const float4* __restrict__ Wfrag /* [KS][NT][32] */,
                                                                       int C, int NB, int N, int ldb,
-                                                                      int* __restrict__ det_count) {
+                                                                      int* __restrict__ det_count, const DiscardArgs dead) {
     __shared__ float4 sW[KS * NT * 32];
     const int tid = threadIdx.x;
+    l2_discard(dead);
     if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
     for (int i = tid; i < KS * NT * 32; i += RSP_DBF_MMA_THREADS) sW[i] = Wfrag[i];
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -224,8 +246,11 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_mma_kernel(const floa
             const float v[4] = {x[s][m].x, x[s][m].z, x[s][m].y, x[s][m].w};   // a0 (re,row0) a1 (re,row1) a2 (im,row0) a3 (im,row1)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                ah[m][i] = to_tf32(v[i]);
-                al[m][i] = to_tf32(v[i] - __uint_as_float(ah[m][i]));
+                // hi = x with the 13 low mantissa bits cleared (a valid tf32), lo = x - hi (exact in
+                // fp32, |lo| < 2^-10 |x|), lo truncated the same way: 3 instructions per value
+                // (cvt.rna.tf32.f32 expands to ~6 on sm_100a).  Dropped terms are O(2^-20 |x w|).
+                ah[m][i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+                al[m][i] = __float_as_uint(v[i] - __uint_as_float(ah[m][i])) & 0xFFFFE000u;
             }
         }
 #pragma unroll
@@ -256,6 +281,150 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_mma_kernel(const floa
                     const int n = n_base + 16 * m + g;
                     if (n < N) row[n] = make_float2(acc[m][nt][0], acc[m][nt][1]);
                     if (n + 8 < N) row[n + 8] = make_float2(acc[m][nt][2], acc[m][nt][3]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// S5, TMA-fed variant: a persistent CTA (4 MMA warps + 1 producer warp) streams [C channels x 128
+// samples] tiles of the raw cube through a 4-stage shared-memory ring with cp.async.bulk (one 1-D bulk
+// copy per channel row, completion counted on an mbarrier), so the bytes in flight per SM are set by
+// the ring (4 x 16.5 KB per CTA), not by registers or occupancy.  Rows are padded by 32 bytes so that
+// the float4 A-fragment reads (4 channels x 2 row groups per quarter warp) hit 8 distinct bank groups.
+// MMA math, fragment mapping and the stores are those of dbf_mma_kernel<.., VEC = true>.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+#define RSP_DBF_TMA_TILE 128                    // samples per tile (32 per MMA warp)
+#define RSP_DBF_TMA_STAGES 4
+#define RSP_DBF_TMA_ROWB (RSP_DBF_TMA_TILE * 8 + 32)
+#define RSP_DBF_TMA_THREADS 160                 // 4 consumer warps + 1 producer warp
+template <int NT, int KS>
+__global__ void __launch_bounds__(RSP_DBF_TMA_THREADS) dbf_tma_kernel(const float2* __restrict__ raw,
+                                                                      float2* __restrict__ beam,
+                                                                      const float4* __restrict__ Wfrag /* [KS][NT][32] */,
+                                                                      int C, int NB, int N, int ldb, int P,
+                                                                      int* __restrict__ det_count, const DiscardArgs dead) {
+    extern __shared__ __align__(128) unsigned char dbf_smem[];
+    l2_discard(dead);
+    __shared__ float4 sW[KS * NT * 32];
+    __shared__ __align__(8) unsigned long long bars[2 * RSP_DBF_TMA_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int stage_bytes = C * RSP_DBF_TMA_ROWB;
+    const int tiles_per_pulse = (N + RSP_DBF_TMA_TILE - 1) / RSP_DBF_TMA_TILE;
+    const int n_tiles = P * tiles_per_pulse;
+    if (det_count && blockIdx.x == 0 && tid == 0) *det_count = 0;          // first kernel of the CPI
+    for (int i = tid; i < KS * NT * 32; i += RSP_DBF_TMA_THREADS) sW[i] = Wfrag[i];
+    if (tid == 0) {
+        for (int s = 0; s < RSP_DBF_TMA_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);                               // full: the producer's expect_tx arrive
+            mbar_init(smem_u32(&bars[RSP_DBF_TMA_STAGES + s]), 4);          // empty: one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (w == 4) {
+        // ------------------------------ producer ------------------------------
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % RSP_DBF_TMA_STAGES, round = it / RSP_DBF_TMA_STAGES;
+                if (round > 0) mbar_wait(smem_u32(&bars[RSP_DBF_TMA_STAGES + s]), (round - 1) & 1);
+                const int p = tile / tiles_per_pulse, n0 = (tile - p * tiles_per_pulse) * RSP_DBF_TMA_TILE;
+                const uint32_t row_bytes = (uint32_t)min(RSP_DBF_TMA_TILE, N - n0) * 8u;
+                const uint32_t full = smem_u32(&bars[s]);
+                mbar_expect_tx(full, row_bytes * (uint32_t)C);
+                const float2* src = raw + (size_t)p * C * N + n0;
+                const uint32_t dst = smem_u32(dbf_smem) + (uint32_t)s * stage_bytes;
+                for (int c = 0; c < C; ++c) bulk_g2s(dst + c * RSP_DBF_TMA_ROWB, src + (size_t)c * N, row_bytes, full);
+            }
+        }
+        return;
+    }
+    // ------------------------------ consumers ------------------------------
+    const int g = lane >> 2, t = lane & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % RSP_DBF_TMA_STAGES, round = it / RSP_DBF_TMA_STAGES;
+        const int p = tile / tiles_per_pulse, n0 = (tile - p * tiles_per_pulse) * RSP_DBF_TMA_TILE;
+        mbar_wait(smem_u32(&bars[s]), round & 1);
+        const unsigned char* st = dbf_smem + (size_t)s * stage_bytes;
+        float4 x[KS][2];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int c = 4 * ks + t;
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                x[ks][m] = c < C ? *reinterpret_cast<const float4*>(st + c * RSP_DBF_TMA_ROWB + (32 * w + 16 * m + 2 * g) * 8)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[RSP_DBF_TMA_STAGES + s]));   // stage may be refilled
+        float acc[2][NT][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float v[4] = {x[ks][m].x, x[ks][m].z, x[ks][m].y, x[ks][m].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ah[m][i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+                    al[m][i] = __float_as_uint(v[i] - __uint_as_float(ah[m][i])) & 0xFFFFE000u;
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float4 wf = sW[(ks * NT + nt) * 32 + lane];
+                const uint32_t b0h = __float_as_uint(wf.x), b1h = __float_as_uint(wf.y);
+                const uint32_t b0l = __float_as_uint(wf.z), b1l = __float_as_uint(wf.w);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    mma_tf32(acc[m][nt], al[m], b0h, b1h);
+                    mma_tf32(acc[m][nt], ah[m], b0l, b1l);
+                    mma_tf32(acc[m][nt], ah[m], b0h, b1h);
+                }
+            }
+        }
+        const int n_base = n0 + 32 * w;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int b = 4 * nt + t;
+            if (b < NB) {
+                float2* row = beam + ((size_t)p * NB + b) * ldb;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int n = n_base + 16 * m + 2 * g;
+                    if (n < N)
+                        *reinterpret_cast<float4*>(row + n) = make_float4(acc[m][nt][0], acc[m][nt][1], acc[m][nt][2], acc[m][nt][3]);
                 }
             }
         }
@@ -374,20 +543,21 @@ struct MtdArgs {
     const int* perm;       // pow2 only: iperm[pos] = pulse stored at position pos
     int P;
     int B, G, ldg;
+    DiscardArgs dead;      // buffer whose last reader has finished (the beam cube), or {nullptr, 0}
 };
 
 template <class Cfg>
 __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
     constexpr int P = Cfg::P, TG = RSP_MTD_TG;
     extern __shared__ float2 mtd_smem[];
+    l2_discard(k.dead);
     float2* tile = mtd_smem;                       // [P][TG + 1]
     float2* stw = mtd_smem + P * (TG + 1);         // [Cfg::TW_COUNT]
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < Cfg::TW_COUNT; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
     const int g0 = blockIdx.x * TG, b = blockIdx.y;
-    // innermost pass straight from global memory (k.perm holds the INVERSE permutation here)
-    mtd_first_pass_t<MtdInner<Cfg>::R, P>(tile, k.pc + (size_t)b * k.ldg + g0, (size_t)k.B * k.ldg, k.perm, k.win,
-                                          g0 + lane < k.G, tid);
+    // innermost pass straight from global memory
+    mtd_first_pass_t<Cfg>(tile, k.pc + (size_t)b * k.ldg + g0, (size_t)k.B * k.ldg, k.win, g0 + lane < k.G, tid);
     __syncthreads();
     if (MtdInner<Cfg>::PASS < 1 && Cfg::R1 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 1); __syncthreads(); }
     if (MtdInner<Cfg>::PASS < 2) { mtd_passes_phase<Cfg>(tile, stw, tid, 2); __syncthreads(); }
@@ -407,6 +577,7 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
 template <int TG>
 __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs k) {
     extern __shared__ float2 mtd_smem[];
+    l2_discard(k.dead);
     const int P = k.P;
     float2* xin = mtd_smem;
     float2* xout = xin + (size_t)P * (TG + 1);
@@ -479,6 +650,7 @@ struct CfarArgs {
     const double* k_slopes;
     double delta_r, delta_v;
     int complex_mode;
+    DiscardArgs dead;            // the pc cube (its last reader, mtd_kernel, has finished)
 };
 
 // S9 for record i (fun_process_single_frame.m:241-298): spline peak search on the fp32 sum map the
@@ -551,6 +723,7 @@ __device__ __forceinline__ void cfar_emit(const CfarArgs& k, int v, int g, int p
 template <int TG>
 __global__ void __launch_bounds__(RSP_CFAR_THREADS, 2) cfar_kernel(const CfarArgs k) {
     extern __shared__ float cfar_smem[];
+    l2_discard(k.dead);
     const int P = k.c.P, G = k.c.G;
     const int mR = k.c.guard_r + k.c.ref_r, mV = k.c.guard_v + k.c.ref_v;
     const int rows = TG + 2 * mR;
@@ -581,8 +754,12 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, 2) cfar_kernel(const CfarArg
 // Vectorised variant for P % 4 == 0 (see cfar4_* in rsp_phases.cuh); RR/RV/GV = compile-time range
 // reference, Doppler reference and Doppler guard lengths (RR = 0: run time).
 template <int TG, int RR, int RV, int GV>
-__global__ void __launch_bounds__(RSP_CFAR_THREADS, 3) cfar4_kernel(const CfarArgs k) {
+#ifndef RSP_CFAR_MINB
+#define RSP_CFAR_MINB 3
+#endif
+__global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(const CfarArgs k) {
     extern __shared__ float cfar_smem[];
+    l2_discard(k.dead);
     const Cfar4Geom g = cfar4_geom(k.c, TG);
     const int P = k.c.P, G = k.c.G;
     const int mR = k.c.guard_r + k.c.ref_r, mV = k.c.guard_v + k.c.ref_v;
@@ -600,16 +777,29 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, 3) cfar4_kernel(const CfarAr
         const int row = idx / (2 * h4), c = idx - row * (2 * h4);
         S4[row * pp4 + (c < h4 ? c : pp4 - 2 * h4 + c)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll 4
-    for (int idx = tid; idx < g.rows * g.P4; idx += RSP_CFAR_THREADS) {
-        int row, c4;
-        cfar4_split(g, idx, row, c4);
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows_valid) {
-            const float4 a = A4[idx], b = B4[idx];
-            s = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    {   // S = A + B: all loads of a batch are issued before the first add (the tile is one contiguous
+        // block of each map, so the loads are full 128-byte lines)
+        constexpr int U = 4;
+        const int n_valid4 = rows_valid * g.P4, n_all4 = g.rows * g.P4;
+        for (int base = tid; base < n_all4; base += RSP_CFAR_THREADS * U) {
+            float4 a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * RSP_CFAR_THREADS;
+                a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                b[u] = a[u];
+                if (idx < n_valid4) { a[u] = A4[idx]; b[u] = B4[idx]; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * RSP_CFAR_THREADS;
+                if (idx < n_all4) {
+                    int row, c4;
+                    cfar4_split(g, idx, row, c4);
+                    S4[row * pp4 + h4 + c4] = make_float4(a[u].x + b[u].x, a[u].y + b[u].y, a[u].z + b[u].z, a[u].w + b[u].w);
+                }
+            }
         }
-        S4[row * pp4 + h4 + c4] = s;
     }
     __syncthreads();
     cfar4_r5_phase<RR>(S, R5, k.c, g, tid, RSP_CFAR_THREADS);

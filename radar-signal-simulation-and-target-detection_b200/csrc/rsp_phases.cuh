@@ -238,32 +238,36 @@ template <int R, int LS, int P> RSP_HD void mtd_dit_pass_t(cf* s, const cf* tw, 
         dit_butterfly<(R > 1 ? R : 2), -1>(s, LS, q, tw, addr);
 }
 
-// Innermost DIT pass straight from global memory: butterfly q takes the pulses iperm[q*R + k]
-// (Ls = R, stride 1, no twiddles), so the digit-reversed placement costs nothing.
-//   src = pc + b*ldg + g0 (pulse stride = pstride elements); gate_ok masks gates beyond G.
-template <int R, int P>
-RSP_HD void mtd_first_pass_t(cf* s, const cf* src, size_t pstride, const int* iperm, const float* win, bool gate_ok,
-                             int tid) {
-    constexpr int NBF = P / R;
-    const int gl = tid & (RSP_MTD_TG - 1);
-#pragma unroll
-    for (int q = tid / RSP_MTD_TG; q < NBF; q += RSP_MTD_THREADS / RSP_MTD_TG) {
-        cf v[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const int p = iperm[q * R + k];
-            v[k] = gate_ok ? cscale(src[(size_t)p * pstride + gl], win[p]) : make_float2(0.f, 0.f);
-        }
-        SmallDft<R, -1>::run(v);
-#pragma unroll
-        for (int m = 0; m < R; ++m) s[(q * R + m) * (RSP_MTD_TG + 1) + gl] = v[m];
-    }
-}
-
 template <class Cfg> struct MtdInner {     // radix of the innermost non-trivial pass and its index
     static constexpr int PASS = Cfg::R2 > 1 ? 0 : (Cfg::R1 > 1 ? 1 : 2);
     static constexpr int R = Cfg::R2 > 1 ? Cfg::R2 : (Cfg::R1 > 1 ? Cfg::R1 : Cfg::R0);
 };
+
+// Innermost DIT pass straight from global memory.  Butterfly q (Ls = R, stride 1, no twiddles) owns
+// positions q*R + k; with the digit reversal of radices (R0,R1,R2) the pulse stored at position
+// q*R + k is  base(q) + k * (P/R)  (affine in k), so the digit-reversed placement needs no table:
+//   (R0,R1,1): base = q              (R0,R1,R2): base = q / R1 + R0 * (q % R1)        (R0,1,1): base = 0
+//   src = pc + b*ldg + g0 (pulse stride = pstride elements); gate_ok masks gates beyond G.
+template <class Cfg>
+RSP_HD void mtd_first_pass_t(cf* s, const cf* src, size_t pstride, const float* win, bool gate_ok, int tid) {
+    constexpr int R = MtdInner<Cfg>::R, P = Cfg::P, NBF = P / R, KSTR = P / R;
+    const int gl = tid & (RSP_MTD_TG - 1);
+#pragma unroll
+    for (int q = tid / RSP_MTD_TG; q < NBF; q += RSP_MTD_THREADS / RSP_MTD_TG) {
+        const int base = Cfg::R2 > 1 ? (q / Cfg::R1 + Cfg::R0 * (q % Cfg::R1)) : q;
+        const cf* col = src + (size_t)base * pstride + gl;
+        const float* wq = win + base;
+        cf v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = gate_ok ? col[(size_t)k * KSTR * pstride] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = cscale(v[k], wq[k * KSTR]);
+        SmallDft<R, -1>::run(v);
+        cf* dst = s + (q * R) * (RSP_MTD_TG + 1) + gl;
+#pragma unroll
+        for (int m = 0; m < R; ++m) dst[m * (RSP_MTD_TG + 1)] = v[m];
+    }
+}
 
 template <class Cfg> RSP_HD void mtd_passes_phase(cf* s, const cf* tw, int tid, int pass) {
     // pass 0 = innermost (radix R2, Ls = R2), 1 = middle (R1, Ls = R1*R2), 2 = outermost (R0, Ls = P)
