@@ -190,6 +190,28 @@ typedef struct {
 int rsp_stage2_configure(rsp_ctx* ctx, const rsp_stage2_config* cfg);
 int rsp_stage2_mtd(rsp_ctx* ctx, const void* iq, rsp_dtype dtype, rsp_c128* mtd_out, rsp_c128* pc_out);
 
+/* ---- S4 + S4.1 on the device (fun_process_single_frame.m:47-88): echo synthesis + noise ----
+ * Fills a device-resident PCN complex64 cube: for every target the delayed transmit pulse scaled by the
+ * SNR amplitude, the pulse-to-pulse Doppler phasor and the per-channel steering phasor (fsf:55-74), plus
+ * (noise_power > 0) complex white Gaussian noise of that power from a counter-based Philox4x32-10
+ * generator keyed by `seed` (the reference draws from MATLAB's global randn stream, fsf:84-85, which no
+ * other generator can reproduce; parity of the echoes is exact, of the noise statistical).
+ * rsp_set_waveform uploads precomputed_data.tx_pulse and the scalars the synthesis needs. */
+typedef struct { double range, velocity, elevation_deg, snr_db; } rsp_target_in;   /* targets(k), fsf:51-61 */
+typedef struct {
+    const rsp_c128* tx_pulse;     /* [N] precomputed_data.tx_pulse (v8_3:132-138) */
+    double c, fs, wavelength, prt, element_spacing;   /* config.Sig_Config.*, config.Array.* */
+    double p_signal_unscaled;     /* precomputed_data.P_signal_unscaled (v8_3:139) */
+} rsp_waveform;
+int rsp_set_waveform(rsp_ctx* ctx, const rsp_waveform* w);
+int rsp_synthesize(rsp_ctx* ctx, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed,
+                   void* raw_dev_out /* NULL = the context's own cube */);
+/* fun_process_single_frame end to end on the device: S4 (rsp_synthesize into the context's cube), S5..S9,
+ * host clustering.  Only the target list crosses the bus. */
+int rsp_process_targets(rsp_ctx* ctx, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed,
+                        const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap, int32_t* n_final,
+                        rsp_detection* dets /* may be NULL */, int32_t det_cap, int32_t* n_dets /* may be NULL */);
+
 /* ---- introspection ---- */
 typedef struct {
     int32_t n_gates_total;        /* G */

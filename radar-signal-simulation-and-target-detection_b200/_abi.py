@@ -57,6 +57,15 @@ class rsp_info(C.Structure):
                 ("algorithmic_bytes_per_cpi", C.c_int64), ("launches_total", C.c_int64)]
 
 
+class rsp_target_in(C.Structure):
+    _fields_ = [("range", C.c_double), ("velocity", C.c_double), ("elevation_deg", C.c_double), ("snr_db", C.c_double)]
+
+
+class rsp_waveform(C.Structure):
+    _fields_ = [("tx_pulse", C.c_void_p), ("c", C.c_double), ("fs", C.c_double), ("wavelength", C.c_double),
+                ("prt", C.c_double), ("element_spacing", C.c_double), ("p_signal_unscaled", C.c_double)]
+
+
 class rsp_stage2_config(C.Structure):
     _fields_ = [("pulse", C.c_void_p * 3), ("n_pulse", C.c_int32 * 3), ("mtd_win", C.c_void_p),
                 ("zero_vel_bins", C.c_int32)]
@@ -98,6 +107,10 @@ SYMBOLS = [
                                     C.POINTER(C.c_int32)]),
     ("rsp_stage2_configure", C.c_int, [_P, C.POINTER(rsp_stage2_config)]),
     ("rsp_stage2_mtd", C.c_int, [_P, _P, C.c_int, _P, _P]),
+    ("rsp_set_waveform", C.c_int, [_P, C.POINTER(rsp_waveform)]),
+    ("rsp_synthesize", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, _P]),
+    ("rsp_process_targets", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, C.POINTER(rsp_cluster_params), _P, C.c_int32,
+                                      C.POINTER(C.c_int32), _P, C.c_int32, C.POINTER(C.c_int32)]),
     ("rsp_get_info", C.c_int, [_P, C.POINTER(rsp_info)]),
     ("rsp_set_profiling", C.c_int, [_P, C.c_int]),
     ("rsp_get_kernel_times", C.c_int, [_P, C.POINTER(rsp_kernel_times)]),

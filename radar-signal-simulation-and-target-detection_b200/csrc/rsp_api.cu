@@ -74,6 +74,13 @@ struct rsp_ctx {
     float* d_win = nullptr;
     double *d_range_axis = nullptr, *d_vel_axis = nullptr, *d_beam_angles = nullptr, *d_k_slopes = nullptr;
     double delta_r = 0, delta_v = 0;
+    // S4 synthesis (rsp_set_waveform)
+    float2* d_tx = nullptr;
+    SynthTarget* d_tg = nullptr;
+    int tg_cap = 0;
+    rsp_waveform wf{};
+    int tx_seg_lo[3] = {0, 0, 0}, tx_seg_hi[3] = {0, 0, 0};
+    bool have_waveform = false;
     // detection ring
     int slots = 0;
     int* d_counts = nullptr;
@@ -91,8 +98,8 @@ struct rsp_ctx {
     std::vector<cudaEvent_t> event_pool;
 };
 
-enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC, K_MTD, K_CFAR, K_NCLASS };
-static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft", "mtd", "cfar_refine"};
+enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC, K_MTD, K_CFAR, K_SYNTH, K_NCLASS };
+static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft", "mtd", "cfar_refine", "synth"};
 
 static cudaEvent_t take_event(rsp_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -188,6 +195,7 @@ void rsp_destroy(rsp_ctx* c) {
     }
     if (c->fork) cudaEventDestroy(c->fork);
     cudaFree(c->d_done);
+    cudaFree(c->d_tx); cudaFree(c->d_tg);
     for (auto& sg : c->s2) { cudaFree(sg.tw1); cudaFree(sg.tw2); cudaFree(sg.H); }
     cudaFree(c->d_s2_win);
     cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_Wfrag); cudaFree(c->d_fir);
@@ -921,6 +929,95 @@ int rsp_stage2_mtd(rsp_ctx* c, const void* iq, rsp_dtype dtype, rsp_c128* mtd_ou
     CU(c, cudaGetLastError());
     c->ran = true;
     c->rdm_in_ctx = true;
+    return RSP_OK;
+}
+
+int rsp_set_waveform(rsp_ctx* c, const rsp_waveform* w) {
+    if (!c || !w || !w->tx_pulse) return RSP_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->prm.device));
+    std::vector<float2> tx(c->N);
+    for (int i = 0; i < c->N; ++i) tx[i] = make_float2((float)w->tx_pulse[i].re, (float)w->tx_pulse[i].im);
+    // the (at most three) non-zero stretches of the pulse train: only these are added per target
+    int nseg = 0;
+    for (int i = 0; i < c->N;) {
+        if (tx[i].x == 0.f && tx[i].y == 0.f) { ++i; continue; }
+        int j = i;
+        while (j < c->N && !(tx[j].x == 0.f && tx[j].y == 0.f)) ++j;
+        if (nseg == 3) { c->tx_seg_hi[2] = j; }              // more than three stretches: merge the tail
+        else { c->tx_seg_lo[nseg] = i; c->tx_seg_hi[nseg] = j; ++nseg; }
+        i = j;
+    }
+    for (int s2 = nseg; s2 < 3; ++s2) c->tx_seg_lo[s2] = c->tx_seg_hi[s2] = 0;
+    CU(c, upload(&c->d_tx, tx));
+    c->wf = *w;
+    c->wf.tx_pulse = nullptr;
+    c->have_waveform = true;
+    return RSP_OK;
+}
+
+static long matlab_round(double x) { return x >= 0 ? (long)std::floor(x + 0.5) : -(long)std::floor(-x + 0.5); }
+
+int rsp_synthesize(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed, void* raw_dev_out) {
+    if (!c || n_targets < 0 || (n_targets > 0 && !targets)) return fail(c, RSP_ERR_INVALID_ARG, "bad synthesis arguments");
+    if (!c->have_waveform) return fail(c, RSP_ERR_NOT_READY, "rsp_set_waveform has not been called");
+    CU(c, cudaSetDevice(c->prm.device));
+    std::vector<SynthTarget> tg;
+    const double kPiD = 3.14159265358979323846;
+    for (int i = 0; i < n_targets; ++i) {
+        const long d = matlab_round(2.0 * targets[i].range / c->wf.c * c->wf.fs);                       // fsf:55-56
+        if (!(d > 0 && d < c->N)) continue;                                                              // fsf:66
+        SynthTarget t;
+        t.delay = (int)d;
+        t.amp = (float)std::sqrt(std::pow(10.0, targets[i].snr_db / 10.0) / c->wf.p_signal_unscaled);   // fsf:61-63
+        t.dop_cycles = 2.0 * targets[i].velocity / c->wf.wavelength * c->wf.prt;                         // fsf:57-58
+        t.steer_cycles = c->wf.element_spacing * std::sin(targets[i].elevation_deg * kPiD / 180.0) / c->wf.wavelength;   // fsf:165
+        tg.push_back(t);
+    }
+    if ((int)tg.size() > c->tg_cap) {
+        if (c->d_tg) cudaFree(c->d_tg);
+        c->d_tg = nullptr;
+        c->tg_cap = std::max<int>(64, (int)tg.size());
+        CU(c, dev_alloc(&c->d_tg, (size_t)c->tg_cap));
+    }
+    if (!tg.empty()) CU(c, cudaMemcpyAsync(c->d_tg, tg.data(), tg.size() * sizeof(SynthTarget), cudaMemcpyHostToDevice, c->stream));
+    SynthArgs a;
+    a.raw = raw_dev_out ? static_cast<float2*>(raw_dev_out) : c->d_raw;
+    a.tx = c->d_tx; a.tg = c->d_tg; a.n_targets = (int)tg.size();
+    a.P = c->P; a.C = c->C; a.N = c->N;
+    for (int i = 0; i < 3; ++i) { a.seg_lo[i] = c->tx_seg_lo[i]; a.seg_hi[i] = c->tx_seg_hi[i]; }
+    a.noise_sigma = noise_power > 0 ? (float)std::sqrt(noise_power / 2.0) : 0.f;
+    a.seed = seed;
+    c->cur = &c->lanes[0];
+    {
+        Timed t(c, K_SYNTH);
+        synth_kernel<<<dim3(c->C, c->P), 256, 0, c->stream>>>(a);
+    }
+    CU(c, cudaGetLastError());
+    // the pageable target vector goes out of scope: make sure its copy has been consumed
+    if (!tg.empty()) CU(c, cudaStreamSynchronize(c->stream));
+    return RSP_OK;
+}
+
+int rsp_process_targets(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed,
+                        const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap, int32_t* n_final,
+                        rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+    if (!c || !cp || !n_final) return fail(c, RSP_ERR_INVALID_ARG, "null argument");
+    int rc = rsp_synthesize(c, targets, n_targets, noise_power, seed, nullptr);
+    if (rc) return rc;
+    std::vector<rsp_detection> own;
+    if (!dets) { own.resize((size_t)c->prm.max_detections); dets = own.data(); det_cap = (int32_t)own.size(); }
+    int32_t n = 0;
+    rc = rsp_process_cpi(c, c->d_raw, RSP_LAYOUT_PCN, RSP_C64, RSP_MEM_DEVICE, nullptr, RSP_MEM_DEVICE, dets, det_cap, &n);
+    if (n_dets) *n_dets = n;
+    if (rc) return rc;
+    std::vector<rsp_target> fin((size_t)std::max(n, 1));
+    int32_t nf = 0, n1 = 0;
+    rc = rsp_cluster(dets, n, cp, nullptr, &n1, fin.data(), &nf);
+    if (rc) return fail(c, rc, "clustering failed");
+    *n_final = nf;
+    if (nf > cap) return fail(c, RSP_ERR_OVERFLOW, "%d targets exceed the caller's capacity %d", nf, cap);
+    if (nf > 0 && !final_targets) return fail(c, RSP_ERR_INVALID_ARG, "null output");
+    std::memcpy(final_targets, fin.data(), (size_t)nf * sizeof(rsp_target));
     return RSP_OK;
 }
 

@@ -98,6 +98,90 @@ __global__ void __launch_bounds__(256) pbg_to_bgp_kernel(const float2* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// S4 + S4.1: echo synthesis and noise (fun_process_single_frame.m:47-88).  One CTA owns one
+// (pulse, channel) line: it first fills the line with Philox noise, then adds every target's delayed
+// pulse (only the three non-zero stretches of tx_pulse are visited), so no atomics are needed.
+// ------------------------------------------------------------------------------------------
+struct SynthTarget {          // per target, prepared on the host in fp64
+    int delay;                // delay_samples (fsf:56); targets with delay outside (0, N) are dropped (fsf:66)
+    float amp;                // sqrt(SNR / P_signal_unscaled) (fsf:61-63)
+    double dop_cycles;        // doppler_freq * prt (cycles per pulse, fsf:57-58)
+    double steer_cycles;      // element_spacing * sin(El) / wavelength (cycles per channel, fsf:163-169)
+};
+struct SynthArgs {
+    float2* raw;              // [P][C][N]
+    const float2* tx;         // [N]
+    const SynthTarget* tg;
+    int n_targets, P, C, N;
+    int seg_lo[3], seg_hi[3]; // non-zero stretches of tx (0-based, half open)
+    float noise_sigma;        // sqrt(noise_power / 2) per component; 0 = no noise
+    unsigned long long seed;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// two uniform words -> one complex standard-normal sample (Box-Muller)
+__device__ __forceinline__ float2 box_muller(unsigned int a, unsigned int b) {
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    return make_float2(r * cs, r * sn);
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(const SynthArgs k) {
+    const int c = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+    float2* line = k.raw + ((size_t)p * k.C + c) * k.N;
+    const size_t line_id = (size_t)p * k.C + c;
+    // noise: counter = (pair index within the line, line id), 2 complex samples per Philox call
+    for (int i = tid; 2 * i < k.N; i += 256) {
+        float2 z0 = make_float2(0.f, 0.f), z1 = z0;
+        if (k.noise_sigma > 0.f) {
+            const uint4 r = philox4x32_10(make_uint4((unsigned)i, (unsigned)line_id, (unsigned)(line_id >> 32), 0u),
+                                          make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32)));
+            z0 = box_muller(r.x, r.y);
+            z1 = box_muller(r.z, r.w);
+            z0.x *= k.noise_sigma; z0.y *= k.noise_sigma; z1.x *= k.noise_sigma; z1.y *= k.noise_sigma;
+        }
+        line[2 * i] = z0;
+        if (2 * i + 1 < k.N) line[2 * i + 1] = z1;
+    }
+    __syncthreads();
+    for (int t = 0; t < k.n_targets; ++t) {
+        const SynthTarget tg = k.tg[t];
+        // phasor = amp * exp(j 2 pi (dop_cycles * p + steer_cycles * c)), argument reduced in fp64
+        double cyc = tg.dop_cycles * (double)p + tg.steer_cycles * (double)c;
+        cyc -= floor(cyc);
+        double sn, cs;
+        sincospi(2.0 * cyc, &sn, &cs);
+        const float2 ph = make_float2((float)(tg.amp * cs), (float)(tg.amp * sn));
+        const int len = min(k.N, k.N - tg.delay);                     // fsf:67
+#pragma unroll
+        for (int sgi = 0; sgi < 3; ++sgi) {
+            const int hi = min(k.seg_hi[sgi], len);
+            for (int i = k.seg_lo[sgi] + tid; i < hi; i += 256) {
+                const float2 x = k.tx[i];
+                float2 v = line[tg.delay + i];
+                v.x += x.x * ph.x - x.y * ph.y;
+                v.y += x.x * ph.y + x.y * ph.x;
+                line[tg.delay + i] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // S5: digital beamforming.  beam[p][b][n] = sum_c raw[p][c][n] * conj(W[b][c]).
 // One thread owns SPT range samples (strided by the CTA width so every load is a coalesced 8-byte
 // lane access with no alignment requirement -- the native N = 5819 is odd) and all NB beams in

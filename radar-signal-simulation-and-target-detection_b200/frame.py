@@ -171,6 +171,51 @@ class RadarChain:
             C.c_void_p(dets.ctypes.data), self.max_detections, C.byref(n)), self._ctx)
         return dets[:n.value].copy()
 
+    # -- S4 on the device ----------------------------------------------------------------------------
+    def set_waveform(self, config, precomputed_data):
+        """Upload tx_pulse and the scalars of fun_process_single_frame.m:47-77 (needed once)."""
+        sc = _field(config, "Sig_Config")
+        tx = _as_c128(_field(precomputed_data, "tx_pulse")).ravel()
+        if len(tx) != self.N:
+            raise ValueError("tx_pulse length must equal point_PRT")
+        w = _abi.rsp_waveform()
+        w.tx_pulse = tx.ctypes.data
+        w.c, w.fs, w.wavelength, w.prt = (float(_field(sc, k)) for k in ("c", "fs", "wavelength", "prt"))
+        w.element_spacing = float(_field(_field(config, "Array"), "element_spacing"))
+        w.p_signal_unscaled = float(_field(precomputed_data, "P_signal_unscaled"))
+        _abi.check(self._lib.rsp_set_waveform(self._ctx, C.byref(w)), self._ctx)
+        self._has_waveform = True
+
+    @staticmethod
+    def _pack_targets(targets):
+        arr = (_abi.rsp_target_in * max(len(targets), 1))()
+        for i, t in enumerate(targets):
+            arr[i].range, arr[i].velocity = float(_field(t, "Range")), float(_field(t, "Velocity"))
+            arr[i].elevation_deg, arr[i].snr_db = float(_field(t, "ElevationAngle")), float(_field(t, "SNR_dB"))
+        return arr
+
+    def synthesize(self, targets, noise_power: float = 1.0, seed: int = 0, out=None):
+        """S4 + S4.1 on the GPU.  ``out``: CUDA tensor [P, C, N] complex64 to fill (default: the context's
+        own cube, which process_targets then consumes)."""
+        arr = self._pack_targets(targets)
+        optr = C.c_void_p(out.data_ptr()) if out is not None else C.c_void_p()
+        _abi.check(self._lib.rsp_synthesize(self._ctx, arr, len(targets), float(noise_power), int(seed) & (2 ** 64 - 1), optr),
+                   self._ctx)
+        return out
+
+    def process_targets(self, targets, cluster_params, noise_power: float = 1.0, seed: int = 0):
+        """fun_process_single_frame on the device end to end -> (final targets, detections)."""
+        arr = self._pack_targets(targets)
+        cp = _abi.rsp_cluster_params(float(_field(cluster_params, "max_range_sep")), float(_field(cluster_params, "max_vel_sep")),
+                                     float(_field(cluster_params, "max_angle_sep")))
+        fin = np.zeros(4096, dtype=TARGET_DTYPE)
+        dets = np.zeros(self.max_detections, dtype=DETECTION_DTYPE)
+        nf, nd = C.c_int32(0), C.c_int32(0)
+        _abi.check(self._lib.rsp_process_targets(self._ctx, arr, len(targets), float(noise_power), int(seed) & (2 ** 64 - 1),
+                                                 C.byref(cp), C.c_void_p(fin.ctypes.data), len(fin), C.byref(nf),
+                                                 C.c_void_p(dets.ctypes.data), len(dets), C.byref(nd)), self._ctx)
+        return fin[:nf.value].copy(), dets[:nd.value].copy()
+
     # -- device-resident stream -----------------------------------------------------------------
     def stream_slots(self) -> int:
         return int(self._lib.rsp_stream_slots(self._ctx))
@@ -287,16 +332,14 @@ _chain_cache = {}
 
 def fun_process_single_frame(targets, config, cfar_params, cluster_params, precomputed_data, frame_idx=1, *,
                              rng: Optional[np.random.Generator] = None, noise: bool = True,
-                             chain: Optional[RadarChain] = None, device: int = 0) -> List[dict]:
+                             chain: Optional[RadarChain] = None, device: int = 0, host_synthesis: bool = False) -> List[dict]:
     """Drop-in for fun_process_single_frame.m:13.  Returns a list of dicts with the reference's
     fields Range, Velocity, Angle, Power (stage-2 cluster order); ``[]`` when nothing is detected.
 
-    Echo synthesis and noise (S4) are prepared on the host and handed to the device chain as one
-    complex64 cube; ``rng`` seeds the noise (the reference draws from MATLAB's global stream)."""
-    raw = synthesize_echo(targets, config, precomputed_data)
-    if noise:
-        raw = add_noise(raw, rng if rng is not None else np.random.default_rng())
-    raw = np.ascontiguousarray(raw.astype(np.complex64))
+    Default: S4 (echo synthesis + noise) runs on the GPU (rsp_process_targets), so only the target list
+    crosses the bus; the noise comes from the device Philox generator seeded from ``rng`` (the reference
+    draws from MATLAB's global randn stream, which cannot be reproduced).  ``host_synthesis=True`` builds
+    the cube with NumPy (``rng`` noise) and hands it to the device chain instead."""
     own = chain is None
     if own:
         key = id(precomputed_data)
@@ -305,7 +348,16 @@ def fun_process_single_frame(targets, config, cfar_params, cluster_params, preco
             chain = RadarChain(config, cfar_params, precomputed_data, device=device)
             _chain_cache.clear()
             _chain_cache[key] = chain
-    dets = chain.process_cpi(raw)
-    _, final = cluster(dets, cluster_params)
+    if host_synthesis:
+        raw = synthesize_echo(targets, config, precomputed_data)
+        if noise:
+            raw = add_noise(raw, rng if rng is not None else np.random.default_rng())
+        dets = chain.process_cpi(np.ascontiguousarray(raw.astype(np.complex64)))
+        _, final = cluster(dets, cluster_params)
+    else:
+        if not getattr(chain, "_has_waveform", False):
+            chain.set_waveform(config, precomputed_data)
+        seed = int((rng if rng is not None else np.random.default_rng()).integers(0, 2 ** 63))
+        final, _ = chain.process_targets(list(targets), cluster_params, 1.0 if noise else 0.0, seed)
     return [dict(Range=float(t["range"]), Velocity=float(t["velocity"]), Angle=float(t["angle"]),
                  Power=float(t["power"])) for t in final]

@@ -213,3 +213,59 @@ def test_process_stage2_mtd_matches_its_specification(P, B):
     for g, seg in ((60, 0), (228 + 300, 1), (951 + 1000, 2)):
         lo, hi = [0, 228, 951][seg], [228, 951, 3404][seg]
         assert lo + int(np.argmax(np.abs(pc[0, lo:hi, 1]))) == g
+
+
+def _philox4x32_10(ctr, key):
+    """NumPy reference of Philox4x32-10 (Salmon et al. 2011) for the device noise generator."""
+    c = [np.asarray(x, dtype=np.uint64) for x in ctr]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & mask, p1 & mask, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def test_device_echo_synthesis_matches_oracle_and_noise_is_philox():
+    """S4 on the device (fsf:47-77): noise-free echoes equal the oracle's; the noise is the documented
+    Philox4x32-10 + Box-Muller stream (bit-level counter check, unit power, white)."""
+    import torch
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    chain.set_waveform(config, pd)
+    cfg, pre, _ = o.make_cube("cfg1", None, targets=[])
+    tg = o.targets_t3(cfg, pre) + [o.Target(20000.0, 3.0, 30.0, 5.0),      # echo truncated at the end of the line
+                                    o.Target(1e6, 1.0, 0.0, 5.0)]            # delay beyond N: dropped (fsf:66)
+    tdicts = [dict(Range=t.Range, Velocity=t.Velocity, ElevationAngle=t.ElevationAngle, SNR_dB=t.SNR_dB) for t in tg]
+    out = torch.empty((chain.P, chain.C, chain.N), dtype=torch.complex64, device="cuda")
+    chain.synthesize(tdicts, noise_power=0.0, seed=0, out=out)
+    chain.synchronize()
+    ref = o.synthesize_echo(tg, cfg, pre)
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.array_equal(got == 0, ref == 0)
+    # noise only
+    seed = 0x1234567887654321
+    chain.synthesize([], noise_power=1.0, seed=seed, out=out)
+    chain.synchronize()
+    z = out.cpu().numpy()
+    assert abs(np.mean(np.abs(z) ** 2) - 1.0) < 5e-3 and abs(z.mean()) < 2e-3
+    assert abs(np.mean(z[:, :, 1:] * np.conj(z[:, :, :-1]))) < 2e-3          # white along range
+    assert abs(np.mean(z.real * z.imag)) < 2e-3
+    # counter check on one line: pair i of line (p, c) uses counter (i, line_id, 0, 0), key = seed
+    p, c = 3, 5
+    line_id = p * chain.C + c
+    i = np.arange(8, dtype=np.uint64)
+    r = _philox4x32_10([i, np.full(8, line_id), np.zeros(8), np.zeros(8)], (seed & 0xFFFFFFFF, seed >> 32))
+    u = lambda w: ((w >> np.uint64(8)).astype(np.float64) + 0.5) / 16777216.0
+    z0 = np.sqrt(-2 * np.log(u(r[0]))) * np.exp(2j * np.pi * u(r[1])) * np.sqrt(0.5)
+    z1 = np.sqrt(-2 * np.log(u(r[2]))) * np.exp(2j * np.pi * u(r[3])) * np.sqrt(0.5)
+    assert np.allclose(z[p, c, 0:16:2], z0, rtol=2e-5, atol=2e-6) and np.allclose(z[p, c, 1:16:2], z1, rtol=2e-5, atol=2e-6)
+    # end to end with the drop-in signature: device synthesis (noise-free) == host synthesis
+    t3 = tdicts[:3]
+    a = rsp.fun_process_single_frame(t3, config, cfar_params, cluster_params, pd, 1, noise=False, chain=chain)
+    b = rsp.fun_process_single_frame(t3, config, cfar_params, cluster_params, pd, 1, noise=False, chain=chain, host_synthesis=True)
+    assert len(a) == len(b) > 0
+    for x, y in zip(a, b):
+        assert all(abs(x[k] - y[k]) <= 1e-3 * max(1.0, abs(y[k])) for k in ("Range", "Velocity", "Angle", "Power")), (x, y)
+    chain.close()
