@@ -13,8 +13,9 @@ from .precompute import (Struct, default_config, named_config, build_precomputed
 from .frame import (RadarChain, fun_process_single_frame, synthesize_echo, add_noise, cluster, sort_detections)
 from .stage2 import Stage2Chain, process_stage2_mtd, reference_pulses
 from . import stream
+from .montecarlo import snr_vs_angle_error
 from ._abi import DETECTION_DTYPE, TARGET_DTYPE, RspError, LIB_PATH
 
 __all__ = ["Struct", "default_config", "named_config", "build_precomputed_data", "read_dbf_csv", "dbf_tables",
            "NAMED_SHAPES", "RadarChain", "fun_process_single_frame", "synthesize_echo", "add_noise", "cluster",
-           "sort_detections", "Stage2Chain", "process_stage2_mtd", "reference_pulses", "stream", "DETECTION_DTYPE", "TARGET_DTYPE", "RspError", "LIB_PATH"]
+           "sort_detections", "Stage2Chain", "process_stage2_mtd", "reference_pulses", "stream", "snr_vs_angle_error", "DETECTION_DTYPE", "TARGET_DTYPE", "RspError", "LIB_PATH"]

@@ -269,3 +269,19 @@ def test_device_echo_synthesis_matches_oracle_and_noise_is_philox():
     for x, y in zip(a, b):
         assert all(abs(x[k] - y[k]) <= 1e-3 * max(1.0, abs(y[k])) for k in ("Range", "Velocity", "Angle", "Power")), (x, y)
     chain.close()
+
+
+def test_monte_carlo_sweep_statistics():
+    """main_plot_snr_vs_angle_error.m on a small shape: detection probability rises with SNR, the angle
+    error shrinks with SNR, and at high SNR the mean measured angle is the target's elevation."""
+    config, cfar_params, cluster_params = rsp.named_config("cfg2")
+    pd = rsp.build_precomputed_data(config)
+    v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+    tt = dict(Range=8000.0, Velocity=0.1 * v_max, ElevationAngle=10.0, pair_idx=5)
+    res = rsp.snr_vs_angle_error(config, cfar_params, cluster_params, pd, [-70.0, -8.0, 6.0, 20.0], num_trials=24,
+                                 true_target=tt, seed=7)
+    pdet, std, mean = res["detection_probability"], res["angle_error_std"], res["angle_error_mean"]
+    assert pdet[0] <= 0.1 and pdet[-1] == 1.0 and pdet[-2] == 1.0
+    assert std[-1] < std[-2] and std[-1] < 0.2
+    assert abs(mean[-1]) < 0.3
+    assert list(res["trials"]) == [24.0] * 4
