@@ -14,8 +14,10 @@ from .frame import (RadarChain, fun_process_single_frame, synthesize_echo, add_n
 from .stage2 import Stage2Chain, process_stage2_mtd, reference_pulses
 from . import stream
 from .montecarlo import snr_vs_angle_error
+from .tracker import run_multiframe_simulation, inter_frame_cluster, init_tracks, evolve, default_scan_and_track_config
 from ._abi import DETECTION_DTYPE, TARGET_DTYPE, RspError, LIB_PATH
 
 __all__ = ["Struct", "default_config", "named_config", "build_precomputed_data", "read_dbf_csv", "dbf_tables",
            "NAMED_SHAPES", "RadarChain", "fun_process_single_frame", "synthesize_echo", "add_noise", "cluster",
-           "sort_detections", "Stage2Chain", "process_stage2_mtd", "reference_pulses", "stream", "snr_vs_angle_error", "DETECTION_DTYPE", "TARGET_DTYPE", "RspError", "LIB_PATH"]
+           "sort_detections", "Stage2Chain", "process_stage2_mtd", "reference_pulses", "stream", "snr_vs_angle_error", "run_multiframe_simulation", "inter_frame_cluster", "init_tracks", "evolve",
+           "default_scan_and_track_config", "DETECTION_DTYPE", "TARGET_DTYPE", "RspError", "LIB_PATH"]
