@@ -420,6 +420,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         c->cfar_tg = 16;
         for (int tg : {64, 32, 16})
             if (smem_for(tg) <= 72 * 1024) { c->cfar_tg = tg; break; }
+        if (const char* e = getenv("RSP_CFAR_TG")) { const int v = atoi(e); if (v == 64 || v == 32 || v == 16) c->cfar_tg = v; }
         c->cfar_smem = smem_for(c->cfar_tg);
         if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
         const int rr = c->prm.ref_r, rv = c->prm.ref_v, gv = c->prm.guard_v;
