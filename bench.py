@@ -118,6 +118,16 @@ def make_pool(rsp, config, pd, n_cubes: int, seed0: int):
     return np.stack(cubes)
 
 
+def _all_threads(n: int):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host thread."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=n)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def cpu_reference_time(name: str, n_cpi: int, workers: int):
     """Time the fp64 NumPy/SciPy oracle (S5..S9, no clustering) on n_cpi cubes; best-effort all cores."""
     o = load_oracle()
@@ -143,12 +153,13 @@ def run_reference(args, rank: int):
     cfg, pre, raw = o.make_cube(name, 0)
     raw = raw.astype(np.complex128)
     per_step = 1
-    for _ in range(max(args.warmup, 1)):
-        o.process_cube(raw, cfg, pre, workers=cores, keep=False, cluster=False)
-    t0 = time.perf_counter()
-    for _ in range(args.steps * per_step):
-        o.process_cube(raw, cfg, pre, workers=cores, keep=False, cluster=False)
-    dt = time.perf_counter() - t0
+    with _all_threads(cores):
+        for _ in range(max(args.warmup, 1)):
+            o.process_cube(raw, cfg, pre, workers=cores, keep=False, cluster=False)
+        t0 = time.perf_counter()
+        for _ in range(args.steps * per_step):
+            o.process_cube(raw, cfg, pre, workers=cores, keep=False, cluster=False)
+        dt = time.perf_counter() - t0
     value = args.steps * per_step / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -174,7 +185,7 @@ def main():
     ap.add_argument("--cpis-per-step", type=int, default=0)
     ap.add_argument("--pool", type=int, default=0, help="distinct input CPIs resident in HBM")
     ap.add_argument("--rdm-pool", type=int, default=0, help="distinct RDM output buffers")
-    ap.add_argument("--e2e-cpis", type=int, default=8)
+    ap.add_argument("--e2e-cpis", type=int, default=24)
     ap.add_argument("--cpu-cpis", type=int, default=0, help="CPIs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -278,41 +289,63 @@ def main():
     d0 = chain.stream_fetch(0)
     assert 50 <= len(d0) <= chain.max_detections, f"implausible detection count {len(d0)}"
 
-    # per-kernel device times (CUDA events on the launching stream), separate pass so that the event
-    # brackets do not perturb the headline number
+    # per-kernel device times: CUDA events around every launch on the launching stream, in a separate
+    # pass (so the brackets do not perturb the headline number) that enqueues one CPI at a time, i.e. on a
+    # single lane: each kernel runs alone, L2 warm, as in the ncu launch list under profiles/
     chain.set_profiling(True)
-    chain.stream_enqueue(pool.data_ptr(), pool_n, rdm_ring.data_ptr(), rdm_n, cps, 0)
+    for i in range(cps):
+        chain.stream_enqueue(pool.data_ptr() + (i % pool_n) * in_bytes, 1, rdm_ring.data_ptr() + (i % rdm_n) * out_bytes, 1, 1, i)
     kt = chain.kernel_times()
     chain.set_profiling(False)
     per_cpi_ms = {k: v[0] / max(v[1], 1) for k, v in kt.items()}
     kern_sum = sum(per_cpi_ms.values())
     peak, peak_src = peaks()
     t_cpi_s = (ms / 1e3) / (args.steps * cps)                 # this rank's device time per CPI
-    achieved = alg_bytes / t_cpi_s / 1e9
+    chain_achieved = alg_bytes / t_cpi_s / 1e9
     dominant = max(per_cpi_ms, key=per_cpi_ms.get) if per_cpi_ms else None
+    # algorithmic bytes of each kernel's own launch: what it must read + write once
+    beam_bytes, pc_bytes = 8 * P * B * N, 8 * P * B * G
+    own_bytes = {"dbf": in_bytes + beam_bytes, "pc_fft": beam_bytes + pc_bytes, "pc_narrow": 0,
+                 "mtd": pc_bytes + out_bytes + out_bytes // 2, "cfar_refine": 2 * (out_bytes // 2) * (B - 1) // B}
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(name)
+            traffic = json.load(fh).get(name, {}).get(dominant)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": f"whole chain ({info['kernels_per_cpi']} kernels per CPI)",
-                "algorithmic_bytes_per_cpi": alg_bytes,
+    dom_ms = per_cpi_ms.get(dominant, 0.0)
+    dom_achieved = own_bytes.get(dominant, 0) / (dom_ms / 1e3) / 1e9 if dom_ms else 0.0
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": dom_achieved, "peak": peak, "unit": "GB/s",
+                "frac": dom_achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": own_bytes.get(dominant), "launch_ms": round(dom_ms, 5),
                 "kernels_ms_per_cpi": {k: round(v, 5) for k, v in per_cpi_ms.items()},
                 "kernels_share": {k: round(v / kern_sum, 4) for k, v in per_cpi_ms.items()} if kern_sum else {},
-                "dominant_kernel": dominant}
+                "note": "dominant kernel by device time; it is fp32-issue bound (ncu: FP32 pipe 38 %, issue 55 %), "
+                        "see DESIGN.md section 4; the chain-level figure is chain_roofline"}
+    chain_roofline = {"bound": "hbm", "achieved": chain_achieved, "peak": peak, "unit": "GB/s", "frac": chain_achieved / peak,
+                      "algorithmic_bytes_per_cpi": alg_bytes, "kernels_per_cpi": info["kernels_per_cpi"],
+                      "note": "8*P*N*C + 8*B*P*G bytes per CPI (SURVEY 8(d)) / device time per CPI of the timed region"}
 
-    # end to end through the C ABI with HOST buffers: H2D of the cube + D2H of the detection list per CPI
+    # end to end through the C ABI with HOST buffers: per CPI a 67 MB H2D copy of the pinned cube and a D2H
+    # read of its sorted detection list, both inside the timed region.  rsp_submit_cpi pipelines the copy of
+    # cube i+1 under the kernels of cube i (depth = lanes); rsp_stream_fetch collects in order.
     pinned = torch.from_numpy(host_pool[: min(pool_n, 4)]).pin_memory()
+    cubes = [pinned[i].numpy() for i in range(len(pinned))]
     e2e_n = max(args.e2e_cpis, 2)
-    for i in range(2):
-        chain.process_cpi(pinned[i % len(pinned)].numpy())
+    depth = 3
+
+    def e2e_pass(n):
+        nd = 0
+        for i in range(n + depth):
+            if i < n:
+                chain.submit_cpi(cubes[i % len(cubes)], i % slots)
+            if i >= depth:
+                nd += len(chain.stream_fetch((i - depth) % slots))
+        return nd
+    e2e_pass(4)
     barrier()
     t0 = time.perf_counter()
-    nd = 0
-    for i in range(e2e_n):
-        nd += len(chain.process_cpi(pinned[i % len(pinned)].numpy()))
+    nd = e2e_pass(e2e_n)
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
     t_e = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
@@ -321,11 +354,31 @@ def main():
     e2e_value = world * e2e_n / float(t_e.item())
     d2h = 4 + 40 * (nd // e2e_n)
 
+    # the reference's own signature: fun_process_single_frame(targets, ...) -> final_targets.  Only the
+    # target list goes in and the clustered targets come out; S4 (echo synthesis + noise) runs on the GPU.
+    chain.set_waveform(config, pd)
+    v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+    tlist = [dict(Range=900.0, Velocity=0.15 * v_max, ElevationAngle=-5.0, SNR_dB=20.0),
+             dict(Range=3000.0, Velocity=-0.10 * v_max, ElevationAngle=8.2, SNR_dB=10.0),
+             dict(Range=8000.0, Velocity=0.05 * v_max, ElevationAngle=15.0, SNR_dB=10.0)]
+    for i in range(2):
+        chain.process_targets(tlist, cluster_params, 1.0, seed=i)
+    barrier()
+    n_t = max(args.e2e_cpis, 8)
+    t0 = time.perf_counter()
+    n_fin = 0
+    for i in range(n_t):
+        fin, _ = chain.process_targets(tlist, cluster_params, 1.0, seed=100 + i)
+        n_fin += len(fin)
+    torch.cuda.synchronize()
+    e2e_targets = world * n_t / (time.perf_counter() - t0)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu = args.cpu_cpis or {"cfg1": 40, "cfg2": 12, "cfg3": 2, "native": 2}[name]
-        v_all, dt_all, _ = cpu_reference_time(name, n_cpu, cores)
+        with _all_threads(cores):
+            v_all, dt_all, _ = cpu_reference_time(name, n_cpu, cores)
         v_one, dt_one, _ = cpu_reference_time(name, max(1, n_cpu // 4), 1)
         cpu_baseline = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n_cpu} CPIs of {name} ({dt_all:.1f} s), fp64 NumPy/SciPy oracle S5..S9 "
@@ -346,9 +399,15 @@ def main():
                        "fft_len_long": info["fft_len_long"]},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
-                    "cpis": e2e_n, "note": "rsp_process_cpi with pinned host cube in, sorted detection list out, per CPI"},
+                    "cpis": e2e_n, "note": "C ABI with host buffers: rsp_submit_cpi (pinned 67 MB cube H2D + chain, pipelined "
+                                           "3 deep) and rsp_stream_fetch (sorted detection list D2H) per CPI; PCIe-bound"},
+            "e2e_targets": {"value": e2e_targets, "unit": "frames/s", "frames": n_t, "final_targets_per_frame": n_fin / n_t,
+                            "note": "the reference's own call signature fun_process_single_frame(targets, ...): "
+                                    "rsp_process_targets = device echo synthesis + noise, S5..S9, host clustering; "
+                                    "synchronous, one frame at a time"},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "chain_roofline": chain_roofline,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

@@ -148,6 +148,10 @@ int rsp_process_cpi(rsp_ctx* ctx, const void* raw, rsp_layout layout, rsp_dtype 
  * (first_slot + i) of the context's device detection ring.  Returns after enqueueing. */
 int rsp_stream_enqueue(rsp_ctx* ctx, const void* raw_dev, int32_t raw_pool, void* rdm_dev, int32_t rdm_pool,
                        int32_t n_cpi, int32_t first_slot);
+/* Pipelined host-input path: enqueue the host->device copy of one PCN complex64 cube (pinned host memory
+ * for true overlap) and its chain on lane (slot % lanes), and return at once; the copy of cube i+1 then
+ * overlaps the kernels of cube i.  Collect with rsp_stream_fetch(ctx, slot, ...), which waits for that slot. */
+int rsp_submit_cpi(rsp_ctx* ctx, const void* raw_host, void* rdm_dev /* may be NULL */, int32_t slot);
 int rsp_stream_slots(const rsp_ctx* ctx);                 /* capacity of the detection ring (CPIs) */
 /* Raw device pointers to the ring: counts[slot] (int32) and records[slot][max_detections] (unsorted). */
 int rsp_stream_device_buffers(rsp_ctx* ctx, void** counts_dev, void** records_dev);

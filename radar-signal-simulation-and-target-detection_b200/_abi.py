@@ -93,6 +93,7 @@ SYMBOLS = [
     ("rsp_synchronize", C.c_int, [_P]),
     ("rsp_process_cpi", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int32, C.POINTER(C.c_int32)]),
     ("rsp_stream_enqueue", C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32]),
+    ("rsp_submit_cpi", C.c_int, [_P, _P, _P, C.c_int32]),
     ("rsp_stream_slots", C.c_int, [_P]),
     ("rsp_stream_device_buffers", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     ("rsp_stream_fetch", C.c_int, [_P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32)]),

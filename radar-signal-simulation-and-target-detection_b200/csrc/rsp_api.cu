@@ -41,8 +41,10 @@ struct rsp_ctx {
         float2* beam = nullptr;
         float2* pc = nullptr;
         float* amp = nullptr;
+        float2* raw = nullptr;            // staging cube of the pipelined host-input path (lazy)
         cudaEvent_t done = nullptr;
     };
+    std::vector<int> slot_lane;           // lane that last produced each ring slot (-1: joined to the caller's stream)
     Lane lanes[8];
     int n_lanes = 1;
     Lane* cur = nullptr;                  // lane the launch helpers enqueue on
@@ -189,7 +191,7 @@ void rsp_destroy(rsp_ctx* c) {
     cudaSetDevice(c->prm.device);
     cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_rdm);
     for (auto& ln : c->lanes) {
-        cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp);
+        cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp); cudaFree(ln.raw);
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
     }
@@ -276,6 +278,7 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     CUC(dev_alloc(&c->d_counts, (size_t)c->slots));
     CUC(dev_alloc(&c->d_recs, (size_t)c->slots * p->max_detections));
     CUC(cudaMemset(c->d_counts, 0, (size_t)c->slots * sizeof(int)));
+    c->slot_lane.assign((size_t)c->slots, -1);
     CUC(dev_alloc(&c->d_done, (size_t)c->slots));
     CUC(cudaMemset(c->d_done, 0, (size_t)c->slots * sizeof(int)));
     CUC(cudaMallocHost(reinterpret_cast<void**>(&c->h_count), sizeof(int)));
@@ -649,6 +652,11 @@ static int stage_input(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype
 }
 
 static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+    const int l = c->slot_lane[slot];
+    if (l > 0) {                          // produced by rsp_submit_cpi on another lane: order the read after it
+        CU(c, cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
+        c->slot_lane[slot] = -1;
+    }
     CU(c, cudaMemcpyAsync(c->h_count, c->d_counts + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     const int n = *c->h_count;
@@ -705,12 +713,33 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
         float2* rdm = (rdm_dev && rdm_pool > 0) ? static_cast<float2*>(rdm_dev) + (size_t)(i % rdm_pool) * out_elems : c->d_rdm;
         int rc = enqueue_chain(c, in, rdm, first_slot + i, i % nl);
         if (rc) return rc;
+        c->slot_lane[first_slot + i] = -1;
     }
     c->discard = false;
     for (int l = 1; l < nl; ++l) {                   // join
         CU(c, cudaEventRecord(c->lanes[l].done, c->lanes[l].s));
         CU(c, cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
     }
+    return RSP_OK;
+}
+
+int rsp_submit_cpi(rsp_ctx* c, const void* raw_host, void* rdm_dev, int32_t slot) {
+    if (!c || !raw_host || slot < 0 || slot >= c->slots) return fail(c, RSP_ERR_INVALID_ARG, "bad submit arguments");
+    if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
+    CU(c, cudaSetDevice(c->prm.device));
+    const int l = slot % c->n_lanes;
+    rsp_ctx::Lane& ln = c->lanes[l];
+    const size_t bytes = (size_t)c->P * c->C * c->N * sizeof(float2);
+    if (!ln.raw) CU(c, cudaMalloc(reinterpret_cast<void**>(&ln.raw), bytes));
+    if (l > 0) {
+        CU(c, cudaEventRecord(c->fork, c->stream));
+        CU(c, cudaStreamWaitEvent(ln.s, c->fork, 0));
+    }
+    CU(c, cudaMemcpyAsync(ln.raw, raw_host, bytes, cudaMemcpyHostToDevice, ln.s));
+    int rc = enqueue_chain(c, ln.raw, rdm_dev ? static_cast<float2*>(rdm_dev) : c->d_rdm, slot, l);
+    if (rc) return rc;
+    if (l > 0) CU(c, cudaEventRecord(ln.done, ln.s));
+    c->slot_lane[slot] = l;
     return RSP_OK;
 }
 

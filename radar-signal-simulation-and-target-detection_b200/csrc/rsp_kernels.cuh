@@ -805,7 +805,7 @@ __device__ __forceinline__ void cfar_emit(const CfarArgs& k, int v, int g, int p
 
 // generic scalar variant (any P, any window)
 template <int TG>
-__global__ void __launch_bounds__(RSP_CFAR_THREADS, 2) cfar_kernel(const CfarArgs k) {
+__global__ void __launch_bounds__(RSP_CFAR_THREADS, 2) cfar_kernel(const __grid_constant__ CfarArgs k) {
     extern __shared__ float cfar_smem[];
     l2_discard(k.dead);
     const int P = k.c.P, G = k.c.G;
@@ -841,7 +841,7 @@ template <int TG, int RR, int RV, int GV>
 #ifndef RSP_CFAR_MINB
 #define RSP_CFAR_MINB 3
 #endif
-__global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(const CfarArgs k) {
+__global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(const __grid_constant__ CfarArgs k) {
     extern __shared__ float cfar_smem[];
     l2_discard(k.dead);
     const Cfar4Geom g = cfar4_geom(k.c, TG);

@@ -226,6 +226,15 @@ class RadarChain:
                                                 C.c_void_p(rdm_dev_ptr) if rdm_dev_ptr else C.c_void_p(), rdm_pool,
                                                 n_cpi, first_slot), self._ctx)
 
+    def submit_cpi(self, raw_host, slot: int, rdm_dev_ptr: int = 0):
+        """Pipelined host-input path: enqueue H2D + chain for one pinned PCN complex64 cube; collect with
+        stream_fetch(slot).  The caller must keep ``raw_host`` alive until the fetch."""
+        ptr, on_dev = _ptr_of(raw_host)
+        if on_dev:
+            raise ValueError("submit_cpi takes a host cube")
+        _abi.check(self._lib.rsp_submit_cpi(self._ctx, ptr, C.c_void_p(rdm_dev_ptr) if rdm_dev_ptr else C.c_void_p(), slot),
+                   self._ctx)
+
     def stream_fetch(self, slot: int) -> np.ndarray:
         dets = np.zeros(self.max_detections, dtype=DETECTION_DTYPE)
         n = C.c_int32(0)

@@ -285,3 +285,18 @@ def test_monte_carlo_sweep_statistics():
     assert std[-1] < std[-2] and std[-1] < 0.2
     assert abs(mean[-1]) < 0.3
     assert list(res["trials"]) == [24.0] * 4
+
+
+def test_pipelined_host_input_path_equals_single_cpi_path():
+    """rsp_submit_cpi / rsp_stream_fetch (host cubes, copies overlapped with kernels) must return exactly
+    what the synchronous rsp_process_cpi returns, in any interleaving of submits and fetches."""
+    import torch
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    cubes = [o.make_cube("cfg1", s)[2] for s in (0, 1, 2, 3)]
+    single = [chain.process_cpi(c) for c in cubes]
+    pinned = [torch.from_numpy(c).pin_memory().numpy() for c in cubes]
+    for i in range(8):
+        chain.submit_cpi(pinned[i % 4], i)
+    for i in (7, 0, 3, 1, 2, 6, 5, 4):
+        assert np.array_equal(chain.stream_fetch(i), single[i % 4]), i
+    chain.close()

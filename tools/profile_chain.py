@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
 ap.add_argument("--cpis", type=int, default=12)
 ap.add_argument("--pool", type=int, default=4)
+ap.add_argument("--range", action="store_true", help="bracket the enqueue with cudaProfilerStart/Stop (ncu --replay-mode range)")
 a = ap.parse_args()
 config, cfar_params, _ = rsp.named_config(a.config)
 pd = rsp.build_precomputed_data(config)
@@ -26,6 +27,14 @@ pool = torch.view_as_complex(torch.randn((a.pool, chain.P, chain.C, chain.N, 2),
 rdm = torch.empty((4, chain.B, chain.G, chain.P), dtype=torch.complex64, device="cuda")
 torch.cuda.synchronize()
 chain.set_stream(torch.cuda.current_stream().cuda_stream)
+if a.range:
+    chain.stream_enqueue(pool.data_ptr(), a.pool, rdm.data_ptr(), 4, a.cpis, 0)      # warm-up outside the range
+    chain.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
 chain.stream_enqueue(pool.data_ptr(), a.pool, rdm.data_ptr(), 4, a.cpis, 0)
 chain.synchronize()
+if a.range:
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 print("done", chain.info())
