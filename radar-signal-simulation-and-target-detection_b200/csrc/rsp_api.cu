@@ -57,6 +57,7 @@ struct rsp_ctx {
     float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
     bool dbf_tma = false;                 // TMA-fed persistent variant
+    bool dbf_tma1 = false;                // TMA-fed one-tile-per-CTA variant (bulk loads and bulk stores)
     int dbf_tma_ctas = 0;
     float* d_fir = nullptr;
     int n_fir = 0;
@@ -86,7 +87,7 @@ struct rsp_ctx {
     // detection ring
     int slots = 0;
     int* d_counts = nullptr;
-    int* d_done = nullptr;                // CFAR completion tickets, one per slot
+    RawDet* d_rawdet = nullptr;           // [slots][max_detections] what cfar_kernel records
     rsp_detection* d_recs = nullptr;
     int* h_count = nullptr;               // pinned
     rsp_detection* h_recs = nullptr;      // pinned [max_detections]
@@ -100,8 +101,8 @@ struct rsp_ctx {
     std::vector<cudaEvent_t> event_pool;
 };
 
-enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC, K_MTD, K_CFAR, K_SYNTH, K_NCLASS };
-static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft", "mtd", "cfar_refine", "synth"};
+enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC, K_MTD, K_CFAR, K_SYNTH, K_REFINE, K_NCLASS };
+static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft", "mtd", "cfar", "synth", "refine"};
 
 static cudaEvent_t take_event(rsp_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -153,6 +154,16 @@ template <typename KernelT> static cudaError_t opt_in_smem(KernelT kern, size_t 
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Cap a kernel's CTAs per SM by asking for more dynamic shared memory than it uses: co-resident kernels
+// of other lanes then keep their share of the SM (measured: CFAR at 4 CTAs/SM costs the chain 10 %).
+static size_t smem_for_occupancy(size_t needed, int max_ctas_per_sm) {
+    if (max_ctas_per_sm <= 0) return needed;
+    const size_t per_sm = 227 * 1024;
+    size_t pad_to = per_sm / (size_t)(max_ctas_per_sm + 1) + 1024;               // max_ctas + 1 no longer fit
+    pad_to = std::min(pad_to, per_sm / (size_t)max_ctas_per_sm - 2048);          // ... but max_ctas still do
+    return std::max(needed, pad_to);                                             // never below what the kernel uses
+}
+
 typedef PcCfg<1024, 16, 16, 4> Pc1024;
 typedef PcCfg<2048, 8, 16, 16> Pc2048;
 typedef PcCfg<4096, 16, 16, 16> Pc4096;
@@ -196,7 +207,7 @@ void rsp_destroy(rsp_ctx* c) {
         if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
     }
     if (c->fork) cudaEventDestroy(c->fork);
-    cudaFree(c->d_done);
+    cudaFree(c->d_rawdet);
     cudaFree(c->d_tx); cudaFree(c->d_tg);
     for (auto& sg : c->s2) { cudaFree(sg.tw1); cudaFree(sg.tw2); cudaFree(sg.H); }
     cudaFree(c->d_s2_win);
@@ -279,8 +290,7 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     CUC(dev_alloc(&c->d_recs, (size_t)c->slots * p->max_detections));
     CUC(cudaMemset(c->d_counts, 0, (size_t)c->slots * sizeof(int)));
     c->slot_lane.assign((size_t)c->slots, -1);
-    CUC(dev_alloc(&c->d_done, (size_t)c->slots));
-    CUC(cudaMemset(c->d_done, 0, (size_t)c->slots * sizeof(int)));
+    CUC(dev_alloc(&c->d_rawdet, (size_t)c->slots * p->max_detections));
     CUC(cudaMallocHost(reinterpret_cast<void**>(&c->h_count), sizeof(int)));
     CUC(cudaMallocHost(reinterpret_cast<void**>(&c->h_recs), (size_t)p->max_detections * sizeof(rsp_detection)));
 #undef CUC
@@ -336,6 +346,15 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             c->dbf_ks = C <= 16 ? 4 : 8;
             CU(c, upload(&c->d_Wfrag, make_dbf_fragments(reinterpret_cast<const double*>(k->dbf_weights), B, C, c->dbf_nt, c->dbf_ks)));
             c->dbf_tma = e && std::string(e) == "tma";             // RSP_DBF=tma: persistent cp.async.bulk-fed variant
+            c->dbf_tma1 = e && std::string(e) == "tma1";           // RSP_DBF=tma1: one tile per CTA, bulk loads + bulk stores
+            if (c->dbf_tma1) {
+                const size_t sm1 = (size_t)(C + B) * RSP_DBF_TMA_ROWB;
+                switch (c->dbf_nt * 10 + c->dbf_ks) {
+#define CASE(nt, ks) case nt * 10 + ks: CU(c, opt_in_smem(dbf_tma1_kernel<nt, ks>, sm1)); break;
+                    CASE(1, 4) CASE(2, 4) CASE(3, 4) CASE(4, 4) CASE(1, 8) CASE(2, 8) CASE(3, 8) CASE(4, 8)
+#undef CASE
+                }
+            }
             if (c->dbf_tma) {
                 const size_t sm = (size_t)RSP_DBF_TMA_STAGES * C * RSP_DBF_TMA_ROWB;
                 int nsm = 148;
@@ -391,6 +410,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         CU(c, upload(&c->d_dop_perm, c->dop.iperm));
         c->mtd_tg = RSP_MTD_TG;
         c->mtd_smem = ((size_t)P * (RSP_MTD_TG + 1) + c->dop.tw.size() + 1) * sizeof(float2);
+        { const char* e = getenv("RSP_OCC_MTD"); c->mtd_smem = smem_for_occupancy(c->mtd_smem, e ? atoi(e) : 0); }
         CU(c, mtd_opt_in(P, c->mtd_smem));
     } else {
         std::vector<float2> tw(P);
@@ -426,6 +446,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         if (const char* e = getenv("RSP_CFAR_TG")) { const int v = atoi(e); if (v == 64 || v == 32 || v == 16) c->cfar_tg = v; }
         c->cfar_smem = smem_for(c->cfar_tg);
         if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
+        { const char* e = getenv("RSP_OCC_CFAR"); c->cfar_smem = smem_for_occupancy(c->cfar_smem, e ? atoi(e) : 3); }
         const int rr = c->prm.ref_r, rv = c->prm.ref_v, gv = c->prm.guard_v;
         c->cfar_variant = (rr == 5 && rv == 5 && gv == 10) ? 1 : (rr == 5 && rv == 4 && gv == 2) ? 2 : 0;
 #define RSP_CFAR_DISPATCH(TGV, ACTION)                                                      \
@@ -477,6 +498,12 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
     const int per_cta = (RSP_DBF_MMA_THREADS / 32) * 32;
     dim3 grid((c->N + per_cta - 1) / per_cta, c->P);
     const bool vec = (c->N % 2 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+    if (vec && c->dbf_tma1) {
+        const size_t sm = (size_t)(c->C + c->B) * RSP_DBF_TMA_ROWB;
+        dim3 g1((c->N + RSP_DBF_TMA_TILE - 1) / RSP_DBF_TMA_TILE, c->P);
+        dbf_tma1_kernel<NT, KS><<<g1, RSP_DBF_T1_THREADS, sm, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
+        return;
+    }
     if (vec && c->dbf_tma) {
         const size_t sm = (size_t)RSP_DBF_TMA_STAGES * c->C * RSP_DBF_TMA_ROWB;
         const int n_tiles = c->P * ((c->N + RSP_DBF_TMA_TILE - 1) / RSP_DBF_TMA_TILE);
@@ -572,11 +599,9 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
     a.c.P = c->P; a.c.G = c->G; a.c.guard_r = c->prm.guard_r; a.c.guard_v = c->prm.guard_v;
     a.c.ref_r = c->prm.ref_r; a.c.ref_v = c->prm.ref_v; a.c.t_cfar = c->prm.t_cfar;
     a.count = c->d_counts + slot;
-    a.done = c->d_done + slot;
-    a.recs = c->d_recs + (size_t)slot * c->prm.max_detections;
+    a.raw = c->d_rawdet + (size_t)slot * c->prm.max_detections;
     a.cap = c->prm.max_detections;
-    a.range_axis = c->d_range_axis; a.vel_axis = c->d_vel_axis; a.beam_angles = c->d_beam_angles; a.k_slopes = c->d_k_slopes;
-    a.delta_r = c->delta_r; a.delta_v = c->delta_v; a.complex_mode = c->prm.monopulse_complex;
+    a.complex_mode = c->prm.monopulse_complex;
     a.dead = dead_pc(c);
     const int mR = c->prm.guard_r + c->prm.ref_r;
     const int ncut = c->G - 2 * mR, tg = c->cfar_tg;
@@ -589,10 +614,21 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
 #undef LAUNCH
 }
 
+// S9 for slots [first, first + n) on stream st: one small launch per batch
+static void launch_refine(rsp_ctx* c, int first, int n, cudaStream_t st) {
+    if (!cfar_testable(c) || n <= 0) return;
+    RefineArgs r;
+    r.counts = c->d_counts; r.raw = c->d_rawdet; r.recs = c->d_recs; r.cap = c->prm.max_detections; r.first_slot = first;
+    r.range_axis = c->d_range_axis; r.vel_axis = c->d_vel_axis; r.beam_angles = c->d_beam_angles; r.k_slopes = c->d_k_slopes;
+    r.delta_r = c->delta_r; r.delta_v = c->delta_v; r.complex_mode = c->prm.monopulse_complex;
+    c->launches++;
+    refine_kernel<<<dim3(4, n), 128, 0, st>>>(r);
+}
+
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
     int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + 1 /*mtd*/;
-    if (cfar_testable(c)) n += 1;   // cfar (+ refine in its last CTA)
+    if (cfar_testable(c)) n += 1;   // cfar (S9 is one refine launch per batch, not per CPI)
     return n;
 }
 
@@ -687,6 +723,7 @@ int rsp_process_cpi(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dt
     float2* rdm = (rdm_out && rdm_mem == RSP_MEM_DEVICE) ? static_cast<float2*>(rdm_out) : c->d_rdm;
     rc = enqueue_chain(c, d_in, rdm, 0, 0);
     if (rc) return rc;
+    launch_refine(c, 0, 1, c->stream);
     if (rdm_out && rdm_mem == RSP_MEM_HOST)
         CU(c, cudaMemcpyAsync(rdm_out, c->d_rdm, (size_t)c->P * c->B * c->G * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
     c->ran = true;
@@ -720,6 +757,8 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
         CU(c, cudaEventRecord(c->lanes[l].done, c->lanes[l].s));
         CU(c, cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
     }
+    launch_refine(c, first_slot, n_cpi, c->stream);  // S9 for the whole batch
+    CU(c, cudaGetLastError());
     return RSP_OK;
 }
 
@@ -738,6 +777,7 @@ int rsp_submit_cpi(rsp_ctx* c, const void* raw_host, void* rdm_dev, int32_t slot
     CU(c, cudaMemcpyAsync(ln.raw, raw_host, bytes, cudaMemcpyHostToDevice, ln.s));
     int rc = enqueue_chain(c, ln.raw, rdm_dev ? static_cast<float2*>(rdm_dev) : c->d_rdm, slot, l);
     if (rc) return rc;
+    launch_refine(c, slot, 1, ln.s);
     if (l > 0) CU(c, cudaEventRecord(ln.done, ln.s));
     c->slot_lane[slot] = l;
     return RSP_OK;

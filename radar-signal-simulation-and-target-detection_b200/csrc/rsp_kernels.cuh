@@ -8,8 +8,8 @@
 //   pc_fft_kernel          S6  fun_process_single_frame.m:115-125 (overlap-save blocks)
 //   mtd_kernel             S7  fun_process_single_frame.m:131-136 (power-of-two P)
 //   mtd_dft_kernel         S7  same, any P (the reference's native P = 332)
-//   cfar_kernel/cfar4_kernel  S8  fun_process_single_frame.m:172-223, with S9 (:241-298, refine_record)
-//                             done by the last CTA of the same launch
+//   cfar_kernel/cfar4_kernel  S8  fun_process_single_frame.m:172-223 (records cell + the 12 values S9 needs)
+//   refine_kernel             S9  fun_process_single_frame.m:241-298, one launch per batch of CPIs
 #pragma once
 #include <cuda_runtime.h>
 #include "rsp.h"
@@ -516,6 +516,92 @@ __global__ void __launch_bounds__(RSP_DBF_TMA_THREADS) dbf_tma_kernel(const floa
 }
 
 // ------------------------------------------------------------------------------------------
+// S5, one-tile-per-CTA TMA variant: like dbf_mma_kernel (one CTA per 128-sample tile, no persistence, many
+// CTAs per SM hide latency) but the tile arrives by cp.async.bulk (no LSU data-pipe wavefronts for the
+// 64 KB/line-strided input: a streaming L1 miss costs the LSU one wavefront per 32-byte sector, a bulk copy
+// none) and leaves by cp.async.bulk stores from a shared-memory staging tile.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+#define RSP_DBF_T1_THREADS 128
+template <int NT, int KS>
+__global__ void __launch_bounds__(RSP_DBF_T1_THREADS) dbf_tma1_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
+                                                                      const float4* __restrict__ Wfrag, int C, int NB, int N,
+                                                                      int ldb, int* __restrict__ det_count, const DiscardArgs dead) {
+    extern __shared__ __align__(128) unsigned char t1_smem[];          // [C rows x ROWB] input | [NB rows x ROWB] output
+    __shared__ __align__(8) unsigned long long bar;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    l2_discard(dead);
+    if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;
+    const int p = blockIdx.y, n0 = blockIdx.x * RSP_DBF_TMA_TILE;
+    const uint32_t row_bytes = (uint32_t)min(RSP_DBF_TMA_TILE, N - n0) * 8u;
+    unsigned char* out_tile = t1_smem + (size_t)C * RSP_DBF_TMA_ROWB;
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(smem_u32(&bar), row_bytes * (uint32_t)C);
+        const float2* src = raw + (size_t)p * C * N + n0;
+        for (int c = 0; c < C; ++c) bulk_g2s(smem_u32(t1_smem) + c * RSP_DBF_TMA_ROWB, src + (size_t)c * N, row_bytes, smem_u32(&bar));
+    }
+    __syncthreads();                                   // barrier initialised and armed before anyone waits
+    mbar_wait(smem_u32(&bar), 0);
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int c = 4 * ks + t;
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const float4 x = c < C ? *reinterpret_cast<const float4*>(t1_smem + c * RSP_DBF_TMA_ROWB + (32 * w + 16 * m + 2 * g) * 8)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float v[4] = {x.x, x.z, x.y, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ah[m][i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+                al[m][i] = __float_as_uint(v[i] - __uint_as_float(ah[m][i]));
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float4 wf = __ldg(Wfrag + (ks * NT + nt) * 32 + lane);
+            const uint32_t b0h = __float_as_uint(wf.x), b1h = __float_as_uint(wf.y);
+            const uint32_t b0l = __float_as_uint(wf.z), b1l = __float_as_uint(wf.w);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                mma_tf32(acc[m][nt], al[m], b0h, b1h);
+                mma_tf32(acc[m][nt], ah[m], b0l, b1l);
+                mma_tf32(acc[m][nt], ah[m], b0h, b1h);
+            }
+        }
+    }
+    // stage the beam tile [NB rows][128 samples] in shared memory, then one bulk store per beam row
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int b = 4 * nt + t;
+        if (b < NB) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                *reinterpret_cast<float4*>(out_tile + b * RSP_DBF_TMA_ROWB + (32 * w + 16 * m + 2 * g) * 8) =
+                    make_float4(acc[m][nt][0], acc[m][nt][1], acc[m][nt][2], acc[m][nt][3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copy
+    __syncthreads();
+    if (tid < NB) {
+        bulk_s2g(beam + ((size_t)p * NB + tid) * ldb + n0, smem_u32(out_tile) + tid * RSP_DBF_TMA_ROWB, row_bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until read
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // S6: pulse compression.  One CTA = Cfg::NG overlap-save blocks (one per group of Cfg::T threads);
 // work item = (line, block).  The medium-segment launch also computes the narrow-pulse FIR gates of
 // its lines (fun_process_single_frame.m:111-112,123).
@@ -719,93 +805,51 @@ __global__ void __launch_bounds__(256) doppler_notch_kernel(float2* __restrict__
 // compare per cell, compaction with one atomic per detection -- detections are rare).
 // S9: refine_kernel, one thread per detection: spline peak search + monopulse angle.
 // ------------------------------------------------------------------------------------------
+// What cfar_kernel records per detection: everything S9 needs, so that the refinement does not depend on
+// the lane's amplitude map (which the lane's next CPI overwrites) and can run once per batch.
+struct RawDet {
+    int v, r, pair;              // 0-based cell
+    float power;                 // S(v, r)
+    float yr[5];                 // S(v, r-2 .. r+2)   (range neighbours, fsf:250-256)
+    float yv[5];                 // S(v-2 .. v+2, r)   (Doppler neighbours, fsf:265-271)
+    float a_re, a_im, b_re, b_im;// amplitude mode: a_re = |rdm_A|, b_re = |rdm_B|; complex mode: rdm_A, rdm_B
+};
+
 struct CfarArgs {
     const float* amp;            // [B][G][P]
     const float2* rdm;           // [B][G][P]
     CfarParams c;
     int* count;                  // detection counter of this CPI slot (zeroed by dbf_kernel)
-    int* done;                   // CTA completion ticket of this slot (self-resetting)
-    rsp_detection* recs;         // records of this CPI slot
+    RawDet* raw;                 // raw records of this CPI slot
     int cap;
-    // S9 tables
-    const double* range_axis;
-    const double* vel_axis;
-    const double* beam_angles;
-    const double* k_slopes;
-    double delta_r, delta_v;
     int complex_mode;
     DiscardArgs dead;            // the pc cube (its last reader, mtd_kernel, has finished)
 };
 
-// S9 for record i (fun_process_single_frame.m:241-298): spline peak search on the fp32 sum map the
-// detector used, monopulse ratio from the two beams' amplitudes at the integer cell.
-__device__ __noinline__ void refine_record(const CfarArgs& k, int i) {
-    const int P = k.c.P, G = k.c.G;
-    rsp_detection d = k.recs[i];
-    const int v = d.v_idx - 1, g = d.r_idx - 1, pair = d.pair_idx - 1;
-    const float* A = k.amp + (size_t)pair * G * P;
-    const float* Bm = A + (size_t)G * P;
-    double yr[5], yv[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const size_t orr = (size_t)(g - 2 + j) * P + v, ov = (size_t)g * P + v - 2 + j;
-        yr[j] = (double)(A[orr] + Bm[orr]);
-        yv[j] = (double)(A[ov] + Bm[ov]);
-    }
-    const double r_off = rsp_spline5_peak(yr, 8) - 2.0;          // fsf:237 rInterpTimes = 8
-    const double v_off = rsp_spline5_peak(yv, 4) - 2.0;          // vInterpTimes = 4
-    d.range = k.range_axis[g] + r_off * k.delta_r;               // fsf:262
-    d.velocity = k.vel_axis[v] + v_off * k.delta_v;              // fsf:278
-    const size_t o = (size_t)g * P + v;
-    double ratio;
-    const double eps = 2.220446049250313e-16;
-    if (k.complex_mode) {                                        // mc:454-461
-        const float2 a = k.rdm[(size_t)pair * G * P + o], bb = k.rdm[(size_t)(pair + 1) * G * P + o];
-        const double nr = (double)a.x - (double)bb.x, ni = (double)a.y - (double)bb.y;
-        const double dr = (double)a.x + (double)bb.x + eps, di = (double)a.y + (double)bb.y;
-        ratio = (nr * dr + ni * di) / (dr * dr + di * di);
-    } else {                                                     // fsf:282-285
-        const double sa = (double)A[o], sb = (double)Bm[o];
-        ratio = (sa - sb) / (sa + sb + eps);
-    }
-    d.angle = 0.5 * (k.beam_angles[pair] + k.beam_angles[pair + 1]) + k.k_slopes[pair] * ratio;   // fsf:286-290
-    k.recs[i] = d;
-}
-
-// The last CTA of the grid to finish (ticket counter) refines every record of the CPI: S9 rides in
-// the tail of the CFAR launch instead of costing a launch of its own.
-__device__ __forceinline__ void cfar_finish(const CfarArgs& k) {
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int total = gridDim.x * gridDim.y;
-        const int ticket = atomicAdd(k.done, 1);
-        s_last = (ticket == total - 1);
-        if (s_last) *k.done = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int n = min(*reinterpret_cast<volatile int*>(k.count), k.cap);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) refine_record(k, i);
-}
-
-__device__ __forceinline__ void cfar_emit(const CfarArgs& k, int v, int g, int pair, float power) {
+// S is the shared-memory sum-map tile; row0 points at S(gl = CUT row, v = 0), ld = its row pitch
+__device__ __forceinline__ void cfar_emit(const CfarArgs& k, const float* row0, int ld, int v, int g, int pair, float power) {
     const int slot = atomicAdd(k.count, 1);
     if (slot >= k.cap) return;              // overflow is reported by the host from the count
-    rsp_detection d;
-    d.v_idx = v + 1;
-    d.r_idx = g + 1;
-    d.pair_idx = pair + 1;
-    d.power = power;
-    d.range = 0.0; d.velocity = 0.0; d.angle = 0.0;
-    k.recs[slot] = d;
+    RawDet d;
+    d.v = v; d.r = g; d.pair = pair; d.power = power;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        d.yr[i] = row0[(i - 2) * ld + v];
+        d.yv[i] = row0[v - 2 + i];
+    }
+    const size_t o = ((size_t)pair * k.c.G + g) * k.c.P + v, nb = (size_t)k.c.G * k.c.P;
+    if (k.complex_mode) {
+        const float2 a = k.rdm[o], b = k.rdm[o + nb];
+        d.a_re = a.x; d.a_im = a.y; d.b_re = b.x; d.b_im = b.y;
+    } else {
+        d.a_re = k.amp[o]; d.a_im = 0.f; d.b_re = k.amp[o + nb]; d.b_im = 0.f;
+    }
+    k.raw[slot] = d;
 }
 
 // generic scalar variant (any P, any window)
 template <int TG>
-__global__ void __launch_bounds__(RSP_CFAR_THREADS, 2) cfar_kernel(const __grid_constant__ CfarArgs k) {
+__global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k) {
     extern __shared__ float cfar_smem[];
     l2_discard(k.dead);
     const int P = k.c.P, G = k.c.G;
@@ -830,9 +874,8 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, 2) cfar_kernel(const __grid_
         const int gl = e / nv, v = mV + (e - gl * nv), g = g_first + gl;
         if (g >= G - mR) break;
         float cut;
-        if (cfar_decide(S, R5, D5, k.c, gl, v, &cut)) cfar_emit(k, v, g, pair, cut);
+        if (cfar_decide(S, R5, D5, k.c, gl, v, &cut)) cfar_emit(k, S + (gl + mR) * P, P, v, g, pair, cut);
     }
-    cfar_finish(k);
 }
 
 // Vectorised variant for P % 4 == 0 (see cfar4_* in rsp_phases.cuh); RR/RV/GV = compile-time range
@@ -841,7 +884,7 @@ template <int TG, int RR, int RV, int GV>
 #ifndef RSP_CFAR_MINB
 #define RSP_CFAR_MINB 3
 #endif
-__global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(const __grid_constant__ CfarArgs k) {
+__global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(const CfarArgs k) {
     extern __shared__ float cfar_smem[];
     l2_discard(k.dead);
     const Cfar4Geom g = cfar4_geom(k.c, TG);
@@ -897,10 +940,57 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(
         while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
-            cfar_emit(k, 4 * c4 + j, g_first + gl, pair, cut[j]);
+            cfar_emit(k, S + (gl + mR) * g.PP + RSP_CFAR_HALO, g.PP, 4 * c4 + j, g_first + gl, pair, cut[j]);
         }
     }
-    cfar_finish(k);
+}
+
+// S9 (fun_process_single_frame.m:241-298) for every raw record of slots [first_slot, first_slot + n_slots):
+// spline peak search on the fp32 sum-map neighbours the detector saw, monopulse ratio from the two
+// beams at the integer cell.  One launch per batch; blockIdx.y = slot.
+struct RefineArgs {
+    const int* counts;           // [slots]
+    const RawDet* raw;           // [slots][cap]
+    rsp_detection* recs;         // [slots][cap]
+    int cap, first_slot;
+    const double* range_axis;
+    const double* vel_axis;
+    const double* beam_angles;
+    const double* k_slopes;
+    double delta_r, delta_v;
+    int complex_mode;
+};
+
+__global__ void __launch_bounds__(128) refine_kernel(const RefineArgs k) {
+    const int slot = k.first_slot + blockIdx.y;
+    const int n = min(k.counts[slot], k.cap);
+    const RawDet* raw = k.raw + (size_t)slot * k.cap;
+    rsp_detection* out = k.recs + (size_t)slot * k.cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const RawDet r = raw[i];
+        double yr[5], yv[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { yr[j] = (double)r.yr[j]; yv[j] = (double)r.yv[j]; }
+        const double r_off = rsp_spline5_peak(yr, 8) - 2.0;          // fsf:237 rInterpTimes = 8
+        const double v_off = rsp_spline5_peak(yv, 4) - 2.0;          // vInterpTimes = 4
+        rsp_detection d;
+        d.v_idx = r.v + 1; d.r_idx = r.r + 1; d.pair_idx = r.pair + 1;
+        d.power = r.power;
+        d.range = k.range_axis[r.r] + r_off * k.delta_r;             // fsf:262
+        d.velocity = k.vel_axis[r.v] + v_off * k.delta_v;            // fsf:278
+        double ratio;
+        const double eps = 2.220446049250313e-16;
+        if (k.complex_mode) {                                        // mc:454-461
+            const double nr = (double)r.a_re - (double)r.b_re, ni = (double)r.a_im - (double)r.b_im;
+            const double dr = (double)r.a_re + (double)r.b_re + eps, di = (double)r.a_im + (double)r.b_im;
+            ratio = (nr * dr + ni * di) / (dr * dr + di * di);
+        } else {                                                     // fsf:282-285
+            const double sa = (double)r.a_re, sb = (double)r.b_re;
+            ratio = (sa - sb) / (sa + sb + eps);
+        }
+        d.angle = 0.5 * (k.beam_angles[r.pair] + k.beam_angles[r.pair + 1]) + k.k_slopes[r.pair] * ratio;   // fsf:286-290
+        out[i] = d;
+    }
 }
 
 }  // namespace rsp

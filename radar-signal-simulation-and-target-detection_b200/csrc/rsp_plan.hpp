@@ -109,7 +109,7 @@ inline int choose_pc_len(int ntaps, int ngates) {
     double bc = 1e300;
     for (int i = 0; i < 3; ++i) {
         const double c = pc_plan_cost(cands[i], ntaps, ngates);
-        if (c <= bc) { bc = c; best = cands[i]; }   // ties: the longer block
+        if (c < bc) { bc = c; best = cands[i]; }    // ties: the shorter block (its first pass is a cheaper radix; measured +2 %)
     }
     return best;
 }
