@@ -300,3 +300,40 @@ def test_pipelined_host_input_path_equals_single_cpi_path():
     for i in (7, 0, 3, 1, 2, 6, 5, 4):
         assert np.array_equal(chain.stream_fetch(i), single[i % 4]), i
     chain.close()
+
+
+def test_every_dbf_variant_and_generic_paths_agree():
+    """The opt-in kernel variants (FFMA DBF, the two TMA-fed DBF kernels) must give the detections of the
+    default tensor-core kernel; odd N / non-power-of-two P / unusual CFAR windows take the generic kernels
+    and must still match the oracle."""
+    import os
+    cfg, pre, raw = o.make_cube("cfg1", 4)
+    results = {}
+    for variant in ("mma", "ffma", "tma", "tma1"):
+        os.environ["RSP_DBF"] = variant
+        try:
+            chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+            results[variant] = (chain.process_cpi(raw), chain.get_rdm())
+            chain.close()
+        finally:
+            os.environ.pop("RSP_DBF", None)
+    ref_d, ref_r = results["mma"]
+    for variant, (d, r) in results.items():
+        assert np.array_equal(d[["v_idx", "r_idx", "pair_idx"]], ref_d[["v_idx", "r_idx", "pair_idx"]]), variant
+        assert rel_errors(r, ref_r.astype(np.complex128))[0] <= 2e-6, variant
+    # generic kernels: odd N (no float4 path), P = 20 (direct Doppler DFT), windows 3/2 and 2/3 (run-time CFAR)
+    config, cfar_params, cluster_params = rsp.default_config(channel_num=16, beam_num=5, prtNum=20, point_PRT=4097)
+    cfar_params.guardCells_R, cfar_params.refCells_R, cfar_params.guardCells_V, cfar_params.refCells_V = 3, 2, 2, 3
+    pd = rsp.build_precomputed_data(config)
+    ocfg = o.shaped_config(16, 5, 20, 4097)
+    ocfg.guardCells_R, ocfg.refCells_R, ocfg.guardCells_V, ocfg.refCells_V = 3, 2, 2, 3
+    opre = o.build_precomputed(ocfg)
+    tg = [o.Target(900.0, 0.1 * opre["v_max"], -5.0, 25.0), o.Target(6000.0, -0.15 * opre["v_max"], 8.0, 20.0)]
+    raw2 = o.add_noise(o.synthesize_echo(tg, ocfg, opre), 9).astype(np.complex64)
+    res = o.process_cube(raw2.astype(np.complex128), ocfg, opre, workers=-1)
+    chain = rsp.RadarChain(config, cfar_params, pd)
+    dets = chain.process_cpi(raw2)
+    assert rel_errors(chain.get_rdm(), res.rdm)[0] <= RDM_REL_TOL
+    stats = compare_detections(dets, res.raw_detections, o.cfar_margin(res.S, ocfg), res.parameterized, opre)
+    assert stats["n_common"] >= 10
+    chain.close()
