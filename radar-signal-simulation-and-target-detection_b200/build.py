@@ -18,7 +18,7 @@ EMUL = os.path.join(LIB_DIR, "librsp_emul.so")
 
 CUDA_SOURCES = ["rsp_api.cu"]
 CXX_SOURCES = ["rsp_cluster.cpp"]
-HEADERS = ["rsp_math.cuh", "rsp_phases.cuh", "rsp_kernels.cuh", "rsp_plan.hpp"]
+HEADERS = ["rsp_math.cuh", "rsp_phases.cuh", "rsp_kernels.cuh", "rsp_plan.hpp", "rsp_dft_big.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", LIB]
         cmd += [os.path.join(CSRC, f) for f in CUDA_SOURCES + CXX_SOURCES]
         subprocess.check_call(cmd)
-    emul_deps = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "rsp_math.cuh", "rsp_phases.cuh", "rsp_plan.hpp")]
+    emul_deps = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "rsp_math.cuh", "rsp_phases.cuh", "rsp_plan.hpp", "rsp_dft_big.cuh")]
     if force or _stale(EMUL, emul_deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
                                os.path.join(CSRC, "host_emul.cpp"), "-I", CSRC, "-o", EMUL])

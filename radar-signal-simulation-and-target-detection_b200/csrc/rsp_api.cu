@@ -62,6 +62,7 @@ struct rsp_ctx {
     float* d_fir = nullptr;
     int n_fir = 0;
     PcPlan med, lng;
+    bool pc_two_pass = false;             // Pc2Cfg plans (64x64 / 32x32), RSP_PC=r64
     // stage-2 (process_stage2_mtd) plans: one per gated segment, own tables
     struct S2Seg { PcPlan pl; float2 *tw1 = nullptr, *tw2 = nullptr, *H = nullptr; int lo = 0, hi = 0; };
     S2Seg s2[3];
@@ -174,6 +175,14 @@ template <class A, class B> static size_t pc_smem_pair() { return std::max(pc_sm
 // X(long plan, medium plan)
 #define RSP_FOR_EACH_PC_PAIR(X) X(Pc1024, Pc1024) X(Pc2048, Pc1024) X(Pc4096, Pc1024) X(Pc1024, Pc2048) X(Pc2048, Pc2048) \
     X(Pc4096, Pc2048) X(Pc1024, Pc4096) X(Pc2048, Pc4096) X(Pc4096, Pc4096)
+
+typedef Pc2Cfg<4096, 64> Pc2L;
+typedef Pc2Cfg<1024, 32> Pc2S;
+template <class Cfg> static size_t pc2_smem_bytes() {
+    return (size_t)(RSP_PC2_THREADS / Cfg::T) * Cfg::SMEM_ELEMS * sizeof(float2) + 256 * sizeof(float);
+}
+template <class A, class B> static size_t pc2_smem_pair() { return std::max(pc2_smem_bytes<A>(), pc2_smem_bytes<B>()); }
+#define RSP_FOR_EACH_PC2_PAIR(X) X(Pc2L, Pc2L) X(Pc2L, Pc2S) X(Pc2S, Pc2L) X(Pc2S, Pc2S)
 
 #define RSP_FOR_EACH_POW2_P(X) X(8, 8, 1, 1) X(16, 16, 1, 1) X(32, 8, 4, 1) X(64, 8, 8, 1) X(128, 16, 8, 1) X(256, 16, 16, 1) X(512, 8, 8, 8)
 static cudaError_t mtd_opt_in(int P, size_t bytes) {
@@ -387,14 +396,26 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         int L = choose_pc_len(nt, ng);
         const char* e = getenv(env);
         if (e && atoi(e) > 0) L = atoi(e);
+        if (c->pc_two_pass) {                        // only 1024 (32 x 32) and 4096 (64 x 64) exist in this plan
+            const int L2 = (nt - 1 < 512 && (ng + 1024 - nt) / (1024 - (nt - 1)) <= 2) ? 1024 : 4096;
+            if (!make_pc2_plan(pl, L2, t.data(), nt, seg_start1 - 1, gate0, ng))
+                return fail(c, RSP_ERR_UNSUPPORTED, "no two-pass block plan for %d taps", nt);
+            return RSP_OK;
+        }
         if (!make_pc_plan(pl, L, t.data(), nt, seg_start1 - 1, gate0, ng))
             return fail(c, RSP_ERR_UNSUPPORTED, "no block plan for %d taps (L=%d)", nt, L);
         return RSP_OK;
     };
+    { const char* e = getenv("RSP_PC"); c->pc_two_pass = e && std::string(e) == "r64"; }
     int rc = plan_seg(c->med, k->mf_medium, k->n_mf_medium, c->prm.seg_start[1], g1, g2, "RSP_PC_LEN_MEDIUM");
     if (rc) return rc;
     rc = plan_seg(c->lng, k->mf_long, k->n_mf_long, c->prm.seg_start[2], g1 + g2, g3, "RSP_PC_LEN_LONG");
     if (rc) return rc;
+    if (c->pc_two_pass) {
+#define X2(A, B) CU(c, opt_in_smem(pc2_fft_kernel<A, B>, pc2_smem_pair<A, B>()));
+        RSP_FOR_EACH_PC2_PAIR(X2)
+#undef X2
+    }
     if (c->med.L) { CU(c, upload(&c->d_med_tw1, c->med.tw1)); CU(c, upload(&c->d_med_tw2, c->med.tw2)); CU(c, upload(&c->d_med_H, c->med.Hmid)); }
     if (c->lng.L) { CU(c, upload(&c->d_lng_tw1, c->lng.tw1)); CU(c, upload(&c->d_lng_tw2, c->lng.tw2)); CU(c, upload(&c->d_lng_H, c->lng.Hmid)); }
 #define X(A, B) CU(c, opt_in_smem(pc_fft_kernel<A, B>, pc_smem_pair<A, B>()));
@@ -539,7 +560,7 @@ static void fill_seg(const rsp_ctx* c, PcSegArgs& sg, const PcPlan& pl, const fl
     sg.seg_start0 = pl.seg_start0; sg.in_lo = pl.seg_start0; sg.in_hi = c->N; sg.taps = pl.taps; sg.gate0 = pl.gate0; sg.g_end = pl.gate0 + pl.ngates; sg.valid = pl.valid;
     sg.nblk = pl.nblk;
     sg.n_items = pl.L ? c->P * c->B * pl.nblk : 0;
-    const int ng = pl.L ? RSP_PC_THREADS / pl.T : 1;
+    const int ng = pl.L ? (c->pc_two_pass ? RSP_PC2_THREADS : RSP_PC_THREADS) / pl.T : 1;
     sg.n_ctas = (sg.n_items + ng - 1) / ng;
 }
 
@@ -563,6 +584,12 @@ static void launch_pc(rsp_ctx* c) {
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
     const int la = c->lng.L ? c->lng.L : 1024, lb = c->med.L ? c->med.L : 1024;
     Timed t(c, K_PC);
+    if (c->pc_two_pass) {
+#define X2(A, B) if (la == A::L && lb == B::L) pc2_fft_kernel<A, B><<<nctas, RSP_PC2_THREADS, pc2_smem_pair<A, B>(), c->cur->s>>>(a);
+        RSP_FOR_EACH_PC2_PAIR(X2)
+#undef X2
+        return;
+    }
 #define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
     RSP_FOR_EACH_PC_PAIR(X)
 #undef X

@@ -686,6 +686,61 @@ __global__ void __launch_bounds__(RSP_PC_THREADS, 3) pc_fft_kernel(const PcKerne
     else pc_role<CfgB>(k, k.seg[1], blockIdx.x - k.seg[0].n_ctas, pc_smem, k.do_narrow != 0);
 }
 
+// Two-pass variant (Pc2Cfg: 64 x 64 = 4096-point and 32 x 32 = 1024-point blocks, N threads per block,
+// N points per thread in registers).  Same roles and work list as pc_fft_kernel.
+#define RSP_PC2_THREADS 128
+#ifndef RSP_PC2_MINB
+#define RSP_PC2_MINB 2
+#endif
+template <class Cfg>
+__device__ __forceinline__ void pc2_role(const PcKernelArgs& k, const PcSegArgs& sg, int cta, float2* smem, bool narrow) {
+    constexpr int NG = RSP_PC2_THREADS / Cfg::T;
+    float* sfir = reinterpret_cast<float*>(smem + NG * Cfg::SMEM_ELEMS);
+    if (narrow)
+        for (int i = threadIdx.x; i < k.nfir; i += RSP_PC2_THREADS) sfir[i] = k.fir[i];
+    const int grp = threadIdx.x / Cfg::T, t = threadIdx.x - grp * Cfg::T;
+    const int item = cta * NG + grp;
+    const bool active = item < sg.n_items;
+    const int line = active ? item / sg.nblk : 0, blk = active ? item - line * sg.nblk : 0;
+    float2* s = smem + grp * Cfg::SMEM_ELEMS;
+    PcBlockArgs a;
+    a.line = k.beam + (size_t)line * k.ldb;
+    a.out_line = k.pc + (size_t)line * k.ldg;
+    a.tw1 = sg.tw1;
+    a.tw2 = nullptr;
+    a.Hmid = sg.Hmid;
+    a.in_lo = sg.in_lo;
+    a.in_hi = sg.in_hi;
+    a.seg_start0 = sg.seg_start0;
+    a.taps = sg.taps;
+    a.g0 = sg.gate0 + blk * sg.valid;
+    a.g_end = sg.g_end;
+    if (active) pc2_phase_a<Cfg>(a, s, t);
+    __syncthreads();
+    if (active) pc2_phase_b<Cfg>(a, s, t);
+    __syncthreads();
+    if (active) pc2_phase_c<Cfg>(a, s, t);
+    if (narrow) {                                   // uniform over the CTA
+        const int need = k.narrow_gates + k.fir_delay;
+        const bool fast = need <= k.N - k.narrow_start0 && need <= Cfg::SMEM_ELEMS;
+        __syncthreads();
+        if (active && blk == 0 && fast)
+            for (int i = t; i < need; i += Cfg::T) s[i] = a.line[k.narrow_start0 + i];
+        __syncthreads();
+        if (active && blk == 0)
+            for (int g = t; g < k.narrow_gates; g += Cfg::T)
+                a.out_line[g] = fast ? pc_narrow_gate_smem(s, sfir, k.nfir, k.fir_delay, g)
+                                     : pc_narrow_gate(a.line, k.N, k.narrow_start0, sfir, k.nfir, k.fir_delay, g);
+    }
+}
+
+template <class CfgA, class CfgB>
+__global__ void __launch_bounds__(RSP_PC2_THREADS, RSP_PC2_MINB) pc2_fft_kernel(const PcKernelArgs k) {
+    extern __shared__ float2 pc_smem[];
+    if ((int)blockIdx.x < k.seg[0].n_ctas) pc2_role<CfgA>(k, k.seg[0], blockIdx.x, pc_smem, false);
+    else pc2_role<CfgB>(k, k.seg[1], blockIdx.x - k.seg[0].n_ctas, pc_smem, k.do_narrow != 0);
+}
+
 __global__ void __launch_bounds__(256) pc_narrow_kernel(const float2* __restrict__ beam, float2* __restrict__ pc,
                                                         const float* __restrict__ fir, int nfir, int fir_delay, int N,
                                                         int ldb, int ldg, int seg_start0, int ngates) {

@@ -32,7 +32,7 @@ def emul_lib():
     """Host-compiled kernel phases (csrc/host_emul.cpp); built on demand with g++ (no GPU)."""
     so = os.path.join(PKG_DIR, "lib", "librsp_emul.so")
     src = os.path.join(PKG_DIR, "csrc", "host_emul.cpp")
-    deps = [src] + [os.path.join(PKG_DIR, "csrc", f) for f in ("rsp_math.cuh", "rsp_phases.cuh", "rsp_plan.hpp")]
+    deps = [src] + [os.path.join(PKG_DIR, "csrc", f) for f in ("rsp_math.cuh", "rsp_phases.cuh", "rsp_plan.hpp", "rsp_dft_big.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src,

@@ -30,7 +30,7 @@ def cfg1():
     return cfg, pre, beam, pc
 
 
-@pytest.mark.parametrize("R", [2, 4, 8, 16])
+@pytest.mark.parametrize("R", [2, 4, 8, 16, 32, 64])
 @pytest.mark.parametrize("sign", [-1, 1])
 def test_small_dft(lib, R, sign):
     rng = np.random.default_rng(R * 7 + sign)
@@ -71,6 +71,29 @@ def test_pc_overlap_save_matches_reference_fft_convolution(lib, cfg1, seg, L):
         ref = pc[p, b, gate0:gate0 + ng]
         assert np.abs(out[gate0:gate0 + ng] - ref).max() <= 2e-6 * np.abs(ref).max()
         # the block writer must not touch gates owned by the other segments
+        assert not out[:gate0].any() and not out[gate0 + ng:].any()
+
+
+@pytest.mark.parametrize("seg,L", [("medium", 1024), ("medium", 4096), ("long", 4096), ("long", 1024)])
+def test_pc_two_pass_blocks_match_reference(lib, cfg1, seg, L):
+    """The N x N register-resident plan (64 x 64, 32 x 32) of pc2_fft_kernel."""
+    cfg, pre, beam, pc = cfg1
+    N, G = cfg.point_PRT, cfg.n_gates
+    g1, g2 = pre["N_gate_narrow"], pre["N_gate_medium"]
+    if seg == "medium":
+        ss, gate0, ng, taps = pre["seg_start_medium"] - 1, g1, g2, pre["MF_medium_win"]
+    else:
+        ss, gate0, ng, taps = pre["seg_start_long"] - 1, g1 + g2, G - g1 - g2, pre["MF_long_win"]
+    t = np.ascontiguousarray(np.stack([taps.real, taps.imag], -1))
+    for (p, b) in ((3, 2), (31, 0)):
+        line = np.ascontiguousarray(beam[p, b].astype(np.complex64))
+        out = np.zeros(G, np.complex64)
+        nb = ctypes.c_int()
+        rc = lib.emul_pc2_segment(line.ctypes.data_as(fp), N, int(ss), int(gate0), int(ng), t.ctypes.data_as(dp), len(taps), L,
+                                  out.ctypes.data_as(fp), ctypes.byref(nb))
+        assert rc == 0
+        ref = pc[p, b, gate0:gate0 + ng]
+        assert np.abs(out[gate0:gate0 + ng] - ref).max() <= 2e-6 * np.abs(ref).max()
         assert not out[:gate0].any() and not out[gate0 + ng:].any()
 
 
