@@ -149,6 +149,30 @@ int emul_mtd_tile(const float* x, int P, int TG, const float* win, float* out /*
     return 0;
 }
 
+// generic Doppler DFT (any P = R * Q): the work items of mtd_dft_kernel<TG, R>
+int emul_mtd_dft_tile(const float* x /* [P][TG] */, int P, int TG, const float* win, float* out /* [TG][P] */) {
+    const int R = (P % 8 == 0) ? 8 : (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1, Q = P / R;
+    const cf* xi = reinterpret_cast<const cf*>(x);
+    std::vector<cf> xin((size_t)P * (TG + 1)), xout((size_t)P * (TG + 1)), stw(P);
+    for (int m = 0; m < P; ++m) {
+        const double ang = -2.0 * kPi * m / P;
+        stw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    for (int p = 0; p < P; ++p)
+        for (int gl = 0; gl < TG; ++gl) xin[(size_t)p * (TG + 1) + gl] = cscale(xi[(size_t)p * TG + gl], win[p]);
+    for (int k = 0; k < Q; ++k)
+        for (int gl = 0; gl < TG; ++gl) {
+            if (R == 8) mtd_dft_item<8>(xin.data(), xout.data(), stw.data(), P, TG, k, gl);
+            else if (R == 4) mtd_dft_item<4>(xin.data(), xout.data(), stw.data(), P, TG, k, gl);
+            else if (R == 2) mtd_dft_item<2>(xin.data(), xout.data(), stw.data(), P, TG, k, gl);
+            else mtd_dft_item<1>(xin.data(), xout.data(), stw.data(), P, TG, k, gl);
+        }
+    cf* o = reinterpret_cast<cf*>(out);
+    for (int gl = 0; gl < TG; ++gl)
+        for (int row = 0; row < P; ++row) o[(size_t)gl * P + row] = xout[(size_t)row * (TG + 1) + gl];
+    return 0;
+}
+
 // CFAR over a full sum map S[G][P] (one pair) using the two tile phases on tiles of TG gates.
 int emul_cfar_map(const float* S, int G, int P, int guard_r, int guard_v, int ref_r, int ref_v, float t_cfar, int TG,
                   unsigned char* det /* [G][P] */) {

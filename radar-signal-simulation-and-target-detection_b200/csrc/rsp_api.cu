@@ -92,7 +92,7 @@ struct rsp_ctx {
     rsp_detection* d_recs = nullptr;
     int* h_count = nullptr;               // pinned
     rsp_detection* h_recs = nullptr;      // pinned [max_detections]
-    int mtd_tg = 32, cfar_tg = 32, cfar_variant = 0;
+    int mtd_tg = 32, mtd_r = 1, cfar_tg = 32, cfar_variant = 0;
     bool cfar_vec = false;
     size_t mtd_smem = 0, cfar_smem = 0;
     // per-kernel event timing (rsp_set_profiling)
@@ -184,6 +184,8 @@ template <class Cfg> static size_t pc2_smem_bytes() {
 template <class A, class B> static size_t pc2_smem_pair() { return std::max(pc2_smem_bytes<A>(), pc2_smem_bytes<B>()); }
 #define RSP_FOR_EACH_PC2_PAIR(X) X(Pc2L, Pc2L) X(Pc2L, Pc2S) X(Pc2S, Pc2L) X(Pc2S, Pc2S)
 
+// generic Doppler DFT kernel: (tile gates, power-of-two factor R of P)
+#define RSP_FOR_EACH_DFT(X) X(32, 1) X(32, 2) X(32, 4) X(32, 8) X(16, 1) X(16, 2) X(16, 4) X(16, 8) X(8, 1) X(8, 2) X(8, 4) X(8, 8)
 #define RSP_FOR_EACH_POW2_P(X) X(8, 8, 1, 1) X(16, 16, 1, 1) X(32, 8, 4, 1) X(64, 8, 8, 1) X(128, 16, 8, 1) X(256, 16, 16, 1) X(512, 8, 8, 8)
 static cudaError_t mtd_opt_in(int P, size_t bytes) {
     switch (P) {
@@ -448,9 +450,10 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             if (sm <= 200 * 1024) { c->mtd_tg = tg; c->mtd_smem = sm; break; }
         }
         if (!c->mtd_tg) return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
-        if (c->mtd_tg == 32) CU(c, opt_in_smem(mtd_dft_kernel<32>, c->mtd_smem));
-        if (c->mtd_tg == 16) CU(c, opt_in_smem(mtd_dft_kernel<16>, c->mtd_smem));
-        if (c->mtd_tg == 8) CU(c, opt_in_smem(mtd_dft_kernel<8>, c->mtd_smem));
+        c->mtd_r = (P % 8 == 0) ? 8 : (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1;
+#define X(tg, r) if (c->mtd_tg == tg && c->mtd_r == r) CU(c, opt_in_smem(mtd_dft_kernel<tg, r>, c->mtd_smem));
+        RSP_FOR_EACH_DFT(X)
+#undef X
     }
     CU(c, upload(&c->d_win, win));
     {   // CFAR tile height: the largest of {64,32,16} whose shared arrays stay under 80 KB
@@ -609,9 +612,11 @@ static void launch_mtd(rsp_ctx* c, float2* rdm) {
             RSP_FOR_EACH_POW2_P(X)
 #undef X
         }
-    } else if (tg == 32) mtd_dft_kernel<32><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
-    else if (tg == 16) mtd_dft_kernel<16><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
-    else mtd_dft_kernel<8><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
+    } else {
+#define X(tgv, r) if (tg == tgv && c->mtd_r == r) mtd_dft_kernel<tgv, r><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
+        RSP_FOR_EACH_DFT(X)
+#undef X
+    }
 }
 
 static bool cfar_testable(const rsp_ctx* c) {
@@ -938,9 +943,10 @@ int rsp_stage2_configure(rsp_ctx* c, const rsp_stage2_config* cfg) {
             if (sm <= 200 * 1024) { c->mtd_tg = tg; c->mtd_smem = sm; break; }
         }
         if (!c->mtd_tg) return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
-        if (c->mtd_tg == 32) CU(c, opt_in_smem(mtd_dft_kernel<32>, c->mtd_smem));
-        if (c->mtd_tg == 16) CU(c, opt_in_smem(mtd_dft_kernel<16>, c->mtd_smem));
-        if (c->mtd_tg == 8) CU(c, opt_in_smem(mtd_dft_kernel<8>, c->mtd_smem));
+        c->mtd_r = (P % 8 == 0) ? 8 : (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1;
+#define X(tg, r) if (c->mtd_tg == tg && c->mtd_r == r) CU(c, opt_in_smem(mtd_dft_kernel<tg, r>, c->mtd_smem));
+        RSP_FOR_EACH_DFT(X)
+#undef X
     }
     c->s2_notch = cfg->zero_vel_bins < 0 ? 0 : cfg->zero_vel_bins;
     c->s2_ready = true;

@@ -799,11 +799,11 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
     }
 }
 
-template <int TG>
+template <int TG, int R>
 __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs k) {
     extern __shared__ float2 mtd_smem[];
     l2_discard(k.dead);
-    const int P = k.P;
+    const int P = k.P, Q = P / R;
     float2* xin = mtd_smem;
     float2* xout = xin + (size_t)P * (TG + 1);
     float2* stw = xout + (size_t)P * (TG + 1);
@@ -817,22 +817,9 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs 
         xin[p * (TG + 1) + gl] = cscale(x, k.win[p]);
     }
     __syncthreads();
-    const int half = P / 2;
-    for (int e = tid; e < P * TG; e += RSP_MTD_THREADS) {
-        const int f = e / TG, gl = e - f * TG;
-        float2 acc = make_float2(0.f, 0.f);
-        int idx = 0;
-        for (int p = 0; p < P; ++p) {
-            const float2 w = stw[idx];
-            const float2 x = xin[p * (TG + 1) + gl];
-            acc.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, acc.x));
-            acc.y = fmaf(x.x, w.y, fmaf(x.y, w.x, acc.y));
-            idx += f;
-            if (idx >= P) idx -= P;
-        }
-        int row = f + half;                 // fftshift(.,1): bin f moves to (f + floor(P/2)) mod P
-        if (row >= P) row -= P;
-        xout[row * (TG + 1) + gl] = acc;
+    for (int e = tid; e < Q * TG; e += RSP_MTD_THREADS) {
+        const int kk = e / TG, gl = e - kk * TG;
+        mtd_dft_item<R>(xin, xout, stw, P, TG, kk, gl);
     }
     __syncthreads();
     for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {

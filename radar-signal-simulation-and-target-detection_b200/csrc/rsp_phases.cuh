@@ -357,6 +357,42 @@ template <class Cfg> RSP_HD void mtd_passes_phase(cf* s, const cf* tw, int tid, 
 }
 
 // =============================================================================================
+// MTD for any P (the reference's native P = 332 = 4 * 83): P = R * Q with R the largest power of two <= 8
+// dividing P.  Work item (k < Q, gate): the R length-Q DFTs of the decimated sequences x[a + R n] share
+// their twiddle W_Q^{nk} (direct sums, Q^2 each), then one radix-R butterfly with W_P^{ak} gives the R
+// outputs X[k + Q d].  R * Q^2 = P * Q multiply-adds per line instead of P^2.
+//   xin[p*(TG+1) + gl] windowed input, xout[row*(TG+1) + gl] fftshifted output, stw[m] = e^{-2 pi i m/P}.
+// =============================================================================================
+template <int R> RSP_HD void mtd_dft_item(const cf* xin, cf* xout, const cf* stw, int P, int TG, int k, int gl) {
+    const int Q = P / R, ld = TG + 1;
+    cf acc[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a) acc[a] = make_float2(0.f, 0.f);
+    int idx = 0;                                        // (n k) mod Q
+    for (int n = 0; n < Q; ++n) {
+        const cf w = stw[R * idx];                      // W_Q^{nk} = W_P^{R (nk mod Q)}
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+            const cf x = xin[(a + R * n) * ld + gl];
+            acc[a].x = fmaf(x.x, w.x, fmaf(-x.y, w.y, acc[a].x));
+            acc[a].y = fmaf(x.x, w.y, fmaf(x.y, w.x, acc[a].y));
+        }
+        idx += k;
+        if (idx >= Q) idx -= Q;
+    }
+#pragma unroll
+    for (int a = 1; a < R; ++a) acc[a] = cmul(acc[a], stw[a * k]);     // W_P^{ak}, a k < P
+    if (R > 1) SmallDft<(R > 1 ? R : 2), -1>::run(acc);                // over a -> d
+    const int half = P / 2;
+#pragma unroll
+    for (int d = 0; d < R; ++d) {
+        int row = k + Q * d + half;                    // fftshift(.,1): bin f moves to (f + floor(P/2)) mod P
+        if (row >= P) row -= P;
+        xout[row * ld + gl] = acc[d];
+    }
+}
+
+// =============================================================================================
 // CFAR on one (pair, gate tile): S tile rows = gates [g_first - mR, g_first + TG + mR), P columns.
 //   fun_process_single_frame.m:192-213.  Two phases: window sums, then the decision.
 //     R5[row][v] = sum_{i<ref_r} S[row+i][v]      rows [0, TG + mR + guard_r + 1)

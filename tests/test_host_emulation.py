@@ -122,6 +122,19 @@ def test_mtd_tile(lib, P):
     assert np.abs(out - ref).max() <= 3e-6 * np.abs(ref).max(), list(rad)
 
 
+@pytest.mark.parametrize("P", [332, 83, 20, 166, 24, 7, 96])
+def test_mtd_generic_dft_tile(lib, P):
+    """mtd_dft_kernel's work items for P = R * Q (the native 332 = 4 * 83, odd P, P with a factor 8)."""
+    TG = 16
+    rng = np.random.default_rng(P)
+    x = (rng.standard_normal((P, TG)) + 1j * rng.standard_normal((P, TG))).astype(np.complex64)
+    win = np.kaiser(P, 4.5).astype(np.float32)
+    out = np.zeros((TG, P), np.complex64)
+    assert lib.emul_mtd_dft_tile(x.ctypes.data_as(fp), P, TG, win.ctypes.data_as(fp), out.ctypes.data_as(fp)) == 0
+    ref = np.fft.fftshift(np.fft.fft(x.astype(np.complex128) * win.astype(np.float64)[:, None], axis=0), axes=0).T
+    assert np.abs(out - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("tg", [16, 32, 64])
 @pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (150, 48, 3, 4, 2, 3)])
 def test_cfar_tiles_match_oracle(lib, shape, tg):
