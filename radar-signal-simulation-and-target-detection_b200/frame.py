@@ -68,6 +68,7 @@ class RadarChain:
         p.max_detections = self.max_detections
         p.monopulse_complex = int(bool(monopulse_complex))
         p.device = int(device)
+        self._device = int(device)
         _abi.check(self._lib.rsp_create(C.byref(p), C.byref(self._ctx)))
         self._upload(pd)
 
@@ -215,6 +216,31 @@ class RadarChain:
                                                  C.byref(cp), C.c_void_p(fin.ctypes.data), len(fin), C.byref(nf),
                                                  C.c_void_p(dets.ctypes.data), len(dets), C.byref(nd)), self._ctx)
         return fin[:nf.value].copy(), dets[:nd.value].copy()
+
+    def process_targets_batch(self, target_lists, cluster_params, noise_power: float = 1.0, seeds=None):
+        """Many independent frames at once (Monte-Carlo trials, a block of a frame stream): every frame's
+        cube is synthesised on the GPU into a device pool, the pool runs through the multi-lane stream path,
+        and only detection lists come back.  Returns [(final targets, detections), ...] in input order."""
+        import torch
+        n = len(target_lists)
+        if n == 0:
+            return []
+        if n > self.stream_slots():
+            raise ValueError(f"at most {self.stream_slots()} frames per batch")
+        seeds = list(range(n)) if seeds is None else list(seeds)
+        pool = getattr(self, "_batch_pool", None)
+        if pool is None or pool.shape[0] < n:
+            pool = torch.empty((n, self.P, self.C, self.N), dtype=torch.complex64, device=f"cuda:{self._device}")
+            self._batch_pool = pool
+        for i, tl in enumerate(target_lists):
+            self.synthesize(tl, noise_power, seeds[i], out=pool[i])
+        self.stream_enqueue(pool.data_ptr(), n, 0, 0, n, 0)
+        out = []
+        for i in range(n):
+            dets = self.stream_fetch(i)
+            _, fin = cluster(dets, cluster_params)
+            out.append((fin, dets))
+        return out
 
     # -- device-resident stream -----------------------------------------------------------------
     def stream_slots(self) -> int:

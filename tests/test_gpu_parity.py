@@ -337,3 +337,18 @@ def test_every_dbf_variant_and_generic_paths_agree():
     stats = compare_detections(dets, res.raw_detections, o.cfar_margin(res.S, ocfg), res.parameterized, opre)
     assert stats["n_common"] >= 10
     chain.close()
+
+
+def test_batched_frames_equal_one_at_a_time():
+    """process_targets_batch (device synthesis of many frames + multi-lane stream) == process_targets per frame."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    chain.set_waveform(config, pd)
+    v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+    lists = [[dict(Range=900.0 + 400 * i, Velocity=0.1 * v_max, ElevationAngle=5.0 + i, SNR_dB=15.0)] for i in range(5)] + [[]]
+    seeds = [11, 12, 13, 14, 15, 16]
+    one = [chain.process_targets(tl, cluster_params, 1.0, s) for tl, s in zip(lists, seeds)]
+    many = chain.process_targets_batch(lists, cluster_params, 1.0, seeds)
+    for (f1, d1), (f2, d2) in zip(one, many):
+        assert np.array_equal(d1, d2) and np.array_equal(f1, f2)
+    assert len(many[-1][0]) == 0
+    chain.close()

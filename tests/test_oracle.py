@@ -118,3 +118,23 @@ def test_known_answer_native_targets():
     assert fin[1, 0] == pytest.approx(9995.1, abs=1.0) and fin[1, 1] == pytest.approx(25.19, abs=0.05)
     assert np.all(np.abs(fin[:, 2] - 10.0) < 0.05)
     assert 150 <= len(g["raw_detections"]) <= 250
+
+
+def test_stage2_specification_is_a_per_segment_correlation():
+    """The semantics this repo specifies for process_stage2_mtd (the reference's callee is not shipped):
+    pc = per-segment cross-correlation with the reference pulse, mtd = fftshift(fft) with a zero-Doppler notch."""
+    rng = np.random.default_rng(0)
+    gates, P, B = [40, 90, 150], 16, 2
+    pulses = [np.ones(4, complex), np.exp(1j * rng.uniform(0, 6, 20)), np.exp(1j * rng.uniform(0, 6, 50))]
+    iq = rng.standard_normal((P, sum(gates), B)) + 1j * rng.standard_normal((P, sum(gates), B))
+    mtd, pc = o.stage2_mtd(iq, gates, pulses, None, 2)
+    g0 = 0
+    for ng, pulse in zip(gates, pulses):
+        seg = iq[3, g0:g0 + ng, 1]
+        want = np.correlate(np.concatenate([seg, np.zeros(len(pulse) - 1)]), pulse, mode="valid")
+        assert np.allclose(pc[3, g0:g0 + ng, 1], want)
+        g0 += ng
+    full = np.fft.fftshift(np.fft.fft(pc, axis=0), axes=0)
+    assert not mtd[P // 2 - 2: P // 2 + 3].any()
+    keep = np.r_[0:P // 2 - 2, P // 2 + 3:P]
+    assert np.allclose(mtd[keep], full[keep])
