@@ -73,6 +73,18 @@ def test_native_reference_shape_matches_oracle():
     chain.close()
 
 
+@pytest.mark.parametrize("scene,seed", [("v8_2", 1), ("v7_7", 2)])
+def test_native_shape_other_reference_scenes(scene, seed):
+    """The other target sets the reference's drivers define (v8_2:28-51 five targets from -20 to +15 dB,
+    v7_7:44-62 three targets at -10 dB), on the literal configuration and with different noise seeds."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("native")
+    targets = getattr(o, "targets_" + scene)()
+    cfg, pre, raw, res = _oracle_run("native", seed=seed, targets=targets)
+    dets, stats = _check_all("native/" + scene, chain, cluster_params, cfg, pre, raw, res, stages=False)
+    assert stats["n_final"] == len(res.final_targets) >= 3
+    chain.close()
+
+
 def test_cfg3_32ch_16beams_matches_oracle():
     chain, config, cfar_params, cluster_params, pd = _device_chain("cfg3")
     cfg, pre, raw, res = _oracle_run("cfg3")
