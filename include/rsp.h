@@ -216,6 +216,16 @@ int rsp_process_targets(rsp_ctx* ctx, const rsp_target_in* targets, int32_t n_ta
                         const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap, int32_t* n_final,
                         rsp_detection* dets /* may be NULL */, int32_t det_cap, int32_t* n_dets /* may be NULL */);
 
+/* Pipelined frame path (the Monte-Carlo sweep and the multi-frame tracker submit many independent frames):
+ * rsp_submit_targets enqueues S4 into the lane's own cube and S5..S9 behind it on lane (slot % lanes) and
+ * returns at once, so frame i+1 is synthesised while frame i is processed; rsp_fetch_targets waits for that
+ * slot, sorts its detections into the reference order and clusters them (S10/S11) on the host. */
+#define RSP_MAX_FRAME_TARGETS 64
+int rsp_submit_targets(rsp_ctx* ctx, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed,
+                       int32_t slot);
+int rsp_fetch_targets(rsp_ctx* ctx, int32_t slot, const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap,
+                      int32_t* n_final, rsp_detection* dets /* may be NULL */, int32_t det_cap, int32_t* n_dets /* may be NULL */);
+
 /* ---- introspection ---- */
 typedef struct {
     int32_t n_gates_total;        /* G */
@@ -223,6 +233,8 @@ typedef struct {
     int32_t kernels_per_cpi;      /* launches rsp_process_cpi / rsp_stream_enqueue issue per CPI */
     int64_t algorithmic_bytes_per_cpi;   /* 8*P*N*C + 8*B*P*G */
     int64_t launches_total;       /* kernels launched by this context so far */
+    int32_t lanes;                /* concurrent CPI lanes of the stream / pipelined paths (RSP_LANES) */
+    int32_t reserved_;
 } rsp_info;
 int rsp_get_info(const rsp_ctx* ctx, rsp_info* info);
 

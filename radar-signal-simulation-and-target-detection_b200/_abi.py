@@ -54,7 +54,8 @@ class rsp_cluster_params(C.Structure):
 class rsp_info(C.Structure):
     _fields_ = [("n_gates_total", C.c_int32), ("fft_len_medium", C.c_int32), ("fft_len_long", C.c_int32),
                 ("blocks_medium", C.c_int32), ("blocks_long", C.c_int32), ("kernels_per_cpi", C.c_int32),
-                ("algorithmic_bytes_per_cpi", C.c_int64), ("launches_total", C.c_int64)]
+                ("algorithmic_bytes_per_cpi", C.c_int64), ("launches_total", C.c_int64), ("lanes", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 class rsp_target_in(C.Structure):
@@ -112,6 +113,9 @@ SYMBOLS = [
     ("rsp_synthesize", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, _P]),
     ("rsp_process_targets", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, C.POINTER(rsp_cluster_params), _P, C.c_int32,
                                       C.POINTER(C.c_int32), _P, C.c_int32, C.POINTER(C.c_int32)]),
+    ("rsp_submit_targets", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, C.c_int32]),
+    ("rsp_fetch_targets", C.c_int, [_P, C.c_int32, C.POINTER(rsp_cluster_params), _P, C.c_int32, C.POINTER(C.c_int32), _P, C.c_int32,
+                                    C.POINTER(C.c_int32)]),
     ("rsp_get_info", C.c_int, [_P, C.POINTER(rsp_info)]),
     ("rsp_set_profiling", C.c_int, [_P, C.c_int]),
     ("rsp_get_kernel_times", C.c_int, [_P, C.POINTER(rsp_kernel_times)]),

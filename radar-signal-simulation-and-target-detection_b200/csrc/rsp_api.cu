@@ -41,7 +41,8 @@ struct rsp_ctx {
         float2* beam = nullptr;
         float2* pc = nullptr;
         float* amp = nullptr;
-        float2* raw = nullptr;            // staging cube of the pipelined host-input path (lazy)
+        float2* raw = nullptr;            // staging cube of the pipelined host-input / frame paths (lazy)
+        float2* rdm = nullptr;            // own RDM of those paths when the caller passes none (lazy; lane 0 uses d_rdm)
         cudaEvent_t done = nullptr;
     };
     std::vector<int> slot_lane;           // lane that last produced each ring slot (-1: joined to the caller's stream)
@@ -82,6 +83,8 @@ struct rsp_ctx {
     float2* d_tx = nullptr;
     SynthTarget* d_tg = nullptr;
     int tg_cap = 0;
+    SynthTarget* d_tg_ring = nullptr;     // [slots][RSP_MAX_FRAME_TARGETS] descriptors of rsp_submit_targets
+    SynthTarget* h_tg_ring = nullptr;     // pinned mirror
     rsp_waveform wf{};
     int tx_seg_lo[3] = {0, 0, 0}, tx_seg_hi[3] = {0, 0, 0};
     bool have_waveform = false;
@@ -92,6 +95,13 @@ struct rsp_ctx {
     rsp_detection* d_recs = nullptr;
     int* h_count = nullptr;               // pinned
     rsp_detection* h_recs = nullptr;      // pinned [max_detections]
+    // pipelined paths (rsp_submit_cpi / rsp_submit_targets): the count and the first prefetch_k records of a slot
+    // are copied to pinned memory behind the slot's kernels, so the fetch is one event wait and no round trip
+    int prefetch_k = 0;
+    int* h_slot_count = nullptr;          // pinned [slots]
+    rsp_detection* h_slot_recs = nullptr; // pinned [slots][prefetch_k]
+    std::vector<cudaEvent_t> slot_done;   // recorded behind the prefetch copies
+    std::vector<char> slot_prefetched;
     int mtd_tg = 32, mtd_r = 1, cfar_tg = 32, cfar_variant = 0;
     bool cfar_vec = false;
     size_t mtd_smem = 0, cfar_smem = 0;
@@ -213,13 +223,14 @@ void rsp_destroy(rsp_ctx* c) {
     cudaSetDevice(c->prm.device);
     cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_rdm);
     for (auto& ln : c->lanes) {
-        cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp); cudaFree(ln.raw);
+        cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp); cudaFree(ln.raw); cudaFree(ln.rdm);
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
     }
     if (c->fork) cudaEventDestroy(c->fork);
     cudaFree(c->d_rawdet);
-    cudaFree(c->d_tx); cudaFree(c->d_tg);
+    cudaFree(c->d_tx); cudaFree(c->d_tg); cudaFree(c->d_tg_ring);
+    if (c->h_tg_ring) cudaFreeHost(c->h_tg_ring);
     for (auto& sg : c->s2) { cudaFree(sg.tw1); cudaFree(sg.tw2); cudaFree(sg.H); }
     cudaFree(c->d_s2_win);
     cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_Wfrag); cudaFree(c->d_fir);
@@ -230,6 +241,9 @@ void rsp_destroy(rsp_ctx* c) {
     cudaFree(c->d_counts); cudaFree(c->d_recs);
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->h_recs) cudaFreeHost(c->h_recs);
+    if (c->h_slot_count) cudaFreeHost(c->h_slot_count);
+    if (c->h_slot_recs) cudaFreeHost(c->h_slot_recs);
+    for (auto e : c->slot_done) cudaEventDestroy(e);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -330,6 +344,8 @@ int rsp_set_stream(rsp_ctx* c, void* s) {
 int rsp_synchronize(rsp_ctx* c) {
     if (!c) return RSP_ERR_INVALID_ARG;
     CU(c, cudaStreamSynchronize(c->stream));
+    for (int l = 1; l < c->n_lanes; ++l)          // pipelined submissions run on the lanes' own streams
+        if (c->lanes[l].s) CU(c, cudaStreamSynchronize(c->lanes[l].s));
     return RSP_OK;
 }
 
@@ -719,25 +735,53 @@ static int stage_input(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype
     return RSP_OK;
 }
 
-static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
-    const int l = c->slot_lane[slot];
-    if (l > 0) {                          // produced by rsp_submit_cpi on another lane: order the read after it
-        CU(c, cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
-        c->slot_lane[slot] = -1;
+// end of a pipelined submission on lane l: prefetch the slot's result to pinned memory and mark the slot
+static int finish_submit(rsp_ctx* c, int slot, int l) {
+    cudaStream_t s = c->lanes[l].s;
+    if (!c->h_slot_count) {
+        c->prefetch_k = std::min(512, c->prm.max_detections);
+        CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_slot_count), (size_t)c->slots * sizeof(int)));
+        CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_slot_recs), (size_t)c->slots * c->prefetch_k * sizeof(rsp_detection)));
+        c->slot_done.resize((size_t)c->slots);
+        for (auto& e : c->slot_done) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->slot_prefetched.assign((size_t)c->slots, 0);
     }
-    CU(c, cudaMemcpyAsync(c->h_count, c->d_counts + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    const int n = *c->h_count;
+    CU(c, cudaMemcpyAsync(c->h_slot_count + slot, c->d_counts + slot, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->h_slot_recs + (size_t)slot * c->prefetch_k, c->d_recs + (size_t)slot * c->prm.max_detections,
+                          (size_t)c->prefetch_k * sizeof(rsp_detection), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaEventRecord(c->slot_done[slot], s));
+    c->slot_prefetched[slot] = 1;
+    c->slot_lane[slot] = l;
+    return RSP_OK;
+}
+
+static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+    const bool pre = !c->slot_prefetched.empty() && c->slot_prefetched[slot];
+    int n;
+    if (pre) {                            // pipelined submission: its result is already on its way to pinned memory
+        CU(c, cudaEventSynchronize(c->slot_done[slot]));
+        c->slot_prefetched[slot] = 0;
+        c->slot_lane[slot] = -1;
+        n = c->h_slot_count[slot];
+    } else {
+        CU(c, cudaMemcpyAsync(c->h_count, c->d_counts + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        n = *c->h_count;
+    }
     if (n_dets) *n_dets = n;
     if (n > c->prm.max_detections)
         return fail(c, RSP_ERR_OVERFLOW, "%d detections exceed max_detections=%d", n, c->prm.max_detections);
     if (n > det_cap) return fail(c, RSP_ERR_OVERFLOW, "%d detections exceed the caller's capacity %d", n, det_cap);
     if (n > 0) {
-        CU(c, cudaMemcpyAsync(c->h_recs, c->d_recs + (size_t)slot * c->prm.max_detections, (size_t)n * sizeof(rsp_detection),
-                              cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        std::sort(c->h_recs, c->h_recs + n, det_less);
-        std::memcpy(dets, c->h_recs, (size_t)n * sizeof(rsp_detection));
+        if (pre && n <= c->prefetch_k) {
+            std::memcpy(dets, c->h_slot_recs + (size_t)slot * c->prefetch_k, (size_t)n * sizeof(rsp_detection));
+        } else {
+            CU(c, cudaMemcpyAsync(c->h_recs, c->d_recs + (size_t)slot * c->prm.max_detections, (size_t)n * sizeof(rsp_detection),
+                                  cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            std::memcpy(dets, c->h_recs, (size_t)n * sizeof(rsp_detection));
+        }
+        std::sort(dets, dets + n, det_less);
     }
     return RSP_OK;
 }
@@ -755,6 +799,7 @@ int rsp_process_cpi(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dt
     float2* rdm = (rdm_out && rdm_mem == RSP_MEM_DEVICE) ? static_cast<float2*>(rdm_out) : c->d_rdm;
     rc = enqueue_chain(c, d_in, rdm, 0, 0);
     if (rc) return rc;
+    if (!c->slot_prefetched.empty()) c->slot_prefetched[0] = 0;
     launch_refine(c, 0, 1, c->stream);
     if (rdm_out && rdm_mem == RSP_MEM_HOST)
         CU(c, cudaMemcpyAsync(rdm_out, c->d_rdm, (size_t)c->P * c->B * c->G * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
@@ -783,6 +828,7 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
         int rc = enqueue_chain(c, in, rdm, first_slot + i, i % nl);
         if (rc) return rc;
         c->slot_lane[first_slot + i] = -1;
+        if (!c->slot_prefetched.empty()) c->slot_prefetched[first_slot + i] = 0;
     }
     c->discard = false;
     for (int l = 1; l < nl; ++l) {                   // join
@@ -792,6 +838,14 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
     launch_refine(c, first_slot, n_cpi, c->stream);  // S9 for the whole batch
     CU(c, cudaGetLastError());
     return RSP_OK;
+}
+
+// RDM buffer of a lane for the pipelined paths: concurrent lanes must not share one
+static float2* lane_rdm(rsp_ctx* c, int l) {
+    if (l == 0) return c->d_rdm;
+    rsp_ctx::Lane& ln = c->lanes[l];
+    if (!ln.rdm && cudaMalloc(reinterpret_cast<void**>(&ln.rdm), (size_t)c->P * c->B * c->G * sizeof(float2)) != cudaSuccess) return nullptr;
+    return ln.rdm;
 }
 
 int rsp_submit_cpi(rsp_ctx* c, const void* raw_host, void* rdm_dev, int32_t slot) {
@@ -807,12 +861,12 @@ int rsp_submit_cpi(rsp_ctx* c, const void* raw_host, void* rdm_dev, int32_t slot
         CU(c, cudaStreamWaitEvent(ln.s, c->fork, 0));
     }
     CU(c, cudaMemcpyAsync(ln.raw, raw_host, bytes, cudaMemcpyHostToDevice, ln.s));
-    int rc = enqueue_chain(c, ln.raw, rdm_dev ? static_cast<float2*>(rdm_dev) : c->d_rdm, slot, l);
+    float2* rdm = rdm_dev ? static_cast<float2*>(rdm_dev) : lane_rdm(c, l);
+    if (!rdm) return fail(c, RSP_ERR_CUDA, "out of device memory for the lane's RDM");
+    int rc = enqueue_chain(c, ln.raw, rdm, slot, l);
     if (rc) return rc;
     launch_refine(c, slot, 1, ln.s);
-    if (l > 0) CU(c, cudaEventRecord(ln.done, ln.s));
-    c->slot_lane[slot] = l;
-    return RSP_OK;
+    return finish_submit(c, slot, l);
 }
 
 int rsp_stream_slots(const rsp_ctx* c) { return c ? c->slots : 0; }
@@ -1060,22 +1114,58 @@ int rsp_set_waveform(rsp_ctx* c, const rsp_waveform* w) {
 
 static long matlab_round(double x) { return x >= 0 ? (long)std::floor(x + 0.5) : -(long)std::floor(-x + 0.5); }
 
-int rsp_synthesize(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed, void* raw_dev_out) {
-    if (!c || n_targets < 0 || (n_targets > 0 && !targets)) return fail(c, RSP_ERR_INVALID_ARG, "bad synthesis arguments");
-    if (!c->have_waveform) return fail(c, RSP_ERR_NOT_READY, "rsp_set_waveform has not been called");
-    CU(c, cudaSetDevice(c->prm.device));
-    std::vector<SynthTarget> tg;
+// frac(cycles) as a 0.64 fixed-point number (the double carries 53 of the 64 bits)
+static unsigned long long cycle_fraction_fix(double cycles) {
+    double f = cycles - std::floor(cycles);                   // [0, 1)
+    if (!(f >= 0.0 && f < 1.0)) f = 0.0;                        // NaN / rounding to 1.0
+    return (unsigned long long)std::ldexp(f, 64 - 11) << 11;   // f * 2^53 is an exact integer below 2^53
+}
+
+// targets(k) -> what the synthesis kernel needs (fsf:55-66); targets outside the range window are dropped
+static int make_synth_targets(const rsp_ctx* c, const rsp_target_in* targets, int n_targets, SynthTarget* out) {
     const double kPiD = 3.14159265358979323846;
+    int n = 0;
     for (int i = 0; i < n_targets; ++i) {
         const long d = matlab_round(2.0 * targets[i].range / c->wf.c * c->wf.fs);                       // fsf:55-56
         if (!(d > 0 && d < c->N)) continue;                                                              // fsf:66
         SynthTarget t;
         t.delay = (int)d;
         t.amp = (float)std::sqrt(std::pow(10.0, targets[i].snr_db / 10.0) / c->wf.p_signal_unscaled);   // fsf:61-63
-        t.dop_cycles = 2.0 * targets[i].velocity / c->wf.wavelength * c->wf.prt;                         // fsf:57-58
-        t.steer_cycles = c->wf.element_spacing * std::sin(targets[i].elevation_deg * kPiD / 180.0) / c->wf.wavelength;   // fsf:165
-        tg.push_back(t);
+        t.dop_fix = cycle_fraction_fix(2.0 * targets[i].velocity / c->wf.wavelength * c->wf.prt);       // fsf:57-58
+        t.steer_fix = cycle_fraction_fix(c->wf.element_spacing * std::sin(targets[i].elevation_deg * kPiD / 180.0) / c->wf.wavelength);   // fsf:165
+        out[n++] = t;
     }
+    return n;
+}
+
+static void launch_synth(rsp_ctx* c, float2* raw, const SynthTarget* d_tg, int n_tg, double noise_power, uint64_t seed, cudaStream_t s) {
+    SynthArgs a;
+    a.raw = raw;
+    a.tx = c->d_tx; a.tg = d_tg; a.n_targets = n_tg;
+    a.P = c->P; a.C = c->C; a.N = c->N;
+    for (int i = 0; i < 3; ++i) { a.seg_lo[i] = c->tx_seg_lo[i]; a.seg_hi[i] = c->tx_seg_hi[i]; }
+    a.noise_sigma = noise_power > 0 ? (float)std::sqrt(noise_power / 2.0) : 0.f;
+    a.seed = seed;
+    for (int r = 0; r < 10; ++r)
+        a.round_key[r] = make_uint2((unsigned)seed + (unsigned)r * 0x9E3779B9u, (unsigned)(seed >> 32) + (unsigned)r * 0xBB67AE85u);
+    a.tx_lo = c->N; a.tx_hi = 0;
+    for (int i = 0; i < 3; ++i)
+        if (a.seg_hi[i] > a.seg_lo[i]) { a.tx_lo = std::min(a.tx_lo, a.seg_lo[i]); a.tx_hi = std::max(a.tx_hi, a.seg_hi[i]); }
+    if (a.tx_hi < a.tx_lo) a.tx_lo = a.tx_hi = 0;
+    static const bool staged_only = [] { const char* e = getenv("RSP_SYNTH"); return e && !strcmp(e, "staged"); }();
+    Timed t(c, K_SYNTH);
+    if (n_tg <= RSP_SYNTH_GATHER_T && !staged_only)
+        synth_gather_kernel<<<dim3(c->C, c->P, (c->N + RSP_SYNTH_GATHER_CHUNK - 1) / RSP_SYNTH_GATHER_CHUNK), 256, 0, s>>>(a);
+    else
+        synth_kernel<<<dim3(c->C, c->P, (c->N + RSP_SYNTH_CHUNK - 1) / RSP_SYNTH_CHUNK), 256, 0, s>>>(a);
+}
+
+int rsp_synthesize(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed, void* raw_dev_out) {
+    if (!c || n_targets < 0 || (n_targets > 0 && !targets)) return fail(c, RSP_ERR_INVALID_ARG, "bad synthesis arguments");
+    if (!c->have_waveform) return fail(c, RSP_ERR_NOT_READY, "rsp_set_waveform has not been called");
+    CU(c, cudaSetDevice(c->prm.device));
+    std::vector<SynthTarget> tg((size_t)std::max(n_targets, 1));
+    tg.resize((size_t)make_synth_targets(c, targets, n_targets, tg.data()));
     if ((int)tg.size() > c->tg_cap) {
         if (c->d_tg) cudaFree(c->d_tg);
         c->d_tg = nullptr;
@@ -1083,21 +1173,66 @@ int rsp_synthesize(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targets, 
         CU(c, dev_alloc(&c->d_tg, (size_t)c->tg_cap));
     }
     if (!tg.empty()) CU(c, cudaMemcpyAsync(c->d_tg, tg.data(), tg.size() * sizeof(SynthTarget), cudaMemcpyHostToDevice, c->stream));
-    SynthArgs a;
-    a.raw = raw_dev_out ? static_cast<float2*>(raw_dev_out) : c->d_raw;
-    a.tx = c->d_tx; a.tg = c->d_tg; a.n_targets = (int)tg.size();
-    a.P = c->P; a.C = c->C; a.N = c->N;
-    for (int i = 0; i < 3; ++i) { a.seg_lo[i] = c->tx_seg_lo[i]; a.seg_hi[i] = c->tx_seg_hi[i]; }
-    a.noise_sigma = noise_power > 0 ? (float)std::sqrt(noise_power / 2.0) : 0.f;
-    a.seed = seed;
     c->cur = &c->lanes[0];
-    {
-        Timed t(c, K_SYNTH);
-        synth_kernel<<<dim3(c->C, c->P), 256, 0, c->stream>>>(a);
-    }
+    launch_synth(c, raw_dev_out ? static_cast<float2*>(raw_dev_out) : c->d_raw, c->d_tg, (int)tg.size(), noise_power, seed, c->stream);
     CU(c, cudaGetLastError());
     // the pageable target vector goes out of scope: make sure its copy has been consumed
     if (!tg.empty()) CU(c, cudaStreamSynchronize(c->stream));
+    return RSP_OK;
+}
+
+// Pipelined frame path: S4 on the device into the lane's own cube, then S5..S9 on the same lane; returns at once.
+int rsp_submit_targets(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed, int32_t slot) {
+    if (!c || n_targets < 0 || (n_targets > 0 && !targets) || slot < 0 || slot >= c->slots)
+        return fail(c, RSP_ERR_INVALID_ARG, "bad submit arguments");
+    if (n_targets > RSP_MAX_FRAME_TARGETS)
+        return fail(c, RSP_ERR_INVALID_ARG, "%d targets exceed RSP_MAX_FRAME_TARGETS=%d", n_targets, RSP_MAX_FRAME_TARGETS);
+    if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
+    if (!c->have_waveform) return fail(c, RSP_ERR_NOT_READY, "rsp_set_waveform has not been called");
+    CU(c, cudaSetDevice(c->prm.device));
+    if (!c->d_tg_ring) {
+        CU(c, dev_alloc(&c->d_tg_ring, (size_t)c->slots * RSP_MAX_FRAME_TARGETS));
+        CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_tg_ring), (size_t)c->slots * RSP_MAX_FRAME_TARGETS * sizeof(SynthTarget)));
+    }
+    const int l = slot % c->n_lanes;
+    rsp_ctx::Lane& ln = c->lanes[l];
+    if (!ln.raw) CU(c, cudaMalloc(reinterpret_cast<void**>(&ln.raw), (size_t)c->P * c->C * c->N * sizeof(float2)));
+    SynthTarget* h = c->h_tg_ring + (size_t)slot * RSP_MAX_FRAME_TARGETS;
+    SynthTarget* d = c->d_tg_ring + (size_t)slot * RSP_MAX_FRAME_TARGETS;
+    const int n_tg = make_synth_targets(c, targets, n_targets, h);
+    if (l > 0) {
+        CU(c, cudaEventRecord(c->fork, c->stream));
+        CU(c, cudaStreamWaitEvent(ln.s, c->fork, 0));
+    }
+    if (n_tg > 0) CU(c, cudaMemcpyAsync(d, h, (size_t)n_tg * sizeof(SynthTarget), cudaMemcpyHostToDevice, ln.s));
+    c->cur = &ln;
+    launch_synth(c, ln.raw, d, n_tg, noise_power, seed, ln.s);
+    float2* rdm = lane_rdm(c, l);
+    if (!rdm) return fail(c, RSP_ERR_CUDA, "out of device memory for the lane's RDM");
+    int rc = enqueue_chain(c, ln.raw, rdm, slot, l);
+    if (rc) return rc;
+    launch_refine(c, slot, 1, ln.s);
+    return finish_submit(c, slot, l);
+}
+
+int rsp_fetch_targets(rsp_ctx* c, int32_t slot, const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap,
+                      int32_t* n_final, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+    if (!c || !cp || !n_final || slot < 0 || slot >= c->slots) return fail(c, RSP_ERR_INVALID_ARG, "bad fetch arguments");
+    CU(c, cudaSetDevice(c->prm.device));
+    std::vector<rsp_detection> own;
+    if (!dets) { own.resize((size_t)c->prm.max_detections); dets = own.data(); det_cap = (int32_t)own.size(); }
+    int32_t n = 0;
+    int rc = fetch_slot(c, slot, dets, det_cap, &n);
+    if (n_dets) *n_dets = n;
+    if (rc) return rc;
+    std::vector<rsp_target> fin((size_t)std::max(n, 1));
+    int32_t nf = 0, n1 = 0;
+    rc = rsp_cluster(dets, n, cp, nullptr, &n1, fin.data(), &nf);
+    if (rc) return fail(c, rc, "clustering failed");
+    *n_final = nf;
+    if (nf > cap) return fail(c, RSP_ERR_OVERFLOW, "%d targets exceed the caller's capacity %d", nf, cap);
+    if (nf > 0 && !final_targets) return fail(c, RSP_ERR_INVALID_ARG, "null output");
+    if (nf > 0) std::memcpy(final_targets, fin.data(), (size_t)nf * sizeof(rsp_target));
     return RSP_OK;
 }
 
@@ -1157,6 +1292,8 @@ int rsp_get_info(const rsp_ctx* c, rsp_info* info) {
     info->kernels_per_cpi = c->have_constants ? kernels_per_cpi(c) : 0;
     info->algorithmic_bytes_per_cpi = 8LL * c->P * c->N * c->C + 8LL * c->B * c->P * c->G;
     info->launches_total = c->launches;
+    info->lanes = c->n_lanes;
+    info->reserved_ = 0;
     return RSP_OK;
 }
 

@@ -1,33 +1,52 @@
-// rsp_cluster.cpp -- S10 + S11 on the host: the two order-dependent BFS clustering stages of
-// fun_process_single_frame.m:302-407.  n is a few hundred detections, so this is O(n^2) host work;
-// cluster ids follow the reference's visiting order (FIFO queue seeded in index order), which is
-// what makes final_targets(1) etc. reproducible.
+// rsp_cluster.cpp -- S10 + S11 on the host: the two clustering stages of fun_process_single_frame.m:302-407.
+//
+// The reference grows each cluster with a FIFO breadth-first search seeded in index order (fsf:313-326,
+// :366-379).  The link relation is symmetric, so what that search computes is exactly the connected
+// components of the link graph, numbered by their smallest member index; the power-weighted sums are then
+// taken in index order (fsf:333-347), not in visiting order.  This file computes the same labelling with a
+// union-find over a range-sorted sweep (only detections within max_range_sep can be linked), which is
+// O(n * window) instead of the O(n^2) of the literal search -- the literal search was the largest host cost
+// of the frame path (89 us for 205 detections vs a 58 us device chain).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <deque>
+#include <numeric>
 #include <vector>
 
 #include "rsp.h"
 
 namespace {
 
-template <typename Linked> std::vector<int> bfs_ids(int n, Linked linked, int* n_clusters) {
-    std::vector<int> ids(n, 0);
-    int cur = 0;
-    std::deque<int> queue;
-    for (int i = 0; i < n; ++i) {
-        if (ids[i] != 0) continue;
-        ++cur;                                   // fsf:315 / :368
-        queue.clear();
-        queue.push_back(i);
-        while (!queue.empty()) {
-            const int k = queue.front();         // fsf:318-319 (FIFO, duplicates allowed)
-            queue.pop_front();
-            if (ids[k] != 0) continue;
-            ids[k] = cur;
-            for (int j = 0; j < n; ++j)
-                if (ids[j] == 0 && linked(k, j)) queue.push_back(j);
+// ids[i] in 1..n_clusters = connected component of i, numbered by smallest member (== the reference's BFS ids).
+// key(i) is the coordinate the sweep sorts by; linked(k, j) implies |key(k) - key(j)| <= sep.
+template <typename Key, typename Linked> std::vector<int> component_ids(int n, Key key, double sep, Linked linked, int* n_clusters) {
+    std::vector<std::pair<double, int>> sorted(n);           // (key, index): ties keep index order
+    for (int i = 0; i < n; ++i) sorted[i] = {key(i), i};
+    std::sort(sorted.begin(), sorted.end());
+    std::vector<int> parent(n);
+    std::iota(parent.begin(), parent.end(), 0);
+    auto find = [&](int x) {
+        while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+        return x;
+    };
+    for (int a = 0; a < n; ++a) {
+        const int k = sorted[a].second;
+        const double limit = sorted[a].first;
+        for (int b = a + 1; b < n && sorted[b].first - limit <= sep; ++b) {
+            const int j = sorted[b].second;
+            if (parent[j] == parent[k]) continue;          // already in one component (cheap test, no path walk)
+            if (linked(k, j)) {
+                const int rk = find(k), rj = find(j);
+                if (rk != rj) parent[std::max(rk, rj)] = std::min(rk, rj);
+            }
         }
+    }
+    std::vector<int> ids(n), label(n, 0);
+    int cur = 0;
+    for (int i = 0; i < n; ++i) {                // index order => a component is numbered when its smallest member is met
+        const int r = find(i);
+        if (label[r] == 0) label[r] = ++cur;     // fsf:315 / :368
+        ids[i] = label[r];
     }
     *n_clusters = cur;
     return ids;
@@ -43,38 +62,35 @@ extern "C" int rsp_cluster(const rsp_detection* dets, int32_t n, const rsp_clust
     if (n == 0) return RSP_OK;                   // fsf:305-308, :358-361 -> []
     // ---- stage 1: R/V/Angle gates, power-weighted mean, Power = sum (fsf:313-351)
     int nc1 = 0;
-    std::vector<int> ids1 = bfs_ids(n, [&](int k, int j) {
+    std::vector<int> ids1 = component_ids(n, [&](int i) { return dets[i].range; }, cp->max_range_sep, [&](int k, int j) {
         return std::fabs(dets[k].range - dets[j].range) <= cp->max_range_sep &&
                std::fabs(dets[k].velocity - dets[j].velocity) <= cp->max_vel_sep &&
                std::fabs(dets[k].angle - dets[j].angle) <= cp->max_angle_sep;
     }, &nc1);
-    std::vector<rsp_target> t1(nc1);
-    for (int cidx = 1; cidx <= nc1; ++cidx) {
-        double tot = 0, sr = 0, sv = 0, sa = 0;
-        for (int i = 0; i < n; ++i)
-            if (ids1[i] == cidx) {
-                const double pw = (double)dets[i].power;
-                tot += pw;
-                sr += dets[i].range * pw;
-                sv += dets[i].velocity * pw;
-                sa += dets[i].angle * pw;
-            }
-        t1[cidx - 1] = rsp_target{sr / tot, sv / tot, sa / tot, tot};
+    std::vector<rsp_target> t1(nc1, rsp_target{0, 0, 0, 0});
+    for (int i = 0; i < n; ++i) {                // one pass; every cluster still sums its members in index order
+        rsp_target& t = t1[ids1[i] - 1];
+        const double pw = (double)dets[i].power;
+        t.power += pw;
+        t.range += dets[i].range * pw;
+        t.velocity += dets[i].velocity * pw;
+        t.angle += dets[i].angle * pw;
     }
+    for (auto& t : t1) { t.range /= t.power; t.velocity /= t.power; t.angle /= t.power; }
     if (n_stage1) *n_stage1 = nc1;
     if (stage1) std::memcpy(stage1, t1.data(), (size_t)nc1 * sizeof(rsp_target));
     // ---- stage 2: R/V gates, winner takes all (fsf:366-406)
     int nc2 = 0;
-    std::vector<int> ids2 = bfs_ids(nc1, [&](int k, int j) {
+    std::vector<int> ids2 = component_ids(nc1, [&](int i) { return t1[i].range; }, cp->max_range_sep, [&](int k, int j) {
         return std::fabs(t1[k].range - t1[j].range) <= cp->max_range_sep &&
                std::fabs(t1[k].velocity - t1[j].velocity) <= cp->max_vel_sep;
     }, &nc2);
-    for (int cidx = 1; cidx <= nc2; ++cidx) {
-        int win = -1;
-        for (int i = 0; i < nc1; ++i)
-            if (ids2[i] == cidx && (win < 0 || t1[i].power > t1[win].power)) win = i;   // first max, fsf:399
-        final_targets[cidx - 1] = t1[win];
+    std::vector<int> win(nc2, -1);
+    for (int i = 0; i < nc1; ++i) {
+        int& w = win[ids2[i] - 1];
+        if (w < 0 || t1[i].power > t1[w].power) w = i;                                  // first max, fsf:399
     }
+    for (int cidx = 0; cidx < nc2; ++cidx) final_targets[cidx] = t1[win[cidx]];
     *n_final = nc2;
     return RSP_OK;
 }

@@ -105,9 +105,20 @@ __global__ void __launch_bounds__(256) pbg_to_bgp_kernel(const float2* __restric
 struct SynthTarget {          // per target, prepared on the host in fp64
     int delay;                // delay_samples (fsf:56); targets with delay outside (0, N) are dropped (fsf:66)
     float amp;                // sqrt(SNR / P_signal_unscaled) (fsf:61-63)
-    double dop_cycles;        // doppler_freq * prt (cycles per pulse, fsf:57-58)
-    double steer_cycles;      // element_spacing * sin(El) / wavelength (cycles per channel, fsf:163-169)
+    // Phase steps as 0.64 fixed-point fractions of a cycle, so that the phase of pulse p, channel c is the
+    // wrapping integer dop_fix * p + steer_fix * c: exact argument reduction without fp64 on the device.
+    unsigned long long dop_fix;     // frac(doppler_freq * prt) * 2^64        (cycles per pulse, fsf:57-58)
+    unsigned long long steer_fix;   // frac(element_spacing * sin(El) / wavelength) * 2^64   (cycles per channel, fsf:163-169)
 };
+// exp(j 2 pi * phase / 2^64): the top 24 bits go through sincospif, the next 24 correct it to first order
+__device__ __forceinline__ float2 unit_phasor(unsigned long long phase) {
+    const float hi = (float)(unsigned)(phase >> 40) * (1.0f / 16777216.0f);                          // [0, 1), exact
+    const float lo = (float)(unsigned)((phase >> 16) & 0xFFFFFFu) * (1.0f / 281474976710656.0f);     // < 2^-24
+    float sn, cs;
+    sincospif(2.0f * hi, &sn, &cs);
+    const float d = 6.283185307179586f * lo;
+    return make_float2(cs - d * sn, sn + d * cs);
+}
 struct SynthArgs {
     float2* raw;              // [P][C][N]
     const float2* tx;         // [N]
@@ -116,68 +127,164 @@ struct SynthArgs {
     int seg_lo[3], seg_hi[3]; // non-zero stretches of tx (0-based, half open)
     float noise_sigma;        // sqrt(noise_power / 2) per component; 0 = no noise
     unsigned long long seed;
+    uint2 round_key[10];      // Philox key schedule of `seed` (host-computed so the kernel reads it as constants)
+    int tx_lo, tx_hi;         // hull of the non-zero stretches
 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+// Philox4x32-10 (Salmon et al., SC'11); round_key[r] = key + r * (0x9E3779B9, 0xBB67AE85)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const uint2 (&round_key)[10]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
         const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u;
-        key.y += 0xBB67AE85u;
+        ctr = make_uint4(hi1 ^ ctr.y ^ round_key[r].x, lo1, hi0 ^ ctr.w ^ round_key[r].y, lo0);
     }
     return ctr;
 }
-// two uniform words -> one complex standard-normal sample (Box-Muller)
+// two uniform words -> one complex standard-normal sample (Box-Muller): z = sqrt(-2 ln u1) * exp(j 2 pi u2),
+// u1 = ((a >> 9) + 1/2) 2^-23, u2 = (b >> 9) 2^-23.
+// Logarithm, square root, sine and cosine are the MUFU approximations (lg2: absolute 2^-22.6, sqrt: relative
+// 2^-23, sin / cos: absolute 2^-21 on [-pi, pi], evaluated at 2 pi (u2 - 1/2) and negated): the radius is
+// off by about 1e-7 / r, which only shows for the 0.1 % of samples with r < 0.05.  An accurate logf costs a
+// third of the whole generator and buys nothing for white Gaussian noise.
 __device__ __forceinline__ float2 box_muller(unsigned int a, unsigned int b) {
-    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
-    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * logf(u1));
-    float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
-    return make_float2(r * cs, r * sn);
+    // 23 random bits under the exponent of 1.0 give 1 + k 2^-23; no integer-to-float conversion (XU pipe, the
+    // kernel's bottleneck together with the four MUFUs below)
+    const float u1 = __uint_as_float(0x3F800000u | (a >> 9)) - (1.0f - 0.5f / 8388608.0f);   // (k + 1/2) 2^-23 in (0, 1)
+    const float h2 = __uint_as_float(0x3F800000u | (b >> 9)) - 1.5f;                          // k 2^-23 - 1/2 in [-1/2, 1/2)
+    float l2, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));   // -2 ln 2 * log2(u1)
+    const float x = 6.283185307179586f * h2;                               // [-pi, pi)
+    return make_float2(-r * __cosf(x), -r * __sinf(x));
 }
 
-__global__ void __launch_bounds__(256) synth_kernel(const SynthArgs k) {
+// One CTA per (channel, pulse, chunk of RSP_SYNTH_CHUNK range samples).  The chunk is built in shared
+// memory -- Philox noise first, then every target's delayed pulse added over the three non-zero stretches of
+// tx_pulse that fall inside the chunk (targets are serialised by a barrier because their echoes may
+// overlap) -- and leaves with one coalesced store, so the cube is written exactly once.
+#define RSP_SYNTH_CHUNK 4096
+#define RSP_SYNTH_TB 64
+__global__ void __launch_bounds__(256) synth_kernel(const __grid_constant__ SynthArgs k) {
+    __shared__ __align__(16) float2 s[RSP_SYNTH_CHUNK];
+    __shared__ float2 s_ph[RSP_SYNTH_TB];
+    __shared__ int s_delay[RSP_SYNTH_TB];
     const int c = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
-    float2* line = k.raw + ((size_t)p * k.C + c) * k.N;
+    const int c0 = blockIdx.z * RSP_SYNTH_CHUNK;                            // even
+    const int cn = min(RSP_SYNTH_CHUNK, k.N - c0);
     const size_t line_id = (size_t)p * k.C + c;
     // noise: counter = (pair index within the line, line id), 2 complex samples per Philox call
-    for (int i = tid; 2 * i < k.N; i += 256) {
-        float2 z0 = make_float2(0.f, 0.f), z1 = z0;
+    for (int i = tid; 2 * i < cn; i += 256) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k.noise_sigma > 0.f) {
-            const uint4 r = philox4x32_10(make_uint4((unsigned)i, (unsigned)line_id, (unsigned)(line_id >> 32), 0u),
-                                          make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32)));
-            z0 = box_muller(r.x, r.y);
-            z1 = box_muller(r.z, r.w);
-            z0.x *= k.noise_sigma; z0.y *= k.noise_sigma; z1.x *= k.noise_sigma; z1.y *= k.noise_sigma;
+            const uint4 r = philox4x32_10(make_uint4((unsigned)(c0 / 2 + i), (unsigned)line_id, (unsigned)(line_id >> 32), 0u), k.round_key);
+            const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+            z = make_float4(z0.x * k.noise_sigma, z0.y * k.noise_sigma, z1.x * k.noise_sigma, z1.y * k.noise_sigma);
         }
-        line[2 * i] = z0;
-        if (2 * i + 1 < k.N) line[2 * i + 1] = z1;
+        *reinterpret_cast<float4*>(&s[2 * i]) = z;                          // the odd tail sample of an odd chunk is never stored
     }
-    __syncthreads();
-    for (int t = 0; t < k.n_targets; ++t) {
-        const SynthTarget tg = k.tg[t];
-        // phasor = amp * exp(j 2 pi (dop_cycles * p + steer_cycles * c)), argument reduced in fp64
-        double cyc = tg.dop_cycles * (double)p + tg.steer_cycles * (double)c;
-        cyc -= floor(cyc);
-        double sn, cs;
-        sincospi(2.0 * cyc, &sn, &cs);
-        const float2 ph = make_float2((float)(tg.amp * cs), (float)(tg.amp * sn));
-        const int len = min(k.N, k.N - tg.delay);                     // fsf:67
-#pragma unroll
-        for (int sgi = 0; sgi < 3; ++sgi) {
-            const int hi = min(k.seg_hi[sgi], len);
-            for (int i = k.seg_lo[sgi] + tid; i < hi; i += 256) {
-                const float2 x = k.tx[i];
-                float2 v = line[tg.delay + i];
-                v.x += x.x * ph.x - x.y * ph.y;
-                v.y += x.x * ph.y + x.y * ph.x;
-                line[tg.delay + i] = v;
-            }
+    for (int t0 = 0; t0 < k.n_targets; t0 += RSP_SYNTH_TB) {
+        const int nb = min(RSP_SYNTH_TB, k.n_targets - t0);
+        __syncthreads();                                                    // noise written / previous batch consumed
+        if (tid < nb) {
+            const SynthTarget tg = k.tg[t0 + tid];
+            // phasor = amp * exp(j 2 pi (dop_cycles * p + steer_cycles * c)), argument reduced in integers
+            const float2 u = unit_phasor(tg.dop_fix * (unsigned long long)p + tg.steer_fix * (unsigned long long)c);
+            s_ph[tid] = make_float2(tg.amp * u.x, tg.amp * u.y);
+            s_delay[tid] = tg.delay;
         }
         __syncthreads();
+        bool dirty = false;                                                 // CTA-uniform: an earlier target wrote this chunk
+        for (int t = 0; t < nb; ++t) {
+            const int delay = s_delay[t];
+            const int len = min(k.N, k.N - delay);                          // fsf:67
+            int lo[3], hi[3];
+            bool any = false;
+#pragma unroll
+            for (int sgi = 0; sgi < 3; ++sgi) {
+                lo[sgi] = max(k.seg_lo[sgi], c0 - delay);
+                hi[sgi] = min(min(k.seg_hi[sgi], len), c0 + cn - delay);
+                any |= lo[sgi] < hi[sgi];
+            }
+            if (!any) continue;                                             // this echo misses the chunk: no work, no barrier
+            if (dirty) __syncthreads();                                     // echoes may overlap: one target at a time
+            dirty = true;
+            const float2 ph = s_ph[t];
+#pragma unroll
+            for (int sgi = 0; sgi < 3; ++sgi)
+                for (int i = lo[sgi] + tid; i < hi[sgi]; i += 256) {
+                    const float2 x = k.tx[i];
+                    float2 v = s[delay + i - c0];
+                    v.x += x.x * ph.x - x.y * ph.y;
+                    v.y += x.x * ph.y + x.y * ph.x;
+                    s[delay + i - c0] = v;
+                }
+        }
+    }
+    __syncthreads();
+    float2* out = k.raw + line_id * k.N + c0;
+    if ((reinterpret_cast<size_t>(out) & 15) == 0) {
+        for (int i = tid; 2 * i + 1 < cn; i += 256) reinterpret_cast<float4*>(out)[i] = *reinterpret_cast<const float4*>(&s[2 * i]);
+        if ((cn & 1) && tid == 0) out[cn - 1] = s[cn - 1];
+    } else {
+        for (int i = tid; i < cn; i += 256) out[i] = s[i];
+    }
+}
+
+// The same cube for frames with at most RSP_SYNTH_GATHER_T targets (the reference's scenes have 1 to 5): no
+// shared-memory staging and no barriers per target.  A thread makes two noise samples, then for every
+// target tests whether the pair falls inside the hull of the delayed pulse train (one compare; about a
+// third of the line does) and only then gathers tx_pulse -- which is zero between the pulses, so no
+// per-stretch test is needed.  Targets are added in index order, like the staged kernel.
+#define RSP_SYNTH_GATHER_T 8
+#define RSP_SYNTH_GATHER_CHUNK 8192
+__global__ void __launch_bounds__(256) synth_gather_kernel(const __grid_constant__ SynthArgs k) {
+    __shared__ float2 s_ph[RSP_SYNTH_GATHER_T];
+    __shared__ int s_delay[RSP_SYNTH_GATHER_T];
+    const int c = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+    const int c0 = blockIdx.z * RSP_SYNTH_GATHER_CHUNK;                     // even
+    const int cn = min(RSP_SYNTH_GATHER_CHUNK, k.N - c0);
+    const size_t line_id = (size_t)p * k.C + c;
+    if (tid < k.n_targets) {
+        const SynthTarget tg = k.tg[tid];
+        const float2 u = unit_phasor(tg.dop_fix * (unsigned long long)p + tg.steer_fix * (unsigned long long)c);
+        s_ph[tid] = make_float2(tg.amp * u.x, tg.amp * u.y);
+        s_delay[tid] = tg.delay;
+    }
+    __syncthreads();
+    float2* out = k.raw + line_id * k.N + c0;
+    const bool aligned = (reinterpret_cast<size_t>(out) & 15) == 0;
+    const unsigned span = (unsigned)(k.tx_hi - k.tx_lo);
+    for (int i = tid; 2 * i < cn; i += 256) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k.noise_sigma > 0.f) {
+            const uint4 r = philox4x32_10(make_uint4((unsigned)(c0 / 2 + i), (unsigned)line_id, (unsigned)(line_id >> 32), 0u), k.round_key);
+            const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+            z = make_float4(z0.x * k.noise_sigma, z0.y * k.noise_sigma, z1.x * k.noise_sigma, z1.y * k.noise_sigma);
+        }
+        const int n0 = c0 + 2 * i;
+        for (int t = 0; t < k.n_targets; ++t) {
+            const int j = n0 - s_delay[t] - k.tx_lo;                        // tx index of sample n0, relative to the hull
+            if ((unsigned)(j + 1) <= span) {                                // sample n0 or n0 + 1 is inside the delayed hull
+                const float2 ph = s_ph[t];
+                if ((unsigned)j < span) {
+                    const float2 x = k.tx[j + k.tx_lo];
+                    z.x += x.x * ph.x - x.y * ph.y;
+                    z.y += x.x * ph.y + x.y * ph.x;
+                }
+                if ((unsigned)(j + 1) < span) {
+                    const float2 x = k.tx[j + 1 + k.tx_lo];
+                    z.z += x.x * ph.x - x.y * ph.y;
+                    z.w += x.x * ph.y + x.y * ph.x;
+                }
+            }
+        }
+        if (aligned && 2 * i + 1 < cn) {
+            reinterpret_cast<float4*>(out)[i] = z;
+        } else {
+            out[2 * i] = make_float2(z.x, z.y);
+            if (2 * i + 1 < cn) out[2 * i + 1] = make_float2(z.z, z.w);
+        }
     }
 }
 

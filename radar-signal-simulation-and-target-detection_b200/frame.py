@@ -217,30 +217,48 @@ class RadarChain:
                                                  C.c_void_p(dets.ctypes.data), len(dets), C.byref(nd)), self._ctx)
         return fin[:nf.value].copy(), dets[:nd.value].copy()
 
-    def process_targets_batch(self, target_lists, cluster_params, noise_power: float = 1.0, seeds=None):
-        """Many independent frames at once (Monte-Carlo trials, a block of a frame stream): every frame's
-        cube is synthesised on the GPU into a device pool, the pool runs through the multi-lane stream path,
-        and only detection lists come back.  Returns [(final targets, detections), ...] in input order."""
-        import torch
+    def submit_targets(self, targets, slot: int, noise_power: float = 1.0, seed: int = 0):
+        """Pipelined frame path: enqueue S4 (device synthesis) + S5..S9 of one frame on lane slot % lanes and
+        return at once; collect with fetch_targets(slot)."""
+        arr = self._pack_targets(targets)
+        _abi.check(self._lib.rsp_submit_targets(self._ctx, arr, len(targets), float(noise_power), int(seed) & (2 ** 64 - 1),
+                                                int(slot)), self._ctx)
+
+    def fetch_targets(self, slot: int, cluster_params):
+        """Wait for a submitted frame -> (final targets, detections)."""
+        cp = _abi.rsp_cluster_params(float(_field(cluster_params, "max_range_sep")), float(_field(cluster_params, "max_vel_sep")),
+                                     float(_field(cluster_params, "max_angle_sep")))
+        fin, dets, pf, pd_ = self._result_buffers()
+        nf, nd = C.c_int32(0), C.c_int32(0)
+        _abi.check(self._lib.rsp_fetch_targets(self._ctx, int(slot), C.byref(cp), pf, len(fin), C.byref(nf),
+                                               pd_, len(dets), C.byref(nd)), self._ctx)
+        return fin[:nf.value].copy(), dets[:nd.value].copy()
+
+    def _result_buffers(self):
+        """Reusable host buffers for one frame's targets and detections (allocating them per call costs more
+        than the fetch itself)."""
+        b = getattr(self, "_res_buf", None)
+        if b is None:
+            fin = np.empty(4096, dtype=TARGET_DTYPE)
+            dets = np.empty(self.max_detections, dtype=DETECTION_DTYPE)
+            b = self._res_buf = (fin, dets, C.c_void_p(fin.ctypes.data), C.c_void_p(dets.ctypes.data))
+        return b
+
+    def process_targets_batch(self, target_lists, cluster_params, noise_power: float = 1.0, seeds=None, depth: int = 0):
+        """Many independent frames (Monte-Carlo trials, a block of a frame stream), pipelined `depth` deep over
+        the lanes: frame i+1 is synthesised on the GPU while frame i runs S5..S9, and only target lists go in
+        and detection lists come back.  Returns [(final targets, detections), ...] in input order."""
         n = len(target_lists)
-        if n == 0:
-            return []
-        if n > self.stream_slots():
-            raise ValueError(f"at most {self.stream_slots()} frames per batch")
         seeds = list(range(n)) if seeds is None else list(seeds)
-        pool = getattr(self, "_batch_pool", None)
-        if pool is None or pool.shape[0] < n:
-            pool = torch.empty((n, self.P, self.C, self.N), dtype=torch.complex64, device=f"cuda:{self._device}")
-            self._batch_pool = pool
-        for i, tl in enumerate(target_lists):
-            self.synthesize(tl, noise_power, seeds[i], out=pool[i])
-        self.stream_enqueue(pool.data_ptr(), n, 0, 0, n, 0)
+        slots = self.stream_slots()
+        depth = min(depth or 2 * max(self.info()["lanes"], 1), slots)
         out = []
-        for i in range(n):
-            dets = self.stream_fetch(i)
-            _, fin = cluster(dets, cluster_params)
-            out.append((fin, dets))
-        return out
+        for i in range(n + depth):
+            if i >= depth:
+                out.append(self.fetch_targets((i - depth) % slots, cluster_params))
+            if i < n:
+                self.submit_targets(target_lists[i], i % slots, noise_power, seeds[i])
+        return out[:n]
 
     # -- device-resident stream -----------------------------------------------------------------
     def stream_slots(self) -> int:
@@ -262,10 +280,9 @@ class RadarChain:
                    self._ctx)
 
     def stream_fetch(self, slot: int) -> np.ndarray:
-        dets = np.zeros(self.max_detections, dtype=DETECTION_DTYPE)
+        _, dets, _, pd_ = self._result_buffers()
         n = C.c_int32(0)
-        _abi.check(self._lib.rsp_stream_fetch(self._ctx, slot, C.c_void_p(dets.ctypes.data), self.max_detections,
-                                              C.byref(n)), self._ctx)
+        _abi.check(self._lib.rsp_stream_fetch(self._ctx, slot, pd_, self.max_detections, C.byref(n)), self._ctx)
         return dets[:n.value].copy()
 
     def stream_device_buffers(self):

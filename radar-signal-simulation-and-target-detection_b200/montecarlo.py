@@ -24,7 +24,7 @@ TRUE_TARGET = dict(Range=10000.0, Velocity=20.0, ElevationAngle=10.0, pair_idx=5
 
 def snr_vs_angle_error(config, cfar_params, cluster_params, precomputed_data, snr_db_vector: Sequence[float] = DEFAULT_SNR_DB,
                        num_trials: int = 100, true_target: Optional[dict] = None, seed: int = 0, device: int = 0,
-                       chain: Optional[RadarChain] = None, rank: int = 0, world: int = 1, batch: int = 16) -> dict:
+                       chain: Optional[RadarChain] = None, rank: int = 0, world: int = 1, batch: int = 0) -> dict:
     """Returns {'snr_db', 'angle_error_std', 'detection_probability', 'theoretical_error_std', 'trials'}.
     With ``world > 1`` (torch.distributed initialised) every rank returns the reduced result."""
     tt = dict(TRUE_TARGET if true_target is None else true_target)
@@ -36,18 +36,24 @@ def snr_vs_angle_error(config, cfar_params, cluster_params, precomputed_data, sn
     lo, hi = shard_range(num_trials, rank, world)
     n_snr = len(snr_db_vector)
     sums = np.zeros((n_snr, 4), dtype=np.float64)               # sum err, sum err^2, detections, trials
+    # every (SNR point, trial) frame is independent: one pipelined pass over all of them
+    frames, point, seeds = [], [], []
     for i, snr in enumerate(snr_db_vector):
         tgt = [dict(Range=tt["Range"], Velocity=tt["Velocity"], ElevationAngle=tt["ElevationAngle"], SNR_dB=float(snr))]
-        for t0 in range(lo, hi, max(batch, 1)):                    # trials are independent: run them in batches
-            trials = range(t0, min(t0 + max(batch, 1), hi))
-            seeds = [(seed << 32) ^ (i << 20) ^ trial for trial in trials]
-            for final, _ in chain.process_targets_batch([tgt] * len(trials), cluster_params, 1.0, seeds):
-                sums[i, 3] += 1
-                if len(final):                                   # mc:270-276: the first final target
-                    err = float(final[0]["angle"]) - tt["ElevationAngle"]
-                    sums[i, 0] += err
-                    sums[i, 1] += err * err
-                    sums[i, 2] += 1
+        for trial in range(lo, hi):
+            frames.append(tgt)
+            point.append(i)
+            seeds.append((seed << 32) ^ (i << 20) ^ trial)
+    step = max(batch, 1) if batch else max(len(frames), 1)
+    for f0 in range(0, len(frames), step):
+        res = chain.process_targets_batch(frames[f0:f0 + step], cluster_params, 1.0, seeds[f0:f0 + step])
+        for i, (final, _) in zip(point[f0:f0 + step], res):
+            sums[i, 3] += 1
+            if len(final):                                       # mc:270-276: the first final target
+                err = float(final[0]["angle"]) - tt["ElevationAngle"]
+                sums[i, 0] += err
+                sums[i, 1] += err * err
+                sums[i, 2] += 1
     if world > 1:
         import torch
         import torch.distributed as dist

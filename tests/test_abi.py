@@ -117,6 +117,33 @@ def test_clustering_is_order_dependent_like_the_reference():
     assert np.allclose(np.stack([s1["range"], s1["velocity"], s1["angle"], s1["power"]], 1), ref1)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_clustering_equals_the_literal_bfs_on_random_scenes(seed):
+    """rsp_cluster labels connected components with a sorted sweep; the oracle runs the reference's FIFO search
+    literally (fsf:313-336).  Random scenes with chains, ties on the gate, duplicates and unsorted input."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 400))
+    d = np.zeros(n, dtype=rsp.DETECTION_DTYPE)
+    centres = rng.uniform(500, 9000, size=max(1, n // 25))
+    d["range"] = rng.choice(centres, n) + np.round(rng.uniform(-60, 60, n) / 7.5) * 7.5     # gate ties are common
+    d["velocity"] = rng.choice([-8.0, 0.0, 5.0, 5.5], n) + rng.normal(0, 0.3, n)
+    d["angle"] = rng.choice([-5.0, 8.0, 10.0], n) + rng.normal(0, 0.8, n)
+    d["power"] = rng.uniform(1, 1e4, n).astype(np.float32)
+    if seed % 2:
+        d[: n // 3] = d[: n // 3][::-1]
+        d[n // 2] = d[0]                                                                      # exact duplicate
+    cfg = o.Config()
+    cp = rsp.Struct(max_range_sep=cfg.max_range_sep, max_vel_sep=cfg.max_vel_sep, max_angle_sep=cfg.max_angle_sep)
+    s1, fin = rsp.cluster(d, cp)
+    par = np.stack([d["range"], d["velocity"], d["angle"], d["power"].astype(np.float64), np.ones(n)], 1)
+    ref1 = o.cluster_stage1(par, cfg)
+    ref2 = o.cluster_stage2(ref1, cfg)
+    assert len(s1) == len(ref1) and len(fin) == len(ref2)
+    for got, want in ((s1, ref1), (fin, ref2)):
+        m = np.stack([got["range"], got["velocity"], got["angle"], got["power"]], 1)
+        assert np.allclose(m, want, rtol=1e-12, atol=0)
+
+
 def test_product_precompute_equals_oracle_precompute():
     for name in ("native", "cfg1", "cfg2", "cfg3"):
         config, cfar_params, _ = rsp.named_config(name)

@@ -256,6 +256,15 @@ def test_device_echo_synthesis_matches_oracle_and_noise_is_philox():
     got = out.cpu().numpy()
     assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
     assert np.array_equal(got == 0, ref == 0)
+    # more than 8 targets take the shared-memory staged kernel (overlapping echoes, one target at a time)
+    many = [o.Target(600.0 + 450.0 * i, (-1) ** i * 0.02 * i * pre["v_max"], -20.0 + 4.0 * i, 3.0 + i) for i in range(12)]
+    mdicts = [dict(Range=t.Range, Velocity=t.Velocity, ElevationAngle=t.ElevationAngle, SNR_dB=t.SNR_dB) for t in many]
+    chain.synthesize(mdicts, noise_power=0.0, seed=0, out=out)
+    chain.synchronize()
+    ref = o.synthesize_echo(many, cfg, pre)
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.array_equal(got == 0, ref == 0)
     # noise only
     seed = 0x1234567887654321
     chain.synthesize([], noise_power=1.0, seed=seed, out=out)
@@ -269,9 +278,10 @@ def test_device_echo_synthesis_matches_oracle_and_noise_is_philox():
     line_id = p * chain.C + c
     i = np.arange(8, dtype=np.uint64)
     r = _philox4x32_10([i, np.full(8, line_id), np.zeros(8), np.zeros(8)], (seed & 0xFFFFFFFF, seed >> 32))
-    u = lambda w: ((w >> np.uint64(8)).astype(np.float64) + 0.5) / 16777216.0
-    z0 = np.sqrt(-2 * np.log(u(r[0]))) * np.exp(2j * np.pi * u(r[1])) * np.sqrt(0.5)
-    z1 = np.sqrt(-2 * np.log(u(r[2]))) * np.exp(2j * np.pi * u(r[3])) * np.sqrt(0.5)
+    u1 = lambda w: ((w >> np.uint64(9)).astype(np.float64) + 0.5) / 8388608.0
+    u2 = lambda w: (w >> np.uint64(9)).astype(np.float64) / 8388608.0
+    z0 = np.sqrt(-2 * np.log(u1(r[0]))) * np.exp(2j * np.pi * u2(r[1])) * np.sqrt(0.5)
+    z1 = np.sqrt(-2 * np.log(u1(r[2]))) * np.exp(2j * np.pi * u2(r[3])) * np.sqrt(0.5)
     assert np.allclose(z[p, c, 0:16:2], z0, rtol=2e-5, atol=2e-6) and np.allclose(z[p, c, 1:16:2], z1, rtol=2e-5, atol=2e-6)
     # end to end with the drop-in signature: device synthesis (noise-free) == host synthesis
     t3 = tdicts[:3]
@@ -363,4 +373,12 @@ def test_batched_frames_equal_one_at_a_time():
     for (f1, d1), (f2, d2) in zip(one, many):
         assert np.array_equal(d1, d2) and np.array_equal(f1, f2)
     assert len(many[-1][0]) == 0
+    # more frames than lanes and than the pipeline depth, ring slots reused, too many targets refused
+    lists2 = [lists[i % 5] for i in range(23)]
+    seeds2 = [seeds[i % 5] for i in range(23)]
+    many2 = chain.process_targets_batch(lists2, cluster_params, 1.0, seeds2, depth=4)
+    for i, (f2, d2) in enumerate(many2):
+        assert np.array_equal(one[i % 5][1], d2) and np.array_equal(one[i % 5][0], f2)
+    with pytest.raises(rsp.RspError):
+        chain.submit_targets([lists[0][0]] * 65, 0)
     chain.close()

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Where does the time of the targets -> final_targets path go?  (synthesis kernel, chain, host fetch + clustering)
+    python tools/frames_probe.py [--config cfg2] [--frames 192]"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rsp_b200 as rsp
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="cfg2")
+ap.add_argument("--frames", type=int, default=192)
+a = ap.parse_args()
+config, cfar_params, cluster_params = rsp.named_config(a.config)
+pd = rsp.build_precomputed_data(config)
+chain = rsp.RadarChain(config, cfar_params, pd)
+chain.set_waveform(config, pd)
+v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+tl = [dict(Range=900.0, Velocity=0.15 * v_max, ElevationAngle=-5.0, SNR_dB=20.0),
+      dict(Range=3000.0, Velocity=-0.10 * v_max, ElevationAngle=8.2, SNR_dB=10.0),
+      dict(Range=8000.0, Velocity=0.05 * v_max, ElevationAngle=15.0, SNR_dB=10.0)]
+out = {"config": a.config, "lanes": chain.info()["lanes"]}
+for _ in range(3):
+    chain.process_targets(tl, cluster_params, 1.0, 1)
+chain.set_profiling(True)
+chain.kernel_times()
+for i in range(8):
+    chain.process_targets(tl, cluster_params, 1.0, i)
+out["kernel_ms_per_frame_sync"] = {k: round(v[0] / 8, 5) for k, v in chain.kernel_times().items()}
+chain.set_profiling(False)
+n = a.frames
+for depth in (1, 2, 3, 6, 12):
+    chain.process_targets_batch([tl] * 8, cluster_params, 1.0, list(range(8)), depth=depth)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    chain.process_targets_batch([tl] * n, cluster_params, 1.0, list(range(n)), depth=depth)
+    torch.cuda.synchronize()
+    out[f"frames_per_s_depth{depth}"] = round(n / (time.perf_counter() - t0), 1)
+# host side only: submit everything, wait, then time the fetch + sort + cluster of finished slots
+slots = min(chain.stream_slots(), 96)
+for i in range(slots):
+    chain.submit_targets(tl, i, 1.0, i)
+chain.synchronize()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for i in range(slots):
+    chain.fetch_targets(i, cluster_params)
+out["host_fetch_cluster_us_per_frame"] = round((time.perf_counter() - t0) / slots * 1e6, 1)
+t0 = time.perf_counter()
+for i in range(slots):
+    chain.submit_targets(tl, i, 1.0, i)
+out["host_submit_us_per_frame"] = round((time.perf_counter() - t0) / slots * 1e6, 1)
+chain.synchronize()
+torch.cuda.synchronize()
+# device only: submit all, one sync
+t0 = time.perf_counter()
+for r in range(2):
+    for i in range(slots):
+        chain.submit_targets(tl, i, 1.0, i)
+chain.synchronize()
+torch.cuda.synchronize()
+out["device_only_frames_per_s"] = round(2 * slots / (time.perf_counter() - t0), 1)
+print(json.dumps(out))
