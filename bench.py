@@ -352,7 +352,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_n / float(t_e.item())
-    d2h = 4 + 40 * (nd // e2e_n)
+    d2h = 4 + 40 * min(512, chain.max_detections)      # the count and the first 512 records are prefetched to pinned memory
 
     # the reference's own signature: fun_process_single_frame(targets, ...) -> final_targets.  Only the
     # target list goes in and the clustered targets come out; S4 (echo synthesis + noise) runs on the GPU.

@@ -43,11 +43,16 @@ struct rsp_ctx {
         float* amp = nullptr;
         float2* raw = nullptr;            // staging cube of the pipelined host-input / frame paths (lazy)
         float2* rdm = nullptr;            // own RDM of those paths when the caller passes none (lazy; lane 0 uses d_rdm)
+        unsigned long long seen_epoch = 0;  // last caller_epoch this lane was ordered behind (pipelined paths)
         cudaEvent_t done = nullptr;
     };
     std::vector<int> slot_lane;           // lane that last produced each ring slot (-1: joined to the caller's stream)
     Lane lanes[8];
     int n_lanes = 1;
+    // Bumped whenever tables the kernels read are (re)written on the caller's stream or that stream changes; a
+    // pipelined submission orders its lane behind the caller's stream only when the lane has not seen the
+    // current epoch -- doing it per submission would serialise lane l behind everything queued on lane 0.
+    unsigned long long caller_epoch = 1;
     Lane* cur = nullptr;                  // lane the launch helpers enqueue on
     bool discard = false;                 // stream path: drop dead intermediates from L2 (see l2_discard)
     cudaEvent_t fork = nullptr;
@@ -325,6 +330,7 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
 
 int rsp_set_stream(rsp_ctx* c, void* s) {
     if (!c) return RSP_ERR_INVALID_ARG;
+    c->caller_epoch++;
     CU(c, cudaSetDevice(c->prm.device));
     CU(c, cudaStreamSynchronize(c->stream));
     if (s == RSP_STREAM_OWN) {
@@ -355,6 +361,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         !k->velocity_axis || !k->beam_angles_deg || !k->k_slopes)
         return fail(c, RSP_ERR_INVALID_ARG, "null table in rsp_constants");
     if (k->n_fir < 1 || k->n_fir > 256) return fail(c, RSP_ERR_UNSUPPORTED, "n_fir must be 1..256");
+    c->caller_epoch++;
     CU(c, cudaSetDevice(c->prm.device));
     const int C = c->C, B = c->B, P = c->P, G = c->G;
     // conj(W) laid out [c][b]
@@ -840,6 +847,16 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
     return RSP_OK;
 }
 
+static int lane_fork(rsp_ctx* c, int l) {
+    rsp_ctx::Lane& ln = c->lanes[l];
+    if (l > 0 && ln.seen_epoch != c->caller_epoch) {
+        CU(c, cudaEventRecord(c->fork, c->stream));
+        CU(c, cudaStreamWaitEvent(ln.s, c->fork, 0));
+    }
+    ln.seen_epoch = c->caller_epoch;
+    return RSP_OK;
+}
+
 // RDM buffer of a lane for the pipelined paths: concurrent lanes must not share one
 static float2* lane_rdm(rsp_ctx* c, int l) {
     if (l == 0) return c->d_rdm;
@@ -856,10 +873,7 @@ int rsp_submit_cpi(rsp_ctx* c, const void* raw_host, void* rdm_dev, int32_t slot
     rsp_ctx::Lane& ln = c->lanes[l];
     const size_t bytes = (size_t)c->P * c->C * c->N * sizeof(float2);
     if (!ln.raw) CU(c, cudaMalloc(reinterpret_cast<void**>(&ln.raw), bytes));
-    if (l > 0) {
-        CU(c, cudaEventRecord(c->fork, c->stream));
-        CU(c, cudaStreamWaitEvent(ln.s, c->fork, 0));
-    }
+    if (int rcf = lane_fork(c, l)) return rcf;
     CU(c, cudaMemcpyAsync(ln.raw, raw_host, bytes, cudaMemcpyHostToDevice, ln.s));
     float2* rdm = rdm_dev ? static_cast<float2*>(rdm_dev) : lane_rdm(c, l);
     if (!rdm) return fail(c, RSP_ERR_CUDA, "out of device memory for the lane's RDM");
@@ -1091,6 +1105,7 @@ int rsp_stage2_mtd(rsp_ctx* c, const void* iq, rsp_dtype dtype, rsp_c128* mtd_ou
 
 int rsp_set_waveform(rsp_ctx* c, const rsp_waveform* w) {
     if (!c || !w || !w->tx_pulse) return RSP_ERR_INVALID_ARG;
+    c->caller_epoch++;
     CU(c, cudaSetDevice(c->prm.device));
     std::vector<float2> tx(c->N);
     for (int i = 0; i < c->N; ++i) tx[i] = make_float2((float)w->tx_pulse[i].re, (float)w->tx_pulse[i].im);
@@ -1200,10 +1215,7 @@ int rsp_submit_targets(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targe
     SynthTarget* h = c->h_tg_ring + (size_t)slot * RSP_MAX_FRAME_TARGETS;
     SynthTarget* d = c->d_tg_ring + (size_t)slot * RSP_MAX_FRAME_TARGETS;
     const int n_tg = make_synth_targets(c, targets, n_targets, h);
-    if (l > 0) {
-        CU(c, cudaEventRecord(c->fork, c->stream));
-        CU(c, cudaStreamWaitEvent(ln.s, c->fork, 0));
-    }
+    if (int rcf = lane_fork(c, l)) return rcf;
     if (n_tg > 0) CU(c, cudaMemcpyAsync(d, h, (size_t)n_tg * sizeof(SynthTarget), cudaMemcpyHostToDevice, ln.s));
     c->cur = &ln;
     launch_synth(c, ln.raw, d, n_tg, noise_power, seed, ln.s);

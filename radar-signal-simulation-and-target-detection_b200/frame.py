@@ -413,3 +413,27 @@ def fun_process_single_frame(targets, config, cfar_params, cluster_params, preco
         final, _ = chain.process_targets(list(targets), cluster_params, 1.0 if noise else 0.0, seed)
     return [dict(Range=float(t["range"]), Velocity=float(t["velocity"]), Angle=float(t["angle"]),
                  Power=float(t["power"])) for t in final]
+
+
+def fun_process_frames(target_lists, config, cfar_params, cluster_params, precomputed_data, first_frame_idx=1, *,
+                       rng: Optional[np.random.Generator] = None, noise: bool = True,
+                       chain: Optional[RadarChain] = None, device: int = 0) -> List[List[dict]]:
+    """fun_process_single_frame for a whole block of independent frames at once (the frame loop of
+    main_simulate_echoes_with_array_v8_3.m:200-248, whose target kinematics do not depend on the detections):
+    same per-frame results as calling fun_process_single_frame frame by frame with the same ``rng`` (one seed
+    is drawn per frame, in order), but the frames are pipelined over the device lanes."""
+    if chain is None:
+        key = id(precomputed_data)
+        chain = _chain_cache.get(key)
+        if chain is None:
+            chain = RadarChain(config, cfar_params, precomputed_data, device=device)
+            _chain_cache.clear()
+            _chain_cache[key] = chain
+    if not getattr(chain, "_has_waveform", False):
+        chain.set_waveform(config, precomputed_data)
+    rng = rng if rng is not None else np.random.default_rng()
+    seeds = [int(rng.integers(0, 2 ** 63)) for _ in target_lists]
+    res = chain.process_targets_batch([list(t) for t in target_lists], cluster_params, 1.0 if noise else 0.0, seeds)
+    return [[dict(Range=float(t["range"]), Velocity=float(t["velocity"]), Angle=float(t["angle"]), Power=float(t["power"]))
+             for t in final] for final, _ in res]
+

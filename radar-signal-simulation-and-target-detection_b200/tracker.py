@@ -11,7 +11,7 @@ from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
-from .frame import fun_process_single_frame, _field
+from .frame import fun_process_single_frame, fun_process_frames, _field
 from .precompute import Struct
 
 
@@ -109,12 +109,21 @@ def run_multiframe_simulation(targets, config, cfar_params, cluster_params, prec
     tracks = init_tracks(targets)
     log: List[dict] = []
     rng = rng if rng is not None else np.random.default_rng()
+    # the kinematics do not depend on the detections, so every frame's truth is known up front (v8_3:207-228)
+    azimuths, scenes = [], []
     for frame_idx in range(1, total_frames + 1):
         azimuth = (azimuth + deg_per_frame) % 360.0                            # v8_3:207
-        current = evolve(tracks, T_frame)                                      # v8_3:210-228
-        final_targets = process_frame(current, config, cfar_params, cluster_params, precomputed_data, frame_idx, rng=rng, **kw)
-        for t in final_targets:                                                # v8_3:236-246
+        azimuths.append(azimuth)
+        scenes.append(evolve(tracks, T_frame))                                 # v8_3:210-228
+    if process_frame is fun_process_single_frame and not kw.get("host_synthesis"):
+        kw.pop("host_synthesis", None)
+        per_frame = fun_process_frames(scenes, config, cfar_params, cluster_params, precomputed_data, 1, rng=rng, **kw)
+    else:
+        per_frame = [process_frame(sc_, config, cfar_params, cluster_params, precomputed_data, i + 1, rng=rng, **kw)
+                     for i, sc_ in enumerate(scenes)]
+    for i, final_targets in enumerate(per_frame):                              # v8_3:236-246
+        for t in final_targets:
             d = dict(t)
-            d["iFrame"], d["iAntAngle"] = frame_idx, azimuth
+            d["iFrame"], d["iAntAngle"] = i + 1, azimuths[i]
             log.append(d)
     return log, inter_frame_cluster(log, scan_cfg)

@@ -382,3 +382,26 @@ def test_batched_frames_equal_one_at_a_time():
     with pytest.raises(rsp.RspError):
         chain.submit_targets([lists[0][0]] * 65, 0)
     chain.close()
+
+
+def test_multiframe_tracker_batched_equals_frame_by_frame():
+    """main_simulate_echoes_with_array_v8_3.m:192-352 on the device: the pipelined block of frames gives the
+    log the frame-by-frame loop gives (same per-frame seeds), and the inter-frame association finds one track
+    per target."""
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+    targets = [dict(Range=3000.0, Velocity=0.10 * v_max, ElevationAngle=10.0, SNR_dB=12.0),
+               dict(Range=6000.0, Velocity=-0.15 * v_max, ElevationAngle=-4.0, SNR_dB=15.0)]
+    frames = 7
+    log_a, tracks_a = rsp.run_multiframe_simulation(targets, config, cfar_params, cluster_params, pd, total_frames=frames,
+                                                    rng=np.random.default_rng(5), chain=chain)
+    one = lambda *a, **k: rsp.fun_process_single_frame(*a, **k)       # not the default object: takes the per-frame loop
+    log_b, tracks_b = rsp.run_multiframe_simulation(targets, config, cfar_params, cluster_params, pd, total_frames=frames,
+                                                    rng=np.random.default_rng(5), process_frame=one, chain=chain)
+    assert log_a == log_b and tracks_a == tracks_b
+    assert sorted(set(d["iFrame"] for d in log_a)) == list(range(1, frames + 1))
+    # every target is followed through all frames (weaker side-lobe clusters may add short tracks of their own)
+    for tgt in targets:
+        near = [t for t in tracks_a if abs(t["Range"] - tgt["Range"]) < 60.0 and abs(t["Angle"] - tgt["ElevationAngle"]) < 1.0]
+        assert near and max(t["NumPoints"] for t in near) == frames, (tgt, tracks_a)
+    chain.close()
