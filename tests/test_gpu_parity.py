@@ -405,3 +405,66 @@ def test_multiframe_tracker_batched_equals_frame_by_frame():
         near = [t for t in tracks_a if abs(t["Range"] - tgt["Range"]) < 60.0 and abs(t["Angle"] - tgt["ElevationAngle"]) < 1.0]
         assert near and max(t["NumPoints"] for t in near) == frames, (tgt, tracks_a)
     chain.close()
+
+
+def test_monte_carlo_angle_error_agrees_with_the_oracle_within_confidence_bands():
+    """SURVEY 8(d) config 5 parity: the std of the monopulse angle error over independent noise draws, device
+    chain with device Philox noise against the fp64 oracle with NumPy noise (independent streams, so the
+    comparison is statistical: ratio of two sample stds of n = 20, 99.9 % band of the F distribution)."""
+    config, cfar_params, cluster_params = rsp.named_config("cfg1")
+    pd = rsp.build_precomputed_data(config)
+    cfg = o.make_config("cfg1")
+    pre = o.build_precomputed(cfg)
+    n, snrs = 20, [4.0, 16.0]
+    tt = dict(Range=8000.0, Velocity=0.1 * pre["v_max"], ElevationAngle=10.0, pair_idx=5)
+    dev = rsp.snr_vs_angle_error(config, cfar_params, cluster_params, pd, snrs, num_trials=n, true_target=tt, seed=3)
+    assert list(dev["detection_probability"]) == [1.0, 1.0]
+    for i, snr in enumerate(snrs):
+        errs = []
+        echo = o.synthesize_echo([o.Target(tt["Range"], tt["Velocity"], tt["ElevationAngle"], snr)], cfg, pre)
+        for trial in range(n):
+            raw = o.add_noise(echo, np.random.default_rng(1000 * i + trial))
+            res = o.process_cube(raw.astype(np.complex128), cfg, pre, workers=-1, complex_ratio=True)
+            assert len(res.final_targets) >= 1
+            errs.append(res.final_targets[0][2] - tt["ElevationAngle"])
+        s_ref, m_ref = float(np.std(errs, ddof=1)), float(np.mean(errs))
+        s_dev, m_dev = float(dev["angle_error_std"][i]), float(dev["angle_error_mean"][i])
+        print(f"SNR {snr} dB: oracle mean {m_ref:+.4f} std {s_ref:.4f} | device mean {m_dev:+.4f} std {s_dev:.4f}")
+        assert 0.45 < s_dev / s_ref < 2.2, (snr, s_dev, s_ref)
+        assert abs(m_dev - m_ref) < 4.0 * max(s_ref, s_dev) / np.sqrt(n) + 1e-3, (snr, m_dev, m_ref)
+    assert dev["angle_error_std"][1] < dev["angle_error_std"][0]
+
+
+def test_dense_scene_64_targets_device_synthesis_then_chain():
+    """K = 64 random targets synthesised on the device with Philox noise (staged kernel),
+    then S5..S9 on the device; the oracle processes the very same cube (copied back), so the parity is exact
+    in the detection cells even though the noise stream is the device's own."""
+    import torch
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg2", max_detections=32768)
+    chain.set_waveform(config, pd)
+    cfg = o.make_config("cfg2")
+    pre = o.build_precomputed(cfg)
+    rng = np.random.default_rng(1)
+    K, G, P = 64, chain.G, chain.P
+    dR = float(pre["deltaR"])
+    vb = (P / 2 - 16) / P * pre["v_max"]
+    tl = [dict(Range=float(rng.uniform(700 * dR, (G - 16) * dR)), Velocity=float(rng.uniform(-vb, vb)),
+               ElevationAngle=float(rng.uniform(-15.0, 60.0)), SNR_dB=float(rng.uniform(-10.0, 20.0))) for _ in range(K)]
+    out = torch.empty((chain.P, chain.C, chain.N), dtype=torch.complex64, device="cuda")
+    chain.synthesize(tl, noise_power=1.0, seed=99, out=out)
+    dets = chain.process_cpi(out)
+    raw = out.cpu().numpy()
+    res = o.process_cube(raw.astype(np.complex128), cfg, pre, workers=-1)
+    margin = o.cfar_margin(res.S, cfg)
+    st = compare_detections(dets, res.raw_detections, margin, res.parameterized, pre)
+    print("config 4:", st)
+    assert st["n_common"] >= 500
+    fin, dets2 = chain.process_targets(tl, cluster_params, 1.0, 99)       # same seed through the one-call path
+    assert np.array_equal(dets, dets2)
+    _, fin_c = rsp.cluster(dets, cluster_params)
+    assert np.array_equal(fin, fin_c) and len(fin) >= 30
+    # pipelined path with more detections than the pinned prefetch holds (falls back to a second copy)
+    assert len(dets) > 512
+    for f3, d3 in chain.process_targets_batch([tl, tl[:1], tl], cluster_params, 1.0, [99, 5, 99])[::2]:
+        assert np.array_equal(d3, dets) and np.array_equal(f3, fin)
+    chain.close()

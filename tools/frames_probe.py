@@ -9,16 +9,24 @@ import rsp_b200 as rsp
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
 ap.add_argument("--frames", type=int, default=192)
+ap.add_argument("--targets", type=int, default=0, help="K random targets per frame (SURVEY 8(d) config 4) instead of T3")
 a = ap.parse_args()
 config, cfar_params, cluster_params = rsp.named_config(a.config)
 pd = rsp.build_precomputed_data(config)
-chain = rsp.RadarChain(config, cfar_params, pd)
+chain = rsp.RadarChain(config, cfar_params, pd, max_detections=32768 if a.targets else 8192)
 chain.set_waveform(config, pd)
 v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
 tl = [dict(Range=900.0, Velocity=0.15 * v_max, ElevationAngle=-5.0, SNR_dB=20.0),
       dict(Range=3000.0, Velocity=-0.10 * v_max, ElevationAngle=8.2, SNR_dB=10.0),
       dict(Range=8000.0, Velocity=0.05 * v_max, ElevationAngle=15.0, SNR_dB=10.0)]
-out = {"config": a.config, "lanes": chain.info()["lanes"]}
+if a.targets:
+    import numpy as np
+    rng = np.random.default_rng(1)
+    dR = float(pd.deltaR)
+    vb = (chain.P / 2 - 16) / chain.P * v_max
+    tl = [dict(Range=float(rng.uniform(700 * dR, (chain.G - 16) * dR)), Velocity=float(rng.uniform(-vb, vb)),
+               ElevationAngle=float(rng.uniform(-15.0, 60.0)), SNR_dB=float(rng.uniform(-10.0, 20.0))) for _ in range(a.targets)]
+out = {"config": a.config, "lanes": chain.info()["lanes"], "targets_per_frame": len(tl)}
 for _ in range(3):
     chain.process_targets(tl, cluster_params, 1.0, 1)
 chain.set_profiling(True)
