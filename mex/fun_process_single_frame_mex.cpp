@@ -101,6 +101,18 @@ static void ensure_context(const mxArray* config, const mxArray* cfar, const mxA
     if (rc) fail(c.ctx, rc, "rsp_upload_constants");
 }
 
+// Device synthesis mode: S4 + S4.1 run on the GPU (rsp_process_targets), so no cube is built in MATLAB memory
+// and only the target list crosses the bus (tens of microseconds per frame instead of seconds).  The noise
+// then comes from the library's Philox generator, seeded with one draw of MATLAB's global stream per frame
+// (so rng(seed) still makes a run reproducible, but the samples differ from the .m file's randn cube).
+// Enabled by config.rsp_device_synthesis = true or the environment variable RSP_MEX_DEVICE_SYNTH=1.
+static bool device_synthesis(const mxArray* config) {
+    const mxArray* f = mxIsStruct(config) ? mxGetField(config, 0, "rsp_device_synthesis") : nullptr;
+    if (f && mxGetNumberOfElements(f) > 0) return mxGetScalar(f) != 0.0;
+    const char* e = std::getenv("RSP_MEX_DEVICE_SYNTH");
+    return e && std::atoi(e) != 0;
+}
+
 static long matlab_round(double x) { return x >= 0 ? (long)std::floor(x + 0.5) : -(long)std::floor(-x + 0.5); }
 
 extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
@@ -117,15 +129,40 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
     const std::vector<rsp_c128> tx = complexes(field(pd, "tx_pulse", "precomputed_data"), "tx_pulse");
     const double p_sig = scalar(pd, "P_signal_unscaled", "precomputed_data");
 
+    rsp_cluster_params cp{scalar(clus, "max_range_sep", "cluster_params"), scalar(clus, "max_vel_sep", "cluster_params"),
+                          scalar(clus, "max_angle_sep", "cluster_params")};
+    std::vector<rsp_target> fin(4096);
+    int32_t nf = 0;
+    const size_t K = mxIsStruct(targets) ? mxGetNumberOfElements(targets) : 0;
+
+    if (device_synthesis(config)) {
+        if (!cache().waveform) {
+            rsp_waveform w{tx.data(), c0, fs, lam, prt, d_el, p_sig};
+            if ((size_t)tx.size() != N) mexErrMsgIdAndTxt("rsp:shape", "tx_pulse must have point_PRT entries");
+            const int rcw = rsp_set_waveform(cache().ctx, &w);
+            if (rcw) fail(cache().ctx, rcw, "rsp_set_waveform");
+            cache().waveform = true;
+        }
+        std::vector<rsp_target_in> tin(K);
+        for (size_t k = 0; k < K; ++k)
+            tin[k] = rsp_target_in{mxGetScalar(field_at(targets, k, "Range")), mxGetScalar(field_at(targets, k, "Velocity")),
+                                   mxGetScalar(field_at(targets, k, "ElevationAngle")), mxGetScalar(field_at(targets, k, "SNR_dB"))};
+        mxArray* u = nullptr;
+        mexCallMATLAB(1, &u, 0, nullptr, "rand");                       // one draw of the global stream per frame
+        const uint64_t seed = (uint64_t)std::ldexp(mxGetScalar(u), 53);
+        mxDestroyArray(u);
+        const int rc = rsp_process_targets(cache().ctx, tin.data(), (int32_t)K, 1.0 /* P_noise, fsf:83 */, seed, &cp, fin.data(),
+                                           (int32_t)fin.size(), &nf, nullptr, 0, nullptr);
+        if (rc) fail(cache().ctx, rc, "rsp_process_targets");
+    } else {
     // S4 (fsf:47-77): raw(p, n, c) in MATLAB order, element index (c*N + n)*P + p
     mwSize dims[3] = {P, N, C};
     mxArray* cube = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxCOMPLEX);
     mxComplexDouble* raw = mxGetComplexDoubles(cube);
-    const size_t K = mxIsStruct(targets) ? mxGetNumberOfElements(targets) : 0;
     const double two_pi = 6.28318530717958647692;
     for (size_t k = 0; k < K; ++k) {
-        const double R = mxGetScalar(mxGetField(targets, k, "Range")), V = mxGetScalar(mxGetField(targets, k, "Velocity"));
-        const double El = mxGetScalar(mxGetField(targets, k, "ElevationAngle")), snr = mxGetScalar(mxGetField(targets, k, "SNR_dB"));
+        const double R = mxGetScalar(field_at(targets, k, "Range")), V = mxGetScalar(field_at(targets, k, "Velocity"));
+        const double El = mxGetScalar(field_at(targets, k, "ElevationAngle")), snr = mxGetScalar(field_at(targets, k, "SNR_dB"));
         const long d = matlab_round(2.0 * R / c0 * fs);                                   // fsf:55-56
         if (!(d > 0 && d < (long)N)) continue;                                            // fsf:66
         const size_t len = std::min(tx.size(), N - (size_t)d);                            // fsf:67
@@ -164,13 +201,10 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
     mxDestroyArray(sz);
 
     // S5..S11 on the GPU
-    rsp_cluster_params cp{scalar(clus, "max_range_sep", "cluster_params"), scalar(clus, "max_vel_sep", "cluster_params"),
-                          scalar(clus, "max_angle_sep", "cluster_params")};
-    std::vector<rsp_target> fin(4096);
-    int32_t nf = 0;
     const int rc = rsp_process_frame(cache().ctx, raw, RSP_LAYOUT_MATLAB, RSP_C128, RSP_MEM_HOST, &cp, fin.data(), (int32_t)fin.size(), &nf);
     mxDestroyArray(cube);
     if (rc) fail(cache().ctx, rc, "rsp_process_frame");
+    }
 
     if (nf == 0) {                                  // fsf:229-232,305-308,358-361: [] when nothing is detected
         plhs[0] = mxCreateDoubleMatrix(0, 0, mxREAL);

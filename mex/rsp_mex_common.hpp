@@ -2,6 +2,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,11 @@ namespace rspmex {
 inline const mxArray* field(const mxArray* s, const char* name, const char* where) {
     const mxArray* f = (s && mxIsStruct(s)) ? mxGetField(s, 0, name) : nullptr;
     if (!f) mexErrMsgIdAndTxt("rsp:missingField", "field %s.%s is missing", where, name);
+    return f;
+}
+inline const mxArray* field_at(const mxArray* s, size_t idx, const char* name) {
+    const mxArray* f = mxGetField(s, idx, name);
+    if (!f) mexErrMsgIdAndTxt("rsp:missingField", "targets(%d).%s is missing", (int)idx + 1, name);
     return f;
 }
 inline double scalar(const mxArray* s, const char* name, const char* where) { return mxGetScalar(field(s, name, where)); }
@@ -42,10 +48,12 @@ inline std::vector<rsp_c128> complexes(const mxArray* a, const char* what) {
 struct Cache {
     rsp_ctx* ctx = nullptr;
     rsp_params prm{};
+    bool waveform = false;        // rsp_set_waveform done for this context (device synthesis mode)
 };
 inline Cache& cache() { static Cache c; return c; }
 inline void release() {
     if (cache().ctx) { rsp_destroy(cache().ctx); cache().ctx = nullptr; }
+    cache().waveform = false;
 }
 inline void fail(rsp_ctx* ctx, int rc, const char* what) {
     std::string msg = rsp_last_error(ctx);      // copy before anything is destroyed
