@@ -173,6 +173,32 @@ int emul_mtd_dft_tile(const float* x /* [P][TG] */, int P, int TG, const float* 
     return 0;
 }
 
+// the k-tiled work items of mtd_dft_kernel<TG, R, KT> (KT = 4 or 11 bins per item)
+int emul_mtd_dft_tile_kt(const float* x /* [P][TG] */, int P, int TG, int KT, const float* win, float* out /* [TG][P] */) {
+    const int R = (P % 8 == 0) ? 8 : (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1, Q = P / R;
+    if (!(KT == 4 || ((KT == 6 || KT == 11) && R <= 4))) return -1;
+    const cf* xi = reinterpret_cast<const cf*>(x);
+    std::vector<cf> xin((size_t)P * (TG + 1)), xout((size_t)P * (TG + 1), make_float2(-7.f, -7.f)), stw(P);
+    for (int m = 0; m < P; ++m) {
+        const double ang = -2.0 * kPi * m / P;
+        stw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    for (int p = 0; p < P; ++p)
+        for (int gl = 0; gl < TG; ++gl) xin[(size_t)p * (TG + 1) + gl] = cscale(xi[(size_t)p * TG + gl], win[p]);
+    const int groups = (Q + KT - 1) / KT;
+    for (int kg = 0; kg < groups; ++kg)
+        for (int gl = 0; gl < TG; ++gl) {
+#define RSP_EMUL_KT(r, kt) if (R == r && KT == kt) mtd_dft_item_kt<r, kt>(xin.data(), xout.data(), stw.data(), P, TG, kg * KT, gl);
+            RSP_EMUL_KT(8, 4) RSP_EMUL_KT(4, 4) RSP_EMUL_KT(2, 4) RSP_EMUL_KT(1, 4)
+            RSP_EMUL_KT(4, 11) RSP_EMUL_KT(2, 11) RSP_EMUL_KT(1, 11) RSP_EMUL_KT(4, 6) RSP_EMUL_KT(2, 6) RSP_EMUL_KT(1, 6)
+#undef RSP_EMUL_KT
+        }
+    cf* o = reinterpret_cast<cf*>(out);
+    for (int gl = 0; gl < TG; ++gl)
+        for (int row = 0; row < P; ++row) o[(size_t)gl * P + row] = xout[(size_t)row * (TG + 1) + gl];
+    return 0;
+}
+
 // CFAR over a full sum map S[G][P] (one pair) using the two tile phases on tiles of TG gates.
 int emul_cfar_map(const float* S, int G, int P, int guard_r, int guard_v, int ref_r, int ref_v, float t_cfar, int TG,
                   unsigned char* det /* [G][P] */) {

@@ -107,7 +107,7 @@ struct rsp_ctx {
     rsp_detection* h_slot_recs = nullptr; // pinned [slots][prefetch_k]
     std::vector<cudaEvent_t> slot_done;   // recorded behind the prefetch copies
     std::vector<char> slot_prefetched;
-    int mtd_tg = 32, mtd_r = 1, cfar_tg = 32, cfar_variant = 0;
+    int mtd_tg = 32, mtd_r = 1, mtd_kt = 1, cfar_tg = 32, cfar_variant = 0;
     bool cfar_vec = false;
     size_t mtd_smem = 0, cfar_smem = 0;
     // per-kernel event timing (rsp_set_profiling)
@@ -200,8 +200,38 @@ template <class A, class B> static size_t pc2_smem_pair() { return std::max(pc2_
 #define RSP_FOR_EACH_PC2_PAIR(X) X(Pc2L, Pc2L) X(Pc2L, Pc2S) X(Pc2S, Pc2L) X(Pc2S, Pc2S)
 
 // generic Doppler DFT kernel: (tile gates, power-of-two factor R of P)
-#define RSP_FOR_EACH_DFT(X) X(32, 1) X(32, 2) X(32, 4) X(32, 8) X(16, 1) X(16, 2) X(16, 4) X(16, 8) X(8, 1) X(8, 2) X(8, 4) X(8, 8)
+// (tile gates, power-of-two factor R of P, output bins per work item KT)
+#define RSP_FOR_EACH_DFT_TR(X, kt) X(32, 1, kt) X(32, 2, kt) X(32, 4, kt) X(16, 1, kt) X(16, 2, kt) X(16, 4, kt) X(8, 1, kt) X(8, 2, kt) X(8, 4, kt)
+#define RSP_FOR_EACH_DFT(X) RSP_FOR_EACH_DFT_TR(X, 1) RSP_FOR_EACH_DFT_TR(X, 4) RSP_FOR_EACH_DFT_TR(X, 6) RSP_FOR_EACH_DFT_TR(X, 11) \
+    X(32, 8, 1) X(16, 8, 1) X(8, 8, 1) X(32, 8, 4) X(16, 8, 4) X(8, 8, 4)
 #define RSP_FOR_EACH_POW2_P(X) X(8, 8, 1, 1) X(16, 16, 1, 1) X(32, 8, 4, 1) X(64, 8, 8, 1) X(128, 16, 8, 1) X(256, 16, 16, 1) X(512, 8, 8, 8)
+// Tile width (gates) and output bins per work item of the generic Doppler DFT kernel.  The kernel's cost per
+// gate is (rounds of the CTA over its work items) x (bins per item) / (tile gates), divided by how many CTAs
+// fit an SM (the load and read-out phases of one tile hide behind the sums of another; measured on the
+// native P = 332 = 4 x 83: (32, 11) 455 us, (16, 6) 376 us, (16, 4) 452 us, (8, 4) 370 us).  Near-ties go to
+// the wider tile (longer contiguous stretches in the pulse-compressed cube).
+static size_t dft_smem_bytes(int P, int tg) { return ((size_t)2 * P * (tg + 1) + P) * sizeof(float2); }
+static bool choose_dft_plan(int P, int R, int* tg_out, int* kt_out) {
+    const int Q = P / R;
+    const int tg_env = getenv("RSP_DFT_TG") ? atoi(getenv("RSP_DFT_TG")) : 0;
+    const int kt_env = getenv("RSP_DFT_KT") ? atoi(getenv("RSP_DFT_KT")) : 0;
+    double best = -1.0;
+    for (int tg : {32, 16, 8}) {
+        const size_t sm = dft_smem_bytes(P, tg);
+        if (sm > 200 * 1024 || (tg_env && tg != tg_env)) continue;
+        for (int kt : {1, 4, 6, 11}) {
+            if ((kt > 4 && R > 4) || (kt_env ? kt != kt_env : kt == 1)) continue;     // kt = 1 only on request
+            const int regs = kt == 11 ? 160 : kt == 6 ? 96 : 64;
+            const int ctas = (int)std::min<size_t>(std::min<size_t>(227 * 1024 / (sm + 1024), 65536 / (regs * RSP_MTD_THREADS)), 3);
+            const long items = (long)((Q + kt - 1) / kt) * tg;
+            const long rounds = (items + RSP_MTD_THREADS - 1) / RSP_MTD_THREADS;
+            const double cost = (double)rounds * kt / tg / std::max(ctas, 1);
+            if (best < 0 || cost < best * 0.85) { best = cost; *tg_out = tg; *kt_out = kt; }
+        }
+    }
+    return best >= 0;
+}
+
 static cudaError_t mtd_opt_in(int P, size_t bytes) {
     switch (P) {
 #define X(p, a, b, c) case p: return opt_in_smem(mtd_kernel<MtdCfg<p, a, b, c>>, bytes);
@@ -466,15 +496,12 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         }
         for (int p = 0; p < P; ++p) win[p] = (float)k->mtd_win[p];
         CU(c, upload(&c->d_dop_tw, tw));
-        const int tgs[3] = {32, 16, 8};
-        c->mtd_tg = 0;
-        for (int tg : tgs) {
-            const size_t sm = ((size_t)2 * P * (tg + 1) + P) * sizeof(float2);
-            if (sm <= 200 * 1024) { c->mtd_tg = tg; c->mtd_smem = sm; break; }
-        }
-        if (!c->mtd_tg) return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
         c->mtd_r = (P % 8 == 0) ? 8 : (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1;
-#define X(tg, r) if (c->mtd_tg == tg && c->mtd_r == r) CU(c, opt_in_smem(mtd_dft_kernel<tg, r>, c->mtd_smem));
+        c->mtd_tg = 0;
+        if (!choose_dft_plan(P, c->mtd_r, &c->mtd_tg, &c->mtd_kt))
+            return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
+        c->mtd_smem = dft_smem_bytes(P, c->mtd_tg);
+#define X(tg, r, kt) if (c->mtd_tg == tg && c->mtd_r == r && c->mtd_kt == kt) CU(c, opt_in_smem(mtd_dft_kernel<tg, r, kt>, c->mtd_smem));
         RSP_FOR_EACH_DFT(X)
 #undef X
     }
@@ -636,7 +663,7 @@ static void launch_mtd(rsp_ctx* c, float2* rdm) {
 #undef X
         }
     } else {
-#define X(tgv, r) if (tg == tgv && c->mtd_r == r) mtd_dft_kernel<tgv, r><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
+#define X(tgv, r, kt) if (tg == tgv && c->mtd_r == r && c->mtd_kt == kt) mtd_dft_kernel<tgv, r, kt><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a);
         RSP_FOR_EACH_DFT(X)
 #undef X
     }
@@ -1005,14 +1032,12 @@ int rsp_stage2_configure(rsp_ctx* c, const rsp_stage2_config* cfg) {
             tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
         }
         CU(c, upload(&c->d_dop_tw, tw));
-        c->mtd_tg = 0;
-        for (int tg : {32, 16, 8}) {
-            const size_t sm = ((size_t)2 * P * (tg + 1) + P) * sizeof(float2);
-            if (sm <= 200 * 1024) { c->mtd_tg = tg; c->mtd_smem = sm; break; }
-        }
-        if (!c->mtd_tg) return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
         c->mtd_r = (P % 8 == 0) ? 8 : (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1;
-#define X(tg, r) if (c->mtd_tg == tg && c->mtd_r == r) CU(c, opt_in_smem(mtd_dft_kernel<tg, r>, c->mtd_smem));
+        c->mtd_tg = 0;
+        if (!choose_dft_plan(P, c->mtd_r, &c->mtd_tg, &c->mtd_kt))
+            return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
+        c->mtd_smem = dft_smem_bytes(P, c->mtd_tg);
+#define X(tg, r, kt) if (c->mtd_tg == tg && c->mtd_r == r && c->mtd_kt == kt) CU(c, opt_in_smem(mtd_dft_kernel<tg, r, kt>, c->mtd_smem));
         RSP_FOR_EACH_DFT(X)
 #undef X
     }

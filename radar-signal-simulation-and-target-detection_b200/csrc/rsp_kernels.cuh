@@ -906,8 +906,10 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
     }
 }
 
-template <int TG, int R>
-__global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs k) {
+// KT = 1: one output bin per work item (mtd_dft_item); KT > 1: KT bins per item share the input loads
+// (mtd_dft_item_kt), which moves the kernel from the shared-memory pipe to the FMA pipe.
+template <int TG, int R, int KT>
+__global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_constant__ MtdArgs k) {
     extern __shared__ float2 mtd_smem[];
     l2_discard(k.dead);
     const int P = k.P, Q = P / R;
@@ -924,9 +926,17 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const MtdArgs 
         xin[p * (TG + 1) + gl] = cscale(x, k.win[p]);
     }
     __syncthreads();
-    for (int e = tid; e < Q * TG; e += RSP_MTD_THREADS) {
-        const int kk = e / TG, gl = e - kk * TG;
-        mtd_dft_item<R>(xin, xout, stw, P, TG, kk, gl);
+    if (KT == 1) {
+        for (int e = tid; e < Q * TG; e += RSP_MTD_THREADS) {
+            const int kk = e / TG, gl = e - kk * TG;
+            mtd_dft_item<R>(xin, xout, stw, P, TG, kk, gl);
+        }
+    } else {
+        const int groups = (Q + KT - 1) / KT;
+        for (int e = tid; e < groups * TG; e += RSP_MTD_THREADS) {
+            const int kg = e / TG, gl = e - kg * TG;
+            mtd_dft_item_kt<R, (KT > 1 ? KT : 2)>(xin, xout, stw, P, TG, kg * KT, gl);
+        }
     }
     __syncthreads();
     for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {

@@ -392,6 +392,54 @@ template <int R> RSP_HD void mtd_dft_item(const cf* xin, cf* xout, const cf* stw
     }
 }
 
+// The same item for KT consecutive output bins k0 .. k0 + KT - 1 of one gate: every decimated input sample is
+// loaded once and used for KT bins (each with its own warp-uniform twiddle), i.e. R + KT shared-memory loads
+// per 4 R KT multiply-adds instead of R + 1 per 4 R.  The single-bin item is limited by the shared-memory
+// pipe (9 wavefronts per 16 FMA instructions at R = 4); this one is limited by the FMA pipe.  Sums run over n
+// in the same order with the same fused operations, so the results are bit-identical to mtd_dft_item.
+template <int R, int KT> RSP_HD void mtd_dft_item_kt(const cf* xin, cf* xout, const cf* stw, int P, int TG, int k0, int gl) {
+    const int Q = P / R, ld = TG + 1;
+    cf acc[KT][R];
+    int idx[KT], kk[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        kk[j] = k0 + j < Q ? k0 + j : Q - 1;                // bins past the end repeat the last one and are not stored
+        idx[j] = 0;
+#pragma unroll
+        for (int a = 0; a < R; ++a) acc[j][a] = make_float2(0.f, 0.f);
+    }
+    for (int n = 0; n < Q; ++n) {
+        cf x[R];
+#pragma unroll
+        for (int a = 0; a < R; ++a) x[a] = xin[(a + R * n) * ld + gl];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            const cf w = stw[R * idx[j]];                   // W_Q^{n k_j}
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+                acc[j][a].x = fmaf(x[a].x, w.x, fmaf(-x[a].y, w.y, acc[j][a].x));
+                acc[j][a].y = fmaf(x[a].x, w.y, fmaf(x[a].y, w.x, acc[j][a].y));
+            }
+            idx[j] += kk[j];
+            if (idx[j] >= Q) idx[j] -= Q;
+        }
+    }
+    const int half = P / 2;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        if (k0 + j >= Q) break;
+#pragma unroll
+        for (int a = 1; a < R; ++a) acc[j][a] = cmul(acc[j][a], stw[a * kk[j]]);
+        if (R > 1) SmallDft<(R > 1 ? R : 2), -1>::run(acc[j]);
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+            int row = kk[j] + Q * d + half;
+            if (row >= P) row -= P;
+            xout[row * ld + gl] = acc[j][d];
+        }
+    }
+}
+
 // =============================================================================================
 // CFAR on one (pair, gate tile): S tile rows = gates [g_first - mR, g_first + TG + mR), P columns.
 //   fun_process_single_frame.m:192-213.  Two phases: window sums, then the decision.
