@@ -24,10 +24,19 @@ snr = np.arange(lo, hi + 1e-9, st)
 config, cfar_params, cluster_params = rsp.named_config(a.config)
 pd = rsp.build_precomputed_data(config)
 t0 = time.perf_counter()
-res = rsp.snr_vs_angle_error(config, cfar_params, cluster_params, pd, snr, a.trials, device=local, rank=rank, world=world)
+chain = rsp.RadarChain(config, cfar_params, pd, device=local, monopulse_complex=True)      # mc:246-262 uses the complex ratio
+chain.set_waveform(config, pd)
+rsp.snr_vs_angle_error(config, cfar_params, cluster_params, pd, snr[:1], 8, device=local, chain=chain)   # warm-up (lane buffers)
+torch.cuda.synchronize()
+setup = time.perf_counter() - t0
+if world > 1:
+    dist.barrier()
+t0 = time.perf_counter()
+res = rsp.snr_vs_angle_error(config, cfar_params, cluster_params, pd, snr, a.trials, device=local, rank=rank, world=world, chain=chain)
+torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if rank == 0:
-    print(json.dumps({"config": a.config, "n_gpus": world, "trials_per_point": a.trials, "seconds": dt,
+    print(json.dumps({"config": a.config, "n_gpus": world, "trials_per_point": a.trials, "seconds": dt, "setup_seconds": setup,
                       "frames_per_sec": len(snr) * a.trials / dt, "snr_db": res["snr_db"],
                       "angle_error_std": [None if np.isnan(x) else round(float(x), 5) for x in res["angle_error_std"]],
                       "detection_probability": [round(float(x), 4) for x in res["detection_probability"]],
