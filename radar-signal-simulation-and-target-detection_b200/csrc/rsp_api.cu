@@ -61,6 +61,8 @@ struct rsp_ctx {
     // constants
     float2* d_W = nullptr;
     float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
+    float4* d_Wfrag_wa = nullptr;         // same for dbf_mma2_kernel (weights as the A operand)
+    bool dbf_wa = true;                   // RSP_DBF=mma selects the older data-as-A kernel
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
     bool dbf_tma = false;                 // TMA-fed persistent variant
     bool dbf_tma1 = false;                // TMA-fed one-tile-per-CTA variant (bulk loads and bulk stores)
@@ -82,6 +84,9 @@ struct rsp_ctx {
     int dop_tw_count = 0;
     int* d_dop_perm = nullptr;
     float* d_win = nullptr;
+    std::vector<float> h_win, h_s2_win;   // host copies: the register MTD kernel takes the window as an argument
+    int mtd_mode = 0;                     // RSP_MTD: 0 = tile (generic, default), 1 = reg (one thread per Doppler line, P = 32 / 64), 2 = p64 (specialised tile)
+    bool mtd_approx_sqrt = false;         // RSP_MTD_SQRT=approx
     double *d_range_axis = nullptr, *d_vel_axis = nullptr, *d_beam_angles = nullptr, *d_k_slopes = nullptr;
     double delta_r = 0, delta_v = 0;
     // S4 synthesis (rsp_set_waveform)
@@ -268,7 +273,7 @@ void rsp_destroy(rsp_ctx* c) {
     if (c->h_tg_ring) cudaFreeHost(c->h_tg_ring);
     for (auto& sg : c->s2) { cudaFree(sg.tw1); cudaFree(sg.tw2); cudaFree(sg.H); }
     cudaFree(c->d_s2_win);
-    cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_Wfrag); cudaFree(c->d_fir);
+    cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_Wfrag); cudaFree(c->d_Wfrag_wa); cudaFree(c->d_fir);
     cudaFree(c->d_med_tw1); cudaFree(c->d_med_tw2); cudaFree(c->d_med_H);
     cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_tw2); cudaFree(c->d_lng_H);
     cudaFree(c->d_dop_tw); cudaFree(c->d_dop_perm); cudaFree(c->d_win);
@@ -409,6 +414,8 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             c->dbf_nt = (B + 3) / 4;
             c->dbf_ks = C <= 16 ? 4 : 8;
             CU(c, upload(&c->d_Wfrag, make_dbf_fragments(reinterpret_cast<const double*>(k->dbf_weights), B, C, c->dbf_nt, c->dbf_ks)));
+            CU(c, upload(&c->d_Wfrag_wa, make_dbf_fragments_wa(reinterpret_cast<const double*>(k->dbf_weights), B, C, (B + 7) / 8, c->dbf_ks)));
+            c->dbf_wa = !(e && std::string(e) == "mma");
             c->dbf_tma = e && std::string(e) == "tma";             // RSP_DBF=tma: persistent cp.async.bulk-fed variant
             c->dbf_tma1 = e && std::string(e) == "tma1";           // RSP_DBF=tma1: one tile per CTA, bulk loads + bulk stores
             if (c->dbf_tma1) {
@@ -506,6 +513,9 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
 #undef X
     }
     CU(c, upload(&c->d_win, win));
+    c->h_win = win;
+    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 0 : !strcmp(e, "p64") ? 2 : !strcmp(e, "reg") ? 1 : 0; }
+    { const char* e = getenv("RSP_MTD_SQRT"); c->mtd_approx_sqrt = e && !strcmp(e, "approx"); }
     {   // CFAR tile height: the largest of {64,32,16} whose shared arrays stay under 80 KB
         const int mR = c->prm.guard_r + c->prm.ref_r;
         c->cfar_vec = (P % 4) == 0;
@@ -585,6 +595,21 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
         dbf_tma_kernel<NT, KS><<<nctas, RSP_DBF_TMA_THREADS, sm, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, c->P, det_count, dead_amp(c));
         return;
     }
+    if (vec && c->dbf_wa) {
+        constexpr int MT = (NT + 1) / 2;       // NT = ceil(B / 4) n-tiles of the old kernel  ->  ceil(B / 8) m-tiles
+        // RSP_DBF_IT = tiles per warp (1, 4, 8); negative = software-pipelined loads (two tiles in registers)
+        static const int it_env = [] { const char* e = getenv("RSP_DBF_IT"); return e ? atoi(e) : 1; }();
+        constexpr bool kPipe = (KS <= 4 && MT == 1);      // two tiles of loads in registers: 64 for C <= 16, too many beyond
+        const int it = std::abs(it_env);
+#define RSP_DBF2(ITV, PIPEV) do { dim3 gg((c->N + ITV * per_cta - 1) / (ITV * per_cta), c->P);                                  \
+            dbf_mma2_kernel<MT, KS, ITV, PIPEV><<<gg, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, \
+                                                                                         c->N, c->ldb, det_count, dead_amp(c)); } while (0)
+        if (it >= 8 && c->N >= 8 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(8, kPipe); else RSP_DBF2(8, false); }
+        else if (it >= 4 && c->N >= 4 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(4, kPipe); else RSP_DBF2(4, false); }
+        else RSP_DBF2(1, false);
+#undef RSP_DBF2
+        return;
+    }
     if (vec) dbf_mma_kernel<NT, KS, true><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
     else dbf_mma_kernel<NT, KS, false><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
 }
@@ -632,6 +657,7 @@ static void launch_pc(rsp_ctx* c) {
     fill_seg(c, a.seg[0], c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H);
     fill_seg(c, a.seg[1], c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H);
     a.do_narrow = fold ? 1 : 0;
+    { static const int gb = [] { const char* e = getenv("RSP_PC_GROUP_BAR"); return e ? atoi(e) : 1; }(); a.group_bar = gb; }
     a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
     a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
@@ -656,6 +682,24 @@ static void launch_mtd(rsp_ctx* c, float2* rdm) {
     const int tg = c->mtd_tg;
     dim3 grid((c->G + tg - 1) / tg, c->B);
     Timed t(c, K_MTD);
+    if (c->pow2_doppler && c->mtd_mode == 2 && c->P == 64 && (int)c->h_win.size() == c->P) {
+        MtdRegArgs r;
+        r.m = a;
+        for (int p = 0; p < 64; ++p) r.win[p] = c->h_win[p];
+        dim3 sgrid((c->G + 31) / 32, c->B);
+        if (c->mtd_approx_sqrt) mtd64_kernel<true><<<sgrid, 256, 0, c->cur->s>>>(r);
+        else mtd64_kernel<false><<<sgrid, 256, 0, c->cur->s>>>(r);
+        return;
+    }
+    if (c->pow2_doppler && c->mtd_mode == 1 && (c->P == 32 || c->P == 64) && (int)c->h_win.size() == c->P) {
+        MtdRegArgs r;
+        r.m = a;
+        for (int p = 0; p < 64; ++p) r.win[p] = p < c->P ? c->h_win[p] : 0.f;
+        dim3 rgrid((c->G + RSP_MTD_REG_THREADS - 1) / RSP_MTD_REG_THREADS, c->B);
+        if (c->P == 64) mtd_reg_kernel<64><<<rgrid, RSP_MTD_REG_THREADS, 0, c->cur->s>>>(r);
+        else mtd_reg_kernel<32><<<rgrid, RSP_MTD_REG_THREADS, 0, c->cur->s>>>(r);
+        return;
+    }
     if (c->pow2_doppler) {
         switch (c->P) {
 #define X(p, r0, r1, r2) case p: mtd_kernel<MtdCfg<p, r0, r1, r2>><<<grid, RSP_MTD_THREADS, c->mtd_smem, c->cur->s>>>(a); break;
@@ -717,11 +761,15 @@ static int kernels_per_cpi(const rsp_ctx* c) {
 // enqueue S5..S9 for one device-resident PCN cube on lane `lane`
 static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, int lane) {
     c->cur = &c->lanes[lane];
-    int rc = launch_dbf_any(c, raw, c->d_counts + slot);      // dbf_kernel also zeroes the slot's counter
+    // RSP_STAGES (bit mask 1 = DBF, 2 = PC, 4 = MTD, 8 = CFAR) is a measurement aid for tools/stage_probe.py: it
+    // leaves stages out so that the steady-state cost of each kernel on the lanes can be timed in isolation.
+    static const int stages = [] { const char* e = getenv("RSP_STAGES"); return e ? atoi(e) : 15; }();
+    int rc = RSP_OK;
+    if (stages & 1) rc = launch_dbf_any(c, raw, c->d_counts + slot);      // dbf_kernel also zeroes the slot's counter
     if (rc) return rc;
-    launch_pc(c);
-    launch_mtd(c, rdm);
-    if (cfar_testable(c)) launch_cfar(c, rdm, slot);
+    if (stages & 2) launch_pc(c);
+    if (stages & 4) launch_mtd(c, rdm);
+    if ((stages & 8) && cfar_testable(c)) launch_cfar(c, rdm, slot);
     c->cur = &c->lanes[0];
     CU(c, cudaGetLastError());
     return RSP_OK;
@@ -1019,6 +1067,9 @@ int rsp_stage2_configure(rsp_ctx* c, const rsp_stage2_config* cfg) {
         win[p] = (float)(c->pow2_doppler ? w * ((p & 1) ? -1.0 : 1.0) : w);
     }
     CU(c, upload(&c->d_s2_win, win));
+    c->h_s2_win = win;
+    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 0 : !strcmp(e, "p64") ? 2 : !strcmp(e, "reg") ? 1 : 0; }
+    { const char* e = getenv("RSP_MTD_SQRT"); c->mtd_approx_sqrt = e && !strcmp(e, "approx"); }
     if (c->pow2_doppler) {
         CU(c, upload(&c->d_dop_tw, c->dop.tw));
         CU(c, upload(&c->d_dop_perm, c->dop.iperm));
@@ -1062,6 +1113,7 @@ static void launch_s2_pair(rsp_ctx* c, const rsp_ctx::S2Seg* a0, const rsp_ctx::
         }
     }
     a.do_narrow = 0; a.fir = nullptr; a.nfir = 0; a.fir_delay = 0; a.narrow_start0 = 0; a.narrow_gates = 0;
+    { static const int gb = [] { const char* e = getenv("RSP_PC_GROUP_BAR"); return e ? atoi(e) : 1; }(); a.group_bar = gb; }
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
     if (nctas == 0) return;
     Timed t(c, K_PC);
@@ -1097,7 +1149,9 @@ int rsp_stage2_mtd(rsp_ctx* c, const void* iq, rsp_dtype dtype, rsp_c128* mtd_ou
     {   // MTD with the stage-2 window
         float* keep = c->d_win;
         c->d_win = c->d_s2_win;
+        c->h_win.swap(c->h_s2_win);
         launch_mtd(c, c->d_rdm);
+        c->h_win.swap(c->h_s2_win);
         c->d_win = keep;
     }
     if (c->s2_notch > 0) {

@@ -479,6 +479,143 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_mma_kernel(const floa
 }
 
 // ------------------------------------------------------------------------------------------
+// S5 on the tensor cores, weights as the A operand (N even): D[16 x 8] = A[16 x 8] * B[8 x 8] with
+//   A rows  r < 8 -> Re of beam 8 mt + r,  r + 8 -> Im of the same beam;   k = t -> (channel 4s + t, Re x), t + 4 -> (.., Im x)
+//   B cols  = 8 range samples.
+// A thread's B fragment {b0, b1} of a k-step is then exactly the (re, im) pair of ONE complex sample of ONE
+// channel, in load order: a float4 load (samples n, n + 1) feeds the "even" and the "odd" n-tile of a 16-sample
+// group without a single register move (the data-as-A kernel above needs the order x, z, y, w and pays ~150
+// moves per warp for it, a third of its instructions; on sm_100a a move costs an issue slot like an FFMA).
+// The D fragments hold Re (row g) and Im (row g + 8) of beam g for samples 4t .. 4t + 3 of the group, i.e. 32
+// contiguous bytes of the beam row per thread, 128 per quad.  Weight fragments (hi, lo) come straight from
+// global memory through L1 (4 KB, read by every warp), so the kernel has no shared memory and no barrier.
+// 3xTF32 as above: Wl*xh + Wh*xl + Wh*xh with xh = x (the MMA ignores the 13 low mantissa bits), xl = x - trunc(x).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_wa(float (&d)[4], const float4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+                   "r"(b0), "r"(b1));
+}
+
+// IT = consecutive 32-sample tiles per warp.  IT > 1 software-pipelines the warp: the loads of tile j + 1 are in
+// flight while tile j goes through the tensor cores, so a warp always has 4 KB of reads outstanding instead of
+// alternating between a load phase and a compute phase (the IT = 1 kernel spends 56 % of its warp-cycles waiting
+// at the first MMA, profiles/r1b_*), and the grid is a single resident wave of long-lived CTAs.
+template <int MT, int KS, int IT, bool PIPE>
+__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : 1)) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
+                                                                       const float4* __restrict__ Wa /* [KS][MT][2][32] */,
+                                                                       int C, int NB, int N, int ldb,
+                                                                       int* __restrict__ det_count, const DiscardArgs dead) {
+    const int tid = threadIdx.x;
+    l2_discard(dead);
+    if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
+    const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int p = blockIdx.y;
+    const int n_first = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (32 * IT);     // IT tiles of 32 samples per warp
+    if (n_first >= N) return;
+    // column g of the even n-tile of a 16-sample group <-> sample sg = g (g even) or g + 7 (g odd), odd n-tile: sg + 1.
+    // With this order the D fragments of lane t are samples 2t, 2t+1 and 2t+8, 2t+9, so each of the two 16-byte stores
+    // of a quad is 64 contiguous bytes (full 32-byte sectors) instead of four 16-byte pieces 32 bytes apart.
+    const int sg = (g & 1) ? g + 7 : g;
+    const float2* rp = raw + (size_t)p * C * N + sg + (unsigned)(t * N);                 // channel t of k-step 0
+    const unsigned cstep = 4u * (unsigned)N;                                           // k-step s: channel 4s + t
+    float2* const brow = beam + (size_t)p * NB * ldb + 2 * t;
+
+    auto load_tile = [&](float4 (&x)[KS][2], int n_base) {
+        const bool in0 = n_base + sg < N, in1 = n_base + 16 + sg < N;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            x[s][0] = x[s][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * s + t < C) {
+                const float2* src = rp + s * cstep + n_base;
+                if (in0) x[s][0] = __ldcs(reinterpret_cast<const float4*>(src));
+                if (in1) x[s][1] = __ldcs(reinterpret_cast<const float4*>(src + 16));
+            }
+        }
+    };
+    auto compute_store = [&](const float4 (&x)[KS][2], int n_base) {
+        float acc[MT][4][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            // n-tile j = 2q + parity: {b0, b1} = (re, im) of sample 16q + sg + parity
+            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float v[4] = {x[s][q].x, x[s][q].y, x[s][q].z, x[s][q].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t hi = __float_as_uint(v[i]) & 0xFFFFE000u;
+                    bh[2 * q + (i >> 1)][i & 1] = hi;
+                    bl[2 * q + (i >> 1)][i & 1] = __float_as_uint(v[i] - __uint_as_float(hi)) & 0xFFFFE000u;
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const float4 ah = __ldg(Wa + ((s * MT + mt) * 2 + 0) * 32 + lane);
+                const float4 al = __ldg(Wa + ((s * MT + mt) * 2 + 1) * 32 + lane);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    mma_tf32_wa(acc[mt][j], al, bh[j][0], bh[j][1]);
+                    mma_tf32_wa(acc[mt][j], ah, bl[j][0], bl[j][1]);
+                    mma_tf32_wa(acc[mt][j], ah, bh[j][0], bh[j][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int b = 8 * mt + g;
+            if (b < NB) {
+                float2* row = brow + (size_t)b * ldb + n_base;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float(&E)[4] = acc[mt][2 * q];
+                    const float(&O)[4] = acc[mt][2 * q + 1];
+                    const int n = n_base + 16 * q + 2 * t;
+                    if (n < N) *reinterpret_cast<float4*>(row + 16 * q) = make_float4(E[0], E[2], O[0], O[2]);
+                    if (n + 8 < N) *reinterpret_cast<float4*>(row + 16 * q + 8) = make_float4(E[1], E[3], O[1], O[3]);
+                }
+            }
+        }
+    };
+
+    if (IT == 1) {
+        float4 x[KS][2];
+        load_tile(x, n_first);
+        compute_store(x, n_first);
+    } else if (!PIPE) {
+        // several tiles per warp, one after the other: the weight fragments stay in registers, the CTA lives longer
+#pragma unroll 1
+        for (int j = 0; j < IT; ++j) {
+            const int n0 = n_first + 32 * j;
+            if (n0 >= N) break;
+            float4 x[KS][2];
+            load_tile(x, n0);
+            compute_store(x, n0);
+        }
+    } else {
+        float4 xa[KS][2], xb[KS][2];
+        load_tile(xa, n_first);
+#pragma unroll 1
+        for (int j = 0; j < IT; j += 2) {
+            const int n0 = n_first + 32 * j;
+            if (n0 >= N) break;
+            if (j + 1 < IT && n0 + 32 < N) load_tile(xb, n0 + 32);
+            compute_store(xa, n0);
+            if (j + 1 >= IT || n0 + 32 >= N) break;
+            if (j + 2 < IT && n0 + 64 < N) load_tile(xa, n0 + 64);
+            compute_store(xb, n0 + 32);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // S5, TMA-fed variant: a persistent CTA (4 MMA warps + 1 producer warp) streams [C channels x 128
 // samples] tiles of the raw cube through a 4-stage shared-memory ring with cp.async.bulk (one 1-D bulk
 // copy per channel row, completion counted on an mbarrier), so the bytes in flight per SM are set by
@@ -730,7 +867,15 @@ struct PcKernelArgs {
     int do_narrow;
     const float* fir;
     int nfir, fir_delay, narrow_start0, narrow_gates;
+    int group_bar;               // 1: the groups of a CTA synchronise separately (named barriers)
 };
+
+// Barrier over one group of T threads (whole warps) that share an overlap-save block: named barrier 1 + grp.
+// The groups of a CTA are independent after the shared tables are loaded, so they need not wait for each other.
+__device__ __forceinline__ void pc_group_sync(bool per_group, int grp, int nthreads) {
+    if (per_group) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
+    else __syncthreads();
+}
 
 template <class Cfg>
 __device__ __forceinline__ void pc_role(const PcKernelArgs& k, const PcSegArgs& sg, int cta, float2* smem, bool narrow) {
@@ -757,25 +902,26 @@ __device__ __forceinline__ void pc_role(const PcKernelArgs& k, const PcSegArgs& 
     a.taps = sg.taps;
     a.g0 = sg.gate0 + blk * sg.valid;
     a.g_end = sg.g_end;
+    const bool pg = k.group_bar != 0 && Cfg::NG > 1;
     if (active) pc_phase_load_pass1<Cfg>(a, s, t);
-    __syncthreads();
+    __syncthreads();                                 // also publishes stw2 / sfir, loaded by the whole CTA
     if (active) pc_phase_pass2<Cfg>(a, s, t);
-    __syncthreads();
+    pc_group_sync(pg, grp, Cfg::T);
     if (active) pc_phase_mid<Cfg>(a, s, t);
-    __syncthreads();
+    pc_group_sync(pg, grp, Cfg::T);
     if (active) pc_phase_ipass2<Cfg>(a, s, t);
-    __syncthreads();
+    pc_group_sync(pg, grp, Cfg::T);
     if (active) pc_phase_ipass1_store<Cfg>(a, s, t);
     if (narrow) {                                   // uniform over the CTA
         const int need = k.narrow_gates + k.fir_delay;
         const bool fast = need <= k.N - k.narrow_start0 && need <= Cfg::SMEM_ELEMS;
-        __syncthreads();
+        pc_group_sync(pg, grp, Cfg::T);
         if (active && blk == 0) {
             if (fast) {
                 for (int i = t; i < need; i += Cfg::T) s[i] = a.line[k.narrow_start0 + i];
             }
         }
-        __syncthreads();
+        pc_group_sync(pg, grp, Cfg::T);
         if (active && blk == 0) {
             for (int g = t; g < k.narrow_gates; g += Cfg::T)
                 a.out_line[g] = fast ? pc_narrow_gate_smem(s, sfir, k.nfir, k.fir_delay, g)
@@ -902,6 +1048,143 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
             const size_t o = ((size_t)b * k.G + g0 + gl) * P + row;
             __stcs(k.rdm + o, v);
             k.amp[o] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
+        }
+    }
+}
+
+// S7, register variant (P = 32 or 64): one thread owns one (beam, gate) Doppler line.  Its P pulses arrive
+// with P independent coalesced loads (lanes = consecutive gates), the whole windowed FFT is straight-line
+// code on registers (generated SmallDft<32/64>, every twiddle an immediate, the window read from the
+// constant bank because it sits in the kernel arguments), and shared memory is used once, for the corner
+// turn: a warp-private [32 gates][32 rows + 1] tile, so only __syncwarp() is ever needed.  Against the tiled
+// kernel this removes two shared-memory round trips per point and all run-time butterfly addressing
+// (84 -> ~35 instructions per point; on sm_100a an integer instruction costs an issue slot just like an FFMA,
+// tools/ubench/opcost.cu).
+struct MtdRegArgs {
+    MtdArgs m;
+    float win[64];          // kaiser(P) * (-1)^p  (fftshift folded in), fun_process_single_frame.m:134-135
+};
+#define RSP_MTD_REG_THREADS 128
+template <int P>
+__global__ void __launch_bounds__(RSP_MTD_REG_THREADS, (P > 32 ? 3 : 4)) mtd_reg_kernel(const __grid_constant__ MtdRegArgs k) {
+    static_assert(P == 32 || P == 64, "register MTD exists for P = 32 and 64");
+    constexpr int H = 32, PITCH = H + 1;
+    __shared__ float2 tiles[(RSP_MTD_REG_THREADS / 32) * 32 * PITCH];
+    l2_discard(k.m.dead);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y, G = k.m.G;
+    const int gw = blockIdx.x * RSP_MTD_REG_THREADS + w * 32;      // first gate of this warp
+    if (gw >= G) return;                                           // whole warp out of range (no CTA-wide barrier below)
+    const int g = gw + lane;
+    const unsigned pstride = (unsigned)k.m.B * (unsigned)k.m.ldg;
+    const float2* src = k.m.pc + (size_t)b * k.m.ldg + (g < G ? g : G - 1);
+    cf v[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) v[p] = src[p * pstride];
+#pragma unroll
+    for (int p = 0; p < P; ++p) v[p] = cscale(v[p], k.win[p]);
+    SmallDft<P, -1>::run(v);
+    float2* tile = tiles + w * 32 * PITCH;
+    const int rows = G - gw < 32 ? G - gw : 32;                    // gates of this warp that exist
+    float2* rdm_w = k.m.rdm + ((size_t)b * G + gw) * P + lane;
+    float* amp_w = k.m.amp + ((size_t)b * G + gw) * P + lane;
+#pragma unroll
+    for (int h = 0; h < P / H; ++h) {
+        if (h) __syncwarp();
+#pragma unroll
+        for (int i = 0; i < H; ++i) tile[lane * PITCH + i] = v[h * H + i];
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            if (r < rows) {
+                const float2 x = tile[r * PITCH + lane];
+                __stcs(rdm_w + r * P + h * H, x);
+                amp_w[r * P + h * H] = sqrtf(fmaf(x.x, x.x, x.y * x.y));
+            }
+        }
+    }
+}
+
+// S7, P = 64 specialisation of the tiled kernel (8 x 8 Cooley-Tukey, every index a compile-time constant).
+//   phase 1, thread (q = warp, gl = lane): pulses p = q + 8m of gate gl -> window -> DFT-8 over m -> . W64^(q k1) -> S1[k1][q][gl]
+//   phase 2, thread (k1 = warp, gl):       S1[k1][.][gl] -> DFT-8 over q -> X[k1 + 8 k2] -> S2[gl][k1 + 8 k2]   (corner turn)
+//   phase 3: the tile is one contiguous 16 KB block of rdm[b][g][v]; consecutive threads store consecutive bins.
+// Same data flow as mtd_kernel<MtdCfg<64, 8, 8, 1>> but without run-time butterfly addressing, with the window in
+// the constant bank (kernel argument) and the 49 twiddles in __constant__ memory (warp-uniform index):
+// 84 -> ~40 instructions per point at the same register footprint, so the co-resident kernels of the other
+// lanes get the issue slots.  Lanes run along gates in phases 1-2 and along Doppler bins in phase 3; the S2 pitch
+// of 65 keeps the transposed 64-bit stores conflict free (lane stride 130 words = 2 banks).
+__constant__ float2 c_tw64[64] = {   // c_tw64[8 q + k1] = exp(-2 pi i q k1 / 64)
+    {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f},
+    {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f},
+    {1.0f, 0.0f}, {0.99518472f, -0.0980171412f}, {0.980785251f, -0.195090324f}, {0.956940353f, -0.290284663f},
+    {0.923879504f, -0.382683426f}, {0.881921291f, -0.471396744f}, {0.831469595f, -0.555570245f}, {0.773010433f, -0.634393275f},
+    {1.0f, 0.0f}, {0.980785251f, -0.195090324f}, {0.923879504f, -0.382683426f}, {0.831469595f, -0.555570245f},
+    {0.707106769f, -0.707106769f}, {0.555570245f, -0.831469595f}, {0.382683426f, -0.923879504f}, {0.195090324f, -0.980785251f},
+    {1.0f, 0.0f}, {0.956940353f, -0.290284663f}, {0.831469595f, -0.555570245f}, {0.634393275f, -0.773010433f},
+    {0.382683426f, -0.923879504f}, {0.0980171412f, -0.99518472f}, {-0.195090324f, -0.980785251f}, {-0.471396744f, -0.881921291f},
+    {1.0f, 0.0f}, {0.923879504f, -0.382683426f}, {0.707106769f, -0.707106769f}, {0.382683426f, -0.923879504f},
+    {6.12323426e-17f, -1.0f}, {-0.382683426f, -0.923879504f}, {-0.707106769f, -0.707106769f}, {-0.923879504f, -0.382683426f},
+    {1.0f, 0.0f}, {0.881921291f, -0.471396744f}, {0.555570245f, -0.831469595f}, {0.0980171412f, -0.99518472f},
+    {-0.382683426f, -0.923879504f}, {-0.773010433f, -0.634393275f}, {-0.980785251f, -0.195090324f}, {-0.956940353f, 0.290284663f},
+    {1.0f, 0.0f}, {0.831469595f, -0.555570245f}, {0.382683426f, -0.923879504f}, {-0.195090324f, -0.980785251f},
+    {-0.707106769f, -0.707106769f}, {-0.980785251f, -0.195090324f}, {-0.923879504f, 0.382683426f}, {-0.555570245f, 0.831469595f},
+    {1.0f, 0.0f}, {0.773010433f, -0.634393275f}, {0.195090324f, -0.980785251f}, {-0.471396744f, -0.881921291f},
+    {-0.923879504f, -0.382683426f}, {-0.956940353f, 0.290284663f}, {-0.555570245f, 0.831469595f}, {0.0980171412f, 0.99518472f}};
+
+#define RSP_MTD64_PITCH 65
+template <bool APPROX_SQRT>
+__global__ void __launch_bounds__(256, 4) mtd64_kernel(const __grid_constant__ MtdRegArgs k) {
+    __shared__ float2 S1[64 * 32];
+    __shared__ float2 S2[32 * RSP_MTD64_PITCH];
+    l2_discard(k.m.dead);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y, G = k.m.G, g0 = blockIdx.x * 32;
+    {   // phase 1
+        const int g = g0 + lane;
+        const unsigned pstride = (unsigned)k.m.B * (unsigned)k.m.ldg;
+        const float2* src = k.m.pc + (size_t)b * k.m.ldg + (g < G ? g : G - 1) + (size_t)w * pstride;
+        cf v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = src[(unsigned)(8 * m) * pstride];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = cscale(v[m], k.win[w + 8 * m]);
+        SmallDft<8, -1>::run(v);
+        S1[(0 * 8 + w) * 32 + lane] = v[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) {
+            const float2 t = c_tw64[8 * w + k1];
+            S1[(k1 * 8 + w) * 32 + lane] = mul_tw<-1>(v[k1], t.x, t.y);
+        }
+    }
+    __syncthreads();
+    {   // phase 2
+        cf v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = S1[(w * 8 + q) * 32 + lane];
+        SmallDft<8, -1>::run(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) S2[lane * RSP_MTD64_PITCH + w + 8 * k2] = v[k2];
+    }
+    __syncthreads();
+    {   // phase 3: element e = gl * 64 + v of the tile, e = tid + 256 i
+        const int v = threadIdx.x & 63, glb = threadIdx.x >> 6;
+        const size_t o = ((size_t)b * G + g0) * 64 + threadIdx.x;
+        float2* rdm = k.m.rdm + o;
+        float* amp = k.m.amp + o;
+        const int rows = G - g0;                 // gates of this tile that exist (>= 1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int gl = glb + 4 * i;
+            if (gl < rows) {
+                const float2 x = S2[gl * RSP_MTD64_PITCH + v];
+                __stcs(rdm + 256 * i, x);
+                const float sq = fmaf(x.x, x.x, x.y * x.y);
+                float a;
+                if (APPROX_SQRT) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(sq));
+                else a = sqrtf(sq);
+                amp[256 * i] = a;
+            }
         }
     }
 }

@@ -213,4 +213,27 @@ inline std::vector<float4> make_dbf_fragments(const double* W_ri /* [B][C][2] */
     return f;
 }
 
+// Weight fragments for dbf_mma2_kernel (weights as the A operand of mma m16n8k8 tf32):
+//   f[((s*MT + mt)*2 + {hi, lo})*32 + lane] = {a0, a1, a2, a3},  lane = 4g + t, beam b = 8 mt + g, channel c = 4 s + t,
+//   a0 = A[Re b][(c, re)] = wr, a1 = A[Im b][(c, re)] = -wi, a2 = A[Re b][(c, im)] = wi, a3 = A[Im b][(c, im)] = wr
+//   for out = sum_c x_c conj(W[b][c]), W = wr + i wi  (fun_process_single_frame.m:95, x * W').
+inline std::vector<float4> make_dbf_fragments_wa(const double* W_ri /* [B][C][2] */, int B, int C, int MT, int KS) {
+    std::vector<float4> f((size_t)KS * MT * 2 * 32);
+    for (int s = 0; s < KS; ++s)
+        for (int mt = 0; mt < MT; ++mt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3, c = 4 * s + t, b = 8 * mt + g;
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+                if (c < C && b < B) {
+                    const float wr = (float)W_ri[((size_t)b * C + c) * 2], wi = (float)W_ri[((size_t)b * C + c) * 2 + 1];
+                    a[0] = wr; a[1] = -wi; a[2] = wi; a[3] = wr;
+                }
+                float h[4], l[4];
+                for (int i = 0; i < 4; ++i) { h[i] = host_tf32(a[i]); l[i] = host_tf32(a[i] - h[i]); }
+                f[((size_t)(s * MT + mt) * 2 + 0) * 32 + lane] = make_float4(h[0], h[1], h[2], h[3]);
+                f[((size_t)(s * MT + mt) * 2 + 1) * 32 + lane] = make_float4(l[0], l[1], l[2], l[3]);
+            }
+    return f;
+}
+
 }  // namespace rsp
