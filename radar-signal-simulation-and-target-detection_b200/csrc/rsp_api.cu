@@ -62,6 +62,7 @@ struct rsp_ctx {
     float2* d_W = nullptr;
     float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
     float4* d_Wfrag_wa = nullptr;         // same for dbf_mma2_kernel (weights as the A operand)
+    int stages = 15;                      // RSP_STAGES at rsp_create (measurement aid, see enqueue_chain)
     bool dbf_wa = true;                   // RSP_DBF=mma selects the older data-as-A kernel
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
     bool dbf_tma = false;                 // TMA-fed persistent variant
@@ -85,7 +86,7 @@ struct rsp_ctx {
     int* d_dop_perm = nullptr;
     float* d_win = nullptr;
     std::vector<float> h_win, h_s2_win;   // host copies: the register MTD kernel takes the window as an argument
-    int mtd_mode = 0;                     // RSP_MTD: 0 = tile (generic, default), 1 = reg (one thread per Doppler line, P = 32 / 64), 2 = p64 (specialised tile)
+    int mtd_mode = 2;                     // RSP_MTD: 0 = tile (generic), 1 = reg (one thread per Doppler line, P = 32 / 64), 2 = p64 (specialised tile; default when P = 64)
     bool mtd_approx_sqrt = false;         // RSP_MTD_SQRT=approx
     double *d_range_axis = nullptr, *d_vel_axis = nullptr, *d_beam_angles = nullptr, *d_k_slopes = nullptr;
     double delta_r = 0, delta_v = 0;
@@ -170,7 +171,16 @@ template <typename T> static cudaError_t upload(T** dptr, const std::vector<T>& 
     return cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
+// RSP_CARVEOUT=1 (experiment, off by default): every chain kernel asks for the same L1 / shared-memory split (maximum
+// shared memory), so that an SM never has to drain to change its carve-out between kernels of different lanes.  Measured:
+// it does not make the kernels of different streams overlap any better (DBF + PC together still cost the sum of their
+// times) and the smaller L1 slows both (DBF 15.3 -> 21.0 us, PC 21.8 -> 24.2 us), profiles/r1_overlap_probe.txt.
+static int carveout_pct() { static const int v = [] { const char* e = getenv("RSP_CARVEOUT"); return e ? atoi(e) : 0; }(); return v == 1 ? 100 : v; }
+template <typename KernelT> static void prefer_max_smem(KernelT kern) {
+    if (carveout_pct() > 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct());
+}
 template <typename KernelT> static cudaError_t opt_in_smem(KernelT kern, size_t bytes) {
+    prefer_max_smem(kern);
     if (bytes <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
@@ -191,7 +201,9 @@ typedef PcCfg<4096, 16, 16, 16> Pc4096;
 template <class Cfg> static size_t pc_smem_bytes() {
     return ((size_t)Cfg::NG * Cfg::SMEM_ELEMS + (Cfg::R2 - 1) * Cfg::SPAN2) * sizeof(float2) + 256 * sizeof(float);
 }
-template <class A, class B> static size_t pc_smem_pair() { return std::max(pc_smem_bytes<A>(), pc_smem_bytes<B>()); }
+// RSP_OCC_PC caps the pulse-compression CTAs per SM (shared-memory padding), leaving registers for the kernels of other lanes
+static int pc_occ_cap() { static const int v = [] { const char* e = getenv("RSP_OCC_PC"); return e ? atoi(e) : 0; }(); return v; }
+template <class A, class B> static size_t pc_smem_pair() { return smem_for_occupancy(std::max(pc_smem_bytes<A>(), pc_smem_bytes<B>()), pc_occ_cap()); }
 // X(long plan, medium plan)
 #define RSP_FOR_EACH_PC_PAIR(X) X(Pc1024, Pc1024) X(Pc2048, Pc1024) X(Pc4096, Pc1024) X(Pc1024, Pc2048) X(Pc2048, Pc2048) \
     X(Pc4096, Pc2048) X(Pc1024, Pc4096) X(Pc2048, Pc4096) X(Pc4096, Pc4096)
@@ -331,16 +343,21 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
         }                                                                                           \
     } while (0)
     CUC(cudaSetDevice(p->device));
-    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // RSP_STREAM_PRIO=high: the context's own streams get the greatest priority (measurement aid, tools/overlap_probe.py)
+    int prio_lo = 0, prio_hi = 0;
+    CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    { const char* e = getenv("RSP_STREAM_PRIO"); if (!(e && !strcmp(e, "high"))) prio_hi = prio_lo > 0 ? 0 : prio_lo; }
+    CUC(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     const size_t PBG = (size_t)c->P * c->B * c->G;
     CUC(dev_alloc(&c->d_raw, (size_t)c->P * c->C * c->N));
     CUC(dev_alloc(&c->d_rdm, PBG));
+    { const char* e = getenv("RSP_STAGES"); c->stages = e ? atoi(e) : 15; }
     const char* el = getenv("RSP_LANES");
     c->n_lanes = el ? std::min(8, std::max(1, atoi(el))) : 3;
     CUC(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
     for (int i = 0; i < c->n_lanes; ++i) {
         rsp_ctx::Lane& ln = c->lanes[i];
-        if (i == 0) ln.s = c->stream; else CUC(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
+        if (i == 0) ln.s = c->stream; else CUC(cudaStreamCreateWithPriority(&ln.s, cudaStreamNonBlocking, prio_hi));
         CUC(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
         CUC(dev_alloc(&ln.beam, (size_t)c->P * c->B * c->ldb));
         CUC(dev_alloc(&ln.pc, (size_t)c->P * c->B * c->ldg));
@@ -514,7 +531,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     }
     CU(c, upload(&c->d_win, win));
     c->h_win = win;
-    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 0 : !strcmp(e, "p64") ? 2 : !strcmp(e, "reg") ? 1 : 0; }
+    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 2 : !strcmp(e, "tile") ? 0 : !strcmp(e, "reg") ? 1 : 2; }
     { const char* e = getenv("RSP_MTD_SQRT"); c->mtd_approx_sqrt = e && !strcmp(e, "approx"); }
     {   // CFAR tile height: the largest of {64,32,16} whose shared arrays stay under 80 KB
         const int mR = c->prm.guard_r + c->prm.ref_r;
@@ -601,8 +618,12 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
         static const int it_env = [] { const char* e = getenv("RSP_DBF_IT"); return e ? atoi(e) : 1; }();
         constexpr bool kPipe = (KS <= 4 && MT == 1);      // two tiles of loads in registers: 64 for C <= 16, too many beyond
         const int it = std::abs(it_env);
+        // RSP_OCC_DBF caps the DBF CTAs per SM (dynamic shared-memory padding the kernel never touches)
+        static const size_t dbf_pad = [] { const char* e = getenv("RSP_OCC_DBF"); return e && atoi(e) > 0 ? smem_for_occupancy(0, atoi(e)) : (size_t)0; }();
 #define RSP_DBF2(ITV, PIPEV) do { dim3 gg((c->N + ITV * per_cta - 1) / (ITV * per_cta), c->P);                                  \
-            dbf_mma2_kernel<MT, KS, ITV, PIPEV><<<gg, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, \
+            { static const bool once = (prefer_max_smem(dbf_mma2_kernel<MT, KS, ITV, PIPEV>), true); (void)once; }                  \
+            if (dbf_pad > 48 * 1024) cudaFuncSetAttribute(dbf_mma2_kernel<MT, KS, ITV, PIPEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dbf_pad); \
+            dbf_mma2_kernel<MT, KS, ITV, PIPEV><<<gg, RSP_DBF_MMA_THREADS, dbf_pad, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, \
                                                                                          c->N, c->ldb, det_count, dead_amp(c)); } while (0)
         if (it >= 8 && c->N >= 8 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(8, kPipe); else RSP_DBF2(8, false); }
         else if (it >= 4 && c->N >= 4 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(4, kPipe); else RSP_DBF2(4, false); }
@@ -687,6 +708,7 @@ static void launch_mtd(rsp_ctx* c, float2* rdm) {
         r.m = a;
         for (int p = 0; p < 64; ++p) r.win[p] = c->h_win[p];
         dim3 sgrid((c->G + 31) / 32, c->B);
+        { static const bool once = (prefer_max_smem(mtd64_kernel<true>), prefer_max_smem(mtd64_kernel<false>), true); (void)once; }
         if (c->mtd_approx_sqrt) mtd64_kernel<true><<<sgrid, 256, 0, c->cur->s>>>(r);
         else mtd64_kernel<false><<<sgrid, 256, 0, c->cur->s>>>(r);
         return;
@@ -763,7 +785,7 @@ static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, i
     c->cur = &c->lanes[lane];
     // RSP_STAGES (bit mask 1 = DBF, 2 = PC, 4 = MTD, 8 = CFAR) is a measurement aid for tools/stage_probe.py: it
     // leaves stages out so that the steady-state cost of each kernel on the lanes can be timed in isolation.
-    static const int stages = [] { const char* e = getenv("RSP_STAGES"); return e ? atoi(e) : 15; }();
+    const int stages = c->stages;
     int rc = RSP_OK;
     if (stages & 1) rc = launch_dbf_any(c, raw, c->d_counts + slot);      // dbf_kernel also zeroes the slot's counter
     if (rc) return rc;
@@ -1068,7 +1090,7 @@ int rsp_stage2_configure(rsp_ctx* c, const rsp_stage2_config* cfg) {
     }
     CU(c, upload(&c->d_s2_win, win));
     c->h_s2_win = win;
-    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 0 : !strcmp(e, "p64") ? 2 : !strcmp(e, "reg") ? 1 : 0; }
+    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 2 : !strcmp(e, "tile") ? 0 : !strcmp(e, "reg") ? 1 : 2; }
     { const char* e = getenv("RSP_MTD_SQRT"); c->mtd_approx_sqrt = e && !strcmp(e, "approx"); }
     if (c->pow2_doppler) {
         CU(c, upload(&c->d_dop_tw, c->dop.tw));

@@ -503,7 +503,7 @@ __device__ __forceinline__ void mma_tf32_wa(float (&d)[4], const float4& a, uint
 // alternating between a load phase and a compute phase (the IT = 1 kernel spends 56 % of its warp-cycles waiting
 // at the first MMA, profiles/r1b_*), and the grid is a single resident wave of long-lived CTAs.
 template <int MT, int KS, int IT, bool PIPE>
-__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : 1)) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
+__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : (MT == 1 && KS <= 4 ? 8 : 1))) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
                                                                        const float4* __restrict__ Wa /* [KS][MT][2][32] */,
                                                                        int C, int NB, int N, int ldb,
                                                                        int* __restrict__ det_count, const DiscardArgs dead) {
@@ -1114,47 +1114,66 @@ __global__ void __launch_bounds__(RSP_MTD_REG_THREADS, (P > 32 ? 3 : 4)) mtd_reg
 // 84 -> ~40 instructions per point at the same register footprint, so the co-resident kernels of the other
 // lanes get the issue slots.  Lanes run along gates in phases 1-2 and along Doppler bins in phase 3; the S2 pitch
 // of 65 keeps the transposed 64-bit stores conflict free (lane stride 130 words = 2 banks).
-__constant__ float2 c_tw64[64] = {   // c_tw64[8 q + k1] = exp(-2 pi i q k1 / 64)
-    {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f},
-    {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 0.0f},
-    {1.0f, 0.0f}, {0.99518472f, -0.0980171412f}, {0.980785251f, -0.195090324f}, {0.956940353f, -0.290284663f},
-    {0.923879504f, -0.382683426f}, {0.881921291f, -0.471396744f}, {0.831469595f, -0.555570245f}, {0.773010433f, -0.634393275f},
-    {1.0f, 0.0f}, {0.980785251f, -0.195090324f}, {0.923879504f, -0.382683426f}, {0.831469595f, -0.555570245f},
-    {0.707106769f, -0.707106769f}, {0.555570245f, -0.831469595f}, {0.382683426f, -0.923879504f}, {0.195090324f, -0.980785251f},
-    {1.0f, 0.0f}, {0.956940353f, -0.290284663f}, {0.831469595f, -0.555570245f}, {0.634393275f, -0.773010433f},
-    {0.382683426f, -0.923879504f}, {0.0980171412f, -0.99518472f}, {-0.195090324f, -0.980785251f}, {-0.471396744f, -0.881921291f},
-    {1.0f, 0.0f}, {0.923879504f, -0.382683426f}, {0.707106769f, -0.707106769f}, {0.382683426f, -0.923879504f},
-    {6.12323426e-17f, -1.0f}, {-0.382683426f, -0.923879504f}, {-0.707106769f, -0.707106769f}, {-0.923879504f, -0.382683426f},
-    {1.0f, 0.0f}, {0.881921291f, -0.471396744f}, {0.555570245f, -0.831469595f}, {0.0980171412f, -0.99518472f},
-    {-0.382683426f, -0.923879504f}, {-0.773010433f, -0.634393275f}, {-0.980785251f, -0.195090324f}, {-0.956940353f, 0.290284663f},
-    {1.0f, 0.0f}, {0.831469595f, -0.555570245f}, {0.382683426f, -0.923879504f}, {-0.195090324f, -0.980785251f},
-    {-0.707106769f, -0.707106769f}, {-0.980785251f, -0.195090324f}, {-0.923879504f, 0.382683426f}, {-0.555570245f, 0.831469595f},
-    {1.0f, 0.0f}, {0.773010433f, -0.634393275f}, {0.195090324f, -0.980785251f}, {-0.471396744f, -0.881921291f},
-    {-0.923879504f, -0.382683426f}, {-0.956940353f, 0.290284663f}, {-0.555570245f, 0.831469595f}, {0.0980171412f, 0.99518472f}};
+__host__ __device__ constexpr float tw64_re(int i) {   // Re exp(-2 pi i q k1 / 64) at i = 8 q + k1
+    constexpr float t[64] = {   // exp(-2 pi i q k1 / 64) at [8 q + k1]
+    1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f,
+    1.0f, 0.99518472f, 0.980785251f, 0.956940353f, 0.923879504f, 0.881921291f, 0.831469595f, 0.773010433f,
+    1.0f, 0.980785251f, 0.923879504f, 0.831469595f, 0.707106769f, 0.555570245f, 0.382683426f, 0.195090324f,
+    1.0f, 0.956940353f, 0.831469595f, 0.634393275f, 0.382683426f, 0.0980171412f, -0.195090324f, -0.471396744f,
+    1.0f, 0.923879504f, 0.707106769f, 0.382683426f, 0.0f, -0.382683426f, -0.707106769f, -0.923879504f,
+    1.0f, 0.881921291f, 0.555570245f, 0.0980171412f, -0.382683426f, -0.773010433f, -0.980785251f, -0.956940353f,
+    1.0f, 0.831469595f, 0.382683426f, -0.195090324f, -0.707106769f, -0.980785251f, -0.923879504f, -0.555570245f,
+    1.0f, 0.773010433f, 0.195090324f, -0.471396744f, -0.923879504f, -0.956940353f, -0.555570245f, 0.0980171412f};
+    return t[i];
+}
+__host__ __device__ constexpr float tw64_im(int i) {
+    constexpr float t[64] = {
+    0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f,
+    0.0f, -0.0980171412f, -0.195090324f, -0.290284663f, -0.382683426f, -0.471396744f, -0.555570245f, -0.634393275f,
+    0.0f, -0.195090324f, -0.382683426f, -0.555570245f, -0.707106769f, -0.831469595f, -0.923879504f, -0.980785251f,
+    0.0f, -0.290284663f, -0.555570245f, -0.773010433f, -0.923879504f, -0.99518472f, -0.980785251f, -0.881921291f,
+    0.0f, -0.382683426f, -0.707106769f, -0.923879504f, -1.0f, -0.923879504f, -0.707106769f, -0.382683426f,
+    0.0f, -0.471396744f, -0.831469595f, -0.99518472f, -0.923879504f, -0.634393275f, -0.195090324f, 0.290284663f,
+    0.0f, -0.555570245f, -0.923879504f, -0.980785251f, -0.707106769f, -0.195090324f, 0.382683426f, 0.831469595f,
+    0.0f, -0.634393275f, -0.980785251f, -0.881921291f, -0.382683426f, 0.290284663f, 0.831469595f, 0.99518472f};
+    return t[i];
+}
+
+template <int Q>
+__device__ __forceinline__ void mtd64_phase1(const MtdRegArgs& k, const float2* src, unsigned pstride, float2* S1, int lane) {
+    cf v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = src[(unsigned)(8 * m) * pstride];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = cscale(v[m], k.win[Q + 8 * m]);
+    SmallDft<8, -1>::run(v);
+    S1[(0 * 8 + Q) * 32 + lane] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1)
+        S1[(k1 * 8 + Q) * 32 + lane] = Q == 0 ? v[k1] : mul_tw<-1>(v[k1], tw64_re(8 * Q + k1), tw64_im(8 * Q + k1));
+}
 
 #define RSP_MTD64_PITCH 65
 template <bool APPROX_SQRT>
-__global__ void __launch_bounds__(256, 4) mtd64_kernel(const __grid_constant__ MtdRegArgs k) {
-    __shared__ float2 S1[64 * 32];
-    __shared__ float2 S2[32 * RSP_MTD64_PITCH];
+__global__ void __launch_bounds__(256, 8) mtd64_kernel(const __grid_constant__ MtdRegArgs k) {
+    __shared__ float2 S2[32 * RSP_MTD64_PITCH];     // S1 (phase 1 -> 2) and S2 (phase 2 -> 3) share the storage
+    float2* const S1 = S2;
     l2_discard(k.m.dead);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.y, G = k.m.G, g0 = blockIdx.x * 32;
-    {   // phase 1
+    {   // phase 1: the warp index picks the compile-time instance, so window and twiddles are immediates
         const int g = g0 + lane;
         const unsigned pstride = (unsigned)k.m.B * (unsigned)k.m.ldg;
         const float2* src = k.m.pc + (size_t)b * k.m.ldg + (g < G ? g : G - 1) + (size_t)w * pstride;
-        cf v[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = src[(unsigned)(8 * m) * pstride];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = cscale(v[m], k.win[w + 8 * m]);
-        SmallDft<8, -1>::run(v);
-        S1[(0 * 8 + w) * 32 + lane] = v[0];
-#pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) {
-            const float2 t = c_tw64[8 * w + k1];
-            S1[(k1 * 8 + w) * 32 + lane] = mul_tw<-1>(v[k1], t.x, t.y);
+        switch (w) {
+            case 0: mtd64_phase1<0>(k, src, pstride, S1, lane); break;
+            case 1: mtd64_phase1<1>(k, src, pstride, S1, lane); break;
+            case 2: mtd64_phase1<2>(k, src, pstride, S1, lane); break;
+            case 3: mtd64_phase1<3>(k, src, pstride, S1, lane); break;
+            case 4: mtd64_phase1<4>(k, src, pstride, S1, lane); break;
+            case 5: mtd64_phase1<5>(k, src, pstride, S1, lane); break;
+            case 6: mtd64_phase1<6>(k, src, pstride, S1, lane); break;
+            default: mtd64_phase1<7>(k, src, pstride, S1, lane); break;
         }
     }
     __syncthreads();
@@ -1163,6 +1182,7 @@ __global__ void __launch_bounds__(256, 4) mtd64_kernel(const __grid_constant__ M
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = S1[(w * 8 + q) * 32 + lane];
         SmallDft<8, -1>::run(v);
+        __syncthreads();                                 // every warp has read its S1 rows
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) S2[lane * RSP_MTD64_PITCH + w + 8 * k2] = v[k2];
     }
