@@ -80,6 +80,10 @@ struct rsp_ctx {
     float* d_s2_win = nullptr;
     float2 *d_med_tw1 = nullptr, *d_med_tw2 = nullptr, *d_med_H = nullptr;
     float2 *d_lng_tw1 = nullptr, *d_lng_tw2 = nullptr, *d_lng_H = nullptr;
+    // mixed block plan of the long segment (choose_pc_mix): `lng` covers the first gates with the longest blocks, the
+    // parts below continue with shorter blocks and go out in a second launch
+    PcPlan lngx[2];
+    float2 *d_lngx_tw1[2] = {nullptr, nullptr}, *d_lngx_tw2[2] = {nullptr, nullptr}, *d_lngx_H[2] = {nullptr, nullptr};
     DopplerPlan dop;
     float2* d_dop_tw = nullptr;
     int dop_tw_count = 0;
@@ -288,6 +292,7 @@ void rsp_destroy(rsp_ctx* c) {
     cudaFree(c->d_aux); cudaFree(c->d_W); cudaFree(c->d_Wfrag); cudaFree(c->d_Wfrag_wa); cudaFree(c->d_fir);
     cudaFree(c->d_med_tw1); cudaFree(c->d_med_tw2); cudaFree(c->d_med_H);
     cudaFree(c->d_lng_tw1); cudaFree(c->d_lng_tw2); cudaFree(c->d_lng_H);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_lngx_tw1[i]); cudaFree(c->d_lngx_tw2[i]); cudaFree(c->d_lngx_H[i]); }
     cudaFree(c->d_dop_tw); cudaFree(c->d_dop_perm); cudaFree(c->d_win);
     cudaFree(c->d_range_axis); cudaFree(c->d_vel_axis); cudaFree(c->d_beam_angles); cudaFree(c->d_k_slopes);
     cudaFree(c->d_counts); cudaFree(c->d_recs);
@@ -490,6 +495,33 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     if (rc) return rc;
     rc = plan_seg(c->lng, k->mf_long, k->n_mf_long, c->prm.seg_start[2], g1 + g2, g3, "RSP_PC_LEN_LONG");
     if (rc) return rc;
+    c->lngx[0] = PcPlan(); c->lngx[1] = PcPlan();
+    {   // mixed block lengths when they transform fewer points than the best single length (RSP_PC_MIX=0: never)
+        const char* em = getenv("RSP_PC_MIX");
+        const char* el = getenv("RSP_PC_LEN_LONG");
+        int counts[3];
+        const int nt = k->n_mf_long;
+        const int mix_pts = (g3 > 0 && nt >= 1 && nt <= 1024) ? choose_pc_mix(nt, g3, counts) : 0;
+        if (!(em && atoi(em) == 0) && !(el && atoi(el) > 0) && !c->pc_two_pass && c->lng.L && mix_pts > 0 &&
+            mix_pts < c->lng.nblk * c->lng.L) {
+            std::vector<zc> t(nt);
+            for (int i = 0; i < nt; ++i) t[i] = zc(k->mf_long[i].re, k->mf_long[i].im);
+            const int Ls[3] = {4096, 2048, 1024};
+            PcPlan* parts[3] = {&c->lng, &c->lngx[0], &c->lngx[1]};
+            int gate = g1 + g2, left = g3, pi = 0;
+            for (int i = 0; i < 3; ++i) {
+                if (!counts[i]) continue;
+                const int take = std::min(left, counts[i] * (Ls[i] - (nt - 1)));
+                if (take <= 0) break;
+                *parts[pi] = PcPlan();
+                if (!make_pc_plan(*parts[pi], Ls[i], t.data(), nt, c->prm.seg_start[2] - 1, gate, take))
+                    return fail(c, RSP_ERR_UNSUPPORTED, "no block plan for %d taps (L=%d)", nt, Ls[i]);
+                gate += take; left -= take; ++pi;
+            }
+        }
+    }
+    for (int i = 0; i < 2; ++i)
+        if (c->lngx[i].L) { CU(c, upload(&c->d_lngx_tw1[i], c->lngx[i].tw1)); CU(c, upload(&c->d_lngx_tw2[i], c->lngx[i].tw2)); CU(c, upload(&c->d_lngx_H[i], c->lngx[i].Hmid)); }
     if (c->pc_two_pass) {
 #define X2(A, B) CU(c, opt_in_smem(pc2_fft_kernel<A, B>, pc2_smem_pair<A, B>()));
         RSP_FOR_EACH_PC2_PAIR(X2)
@@ -693,6 +725,17 @@ static void launch_pc(rsp_ctx* c) {
 #define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
     RSP_FOR_EACH_PC_PAIR(X)
 #undef X
+    if (c->lngx[0].L) {            // the shorter blocks of a mixed long-segment plan
+        fill_seg(c, a.seg[0], c->lngx[0], c->d_lngx_tw1[0], c->d_lngx_tw2[0], c->d_lngx_H[0]);
+        fill_seg(c, a.seg[1], c->lngx[1], c->d_lngx_tw1[1], c->d_lngx_tw2[1], c->d_lngx_H[1]);
+        a.do_narrow = 0;
+        const int n2 = a.seg[0].n_ctas + a.seg[1].n_ctas;
+        const int l0 = c->lngx[0].L, l1 = c->lngx[1].L ? c->lngx[1].L : 1024;
+        c->launches++;
+#define X(A, B) if (l0 == A::L && l1 == B::L) pc_fft_kernel<A, B><<<n2, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
+        RSP_FOR_EACH_PC_PAIR(X)
+#undef X
+    }
 }
 
 static void launch_mtd(rsp_ctx* c, float2* rdm) {
@@ -775,7 +818,7 @@ static void launch_refine(rsp_ctx* c, int first, int n, cudaStream_t st) {
 
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
-    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + 1 /*mtd*/;
+    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + (c->lngx[0].L ? 1 : 0) + 1 /*mtd*/;
     if (cfar_testable(c)) n += 1;   // cfar (S9 is one refine launch per batch, not per CPI)
     return n;
 }
@@ -1401,7 +1444,7 @@ int rsp_get_info(const rsp_ctx* c, rsp_info* info) {
     if (!c || !info) return RSP_ERR_INVALID_ARG;
     info->n_gates_total = c->G;
     info->fft_len_medium = c->med.L; info->fft_len_long = c->lng.L;
-    info->blocks_medium = c->med.nblk; info->blocks_long = c->lng.nblk;
+    info->blocks_medium = c->med.nblk; info->blocks_long = c->lng.nblk + c->lngx[0].nblk + c->lngx[1].nblk;
     info->kernels_per_cpi = c->have_constants ? kernels_per_cpi(c) : 0;
     info->algorithmic_bytes_per_cpi = 8LL * c->P * c->N * c->C + 8LL * c->B * c->P * c->G;
     info->launches_total = c->launches;

@@ -57,6 +57,28 @@ struct PcBlockArgs {
 // other addresses are compile-time immediates.
 #define RSP_POFF(off) ((off) + ((off) >> 4))
 
+// Twiddles w[k] = W^(k j), k = 1 .. R-1, of one butterfly from the table row entries tw[(k-1)*stride].
+// RSP_PC_DERIVE_TW: only the powers k = 1, 2, 4, 8 are loaded, the others are products of those (at most three
+// factors, so the error stays at a few ulp).  Loads cost shared-memory / L1 wavefronts, which is what bounds the
+// chain; the extra complex multiplies go to the FP32 pipe, which has room.
+#ifndef RSP_PC_DERIVE_TW
+#define RSP_PC_DERIVE_TW 1
+#endif
+template <int R> RSP_HD void pc_twiddles(const cf* tw, int stride, cf* w) {
+#if RSP_PC_DERIVE_TW
+#pragma unroll
+    for (int k = 1; k < R; k <<= 1) w[k] = tw[(k - 1) * stride];
+#pragma unroll
+    for (int k = 3; k < R; ++k) {
+        const int low = k & (-k);                      // lowest set bit: k = (k - low) + low, both already known
+        if (low != k) w[k] = cmul(w[k - low], w[low]);
+    }
+#else
+#pragma unroll
+    for (int k = 1; k < R; ++k) w[k] = tw[(k - 1) * stride];
+#endif
+}
+
 template <class Cfg> RSP_HD void pc_phase_load_pass1(const PcBlockArgs& a, cf* s, int t) {
     const int s0 = a.seg_start0 + a.g0 - (a.taps - 1);
     const bool interior = s0 >= a.in_lo && s0 + Cfg::L <= a.in_hi;       // uniform over the group
@@ -75,15 +97,13 @@ template <class Cfg> RSP_HD void pc_phase_load_pass1(const PcBlockArgs& a, cf* s
                 v[m] = (idx >= a.in_lo && idx < a.in_hi) ? a.line[idx] : make_float2(0.f, 0.f);
             }
         }
+        cf w[Cfg::R1];
+        pc_twiddles<Cfg::R1>(a.tw1 + q, Cfg::SPAN1, w);
         SmallDft<Cfg::R1, -1>::run(v);
         cf* sb = s + rsp_pad16(q);
-        const cf* tw = a.tw1 + q;
         sb[0] = v[0];
 #pragma unroll
-        for (int k = 1; k < Cfg::R1; ++k) {
-            const cf w = tw[(k - 1) * Cfg::SPAN1];
-            sb[RSP_POFF(k * Cfg::SPAN1)] = mul_tw<-1>(v[k], w.x, w.y);
-        }
+        for (int k = 1; k < Cfg::R1; ++k) sb[RSP_POFF(k * Cfg::SPAN1)] = mul_tw<-1>(v[k], w[k].x, w[k].y);
     }
 }
 
@@ -92,25 +112,21 @@ template <class Cfg, int SIGN, bool DIF> RSP_HD void pc_pass2_butterfly(cf* s, c
     constexpr int R = Cfg::R2, SPAN = Cfg::SPAN2;
     const int blk = q / SPAN, j = q - blk * SPAN;
     cf* sb = s + rsp_pad16(blk * Cfg::LS2 + j);
-    const cf* tw = tw2 + j;
-    cf v[R];
+    cf v[R], w[R];
+    pc_twiddles<R>(tw2 + j, SPAN, w);
     if (DIF) {
 #pragma unroll
         for (int m = 0; m < R; ++m) v[m] = sb[RSP_POFF(m * SPAN)];
         SmallDft<R, SIGN>::run(v);
         sb[0] = v[0];
 #pragma unroll
-        for (int k = 1; k < R; ++k) {
-            const cf w = tw[(k - 1) * SPAN];
-            sb[RSP_POFF(k * SPAN)] = mul_tw<SIGN>(v[k], w.x, w.y);
-        }
+        for (int k = 1; k < R; ++k) sb[RSP_POFF(k * SPAN)] = mul_tw<SIGN>(v[k], w[k].x, w[k].y);
     } else {
         v[0] = sb[0];
 #pragma unroll
         for (int k = 1; k < R; ++k) {
-            const cf w = tw[(k - 1) * SPAN];
             const cf x = sb[RSP_POFF(k * SPAN)];
-            v[k] = mul_tw<SIGN>(x, w.x, w.y);
+            v[k] = mul_tw<SIGN>(x, w[k].x, w[k].y);
         }
         SmallDft<R, SIGN>::run(v);
 #pragma unroll
@@ -154,14 +170,13 @@ template <class Cfg> RSP_HD void pc_phase_ipass1_store(const PcBlockArgs& a, con
     for (int i = 0; i < Cfg::NB1; ++i) {
         const int q = t + i * Cfg::T;
         const cf* sb = s + rsp_pad16(q);
-        const cf* tw = a.tw1 + q;
-        cf v[Cfg::R1];
+        cf v[Cfg::R1], w[Cfg::R1];
+        pc_twiddles<Cfg::R1>(a.tw1 + q, Cfg::SPAN1, w);
         v[0] = sb[0];
 #pragma unroll
         for (int k = 1; k < Cfg::R1; ++k) {
-            const cf w = tw[(k - 1) * Cfg::SPAN1];
             const cf x = sb[RSP_POFF(k * Cfg::SPAN1)];
-            v[k] = mul_tw<+1>(x, w.x, w.y);
+            v[k] = mul_tw<+1>(x, w[k].x, w[k].y);
         }
         SmallDft<Cfg::R1, +1>::run(v);
         cf* dst = a.out_line + a.g0 + q - (a.taps - 1);

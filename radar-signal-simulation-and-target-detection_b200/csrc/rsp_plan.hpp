@@ -136,6 +136,37 @@ inline int choose_pc_len(int ntaps, int ngates) {
     return best;
 }
 
+// Mixed block plan: counts[i] blocks of length {4096, 2048, 1024}[i] laid end to end over the segment's gates, chosen to
+// minimise the transformed points.  At config 2 the long segment has 4826 gates and 700 taps: four 2048-point blocks
+// (1349 valid gates each) transform 8192 points, one 4096 + one 2048 + one 1024 block (3397 + 1349 + 325 >= 4826) only
+// 7168.  Returns the total points, or 0 when no block length fits the filter.
+inline int choose_pc_mix(int ntaps, int ngates, int counts[3]) {
+    const int Ls[3] = {4096, 2048, 1024};
+    int best = 0, best_blocks = 0;
+    counts[0] = counts[1] = counts[2] = 0;
+    for (int a = 0; a <= 16; ++a)
+        for (int b = 0; b <= 16; ++b)
+            for (int c = 0; c <= 16; ++c) {
+                const int n[3] = {a, b, c};
+                long cover = 0;
+                int pts = 0, blocks = 0;
+                bool ok = true;
+                for (int i = 0; i < 3; ++i) {
+                    const int valid = Ls[i] - (ntaps - 1);
+                    if (n[i] > 0 && valid < 1) ok = false;
+                    cover += (long)n[i] * (valid > 0 ? valid : 0);
+                    pts += n[i] * Ls[i];
+                    blocks += n[i];
+                }
+                if (!ok || blocks == 0 || cover < ngates) continue;
+                if (best == 0 || pts < best || (pts == best && blocks < best_blocks)) {
+                    best = pts; best_blocks = blocks;
+                    counts[0] = a; counts[1] = b; counts[2] = c;
+                }
+            }
+    return best;
+}
+
 // Doppler plan for power-of-two P: radices (R0,R1,R2) in DIF order, fixed per P so that the kernel
 // template (MtdCfg) and the host tables agree.
 inline bool mtd_radices(int P, int* r) {
