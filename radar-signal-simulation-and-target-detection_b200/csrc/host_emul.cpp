@@ -234,7 +234,7 @@ int emul_cfar4_map(const float* S, int G, int P, int guard_r, int guard_v, int r
     const Cfar4Geom g = cfar4_geom(c, TG);
     const int mR = guard_r + ref_r, mV = guard_v + ref_v;
     std::memset(det, 0, (size_t)G * P);
-    std::vector<float> tile((size_t)g.rows * g.PP, 0.f), R5((size_t)g.r5_rows * P);
+    std::vector<float> tile((size_t)g.rows * g.PP, 0.f), R5((size_t)g.r5_rows * g.RP);
     for (int g_first = mR; g_first < G - mR; g_first += TG) {
         std::fill(tile.begin(), tile.end(), 0.f);
         for (int row = 0; row < g.rows; ++row) {

@@ -569,8 +569,8 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         const int mR = c->prm.guard_r + c->prm.ref_r;
         c->cfar_vec = (P % 4) == 0;
         auto smem_for = [&](int tg) {
-            const size_t r5 = (size_t)(tg + mR + c->prm.guard_r + 1) * P;
-            return c->cfar_vec ? ((size_t)(tg + 2 * mR) * (P + 2 * RSP_CFAR_HALO) + r5) * sizeof(float)
+            const size_t r5 = (size_t)(tg + mR + c->prm.guard_r + 1) * (c->cfar_vec ? cfar4_pitch(P) : P);
+            return c->cfar_vec ? ((size_t)(tg + 2 * mR) * cfar4_pitch(P + 2 * RSP_CFAR_HALO) + r5) * sizeof(float)
                                : ((size_t)(tg + 2 * mR) * P + r5 + (size_t)tg * P) * sizeof(float);
         };
         c->cfar_tg = 16;

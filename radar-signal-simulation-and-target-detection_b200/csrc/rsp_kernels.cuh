@@ -1353,7 +1353,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(
     const int P = k.c.P, G = k.c.G;
     const int mR = k.c.guard_r + k.c.ref_r, mV = k.c.guard_v + k.c.ref_v;
     float* S = cfar_smem;                       // [rows][PP]
-    float* R5 = S + g.rows * g.PP;              // [r5_rows][P]
+    float* R5 = S + g.rows * g.PP;              // [r5_rows][RP]
     const int pair = blockIdx.y;
     const int g_first = mR + blockIdx.x * TG;
     const int tid = threadIdx.x;
@@ -1364,7 +1364,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(
     const int rows_valid = min(g.rows, G - (g_first - mR));
     for (int idx = tid; idx < g.rows * 2 * h4; idx += RSP_CFAR_THREADS) {      // zero the halo columns
         const int row = idx / (2 * h4), c = idx - row * (2 * h4);
-        S4[row * pp4 + (c < h4 ? c : pp4 - 2 * h4 + c)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        S4[row * pp4 + (c < h4 ? c : g.P4 + c)] = make_float4(0.f, 0.f, 0.f, 0.f);       // columns [0, h4) and [h4 + P4, 2 h4 + P4)
     }
     {   // S = A + B: all loads of a batch are issued before the first add (the tile is one contiguous
         // block of each map, so the loads are full 128-byte lines)

@@ -520,9 +520,20 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 
 struct Cfar4Geom {
     int P, P4, sh;        // P4 = P/4; sh = log2(P4) when P4 is a power of two, else -1
-    int PP;               // padded row pitch of S (floats) = P + 2*RSP_CFAR_HALO
+    int PP;               // padded row pitch of S (floats): >= P + 2*RSP_CFAR_HALO and == 8 (mod 32), see cfar4_pitch
+    int RP;               // row pitch of R5 (floats): >= P and == 8 (mod 32)
     int TG, rows, r5_rows;
 };
+
+// Row pitch (floats) >= need with pitch == 8 (mod 32), i.e. 32 bytes (mod 128): the decision phase walks the CUT quads
+// of a row and then jumps to the next row; with such a pitch the 16-byte accesses of a quarter-warp that straddles two
+// rows still fall into eight different 16-byte bank groups (the old pitches 80 and 64 floats gave 2-way conflicts on
+// every straddling quarter: 37 % extra wavefronts on the seven LDS.128 of the decision, profiles/r1b_*).
+RSP_HD int cfar4_pitch(int need) {
+    int p = (need + 3) & ~3;
+    while ((p & 31) != 8) p += 4;
+    return p;
+}
 
 RSP_HD Cfar4Geom cfar4_geom(const CfarParams& c, int TG) {
     Cfar4Geom g;
@@ -531,7 +542,8 @@ RSP_HD Cfar4Geom cfar4_geom(const CfarParams& c, int TG) {
     g.sh = -1;
     for (int s = 0; s < 16; ++s)
         if ((1 << s) == g.P4) g.sh = s;
-    g.PP = c.P + 2 * RSP_CFAR_HALO;
+    g.PP = cfar4_pitch(c.P + 2 * RSP_CFAR_HALO);
+    g.RP = cfar4_pitch(c.P);
     g.TG = TG;
     g.rows = TG + 2 * (c.guard_r + c.ref_r);
     g.r5_rows = cfar_r5_rows(c, TG);
@@ -558,7 +570,7 @@ RSP_HD void cfar4_r5_phase(const float* S, float* R5, const CfarParams& c, const
         float4 acc = S4[row * pp4 + c4];
 #pragma unroll
         for (int i = 1; i < rr; ++i) acc = f4add(acc, S4[(row + i) * pp4 + c4]);
-        R4[idx] = acc;
+        R4[row * (g.RP / 4) + c4] = acc;
     }
 }
 
@@ -592,8 +604,8 @@ RSP_HD unsigned cfar4_decide_quad(const float* S, const float* R5, const CfarPar
     const int v0 = 4 * c4;
     const float* row = S + (gl + mR) * g.PP + RSP_CFAR_HALO;             // row[v] = S(gl, v)
     const float4 cq = *reinterpret_cast<const float4*>(row + v0);
-    const float4 lr = *reinterpret_cast<const float4*>(R5 + gl * g.P + v0);
-    const float4 tr = *reinterpret_cast<const float4*>(R5 + (gl + mR + c.guard_r + 1) * g.P + v0);
+    const float4 lr = *reinterpret_cast<const float4*>(R5 + gl * g.RP + v0);
+    const float4 tr = *reinterpret_cast<const float4*>(R5 + (gl + mR + c.guard_r + 1) * g.RP + v0);
     float lead[4], trail[4];
     if (RR > 0) {
         cfar4_window4<(RR > 0 ? RV : 1), -(GV + RV)>(row + v0, lead);
