@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE: lets tests/test_host_emulation.py check the exact per-thread code of the
 // CUDA kernels against NumPy on a machine without a GPU.  Barriers become loops over tid.
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include "rsp_plan.hpp"
 #include "rsp_dft_big.cuh"
@@ -111,6 +112,31 @@ int emul_pc_segment(const float* line, int N, int seg_start0, int gate0, int nga
     if (nblk_used) *nblk_used = pl.nblk;
     return 0;
 }
+
+// The mixed block plan of a segment (choose_pc_mix): parts laid end to end exactly as rsp_upload_constants builds them.
+// counts_out = blocks of {4096, 2048, 1024}; returns the transformed points per line, or < 0 on error.
+int emul_pc_segment_mixed(const float* line, int N, int seg_start0, int gate0, int ngates, const double* taps_ri,
+                          int ntaps, float* out_line, int* counts_out) {
+    int counts[3];
+    const int pts = choose_pc_mix(ntaps, ngates, counts);
+    if (pts <= 0) return -1;
+    const int Ls[3] = {4096, 2048, 1024};
+    int gate = gate0, left = ngates;
+    for (int i = 0; i < 3; ++i) {
+        counts_out[i] = counts[i];
+        if (!counts[i]) continue;
+        const int take = std::min(left, counts[i] * (Ls[i] - (ntaps - 1)));
+        if (take <= 0) break;
+        int lu = 0, nb = 0;
+        const int rc = emul_pc_segment(line, N, seg_start0, gate, take, taps_ri, ntaps, Ls[i], out_line, &lu, &nb);
+        if (rc) return rc - 10;
+        if (nb > counts[i]) return -3;
+        gate += take; left -= take;
+    }
+    return left == 0 ? pts : -4;
+}
+
+int emul_cfar4_pitch(int need) { return cfar4_pitch(need); }
 
 int emul_pc_narrow(const float* line, int N, int seg_start0, const float* fir, int nfir, int fir_delay, int ngates,
                    float* out_line) {

@@ -90,6 +90,7 @@ struct rsp_ctx {
     int* d_dop_perm = nullptr;
     float* d_win = nullptr;
     std::vector<float> h_win, h_s2_win;   // host copies: the register MTD kernel takes the window as an argument
+    bool cfar_pad = true;                 // conflict-free CFAR tile pitches (P <= 64)
     int mtd_mode = 2;                     // RSP_MTD: 0 = tile (generic), 1 = reg (one thread per Doppler line, P = 32 / 64), 2 = p64 (specialised tile; default when P = 64)
     bool mtd_approx_sqrt = false;         // RSP_MTD_SQRT=approx
     double *d_range_axis = nullptr, *d_vel_axis = nullptr, *d_beam_angles = nullptr, *d_k_slopes = nullptr;
@@ -565,12 +566,17 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     c->h_win = win;
     { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 2 : !strcmp(e, "tile") ? 0 : !strcmp(e, "reg") ? 1 : 2; }
     { const char* e = getenv("RSP_MTD_SQRT"); c->mtd_approx_sqrt = e && !strcmp(e, "approx"); }
-    {   // CFAR tile height: the largest of {64,32,16} whose shared arrays stay under 80 KB
+    {   // CFAR tile height: the largest of {64,32,16} whose shared arrays let three CTAs share an SM
         const int mR = c->prm.guard_r + c->prm.ref_r;
         c->cfar_vec = (P % 4) == 0;
+        // padded (conflict-free) pitches only where the tile keeps its size: at P = 128 they push the 32-gate tile from
+        // 65 KB to 73 KB and the kernel gets slower (0.101 -> 0.115 ms at config 3), at P <= 64 they are a net gain
+        c->cfar_pad = P <= 64;
+        { const char* e = getenv("RSP_CFAR_PAD"); if (e) c->cfar_pad = atoi(e) != 0; }
         auto smem_for = [&](int tg) {
-            const size_t r5 = (size_t)(tg + mR + c->prm.guard_r + 1) * (c->cfar_vec ? cfar4_pitch(P) : P);
-            return c->cfar_vec ? ((size_t)(tg + 2 * mR) * cfar4_pitch(P + 2 * RSP_CFAR_HALO) + r5) * sizeof(float)
+            const bool pad = c->cfar_vec && c->cfar_pad;
+            const size_t r5 = (size_t)(tg + mR + c->prm.guard_r + 1) * (pad ? cfar4_pitch(P) : P);
+            return c->cfar_vec ? ((size_t)(tg + 2 * mR) * (pad ? cfar4_pitch(P + 2 * RSP_CFAR_HALO) : P + 2 * RSP_CFAR_HALO) + r5) * sizeof(float)
                                : ((size_t)(tg + 2 * mR) * P + r5 + (size_t)tg * P) * sizeof(float);
         };
         c->cfar_tg = 16;
@@ -788,7 +794,7 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
     CfarArgs a;
     a.amp = c->cur->amp; a.rdm = rdm;
     a.c.P = c->P; a.c.G = c->G; a.c.guard_r = c->prm.guard_r; a.c.guard_v = c->prm.guard_v;
-    a.c.ref_r = c->prm.ref_r; a.c.ref_v = c->prm.ref_v; a.c.t_cfar = c->prm.t_cfar;
+    a.c.ref_r = c->prm.ref_r; a.c.ref_v = c->prm.ref_v; a.c.t_cfar = c->prm.t_cfar; a.c.pad_pitch = c->cfar_pad ? 1 : 0;
     a.count = c->d_counts + slot;
     a.raw = c->d_rawdet + (size_t)slot * c->prm.max_detections;
     a.cap = c->prm.max_detections;

@@ -468,6 +468,7 @@ struct CfarParams {
     int P, G;
     int guard_r, guard_v, ref_r, ref_v;
     float t_cfar;
+    int pad_pitch = 1;     // vectorised kernel: 1 = conflict-free row pitches (cfar4_pitch), 0 = dense rows
 };
 
 RSP_HD int cfar_r5_rows(const CfarParams& c, int TG) { return TG + c.guard_r + c.ref_r + c.guard_r + 1; }
@@ -542,8 +543,8 @@ RSP_HD Cfar4Geom cfar4_geom(const CfarParams& c, int TG) {
     g.sh = -1;
     for (int s = 0; s < 16; ++s)
         if ((1 << s) == g.P4) g.sh = s;
-    g.PP = cfar4_pitch(c.P + 2 * RSP_CFAR_HALO);
-    g.RP = cfar4_pitch(c.P);
+    g.PP = c.pad_pitch ? cfar4_pitch(c.P + 2 * RSP_CFAR_HALO) : c.P + 2 * RSP_CFAR_HALO;
+    g.RP = c.pad_pitch ? cfar4_pitch(c.P) : c.P;
     g.TG = TG;
     g.rows = TG + 2 * (c.guard_r + c.ref_r);
     g.r5_rows = cfar_r5_rows(c, TG);

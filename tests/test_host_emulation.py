@@ -74,6 +74,42 @@ def test_pc_overlap_save_matches_reference_fft_convolution(lib, cfg1, seg, L):
         assert not out[:gate0].any() and not out[gate0 + ng:].any()
 
 
+@pytest.mark.parametrize("N,expect", [(8192, (1, 1, 1)), (4096, (0, 1, 0)), (16384, (4, 0, 0)), (5819, None)])
+def test_pc_mixed_block_plan_covers_the_segment_with_fewest_points(lib, cfg1, N, expect):
+    """choose_pc_mix: the long segment of config 2 (4826 gates, 700 taps) is one 4096 + one 2048 + one 1024 block
+    (7168 points instead of four 2048-point blocks); the parts laid end to end equal a plain linear convolution."""
+    cfg, pre, beam, pc = cfg1
+    taps = pre["MF_long_win"]
+    ss, gate0 = pre["seg_start_long"] - 1, pre["N_gate_narrow"] + pre["N_gate_medium"]
+    ng = (N - 2415) - gate0                                  # G = N - 2415 (SURVEY 8d)
+    rng = np.random.default_rng(N)
+    line = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    out = np.zeros(N, np.complex64)
+    counts = (ctypes.c_int * 3)()
+    t = np.ascontiguousarray(np.stack([taps.real, taps.imag], -1))
+    pts = lib.emul_pc_segment_mixed(line.ctypes.data_as(fp), N, int(ss), int(gate0), int(ng), t.ctypes.data_as(dp),
+                                    len(taps), out.ctypes.data_as(fp), counts)
+    assert pts > 0
+    c = tuple(counts)
+    if expect is not None:
+        assert c == expect
+    valid = [L - (len(taps) - 1) for L in (4096, 2048, 1024)]
+    assert sum(n * v for n, v in zip(c, valid)) >= ng
+    assert pts == sum(n * L for n, L in zip(c, (4096, 2048, 1024)))
+    single = min(-(-ng // v) * L for v, L in zip(valid, (4096, 2048, 1024)) if v > 0)
+    assert pts <= single
+    full = np.convolve(line[ss:].astype(np.complex128), taps)            # full[j] = sum_k taps[k] y[ss + j - k]
+    ref = full[gate0:gate0 + ng]
+    assert np.abs(out[gate0:gate0 + ng] - ref).max() <= 3e-6 * np.abs(ref).max()
+    assert not out[:gate0].any() and not out[gate0 + ng:].any()
+
+
+def test_cfar_pitch_is_conflict_free_across_rows(lib):
+    for need in (32, 48, 64, 80, 128, 144, 272):
+        p = lib.emul_cfar4_pitch(need)
+        assert p >= need and p % 4 == 0 and p % 32 == 8 and p - need < 32
+
+
 @pytest.mark.parametrize("seg,L", [("medium", 1024), ("medium", 4096), ("long", 4096), ("long", 1024)])
 def test_pc_two_pass_blocks_match_reference(lib, cfg1, seg, L):
     """The N x N register-resident plan (64 x 64, 32 x 32) of pc2_fft_kernel."""
