@@ -320,8 +320,10 @@ def main():
                 "algorithmic_bytes_per_launch": own_bytes.get(dominant), "launch_ms": round(dom_ms, 5),
                 "kernels_ms_per_cpi": {k: round(v, 5) for k, v in per_cpi_ms.items()},
                 "kernels_share": {k: round(v / kern_sum, 4) for k, v in per_cpi_ms.items()} if kern_sum else {},
-                "note": "dominant kernel by device time; it is fp32-issue bound (ncu: FP32 pipe 38 %, issue 55 %), "
-                        "see DESIGN.md section 4; the chain-level figure is chain_roofline"}
+                "note": "dominant kernel class by device time, timed per CPI with CUDA events on its stream (pc_fft = both "
+                        "launches of the mixed block plan); it works out of L2 and is bound by FP32 issue + the shared-memory "
+                        "pipe (ncu: issue 52-57 %, L1 data pipe 34-59 %), see DESIGN.md sections 4-5; the chain-level figure is "
+                        "chain_roofline"}
     chain_roofline = {"bound": "hbm", "achieved": chain_achieved, "peak": peak, "unit": "GB/s", "frac": chain_achieved / peak,
                       "algorithmic_bytes_per_cpi": alg_bytes, "kernels_per_cpi": info["kernels_per_cpi"],
                       "note": "8*P*N*C + 8*B*P*G bytes per CPI (SURVEY 8(d)) / device time per CPI of the timed region"}
@@ -406,7 +408,8 @@ def main():
                                     f"({rdm_n * out_bytes / 1e6:.0f} MB) cycled through pools larger than 2x L2 "
                                     f"({l2_bytes / 1e6:.0f} MB)",
                        "parallelism": f"cpi-sharded x{world}", "fft_len_medium": info["fft_len_medium"],
-                       "fft_len_long": info["fft_len_long"]},
+                       "fft_len_long": info["fft_len_long"], "blocks_long": info["blocks_long"],
+                       "kernels_per_cpi": info["kernels_per_cpi"]},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
                     "cpis": e2e_n, "note": "C ABI with host buffers: rsp_submit_cpi (pinned 67 MB cube H2D + chain, pipelined "
