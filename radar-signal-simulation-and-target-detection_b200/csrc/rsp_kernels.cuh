@@ -502,8 +502,10 @@ __device__ __forceinline__ void mma_tf32_wa(float (&d)[4], const float4& a, uint
 // flight while tile j goes through the tensor cores, so a warp always has 4 KB of reads outstanding instead of
 // alternating between a load phase and a compute phase (the IT = 1 kernel spends 56 % of its warp-cycles waiting
 // at the first MMA, profiles/r1b_*), and the grid is a single resident wave of long-lived CTAs.
-template <int MT, int KS, int IT, bool PIPE>
-__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : (MT == 1 && KS <= 4 ? 8 : 1))) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
+// NQ = 16-sample groups per warp tile (2: 32 samples; 1 for the big shapes, C > 16 or B > 8, whose 32-sample tile would
+// need 64 registers of loads + 32 accumulators: 178 registers and 8 warps per SM at config 3).
+template <int MT, int KS, int IT, bool PIPE, int NQ>
+__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : ((MT == 1 && KS <= 4) || NQ == 1 ? (MT * KS * NQ <= 8 ? 8 : 5) : 1))) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
                                                                        const float4* __restrict__ Wa /* [KS][MT][2][32] */,
                                                                        int C, int NB, int N, int ldb,
                                                                        int* __restrict__ det_count, const DiscardArgs dead) {
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : (MT == 1 &&
     if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const int p = blockIdx.y;
-    const int n_first = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (32 * IT);     // IT tiles of 32 samples per warp
+    const int n_first = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (16 * NQ * IT);  // IT tiles of 16 NQ samples per warp
     if (n_first >= N) return;
     // column g of the even n-tile of a 16-sample group <-> sample sg = g (g even) or g + 7 (g odd), odd n-tile: sg + 1.
     // With this order the D fragments of lane t are samples 2t, 2t+1 and 2t+8, 2t+9, so each of the two 16-byte stores
@@ -522,32 +524,31 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : (MT == 1 &&
     const unsigned cstep = 4u * (unsigned)N;                                           // k-step s: channel 4s + t
     float2* const brow = beam + (size_t)p * NB * ldb + 2 * t;
 
-    auto load_tile = [&](float4 (&x)[KS][2], int n_base) {
-        const bool in0 = n_base + sg < N, in1 = n_base + 16 + sg < N;
+    auto load_tile = [&](float4 (&x)[KS][NQ], int n_base) {
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
-            x[s][0] = x[s][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * s + t < C) {
-                const float2* src = rp + s * cstep + n_base;
-                if (in0) x[s][0] = __ldcs(reinterpret_cast<const float4*>(src));
-                if (in1) x[s][1] = __ldcs(reinterpret_cast<const float4*>(src + 16));
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (4 * s + t < C && n_base + 16 * q + sg < N)
+                    x[s][q] = __ldcs(reinterpret_cast<const float4*>(rp + s * cstep + n_base + 16 * q));
             }
         }
     };
-    auto compute_store = [&](const float4 (&x)[KS][2], int n_base) {
-        float acc[MT][4][4];
+    auto compute_store = [&](const float4 (&x)[KS][NQ], int n_base) {
+        float acc[MT][2 * NQ][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 2 * NQ; ++j)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             // n-tile j = 2q + parity: {b0, b1} = (re, im) of sample 16q + sg + parity
-            uint32_t bh[4][2], bl[4][2];
+            uint32_t bh[2 * NQ][2], bl[2 * NQ][2];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < NQ; ++q) {
                 const float v[4] = {x[s][q].x, x[s][q].y, x[s][q].z, x[s][q].w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : (MT == 1 &&
                 const float4 ah = __ldg(Wa + ((s * MT + mt) * 2 + 0) * 32 + lane);
                 const float4 al = __ldg(Wa + ((s * MT + mt) * 2 + 1) * 32 + lane);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2 * NQ; ++j) {
                     mma_tf32_wa(acc[mt][j], al, bh[j][0], bh[j][1]);
                     mma_tf32_wa(acc[mt][j], ah, bl[j][0], bl[j][1]);
                     mma_tf32_wa(acc[mt][j], ah, bh[j][0], bh[j][1]);
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : (MT == 1 &&
             if (b < NB) {
                 float2* row = brow + (size_t)b * ldb + n_base;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < NQ; ++q) {
                     const float(&E)[4] = acc[mt][2 * q];
                     const float(&O)[4] = acc[mt][2 * q + 1];
                     const int n = n_base + 16 * q + 2 * t;
@@ -586,31 +587,31 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : (MT == 1 &&
     };
 
     if (IT == 1) {
-        float4 x[KS][2];
+        float4 x[KS][NQ];
         load_tile(x, n_first);
         compute_store(x, n_first);
     } else if (!PIPE) {
         // several tiles per warp, one after the other: the weight fragments stay in registers, the CTA lives longer
 #pragma unroll 1
         for (int j = 0; j < IT; ++j) {
-            const int n0 = n_first + 32 * j;
+            const int n0 = n_first + 16 * NQ * j;
             if (n0 >= N) break;
-            float4 x[KS][2];
+            float4 x[KS][NQ];
             load_tile(x, n0);
             compute_store(x, n0);
         }
     } else {
-        float4 xa[KS][2], xb[KS][2];
+        float4 xa[KS][NQ], xb[KS][NQ];
         load_tile(xa, n_first);
 #pragma unroll 1
         for (int j = 0; j < IT; j += 2) {
-            const int n0 = n_first + 32 * j;
+            const int n0 = n_first + 16 * NQ * j;
             if (n0 >= N) break;
-            if (j + 1 < IT && n0 + 32 < N) load_tile(xb, n0 + 32);
+            if (j + 1 < IT && n0 + 16 * NQ < N) load_tile(xb, n0 + 16 * NQ);
             compute_store(xa, n0);
-            if (j + 1 >= IT || n0 + 32 >= N) break;
-            if (j + 2 < IT && n0 + 64 < N) load_tile(xa, n0 + 64);
-            compute_store(xb, n0 + 32);
+            if (j + 1 >= IT || n0 + 16 * NQ >= N) break;
+            if (j + 2 < IT && n0 + 32 * NQ < N) load_tile(xa, n0 + 32 * NQ);
+            compute_store(xb, n0 + 16 * NQ);
         }
     }
 }
