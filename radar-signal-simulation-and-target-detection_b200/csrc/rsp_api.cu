@@ -62,6 +62,7 @@ struct rsp_ctx {
     float2* d_W = nullptr;
     float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
     float4* d_Wfrag_wa = nullptr;         // same for dbf_mma2_kernel (weights as the A operand)
+    int pc_group_bar = 1;                 // RSP_PC_GROUP_BAR at rsp_create: per-group named barriers in pc_fft_kernel
     int stages = 15;                      // RSP_STAGES at rsp_create (measurement aid, see enqueue_chain)
     bool dbf_wa = true;                   // RSP_DBF=mma selects the older data-as-A kernel
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
@@ -358,6 +359,7 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     CUC(dev_alloc(&c->d_raw, (size_t)c->P * c->C * c->N));
     CUC(dev_alloc(&c->d_rdm, PBG));
     { const char* e = getenv("RSP_STAGES"); c->stages = e ? atoi(e) : 15; }
+    { const char* e = getenv("RSP_PC_GROUP_BAR"); c->pc_group_bar = e ? atoi(e) : 1; }
     const char* el = getenv("RSP_LANES");
     c->n_lanes = el ? std::min(8, std::max(1, atoi(el))) : 3;
     CUC(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
@@ -717,7 +719,7 @@ static void launch_pc(rsp_ctx* c) {
     fill_seg(c, a.seg[0], c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H);
     fill_seg(c, a.seg[1], c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H);
     a.do_narrow = fold ? 1 : 0;
-    { static const int gb = [] { const char* e = getenv("RSP_PC_GROUP_BAR"); return e ? atoi(e) : 1; }(); a.group_bar = gb; }
+    a.group_bar = c->pc_group_bar;
     a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
     a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
@@ -1185,7 +1187,7 @@ static void launch_s2_pair(rsp_ctx* c, const rsp_ctx::S2Seg* a0, const rsp_ctx::
         }
     }
     a.do_narrow = 0; a.fir = nullptr; a.nfir = 0; a.fir_delay = 0; a.narrow_start0 = 0; a.narrow_gates = 0;
-    { static const int gb = [] { const char* e = getenv("RSP_PC_GROUP_BAR"); return e ? atoi(e) : 1; }(); a.group_bar = gb; }
+    a.group_bar = c->pc_group_bar;
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
     if (nctas == 0) return;
     Timed t(c, K_PC);

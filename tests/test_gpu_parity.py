@@ -331,7 +331,7 @@ def test_every_dbf_variant_and_generic_paths_agree():
     import os
     cfg, pre, raw = o.make_cube("cfg1", 4)
     results = {}
-    for variant in ("mma", "ffma", "tma", "tma1"):
+    for variant in ("mma", "mma2", "ffma", "tma", "tma1"):      # mma2 (weights as the A operand) is the default
         os.environ["RSP_DBF"] = variant
         try:
             chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
@@ -359,6 +359,40 @@ def test_every_dbf_variant_and_generic_paths_agree():
     stats = compare_detections(dets, res.raw_detections, o.cfar_margin(res.S, ocfg), res.parameterized, opre)
     assert stats["n_common"] >= 10
     chain.close()
+
+
+def test_config2_kernel_variants_agree():
+    """Config 2 takes the specialised kernels (P = 64 MTD, mixed PC block lengths, padded CFAR pitches, DBF with the
+    weights as the A operand).  Every one of them switched back to its generic counterpart must reproduce the same
+    detections and the same range-Doppler map to fp32 rounding."""
+    import os
+    cfg, pre, raw = o.make_cube("cfg2", 2)
+    variants = [{}, {"RSP_MTD": "tile"}, {"RSP_MTD": "reg"}, {"RSP_MTD_SQRT": "approx"}, {"RSP_PC_MIX": "0"},
+                {"RSP_CFAR_PAD": "0"}, {"RSP_DBF": "mma"}, {"RSP_PC_GROUP_BAR": "0"}]
+    results = []
+    for env in variants:
+        os.environ.update(env)
+        try:
+            chain, config, cfar_params, cluster_params, pd = _device_chain("cfg2")
+            info = chain.info()
+            results.append((env, chain.process_cpi(raw), chain.get_rdm(), info))
+            chain.close()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    _, ref_d, ref_r, ref_info = results[0]
+    assert ref_info["blocks_long"] == 3 and ref_info["kernels_per_cpi"] == 5          # 4096 + 2048 + 1024, two PC launches
+    assert len(ref_d) >= 50
+    for env, d, r, info in results[1:]:
+        if env.get("RSP_PC_MIX") == "0":
+            assert info["blocks_long"] == 4 and info["kernels_per_cpi"] == 4
+        assert rel_errors(r, ref_r.astype(np.complex128))[0] <= 2e-6, env
+        if env.get("RSP_MTD_SQRT") == "approx":      # amplitudes differ in the last bit: cells at the threshold may flip
+            a = set(map(tuple, d[["v_idx", "r_idx", "pair_idx"]].tolist()))
+            b = set(map(tuple, ref_d[["v_idx", "r_idx", "pair_idx"]].tolist()))
+            assert len(a ^ b) <= 2, env
+        else:
+            assert np.array_equal(d[["v_idx", "r_idx", "pair_idx"]], ref_d[["v_idx", "r_idx", "pair_idx"]]), env
 
 
 def test_batched_frames_equal_one_at_a_time():
