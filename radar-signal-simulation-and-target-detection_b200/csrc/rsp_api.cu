@@ -62,6 +62,8 @@ struct rsp_ctx {
     float2* d_W = nullptr;
     float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
     float4* d_Wfrag_wa = nullptr;         // same for dbf_mma2_kernel (weights as the A operand)
+    bool pc_one_launch = false;           // RSP_PC_ONE_LAUNCH=1: the mixed PC plan in one multi-role launch instead of two launches
+    size_t pc_multi_smem = 0;
     int pc_group_bar = 1;                 // RSP_PC_GROUP_BAR at rsp_create: per-group named barriers in pc_fft_kernel
     int stages = 15;                      // RSP_STAGES at rsp_create (measurement aid, see enqueue_chain)
     bool dbf_wa = true;                   // RSP_DBF=mma selects the older data-as-A kernel
@@ -523,6 +525,9 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             }
         }
     }
+    { const char* e = getenv("RSP_PC_ONE_LAUNCH"); c->pc_one_launch = e && atoi(e) != 0; }
+    c->pc_multi_smem = smem_for_occupancy(std::max(std::max(pc_smem_bytes<Pc1024>(), pc_smem_bytes<Pc2048>()), pc_smem_bytes<Pc4096>()), pc_occ_cap());
+    CU(c, opt_in_smem(pc_fft_multi_kernel, c->pc_multi_smem));
     for (int i = 0; i < 2; ++i)
         if (c->lngx[i].L) { CU(c, upload(&c->d_lngx_tw1[i], c->lngx[i].tw1)); CU(c, upload(&c->d_lngx_tw2[i], c->lngx[i].tw2)); CU(c, upload(&c->d_lngx_H[i], c->lngx[i].Hmid)); }
     if (c->pc_two_pass) {
@@ -731,6 +736,27 @@ static void launch_pc(rsp_ctx* c) {
 #undef X2
         return;
     }
+    if (c->lngx[0].L && c->pc_one_launch) {      // mixed plan: every role in one launch, longest blocks first
+        PcMultiArgs m;
+        m.k = a;
+        const PcPlan* pl[4] = {&c->lng, &c->lngx[0], &c->lngx[1], &c->med};
+        const float2* tw1[4] = {c->d_lng_tw1, c->d_lngx_tw1[0], c->d_lngx_tw1[1], c->d_med_tw1};
+        const float2* tw2[4] = {c->d_lng_tw2, c->d_lngx_tw2[0], c->d_lngx_tw2[1], c->d_med_tw2};
+        const float2* H[4] = {c->d_lng_H, c->d_lngx_H[0], c->d_lngx_H[1], c->d_med_H};
+        int order[4] = {0, 1, 2, 3};                 // roles sorted by block length, descending (stable)
+        std::stable_sort(order, order + 4, [&](int x, int y) { return pl[x]->L > pl[y]->L; });
+        int total = 0;
+        m.narrow_role = -1;
+        for (int r = 0; r < 4; ++r) {
+            const int i = order[r];
+            fill_seg(c, m.seg[r], *pl[i], tw1[i], tw2[i], H[i]);
+            m.len[r] = pl[i]->L;
+            if (i == 3 && pl[i]->L) m.narrow_role = r;
+            total += m.seg[r].n_ctas;
+        }
+        pc_fft_multi_kernel<<<total, RSP_PC_THREADS, c->pc_multi_smem, c->cur->s>>>(m);
+        return;
+    }
 #define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
     RSP_FOR_EACH_PC_PAIR(X)
 #undef X
@@ -827,7 +853,7 @@ static void launch_refine(rsp_ctx* c, int first, int n, cudaStream_t st) {
 
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
-    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + (c->lngx[0].L ? 1 : 0) + 1 /*mtd*/;
+    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + ((c->lngx[0].L && !c->pc_one_launch) ? 1 : 0) + 1 /*mtd*/;
     if (cfar_testable(c)) n += 1;   // cfar (S9 is one refine launch per batch, not per CPI)
     return n;
 }

@@ -940,6 +940,33 @@ __global__ void __launch_bounds__(RSP_PC_THREADS, 3) pc_fft_kernel(const PcKerne
     else pc_role<CfgB>(k, k.seg[1], blockIdx.x - k.seg[0].n_ctas, pc_smem, k.do_narrow != 0);
 }
 
+// Any mix of block lengths in ONE launch: up to four roles, each a (segment, block length) pair, CTAs of the roles laid
+// end to end (longest blocks first, so the short ones fill the tail).  Used for the mixed long-segment plan, where the
+// 4096-, 2048- and 1024-point blocks of the long filter and the 1024-point medium block (+ narrow FIR) are independent.
+struct PcMultiArgs {
+    PcKernelArgs k;              // k.seg[] unused here; beam / pc / pitches / FIR / barrier mode as in pc_fft_kernel
+    PcSegArgs seg[4];
+    int len[4];                  // block length of the role (4096 / 2048 / 1024), 0 = role absent
+    int narrow_role;             // role whose groups also compute the narrow-pulse gates, or -1
+};
+
+__global__ void __launch_bounds__(RSP_PC_THREADS, 3) pc_fft_multi_kernel(const __grid_constant__ PcMultiArgs m) {
+    extern __shared__ float2 pc_smem[];
+    int cta = blockIdx.x;
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        if (m.len[r] == 0) continue;
+        if (cta < m.seg[r].n_ctas) {
+            const bool narrow = r == m.narrow_role && m.k.do_narrow != 0;
+            if (m.len[r] == 4096) pc_role<PcCfg<4096, 16, 16, 16>>(m.k, m.seg[r], cta, pc_smem, narrow);
+            else if (m.len[r] == 2048) pc_role<PcCfg<2048, 8, 16, 16>>(m.k, m.seg[r], cta, pc_smem, narrow);
+            else pc_role<PcCfg<1024, 16, 16, 4>>(m.k, m.seg[r], cta, pc_smem, narrow);
+            return;
+        }
+        cta -= m.seg[r].n_ctas;
+    }
+}
+
 // Two-pass variant (Pc2Cfg: 64 x 64 = 4096-point and 32 x 32 = 1024-point blocks, N threads per block,
 // N points per thread in registers).  Same roles and work list as pc_fft_kernel.
 #define RSP_PC2_THREADS 128

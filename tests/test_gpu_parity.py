@@ -368,7 +368,7 @@ def test_config2_kernel_variants_agree():
     import os
     cfg, pre, raw = o.make_cube("cfg2", 2)
     variants = [{}, {"RSP_MTD": "tile"}, {"RSP_MTD": "reg"}, {"RSP_MTD_SQRT": "approx"}, {"RSP_PC_MIX": "0"},
-                {"RSP_CFAR_PAD": "0"}, {"RSP_DBF": "mma"}, {"RSP_PC_GROUP_BAR": "0"}]
+                {"RSP_CFAR_PAD": "0"}, {"RSP_DBF": "mma"}, {"RSP_PC_GROUP_BAR": "0"}, {"RSP_PC_ONE_LAUNCH": "1"}]
     results = []
     for env in variants:
         os.environ.update(env)
@@ -386,6 +386,8 @@ def test_config2_kernel_variants_agree():
     for env, d, r, info in results[1:]:
         if env.get("RSP_PC_MIX") == "0":
             assert info["blocks_long"] == 4 and info["kernels_per_cpi"] == 4
+        if env.get("RSP_PC_ONE_LAUNCH") == "1":
+            assert info["blocks_long"] == 3 and info["kernels_per_cpi"] == 4
         assert rel_errors(r, ref_r.astype(np.complex128))[0] <= 2e-6, env
         if env.get("RSP_MTD_SQRT") == "approx":      # amplitudes differ in the last bit: cells at the threshold may flip
             a = set(map(tuple, d[["v_idx", "r_idx", "pair_idx"]].tolist()))
