@@ -136,6 +136,62 @@ int emul_pc_segment_mixed(const float* line, int N, int seg_start0, int gate0, i
     return left == 0 ? pts : -4;
 }
 
+// The DBF of dbf_mma2_kernel on the host: same weight fragments (make_dbf_fragments_wa), same lane <-> (row, column, k)
+// mapping of mma.m16n8k8 (A row-major 16x8: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4); B 8x8: b0=(t,g) b1=(t+4,g);
+// D 16x8: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)), same sample order sg and the same store addresses.
+// The MMA itself is done in double on hi + lo, so this checks the index algebra, not the TF32 rounding.
+int emul_dbf_wa(const float* raw /* [C][N] complex */, int C, int N, const double* W_ri /* [B][C][2] */, int B,
+                float* beam /* [B][N] complex, zero-initialised by the caller */) {
+    if (N % 2) return -1;
+    const int MT = (B + 7) / 8, KS = C <= 16 ? 4 : 8;
+    if (C > 32 || B > 16) return -2;
+    const std::vector<float4> Wa = make_dbf_fragments_wa(W_ri, B, C, MT, KS);
+    for (int n_base = 0; n_base < N; n_base += 32) {
+        // acc[lane][mt][tile j][4]
+        std::vector<double> acc((size_t)32 * MT * 4 * 4, 0.0);
+        for (int s = 0; s < KS; ++s)
+            for (int mt = 0; mt < MT; ++mt)
+                for (int j = 0; j < 4; ++j) {                    // n-tile j = 2q + parity
+                    const int q = j >> 1, par = j & 1;
+                    double A[16][8], Bm[8][8];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3;
+                        const float4 h = Wa[((size_t)(s * MT + mt) * 2 + 0) * 32 + lane], l = Wa[((size_t)(s * MT + mt) * 2 + 1) * 32 + lane];
+                        A[g][t] = (double)h.x + l.x; A[g + 8][t] = (double)h.y + l.y;
+                        A[g][t + 4] = (double)h.z + l.z; A[g + 8][t + 4] = (double)h.w + l.w;
+                        const int sg = (g & 1) ? g + 7 : g, c = 4 * s + t, n = n_base + 16 * q + sg + par;
+                        double re = 0.0, im = 0.0;
+                        if (c < C && n < N) { re = raw[((size_t)c * N + n) * 2]; im = raw[((size_t)c * N + n) * 2 + 1]; }
+                        Bm[t][g] = re; Bm[t + 4][g] = im;
+                    }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3;
+                        double* d = &acc[(((size_t)lane * MT + mt) * 4 + j) * 4];
+                        for (int k = 0; k < 8; ++k) {
+                            d[0] += A[g][k] * Bm[k][2 * t]; d[1] += A[g][k] * Bm[k][2 * t + 1];
+                            d[2] += A[g + 8][k] * Bm[k][2 * t]; d[3] += A[g + 8][k] * Bm[k][2 * t + 1];
+                        }
+                    }
+                }
+        for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3;
+            for (int mt = 0; mt < MT; ++mt) {
+                const int b = 8 * mt + g;
+                if (b >= B) continue;
+                for (int q = 0; q < 2; ++q) {
+                    const double* E = &acc[(((size_t)lane * MT + mt) * 4 + 2 * q) * 4];
+                    const double* O = &acc[(((size_t)lane * MT + mt) * 4 + 2 * q + 1) * 4];
+                    const int n = n_base + 16 * q + 2 * t;
+                    float* row = beam + (size_t)b * N * 2;
+                    if (n < N) { row[2 * n] = (float)E[0]; row[2 * n + 1] = (float)E[2]; row[2 * n + 2] = (float)O[0]; row[2 * n + 3] = (float)O[2]; }
+                    if (n + 8 < N) { row[2 * (n + 8)] = (float)E[1]; row[2 * (n + 8) + 1] = (float)E[3]; row[2 * (n + 8) + 2] = (float)O[1]; row[2 * (n + 8) + 3] = (float)O[3]; }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 int emul_cfar4_pitch(int need) { return cfar4_pitch(need); }
 
 int emul_pc_narrow(const float* line, int N, int seg_start0, const float* fir, int nfir, int fir_delay, int ngates,

@@ -104,6 +104,21 @@ def test_pc_mixed_block_plan_covers_the_segment_with_fewest_points(lib, cfg1, N,
     assert not out[:gate0].any() and not out[gate0 + ng:].any()
 
 
+@pytest.mark.parametrize("C,B,N", [(16, 8, 96), (16, 13, 70), (32, 16, 64), (10, 5, 40)])
+def test_dbf_weight_fragments_and_lane_mapping(lib, C, B, N):
+    """dbf_mma2_kernel's index algebra on the host: weight fragments as the MMA A operand, the B-fragment sample order,
+    the D-fragment store addresses.  Result must be x . W' (fun_process_single_frame.m:95)."""
+    rng = np.random.default_rng(C * 100 + B)
+    x = (rng.standard_normal((C, N)) + 1j * rng.standard_normal((C, N))).astype(np.complex64)
+    W = rng.standard_normal((B, C)) + 1j * rng.standard_normal((B, C))
+    Wri = np.ascontiguousarray(np.stack([W.real, W.imag], -1))
+    out = np.zeros((B, N), np.complex64)
+    rc = lib.emul_dbf_wa(np.ascontiguousarray(x).ctypes.data_as(fp), C, N, Wri.ctypes.data_as(dp), B, out.ctypes.data_as(fp))
+    assert rc == 0
+    ref = (x.astype(np.complex128).T @ W.conj().T).T                     # [B][N]: sum_c x[c][n] conj(W[b][c])
+    assert np.abs(out - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
 def test_cfar_pitch_is_conflict_free_across_rows(lib):
     for need in (32, 48, 64, 80, 128, 144, 272):
         p = lib.emul_cfar4_pitch(need)
