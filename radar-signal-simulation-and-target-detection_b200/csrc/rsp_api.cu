@@ -665,12 +665,13 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
         const int it = std::abs(it_env);
         // RSP_OCC_DBF caps the DBF CTAs per SM (dynamic shared-memory padding the kernel never touches)
         static const size_t dbf_pad = [] { const char* e = getenv("RSP_OCC_DBF"); return e && atoi(e) > 0 ? smem_for_occupancy(0, atoi(e)) : (size_t)0; }();
+        static const int dbf_ld = [] { const char* e = getenv("RSP_DBF_LD"); return e ? atoi(e) : 0; }();   // 1: L1::no_allocate loads
         constexpr int NQ = (KS <= 4 && MT == 1) ? 2 : 1;  // 16-sample warp tiles for the big shapes (registers)
 #define RSP_DBF2(ITV, PIPEV) do { const int span = ITV * per_cta * NQ / 2; dim3 gg((c->N + span - 1) / span, c->P);                    \
             { static const bool once = (prefer_max_smem(dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ>), true); (void)once; }                \
             if (dbf_pad > 48 * 1024) cudaFuncSetAttribute(dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dbf_pad); \
             dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ><<<gg, RSP_DBF_MMA_THREADS, dbf_pad, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, \
-                                                                                         c->N, c->ldb, det_count, dead_amp(c)); } while (0)
+                                                                                         c->N, c->ldb, det_count, dead_amp(c), dbf_ld); } while (0)
         if (it >= 8 && c->N >= 8 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(8, kPipe); else RSP_DBF2(8, false); }
         else if (it >= 4 && c->N >= 4 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(4, kPipe); else RSP_DBF2(4, false); }
         else RSP_DBF2(1, false);

@@ -502,13 +502,21 @@ __device__ __forceinline__ void mma_tf32_wa(float (&d)[4], const float4& a, uint
 // flight while tile j goes through the tensor cores, so a warp always has 4 KB of reads outstanding instead of
 // alternating between a load phase and a compute phase (the IT = 1 kernel spends 56 % of its warp-cycles waiting
 // at the first MMA, profiles/r1b_*), and the grid is a single resident wave of long-lived CTAs.
+// streaming 16-byte load that does not allocate in L1 (RSP_DBF_LD=1; experiment against ld.global.cs)
+__device__ __forceinline__ float4 ld_stream_noalloc(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // NQ = 16-sample groups per warp tile (2: 32 samples; 1 for the big shapes, C > 16 or B > 8, whose 32-sample tile would
 // need 64 registers of loads + 32 accumulators: 178 registers and 8 warps per SM at config 3).
 template <int MT, int KS, int IT, bool PIPE, int NQ>
 __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : ((MT == 1 && KS <= 4) || NQ == 1 ? (MT * KS * NQ <= 8 ? 8 : 5) : 1))) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
                                                                        const float4* __restrict__ Wa /* [KS][MT][2][32] */,
                                                                        int C, int NB, int N, int ldb,
-                                                                       int* __restrict__ det_count, const DiscardArgs dead) {
+                                                                       int* __restrict__ det_count, const DiscardArgs dead, int ld_mode) {
     const int tid = threadIdx.x;
     l2_discard(dead);
     if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
@@ -530,8 +538,10 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : ((MT == 1 &
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (4 * s + t < C && n_base + 16 * q + sg < N)
-                    x[s][q] = __ldcs(reinterpret_cast<const float4*>(rp + s * cstep + n_base + 16 * q));
+                if (4 * s + t < C && n_base + 16 * q + sg < N) {
+                    const float4* src = reinterpret_cast<const float4*>(rp + s * cstep + n_base + 16 * q);
+                    x[s][q] = ld_mode ? ld_stream_noalloc(src) : __ldcs(src);
+                }
             }
         }
     };
