@@ -505,7 +505,7 @@ __device__ __forceinline__ void mma_tf32_wa(float (&d)[4], const float4& a, uint
 // streaming 16-byte load that does not allocate in L1 (RSP_DBF_LD=1; experiment against ld.global.cs)
 __device__ __forceinline__ float4 ld_stream_noalloc(const float4* p) {
     float4 v;
-    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
