@@ -1096,8 +1096,9 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
 // constant bank because it sits in the kernel arguments), and shared memory is used once, for the corner
 // turn: a warp-private [32 gates][32 rows + 1] tile, so only __syncwarp() is ever needed.  Against the tiled
 // kernel this removes two shared-memory round trips per point and all run-time butterfly addressing
-// (84 -> ~35 instructions per point; on sm_100a an integer instruction costs an issue slot just like an FFMA,
-// tools/ubench/opcost.cu).
+// (84 -> ~45 instructions per point; on sm_100a an integer instruction costs an issue slot just like an FFMA,
+// tools/ubench/opcost.cu).  Opt-in (RSP_MTD=reg): a CPI has only 46 k Doppler lines = 1444 warps, ~10 per SM at 159
+// registers, so there is nothing to hide the load and store latency with -- 16.9 us alone against 14.7 us tiled.
 struct MtdRegArgs {
     MtdArgs m;
     float win[64];          // kaiser(P) * (-1)^p  (fftshift folded in), fun_process_single_frame.m:134-135
@@ -1147,11 +1148,13 @@ __global__ void __launch_bounds__(RSP_MTD_REG_THREADS, (P > 32 ? 3 : 4)) mtd_reg
 //   phase 1, thread (q = warp, gl = lane): pulses p = q + 8m of gate gl -> window -> DFT-8 over m -> . W64^(q k1) -> S1[k1][q][gl]
 //   phase 2, thread (k1 = warp, gl):       S1[k1][.][gl] -> DFT-8 over q -> X[k1 + 8 k2] -> S2[gl][k1 + 8 k2]   (corner turn)
 //   phase 3: the tile is one contiguous 16 KB block of rdm[b][g][v]; consecutive threads store consecutive bins.
-// Same data flow as mtd_kernel<MtdCfg<64, 8, 8, 1>> but without run-time butterfly addressing, with the window in
-// the constant bank (kernel argument) and the 49 twiddles in __constant__ memory (warp-uniform index):
-// 84 -> ~40 instructions per point at the same register footprint, so the co-resident kernels of the other
-// lanes get the issue slots.  Lanes run along gates in phases 1-2 and along Doppler bins in phase 3; the S2 pitch
-// of 65 keeps the transposed 64-bit stores conflict free (lane stride 130 words = 2 banks).
+// Same data flow as mtd_kernel<MtdCfg<64, 8, 8, 1>> but without run-time butterfly addressing: phase 1 is instantiated
+// once per warp index (switch), so the window comes from the constant bank (kernel argument) and the 49 twiddles are
+// immediates.  5.3 M instead of 7.8 M warp instructions per CPI, 32 registers.  S1 and S2 share one 16.6 KB tile (an
+// extra barrier between the phase-2 loads and stores): with separate tiles (33 KB) the kernel was slower than the
+// generic one -- it lives on residency (8 CTAs per SM), not on its instruction count.  Lanes run along gates in phases
+// 1-2 and along Doppler bins in phase 3; the S2 pitch of 65 keeps the transposed 64-bit stores conflict free (lane
+// stride 130 words = 2 banks).
 __host__ __device__ constexpr float tw64_re(int i) {   // Re exp(-2 pi i q k1 / 64) at i = 8 q + k1
     constexpr float t[64] = {   // exp(-2 pi i q k1 / 64) at [8 q + k1]
     1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f,
