@@ -667,11 +667,19 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
         static const size_t dbf_pad = [] { const char* e = getenv("RSP_OCC_DBF"); return e && atoi(e) > 0 ? smem_for_occupancy(0, atoi(e)) : (size_t)0; }();
         static const int dbf_ld = [] { const char* e = getenv("RSP_DBF_LD"); return e ? atoi(e) : 0; }();   // 1: L1::no_allocate loads
         constexpr int NQ = (KS <= 4 && MT == 1) ? 2 : 1;  // 16-sample warp tiles for the big shapes (registers)
-#define RSP_DBF2(ITV, PIPEV) do { const int span = ITV * per_cta * NQ / 2; dim3 gg((c->N + span - 1) / span, c->P);                    \
+        // RSP_DBF_SPLIT = n: the pulses of a CPI go out in n launches (experiment: shorter kernels interleave better
+        // across the lanes; the mixed PC plan as two launches beats the same work in one launch by 5 % of the chain)
+        static const int dbf_split = [] { const char* e = getenv("RSP_DBF_SPLIT"); return e ? std::max(1, atoi(e)) : 1; }();
+#define RSP_DBF2(ITV, PIPEV) do { const int span = ITV * per_cta * NQ / 2;                                                              \
             { static const bool once = (prefer_max_smem(dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ>), true); (void)once; }                \
             if (dbf_pad > 48 * 1024) cudaFuncSetAttribute(dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dbf_pad); \
-            dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ><<<gg, RSP_DBF_MMA_THREADS, dbf_pad, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, \
-                                                                                         c->N, c->ldb, det_count, dead_amp(c), dbf_ld); } while (0)
+            const int ns = std::min(dbf_split, c->P);                                                                                \
+            for (int part = 0; part < ns; ++part) {                                                                                  \
+                const int pa = (int)((long)c->P * part / ns), pb = (int)((long)c->P * (part + 1) / ns);                              \
+                dim3 gg((c->N + span - 1) / span, pb - pa);                                                                          \
+                if (part) c->launches++;                                                                                            \
+                dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ><<<gg, RSP_DBF_MMA_THREADS, dbf_pad, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, \
+                    c->N, c->ldb, part ? nullptr : det_count, part ? DiscardArgs{nullptr, 0} : dead_amp(c), dbf_ld, pa); } } while (0)
         if (it >= 8 && c->N >= 8 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(8, kPipe); else RSP_DBF2(8, false); }
         else if (it >= 4 && c->N >= 4 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(4, kPipe); else RSP_DBF2(4, false); }
         else RSP_DBF2(1, false);

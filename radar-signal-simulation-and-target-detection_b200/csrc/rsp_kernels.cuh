@@ -516,12 +516,13 @@ template <int MT, int KS, int IT, bool PIPE, int NQ>
 __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : ((MT == 1 && KS <= 4) || NQ == 1 ? (MT * KS * NQ <= 8 ? 8 : 5) : 1))) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
                                                                        const float4* __restrict__ Wa /* [KS][MT][2][32] */,
                                                                        int C, int NB, int N, int ldb,
-                                                                       int* __restrict__ det_count, const DiscardArgs dead, int ld_mode) {
+                                                                       int* __restrict__ det_count, const DiscardArgs dead, int ld_mode,
+                                                                       int p0 /* first pulse of this launch */) {
     const int tid = threadIdx.x;
     l2_discard(dead);
     if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int p = blockIdx.y;
+    const int p = blockIdx.y + p0;
     const int n_first = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (16 * NQ * IT);  // IT tiles of 16 NQ samples per warp
     if (n_first >= N) return;
     // column g of the even n-tile of a 16-sample group <-> sample sg = g (g even) or g + 7 (g odd), odd n-tile: sg + 1.
