@@ -65,6 +65,8 @@ struct rsp_ctx {
     bool pc_one_launch = false;           // RSP_PC_ONE_LAUNCH=1: the mixed PC plan in one multi-role launch instead of two launches
     size_t pc_multi_smem = 0;
     int pc_group_bar = 1;                 // RSP_PC_GROUP_BAR at rsp_create: per-group named barriers in pc_fft_kernel
+    const SynthArgs* fused = nullptr;     // set while rsp_submit_targets enqueues a frame whose S4 is fused into the DBF
+    bool fuse_synth = false;              // RSP_FUSE_SYNTH=1: dbf_synth_kernel on the pipelined frame path (<= 8 targets)
     int stages = 15;                      // RSP_STAGES at rsp_create (measurement aid, see enqueue_chain)
     bool dbf_wa = true;                   // RSP_DBF=mma selects the older data-as-A kernel
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
@@ -361,6 +363,7 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     CUC(dev_alloc(&c->d_raw, (size_t)c->P * c->C * c->N));
     CUC(dev_alloc(&c->d_rdm, PBG));
     { const char* e = getenv("RSP_STAGES"); c->stages = e ? atoi(e) : 15; }
+    { const char* e = getenv("RSP_FUSE_SYNTH"); c->fuse_synth = e && atoi(e) != 0; }
     { const char* e = getenv("RSP_PC_GROUP_BAR"); c->pc_group_bar = e ? atoi(e) : 1; }
     const char* el = getenv("RSP_LANES");
     c->n_lanes = el ? std::min(8, std::max(1, atoi(el))) : 3;
@@ -690,7 +693,29 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
     else dbf_mma_kernel<NT, KS, false><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
 }
 
+template <int MT, int KS> static void launch_dbf_synth(rsp_ctx* c, int* det_count) {
+    constexpr int NQ = (KS <= 4 && MT == 1) ? 2 : 1;
+    Timed t(c, K_DBF);
+    const int per_cta = (RSP_DBF_MMA_THREADS / 32) * 16 * NQ;
+    dim3 grid((c->N + per_cta - 1) / per_cta, c->P);
+    dbf_synth_kernel<MT, KS, NQ><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(*c->fused, c->cur->beam, c->d_Wfrag_wa, c->B, c->ldb, det_count, dead_amp(c));
+}
+
+static bool fused_synth_possible(const rsp_ctx* c, int n_tg) {
+    return c->fuse_synth && c->dbf_nt && c->dbf_wa && !c->dbf_tma && !c->dbf_tma1 && (c->N % 2 == 0) && n_tg <= RSP_SYNTH_GATHER_T &&
+           c->C <= 4 * c->dbf_ks;
+}
+
 static int launch_dbf_any(rsp_ctx* c, const float2* raw, int* det_count) {
+    if (c->fused) {                        // S4 + S5 in one kernel (rsp_submit_targets)
+        const int key = ((c->B + 7) / 8) * 10 + c->dbf_ks;
+        switch (key) {
+#define CASE(mt, ks) case mt * 10 + ks: launch_dbf_synth<mt, ks>(c, det_count); return RSP_OK;
+            CASE(1, 4) CASE(2, 4) CASE(1, 8) CASE(2, 8)
+#undef CASE
+        }
+        return fail(c, RSP_ERR_UNSUPPORTED, "no fused synthesis kernel for %d beams / %d channels", c->B, c->C);
+    }
     if (c->dbf_nt) {
         const int key = c->dbf_nt * 10 + c->dbf_ks;
         switch (key) {
@@ -1341,8 +1366,20 @@ static int make_synth_targets(const rsp_ctx* c, const rsp_target_in* targets, in
     return n;
 }
 
+static void fill_synth_args(const rsp_ctx* c, SynthArgs& a, float2* raw, const SynthTarget* d_tg, int n_tg, double noise_power, uint64_t seed);
+
 static void launch_synth(rsp_ctx* c, float2* raw, const SynthTarget* d_tg, int n_tg, double noise_power, uint64_t seed, cudaStream_t s) {
     SynthArgs a;
+    fill_synth_args(c, a, raw, d_tg, n_tg, noise_power, seed);
+    static const bool staged_only = [] { const char* e = getenv("RSP_SYNTH"); return e && !strcmp(e, "staged"); }();
+    Timed t(c, K_SYNTH);
+    if (n_tg <= RSP_SYNTH_GATHER_T && !staged_only)
+        synth_gather_kernel<<<dim3(c->C, c->P, (c->N + RSP_SYNTH_GATHER_CHUNK - 1) / RSP_SYNTH_GATHER_CHUNK), 256, 0, s>>>(a);
+    else
+        synth_kernel<<<dim3(c->C, c->P, (c->N + RSP_SYNTH_CHUNK - 1) / RSP_SYNTH_CHUNK), 256, 0, s>>>(a);
+}
+
+static void fill_synth_args(const rsp_ctx* c, SynthArgs& a, float2* raw, const SynthTarget* d_tg, int n_tg, double noise_power, uint64_t seed) {
     a.raw = raw;
     a.tx = c->d_tx; a.tg = d_tg; a.n_targets = n_tg;
     a.P = c->P; a.C = c->C; a.N = c->N;
@@ -1355,12 +1392,6 @@ static void launch_synth(rsp_ctx* c, float2* raw, const SynthTarget* d_tg, int n
     for (int i = 0; i < 3; ++i)
         if (a.seg_hi[i] > a.seg_lo[i]) { a.tx_lo = std::min(a.tx_lo, a.seg_lo[i]); a.tx_hi = std::max(a.tx_hi, a.seg_hi[i]); }
     if (a.tx_hi < a.tx_lo) a.tx_lo = a.tx_hi = 0;
-    static const bool staged_only = [] { const char* e = getenv("RSP_SYNTH"); return e && !strcmp(e, "staged"); }();
-    Timed t(c, K_SYNTH);
-    if (n_tg <= RSP_SYNTH_GATHER_T && !staged_only)
-        synth_gather_kernel<<<dim3(c->C, c->P, (c->N + RSP_SYNTH_GATHER_CHUNK - 1) / RSP_SYNTH_GATHER_CHUNK), 256, 0, s>>>(a);
-    else
-        synth_kernel<<<dim3(c->C, c->P, (c->N + RSP_SYNTH_CHUNK - 1) / RSP_SYNTH_CHUNK), 256, 0, s>>>(a);
 }
 
 int rsp_synthesize(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targets, double noise_power, uint64_t seed, void* raw_dev_out) {
@@ -1406,10 +1437,19 @@ int rsp_submit_targets(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targe
     if (int rcf = lane_fork(c, l)) return rcf;
     if (n_tg > 0) CU(c, cudaMemcpyAsync(d, h, (size_t)n_tg * sizeof(SynthTarget), cudaMemcpyHostToDevice, ln.s));
     c->cur = &ln;
-    launch_synth(c, ln.raw, d, n_tg, noise_power, seed, ln.s);
     float2* rdm = lane_rdm(c, l);
     if (!rdm) return fail(c, RSP_ERR_CUDA, "out of device memory for the lane's RDM");
-    int rc = enqueue_chain(c, ln.raw, rdm, slot, l);
+    int rc;
+    if (fused_synth_possible(c, n_tg)) {       // S4 generated inside the DBF: the cube is never materialised
+        SynthArgs a;
+        fill_synth_args(c, a, nullptr, d, n_tg, noise_power, seed);
+        c->fused = &a;
+        rc = enqueue_chain(c, ln.raw, rdm, slot, l);
+        c->fused = nullptr;
+    } else {
+        launch_synth(c, ln.raw, d, n_tg, noise_power, seed, ln.s);
+        rc = enqueue_chain(c, ln.raw, rdm, slot, l);
+    }
     if (rc) return rc;
     launch_refine(c, slot, 1, ln.s);
     return finish_submit(c, slot, l);

@@ -238,6 +238,35 @@ __global__ void __launch_bounds__(256) synth_kernel(const __grid_constant__ Synt
 // per-stretch test is needed.  Targets are added in index order, like the staged kernel.
 #define RSP_SYNTH_GATHER_T 8
 #define RSP_SYNTH_GATHER_CHUNK 8192
+// Samples n0 (even) and n0 + 1 of line `line_id` = pulse * C + channel: Philox noise, then the targets in index order.
+// ph[t * ph_stride] is target t's phasor for this (pulse, channel).  Statement for statement the per-pair body of
+// synth_gather_kernel (kept in its measured form above), used by the fused dbf_synth_kernel.
+__device__ __forceinline__ float4 synth_pair(const SynthArgs& k, const float2* ph, int ph_stride, const int* delay, int n0, size_t line_id) {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k.noise_sigma > 0.f) {
+        const uint4 r = philox4x32_10(make_uint4((unsigned)(n0 / 2), (unsigned)line_id, (unsigned)(line_id >> 32), 0u), k.round_key);
+        const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+        z = make_float4(z0.x * k.noise_sigma, z0.y * k.noise_sigma, z1.x * k.noise_sigma, z1.y * k.noise_sigma);
+    }
+    const unsigned span = (unsigned)(k.tx_hi - k.tx_lo);
+    for (int t = 0; t < k.n_targets; ++t) {
+        const int j = n0 - delay[t] - k.tx_lo;                          // tx index of sample n0, relative to the hull
+        if ((unsigned)(j + 1) <= span) {                                // sample n0 or n0 + 1 is inside the delayed hull
+            const float2 p = ph[t * ph_stride];
+            if ((unsigned)j < span) {
+                const float2 x = k.tx[j + k.tx_lo];
+                z.x += x.x * p.x - x.y * p.y;
+                z.y += x.x * p.y + x.y * p.x;
+            }
+            if ((unsigned)(j + 1) < span) {
+                const float2 x = k.tx[j + 1 + k.tx_lo];
+                z.z += x.x * p.x - x.y * p.y;
+                z.w += x.x * p.y + x.y * p.x;
+            }
+        }
+    }
+    return z;
+}
 __global__ void __launch_bounds__(256) synth_gather_kernel(const __grid_constant__ SynthArgs k) {
     __shared__ float2 s_ph[RSP_SYNTH_GATHER_T];
     __shared__ int s_delay[RSP_SYNTH_GATHER_T];
@@ -623,6 +652,99 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : ((MT == 1 &
             if (j + 1 >= IT || n0 + 16 * NQ >= N) break;
             if (j + 2 < IT && n0 + 32 * NQ < N) load_tile(xa, n0 + 32 * NQ);
             compute_store(xb, n0 + 16 * NQ);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// S4 + S5 fused (BASELINE config 4: echo synthesis ahead of the chain, frames with <= RSP_SYNTH_GATHER_T targets): the
+// samples a thread would load for its MMA B fragments are generated in registers instead -- one Philox call + Box-Muller
+// per (re, im) x 2 pair and the delayed pulses of the targets gathered from tx_pulse, exactly synth_gather_kernel's
+// arithmetic (synth_pair) with the same counters, so the beams equal those of the two-kernel path bit for bit -- and
+// the raw cube is never written or read: 2 x 67 MB of HBM traffic per frame disappear and the DBF's load latency with
+// them.  The target phasors of the CTA's pulse (n_targets x C) are computed once per CTA into shared memory.
+// MMA part, fragment layout and stores as in dbf_mma2_kernel.
+// ------------------------------------------------------------------------------------------
+template <int MT, int KS, int NQ>
+__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_synth_kernel(const __grid_constant__ SynthArgs k, float2* __restrict__ beam,
+                                                                        const float4* __restrict__ Wa /* [KS][MT][2][32] */,
+                                                                        int NB, int ldb, int* __restrict__ det_count, const DiscardArgs dead) {
+    __shared__ float2 s_ph[RSP_SYNTH_GATHER_T * 4 * KS];      // [target][channel], channel stride 4 KS >= C
+    __shared__ int s_delay[RSP_SYNTH_GATHER_T];
+    const int tid = threadIdx.x;
+    const int C = k.C, N = k.N;
+    l2_discard(dead);
+    if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the frame
+    const int p = blockIdx.y;
+    for (int i = tid; i < k.n_targets * C; i += RSP_DBF_MMA_THREADS) {
+        const int tt = i / C, c = i - tt * C;
+        const SynthTarget tg = k.tg[tt];
+        const float2 u = unit_phasor(tg.dop_fix * (unsigned long long)p + tg.steer_fix * (unsigned long long)c);
+        s_ph[tt * (4 * KS) + c] = make_float2(tg.amp * u.x, tg.amp * u.y);
+        if (c == 0) s_delay[tt] = tg.delay;
+    }
+    __syncthreads();
+    const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int n_base = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (16 * NQ);
+    if (n_base >= N) return;
+    const int sg = (g & 1) ? g + 7 : g;                                  // even: a float4 is one (n0, n0 + 1) pair of a line
+    float4 x[KS][NQ];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        const int c = 4 * s + t;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int n0 = n_base + 16 * q + sg;
+            x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C && n0 < N) x[s][q] = synth_pair(k, s_ph + c, 4 * KS, s_delay, n0, (size_t)p * C + c);
+        }
+    }
+    float acc[MT][2 * NQ][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 2 * NQ; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        uint32_t bh[2 * NQ][2], bl[2 * NQ][2];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float v[4] = {x[s][q].x, x[s][q].y, x[s][q].z, x[s][q].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t hi = __float_as_uint(v[i]) & 0xFFFFE000u;
+                bh[2 * q + (i >> 1)][i & 1] = hi;
+                bl[2 * q + (i >> 1)][i & 1] = __float_as_uint(v[i] - __uint_as_float(hi)) & 0xFFFFE000u;
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const float4 ah = __ldg(Wa + ((s * MT + mt) * 2 + 0) * 32 + lane);
+            const float4 al = __ldg(Wa + ((s * MT + mt) * 2 + 1) * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < 2 * NQ; ++j) {
+                mma_tf32_wa(acc[mt][j], al, bh[j][0], bh[j][1]);
+                mma_tf32_wa(acc[mt][j], ah, bl[j][0], bl[j][1]);
+                mma_tf32_wa(acc[mt][j], ah, bh[j][0], bh[j][1]);
+            }
+        }
+    }
+    float2* const brow = beam + (size_t)p * NB * ldb + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int b = 8 * mt + g;
+        if (b < NB) {
+            float2* row = brow + (size_t)b * ldb + n_base;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float(&E)[4] = acc[mt][2 * q];
+                const float(&O)[4] = acc[mt][2 * q + 1];
+                const int n = n_base + 16 * q + 2 * t;
+                if (n < N) *reinterpret_cast<float4*>(row + 16 * q) = make_float4(E[0], E[2], O[0], O[2]);
+                if (n + 8 < N) *reinterpret_cast<float4*>(row + 16 * q + 8) = make_float4(E[1], E[3], O[1], O[3]);
+            }
         }
     }
 }

@@ -420,6 +420,35 @@ def test_batched_frames_equal_one_at_a_time():
     chain.close()
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_fused_synthesis_equals_the_two_kernel_path(name):
+    """RSP_FUSE_SYNTH=1: the pipelined frame path generates the echoes inside the DBF (dbf_synth_kernel, same Philox
+    counters and the same arithmetic as synth_gather_kernel) and never writes the raw cube.  Its detections and targets
+    must equal those of the synchronous path (synthesis kernel + chain) frame by frame; frames with more than 8 targets
+    fall back to the two-kernel path inside the same batch."""
+    import os
+    os.environ["RSP_FUSE_SYNTH"] = "1"
+    try:
+        chain, config, cfar_params, cluster_params, pd = _device_chain(name)
+    finally:
+        os.environ.pop("RSP_FUSE_SYNTH", None)
+    chain.set_waveform(config, pd)
+    v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+    lists = [[dict(Range=900.0 + 400 * i, Velocity=0.1 * v_max, ElevationAngle=5.0 + i, SNR_dB=15.0),
+              dict(Range=3000.0 + 100 * i, Velocity=-0.1 * v_max, ElevationAngle=8.2, SNR_dB=10.0)][: 1 + i % 2] for i in range(5)]
+    lists.append([])                                                                      # noise only
+    lists.append([dict(Range=700.0 + 350.0 * j, Velocity=0.02 * j * v_max, ElevationAngle=-10.0 + 3 * j, SNR_dB=12.0)
+                  for j in range(10)])                                                    # 10 targets: not fused
+    seeds = [21, 22, 23, 24, 25, 26, 27]
+    one = [chain.process_targets(tl, cluster_params, 1.0, s) for tl, s in zip(lists, seeds)]
+    many = chain.process_targets_batch(lists, cluster_params, 1.0, seeds)
+    assert sum(len(d) for _, d in one) > 20
+    for i, ((f1, d1), (f2, d2)) in enumerate(zip(one, many)):
+        assert np.array_equal(d1, d2), i
+        assert np.array_equal(f1, f2), i
+    chain.close()
+
+
 def test_multiframe_tracker_batched_equals_frame_by_frame():
     """main_simulate_echoes_with_array_v8_3.m:192-352 on the device: the pipelined block of frames gives the
     log the frame-by-frame loop gives (same per-frame seeds), and the inter-frame association finds one track
