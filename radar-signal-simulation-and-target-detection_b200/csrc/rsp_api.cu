@@ -66,7 +66,7 @@ struct rsp_ctx {
     size_t pc_multi_smem = 0;
     int pc_group_bar = 1;                 // RSP_PC_GROUP_BAR at rsp_create: per-group named barriers in pc_fft_kernel
     const SynthArgs* fused = nullptr;     // set while rsp_submit_targets enqueues a frame whose S4 is fused into the DBF
-    bool fuse_synth = false;              // RSP_FUSE_SYNTH=1: dbf_synth_kernel on the pipelined frame path (<= 8 targets)
+    bool fuse_synth = true;               // dbf_synth_kernel on the pipelined frame path (<= 8 targets); RSP_FUSE_SYNTH=0: two kernels
     int stages = 15;                      // RSP_STAGES at rsp_create (measurement aid, see enqueue_chain)
     bool dbf_wa = true;                   // RSP_DBF=mma selects the older data-as-A kernel
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
@@ -363,7 +363,7 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     CUC(dev_alloc(&c->d_raw, (size_t)c->P * c->C * c->N));
     CUC(dev_alloc(&c->d_rdm, PBG));
     { const char* e = getenv("RSP_STAGES"); c->stages = e ? atoi(e) : 15; }
-    { const char* e = getenv("RSP_FUSE_SYNTH"); c->fuse_synth = e && atoi(e) != 0; }
+    { const char* e = getenv("RSP_FUSE_SYNTH"); c->fuse_synth = !(e && atoi(e) == 0); }
     { const char* e = getenv("RSP_PC_GROUP_BAR"); c->pc_group_bar = e ? atoi(e) : 1; }
     const char* el = getenv("RSP_LANES");
     c->n_lanes = el ? std::min(8, std::max(1, atoi(el))) : 3;

@@ -422,16 +422,11 @@ def test_batched_frames_equal_one_at_a_time():
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2"])
 def test_fused_synthesis_equals_the_two_kernel_path(name):
-    """RSP_FUSE_SYNTH=1: the pipelined frame path generates the echoes inside the DBF (dbf_synth_kernel, same Philox
+    """The pipelined frame path generates the echoes inside the DBF (dbf_synth_kernel, same Philox
     counters and the same arithmetic as synth_gather_kernel) and never writes the raw cube.  Its detections and targets
     must equal those of the synchronous path (synthesis kernel + chain) frame by frame; frames with more than 8 targets
     fall back to the two-kernel path inside the same batch."""
-    import os
-    os.environ["RSP_FUSE_SYNTH"] = "1"
-    try:
-        chain, config, cfar_params, cluster_params, pd = _device_chain(name)
-    finally:
-        os.environ.pop("RSP_FUSE_SYNTH", None)
+    chain, config, cfar_params, cluster_params, pd = _device_chain(name)        # fused by default (RSP_FUSE_SYNTH=0: off)
     chain.set_waveform(config, pd)
     v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
     lists = [[dict(Range=900.0 + 400 * i, Velocity=0.1 * v_max, ElevationAngle=5.0 + i, SNR_dB=15.0),
