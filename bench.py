@@ -418,7 +418,7 @@ def main():
                             "h2d_bytes_per_frame": 32 * len(tlist), "d2h_bytes_per_frame": d2h,
                             "one_frame_at_a_time": e2e_targets_sync, "one_at_a_time_targets_per_frame": n_fin / n_t,
                             "note": "the reference's own call signature fun_process_single_frame(targets, ...) -> "
-                                    "final_targets: device echo synthesis + Philox noise (S4), S5..S9, host clustering; "
+                                    "final_targets: device echo synthesis + Philox noise (S4, fused into the DBF kernel on the pipelined path), S5..S9, host clustering; "
                                     "only target lists go in and detection lists come back.  value = frames pipelined "
                                     "over the lanes (rsp_submit_targets / rsp_fetch_targets); one_frame_at_a_time = "
                                     "synchronous rsp_process_targets"},
