@@ -237,12 +237,16 @@ typedef struct {
     int32_t reserved_;
 } rsp_info;
 int rsp_get_info(const rsp_ctx* ctx, rsp_info* info);
+/* Measurement aid of the fused DBF + pulse-compression kernel: when the context was created under RSP_FUSED_DEBUG=<flags>,
+ * the last launch recorded for every CTA {start, cluster up, DBF done, lines complete, round 0..2 done} in globaltimer ns
+ * and its SM id; dst receives 8 int64 per CTA (CTA = pulse * B + beam).  *n_ctas = 0 when tracing is off. */
+int rsp_get_fused_trace(rsp_ctx* ctx, int64_t* dst, int32_t cap_ctas, int32_t* n_ctas);
 
 /* ---- per-kernel device timing (bench.py's roofline leg) ----
  * While enabled, every kernel of subsequently enqueued CPIs is bracketed by CUDA events on the
  * context's stream.  rsp_get_kernel_times synchronises, returns for each kernel class its name,
  * accumulated device milliseconds and launch count, and clears the accumulators. */
-#define RSP_MAX_KERNEL_CLASSES 8
+#define RSP_MAX_KERNEL_CLASSES 12
 typedef struct {
     int32_t n;
     const char* name[RSP_MAX_KERNEL_CLASSES];

@@ -73,7 +73,7 @@ class rsp_stage2_config(C.Structure):
 
 
 class rsp_kernel_times(C.Structure):
-    _fields_ = [("n", C.c_int32), ("name", C.c_char_p * 8), ("total_ms", C.c_double * 8), ("launches", C.c_int64 * 8)]
+    _fields_ = [("n", C.c_int32), ("name", C.c_char_p * 12), ("total_ms", C.c_double * 12), ("launches", C.c_int64 * 12)]
 
 
 # numpy dtype with the exact memory layout of rsp_detection (40 bytes)
@@ -119,6 +119,7 @@ SYMBOLS = [
     ("rsp_get_info", C.c_int, [_P, C.POINTER(rsp_info)]),
     ("rsp_set_profiling", C.c_int, [_P, C.c_int]),
     ("rsp_get_kernel_times", C.c_int, [_P, C.POINTER(rsp_kernel_times)]),
+    ("rsp_get_fused_trace", C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32)]),
 ]
 
 _lib = None

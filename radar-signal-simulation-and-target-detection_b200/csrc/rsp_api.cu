@@ -10,6 +10,7 @@
 
 #include "rsp.h"
 #include "rsp_kernels.cuh"
+#include "rsp_fused.cuh"
 #include "rsp_plan.hpp"
 
 using namespace rsp;
@@ -65,6 +66,17 @@ struct rsp_ctx {
     bool pc_one_launch = false;           // RSP_PC_ONE_LAUNCH=1: the mixed PC plan in one multi-role launch instead of two launches
     size_t pc_multi_smem = 0;
     int pc_group_bar = 1;                 // RSP_PC_GROUP_BAR at rsp_create: per-group named barriers in pc_fft_kernel
+    // S5 + S6 in one launch (dbf_pc_kernel, rsp_fused.cuh): cluster per pulse, TMA-fed DBF, beam lines in shared memory
+    bool dbf_pc_ok = false;               // the shape and block plan fit the fused kernel (else: dbf + pc_fft launches)
+    bool dbf_pc_enabled = true;           // RSP_FUSE_DBF_PC=0: two-kernel path (A/B measurements)
+    bool keep_beam = false;               // single-CPI path: the fused kernel also writes the beam cube for rsp_get_beam
+    DbfPcArgs dbf_pc{};                   // everything but the per-launch pointers
+    size_t dbf_pc_smem = 0;
+    int dbf_pc_tma_rank4 = 1;
+    struct TmapEntry { const void* ptr; CUtensorMap map; };
+    std::vector<TmapEntry> tmaps;         // tensor maps of the raw cubes seen so far (keyed by device pointer)
+    long long* d_fused_dbg = nullptr;     // RSP_FUSED_DEBUG: phase timestamps of the last dbf_pc launch [grid][8]
+    int fused_dbg_flags = -1;
     const SynthArgs* fused = nullptr;     // set while rsp_submit_targets enqueues a frame whose S4 is fused into the DBF
     bool fuse_synth = true;               // dbf_synth_kernel on the pipelined frame path (<= 8 targets); RSP_FUSE_SYNTH=0: two kernels
     int stages = 15;                      // RSP_STAGES at rsp_create (measurement aid, see enqueue_chain)
@@ -133,8 +145,9 @@ struct rsp_ctx {
     std::vector<cudaEvent_t> event_pool;
 };
 
-enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC, K_MTD, K_CFAR, K_SYNTH, K_REFINE, K_NCLASS };
-static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft", "mtd", "cfar", "synth", "refine"};
+enum KernelClass { K_CONVERT = 0, K_DBF, K_PC_NARROW, K_PC, K_MTD, K_CFAR, K_SYNTH, K_REFINE, K_DBF_PC, K_MTD_CFAR, K_NCLASS };
+static const char* kKernelNames[K_NCLASS] = {"convert", "dbf", "pc_narrow", "pc_fft", "mtd", "cfar", "synth", "refine", "dbf_pc", "mtd_cfar"};
+static_assert(K_NCLASS <= RSP_MAX_KERNEL_CLASSES, "rsp_kernel_times is too small");
 
 static cudaEvent_t take_event(rsp_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -268,6 +281,8 @@ static cudaError_t mtd_opt_in(int P, size_t bytes) {
     return cudaErrorInvalidValue;
 }
 
+static void plan_dbf_pc(rsp_ctx* c);
+
 extern "C" {
 
 int rsp_abi_version(void) { return RSP_ABI_VERSION; }
@@ -290,7 +305,7 @@ void rsp_destroy(rsp_ctx* c) {
         if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
     }
     if (c->fork) cudaEventDestroy(c->fork);
-    cudaFree(c->d_rawdet);
+    cudaFree(c->d_rawdet); cudaFree(c->d_fused_dbg);
     cudaFree(c->d_tx); cudaFree(c->d_tg); cudaFree(c->d_tg_ring);
     if (c->h_tg_ring) cudaFreeHost(c->h_tg_ring);
     for (auto& sg : c->s2) { cudaFree(sg.tw1); cudaFree(sg.tw2); cudaFree(sg.H); }
@@ -616,6 +631,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     CU(c, upload(&c->d_k_slopes, std::vector<double>(k->k_slopes, k->k_slopes + (B - 1))));
     c->delta_r = k->delta_r;
     c->delta_v = k->delta_v;
+    plan_dbf_pc(c);
     c->have_constants = true;
     return RSP_OK;
 }
@@ -634,6 +650,168 @@ static DiscardArgs dead_buf(const rsp_ctx* c, void* p, size_t bytes) {
 static DiscardArgs dead_amp(const rsp_ctx* c) { return dead_buf(c, c->cur->amp, (size_t)c->P * c->B * c->G * sizeof(float)); }
 static DiscardArgs dead_beam(const rsp_ctx* c) { return dead_buf(c, c->cur->beam, (size_t)c->P * c->B * c->ldb * sizeof(float2)); }
 static DiscardArgs dead_pc(const rsp_ctx* c) { return dead_buf(c, c->cur->pc, (size_t)c->P * c->B * c->ldg * sizeof(float2)); }
+
+
+// ------------------------------------------------------------------------------------------
+// dbf_pc_kernel (rsp_fused.cuh): round schedule, shared-memory layout, tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// Tensor map of one raw cube raw[p][c][n] (complex64 = 2 floats).  rank4: {32 floats of a 16-sample group, C channels,
+// N/16 groups, P pulses} with box {32, C, 8, 1}: ONE copy lands a [8 groups][C][16 samples] tile, the layout in which the
+// MMA fragment loads (4 channels x 8 sample pairs per warp instruction) are 512 contiguous bytes.  rank2 (fallback should a
+// driver reject the non-monotonic strides): {2 N floats, C P rows} with box {32, C}, eight copies per tile.
+static bool encode_raw_tmap(const rsp_ctx* c, const void* raw, bool rank4, CUtensorMap* out) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t N = (cuuint64_t)c->N, C = (cuuint64_t)c->C, P = (cuuint64_t)c->P;
+    if (rank4) {
+        const cuuint64_t dims[4] = {32, C, N / 16, P};
+        const cuuint64_t strides[3] = {N * 8, 128, C * N * 8};
+        const cuuint32_t box[4] = {32, (cuuint32_t)C, RSP_FUSED_TILE / 16, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(raw), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    const cuuint64_t dims[2] = {2 * N, C * P};
+    const cuuint64_t strides[1] = {N * 8};
+    const cuuint32_t box[2] = {32, (cuuint32_t)C};
+    const cuuint32_t es[2] = {1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(raw), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int pc_cfg_id(int L) { return L == 4096 ? 3 : L == 2048 ? 2 : L == 1024 ? 1 : 0; }
+static int pc_smem_elems(int L) { return L + L / 16 + 16; }
+
+// Decide whether the fused kernel covers this context and lay out its rounds: every overlap-save block of one line
+// (long segment, its mixed-length continuation, medium segment) is a group of L/512 warps; first-fit decreasing into
+// rounds of 8 warps.  Called at the end of rsp_upload_constants.
+static void plan_dbf_pc(rsp_ctx* c) {
+    c->dbf_pc_ok = false;
+    { const char* e = getenv("RSP_FUSE_DBF_PC"); c->dbf_pc_enabled = !(e && atoi(e) == 0); }
+    if (!c->dbf_pc_enabled || !c->dbf_nt || !c->dbf_wa || c->dbf_tma || c->dbf_tma1 || c->pc_two_pass) return;
+    if (c->B > 8 || c->C > 16 || c->N % 16 != 0 || c->N > 8192 || (c->ldb & 1) || !encode_tiled_fn()) return;
+    const bool narrow = c->prm.n_gates[0] > 0;
+    if (narrow && !c->med.L) return;                   // the narrow FIR rides on the medium group
+    if (!c->med.L && !c->lng.L) return;
+    DbfPcArgs& a = c->dbf_pc;
+    a = DbfPcArgs{};
+    const PcPlan* pl[4] = {&c->lng, &c->lngx[0], &c->lngx[1], &c->med};
+    const float2* tw1[4] = {c->d_lng_tw1, c->d_lngx_tw1[0], c->d_lngx_tw1[1], c->d_med_tw1};
+    const float2* tw2[4] = {c->d_lng_tw2, c->d_lngx_tw2[0], c->d_lngx_tw2[1], c->d_med_tw2};
+    const float2* H[4] = {c->d_lng_H, c->d_lngx_H[0], c->d_lngx_H[1], c->d_med_H};
+    struct Item { int L, seg, blk; };
+    std::vector<Item> items;
+    int tab = 0;
+    for (int i = 0; i < 4; ++i) {
+        a.tw2_off[i] = tab;
+        a.tw2_len[i] = 0;
+        std::memset(&a.seg[i], 0, sizeof a.seg[i]);
+        if (!pl[i]->L) continue;
+        if (!pc_cfg_id(pl[i]->L)) return;
+        // fill_seg without the CTA bookkeeping
+        PcSegArgs& sg = a.seg[i];
+        sg.tw1 = tw1[i]; sg.tw2 = tw2[i]; sg.Hmid = H[i];
+        sg.seg_start0 = pl[i]->seg_start0; sg.in_lo = pl[i]->seg_start0; sg.in_hi = c->N; sg.taps = pl[i]->taps;
+        sg.gate0 = pl[i]->gate0; sg.g_end = pl[i]->gate0 + pl[i]->ngates; sg.valid = pl[i]->valid; sg.nblk = pl[i]->nblk;
+        a.tw2_len[i] = (int)pl[i]->tw2.size();
+        tab += a.tw2_len[i];
+        for (int b = 0; b < pl[i]->nblk; ++b) items.push_back({pl[i]->L, i, b});
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.L > y.L; });
+    int used[RSP_FUSED_MAX_ROUNDS] = {0, 0, 0, 0}, ngrp[RSP_FUSED_MAX_ROUNDS] = {0, 0, 0, 0}, work[RSP_FUSED_MAX_ROUNDS] = {0, 0, 0, 0};
+    std::memset(a.warp_group, -1, sizeof a.warp_group);
+    a.n_rounds = 0;
+    bool narrow_placed = !narrow;
+    for (const Item& it : items) {
+        const int nw = it.L / 512;
+        int r = 0;
+        while (r < RSP_FUSED_MAX_ROUNDS && (used[r] + nw > RSP_FUSED_WARPS || ngrp[r] >= RSP_FUSED_MAX_GROUPS)) ++r;
+        if (r == RSP_FUSED_MAX_ROUNDS) return;         // too many blocks per line for this kernel
+        DbfPcGroup& g = a.grp[r][ngrp[r]];
+        g.cfg = pc_cfg_id(it.L); g.seg = it.seg; g.blk = it.blk; g.warp0 = used[r]; g.work_off = work[r];
+        g.narrow = (!narrow_placed && it.seg == 3 && it.blk == 0) ? 1 : 0;
+        if (g.narrow) narrow_placed = true;
+        for (int w = 0; w < nw; ++w) a.warp_group[r][used[r] + w] = (signed char)ngrp[r];
+        used[r] += nw; work[r] += pc_smem_elems(it.L); ++ngrp[r];
+        a.n_rounds = std::max(a.n_rounds, r + 1);
+    }
+    if (!narrow_placed) return;
+    int work_elems = 0;
+    for (int r = 0; r < a.n_rounds; ++r) work_elems = std::max(work_elems, work[r]);
+    const size_t ring = (size_t)RSP_FUSED_STAGES * (RSP_FUSED_TILE / 16) * c->C * 128;
+    a.line_bytes = (int)(((size_t)c->N * 8 + 127) & ~(size_t)127);
+    a.work_bytes = (int)((std::max((size_t)work_elems * sizeof(float2), ring) + 127) & ~(size_t)127);
+    c->dbf_pc_smem = (size_t)a.line_bytes + a.work_bytes + (size_t)tab * sizeof(float2) + 256 * sizeof(float) + 64;
+    if (c->dbf_pc_smem > 227 * 1024) return;
+    a.Wa = c->d_Wfrag_wa;
+    a.C = c->C; a.B = c->B; a.P = c->P; a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
+    a.tiles = (c->N + RSP_FUSED_TILE - 1) / RSP_FUSED_TILE;
+    a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
+    a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
+    {   // tensor-map form: probe the single-copy rank-4 map once (any 16-byte aligned address will do for the encoder)
+        const char* e = getenv("RSP_FUSED_TMA");
+        CUtensorMap probe;
+        c->dbf_pc_tma_rank4 = !(e && !strcmp(e, "2d")) && encode_raw_tmap(c, c->d_raw, true, &probe);
+        if (!c->dbf_pc_tma_rank4 && !encode_raw_tmap(c, c->d_raw, false, &probe)) return;
+    }
+    a.tma_rank4 = c->dbf_pc_tma_rank4;
+    if (cudaFuncSetAttribute(dbf_pc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dbf_pc_smem) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaFuncSetAttribute(dbf_pc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaGetLastError();
+    c->tmaps.clear();
+    if (const char* e = getenv("RSP_FUSED_DEBUG")) {   // measurement aid (tools/fused_diag.py): per-CTA phase timestamps
+        c->fused_dbg_flags = atoi(e);
+        if (!c->d_fused_dbg && cudaMalloc(reinterpret_cast<void**>(&c->d_fused_dbg), (size_t)c->P * c->B * 8 * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); c->d_fused_dbg = nullptr; }
+    }
+    c->dbf_pc_ok = true;
+}
+
+static int launch_dbf_pc(rsp_ctx* c, const float2* raw, int* det_count) {
+    const CUtensorMap* map = nullptr;
+    for (auto& e : c->tmaps) if (e.ptr == raw) { map = &e.map; break; }
+    if (!map) {
+        if (c->tmaps.size() >= 64) c->tmaps.erase(c->tmaps.begin());
+        rsp_ctx::TmapEntry e;
+        e.ptr = raw;
+        if ((reinterpret_cast<uintptr_t>(raw) & 15) || !encode_raw_tmap(c, raw, c->dbf_pc_tma_rank4 != 0, &e.map))
+            return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
+        c->tmaps.push_back(e);
+        map = &c->tmaps.back().map;
+    }
+    DbfPcArgs a = c->dbf_pc;
+    a.pc = c->cur->pc;
+    a.beam_out = c->keep_beam ? c->cur->beam : nullptr;
+    a.det_count = det_count;
+    a.dead = dead_amp(c);
+    a.dbg = c->d_fused_dbg;
+    a.dbg_flags = c->fused_dbg_flags > 0 ? c->fused_dbg_flags : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(c->P * c->B));
+    cfg.blockDim = dim3(RSP_FUSED_THREADS);
+    cfg.dynamicSmemBytes = c->dbf_pc_smem;
+    cfg.stream = c->cur->s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)c->B; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    Timed t(c, K_DBF_PC);
+    CU(c, cudaLaunchKernelEx(&cfg, dbf_pc_kernel<4>, *map, a));
+    return RSP_OK;
+}
 
 template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw, int* det_count) {
     constexpr int SPT = 2, CU_ = 4;
@@ -888,6 +1066,7 @@ static void launch_refine(rsp_ctx* c, int first, int n, cudaStream_t st) {
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
     int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + ((c->lngx[0].L && !c->pc_one_launch) ? 1 : 0) + 1 /*mtd*/;
+    if (c->dbf_pc_ok) n = 1 /*dbf_pc*/ + 1 /*mtd*/;
     if (cfar_testable(c)) n += 1;   // cfar (S9 is one refine launch per batch, not per CPI)
     return n;
 }
@@ -899,9 +1078,14 @@ static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, i
     // leaves stages out so that the steady-state cost of each kernel on the lanes can be timed in isolation.
     const int stages = c->stages;
     int rc = RSP_OK;
-    if (stages & 1) rc = launch_dbf_any(c, raw, c->d_counts + slot);      // dbf_kernel also zeroes the slot's counter
-    if (rc) return rc;
-    if (stages & 2) launch_pc(c);
+    if (c->dbf_pc_ok && !c->fused && (stages & 3) == 3) {
+        rc = launch_dbf_pc(c, raw, c->d_counts + slot);                   // S5 + S6 in one launch; zeroes the slot's counter
+        if (rc) return rc;
+    } else {
+        if (stages & 1) rc = launch_dbf_any(c, raw, c->d_counts + slot);  // dbf_kernel also zeroes the slot's counter
+        if (rc) return rc;
+        if (stages & 2) launch_pc(c);
+    }
     if (stages & 4) launch_mtd(c, rdm);
     if ((stages & 8) && cfar_testable(c)) launch_cfar(c, rdm, slot);
     c->cur = &c->lanes[0];
@@ -1013,7 +1197,9 @@ int rsp_process_cpi(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dt
     int rc = stage_input(c, raw, layout, dtype, raw_mem, &d_in);
     if (rc) return rc;
     float2* rdm = (rdm_out && rdm_mem == RSP_MEM_DEVICE) ? static_cast<float2*>(rdm_out) : c->d_rdm;
+    c->keep_beam = true;                       // rsp_get_beam: the fused kernel writes the beam lines out as well
     rc = enqueue_chain(c, d_in, rdm, 0, 0);
+    c->keep_beam = false;
     if (rc) return rc;
     if (!c->slot_prefetched.empty()) c->slot_prefetched[0] = 0;
     launch_refine(c, 0, 1, c->stream);
@@ -1521,6 +1707,18 @@ int rsp_get_kernel_times(rsp_ctx* c, rsp_kernel_times* out) {
         c->event_pool.push_back(sp.b);
     }
     c->spans.clear();
+    return RSP_OK;
+}
+
+int rsp_get_fused_trace(rsp_ctx* c, int64_t* dst, int32_t cap_ctas, int32_t* n_ctas) {
+    if (!c || !dst || !n_ctas) return RSP_ERR_INVALID_ARG;
+    *n_ctas = 0;
+    if (!c->d_fused_dbg || !c->dbf_pc_ok) return RSP_OK;
+    const int n = std::min(cap_ctas, c->P * c->B);
+    CU(c, cudaSetDevice(c->prm.device));
+    CU(c, rsp_synchronize(c) == RSP_OK ? cudaSuccess : cudaErrorUnknown);
+    CU(c, cudaMemcpy(dst, c->d_fused_dbg, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    *n_ctas = n;
     return RSP_OK;
 }
 

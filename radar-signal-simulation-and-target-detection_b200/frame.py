@@ -138,6 +138,13 @@ class RadarChain:
         _abi.check(self._lib.rsp_get_kernel_times(self._ctx, C.byref(kt)), self._ctx)
         return {kt.name[i].decode(): (kt.total_ms[i], kt.launches[i]) for i in range(kt.n) if kt.launches[i]}
 
+    def fused_trace(self) -> np.ndarray:
+        """[ctas, 8] int64 phase timestamps of the last dbf_pc launch (context created under RSP_FUSED_DEBUG)."""
+        buf = np.zeros((self.P * self.B, 8), np.int64)
+        n = C.c_int32(0)
+        _abi.check(self._lib.rsp_get_fused_trace(self._ctx, buf.ctypes.data, buf.shape[0], C.byref(n)), self._ctx)
+        return buf[: n.value]
+
     # -- S5..S9 ---------------------------------------------------------------------------------
     def process_cpi(self, raw, layout: str = "pcn", rdm_out=None) -> np.ndarray:
         """Run DBF -> PC -> MTD -> CFAR -> monopulse on one cube.

@@ -362,32 +362,36 @@ def test_every_dbf_variant_and_generic_paths_agree():
 
 
 def test_config2_kernel_variants_agree():
-    """Config 2 takes the specialised kernels (P = 64 MTD, mixed PC block lengths, padded CFAR pitches, DBF with the
-    weights as the A operand).  Every one of them switched back to its generic counterpart must reproduce the same
-    detections and the same range-Doppler map to fp32 rounding."""
+    """Config 2 takes the specialised kernels (fused DBF + pulse compression, P = 64 MTD, mixed PC block lengths, padded
+    CFAR pitches).  Every one of them switched back to its generic counterpart must reproduce the same detections and the
+    same range-Doppler map to fp32 rounding; the two-kernel DBF / PC path must reproduce it bit for bit (same arithmetic)."""
     import os
     cfg, pre, raw = o.make_cube("cfg2", 2)
-    variants = [{}, {"RSP_MTD": "tile"}, {"RSP_MTD": "reg"}, {"RSP_MTD_SQRT": "approx"}, {"RSP_PC_MIX": "0"},
-                {"RSP_CFAR_PAD": "0"}, {"RSP_DBF": "mma"}, {"RSP_PC_GROUP_BAR": "0"}, {"RSP_PC_ONE_LAUNCH": "1"}]
+    unfused = {"RSP_FUSE_DBF_PC": "0"}
+    variants = [{}, unfused, {"RSP_MTD": "tile"}, {"RSP_MTD_SQRT": "approx"}, {"RSP_PC_MIX": "0"}, {"RSP_CFAR_PAD": "0"},
+                {"RSP_FUSED_TMA": "2d"}, dict(unfused, RSP_PC_MIX="0"), dict(unfused, RSP_DBF="mma"), dict(unfused, RSP_PC_GROUP_BAR="0")]
     results = []
     for env in variants:
         os.environ.update(env)
         try:
             chain, config, cfar_params, cluster_params, pd = _device_chain("cfg2")
             info = chain.info()
-            results.append((env, chain.process_cpi(raw), chain.get_rdm(), info))
+            results.append((env, chain.process_cpi(raw), chain.get_rdm(), info, chain.get_beam(), chain.get_pc()))
             chain.close()
         finally:
             for k in env:
                 os.environ.pop(k, None)
-    _, ref_d, ref_r, ref_info = results[0]
-    assert ref_info["blocks_long"] == 3 and ref_info["kernels_per_cpi"] == 5          # 4096 + 2048 + 1024, two PC launches
+    _, ref_d, ref_r, ref_info, ref_beam, ref_pc = results[0]
+    assert ref_info["blocks_long"] == 3 and ref_info["kernels_per_cpi"] == 3          # dbf_pc, mtd, cfar
     assert len(ref_d) >= 50
-    for env, d, r, info in results[1:]:
+    for env, d, r, info, beam, pc in results[1:]:
+        fused = env.get("RSP_FUSE_DBF_PC") != "0"
         if env.get("RSP_PC_MIX") == "0":
-            assert info["blocks_long"] == 4 and info["kernels_per_cpi"] == 4
-        if env.get("RSP_PC_ONE_LAUNCH") == "1":
-            assert info["blocks_long"] == 3 and info["kernels_per_cpi"] == 4
+            assert info["blocks_long"] == 4 and info["kernels_per_cpi"] == (3 if fused else 4)
+        elif not fused:
+            assert info["blocks_long"] == 3 and info["kernels_per_cpi"] == 5          # dbf, two pc_fft launches, mtd, cfar
+        if env == unfused or env.get("RSP_FUSED_TMA") == "2d":
+            assert np.array_equal(beam, ref_beam) and np.array_equal(pc, ref_pc) and np.array_equal(r, ref_r), env
         assert rel_errors(r, ref_r.astype(np.complex128))[0] <= 2e-6, env
         if env.get("RSP_MTD_SQRT") == "approx":      # amplitudes differ in the last bit: cells at the threshold may flip
             a = set(map(tuple, d[["v_idx", "r_idx", "pair_idx"]].tolist()))
@@ -395,6 +399,39 @@ def test_config2_kernel_variants_agree():
             assert len(a ^ b) <= 2, env
         else:
             assert np.array_equal(d[["v_idx", "r_idx", "pair_idx"]], ref_d[["v_idx", "r_idx", "pair_idx"]]), env
+
+
+@pytest.mark.parametrize("C,B,P,N", [(16, 8, 8, 8192), (12, 5, 6, 4112), (16, 2, 4, 4096), (7, 3, 4, 6000)])
+def test_fused_dbf_pc_equals_the_two_kernel_path(C, B, P, N):
+    """dbf_pc_kernel (cluster per pulse, TMA-fed DBF, beam lines in shared memory, overlap-save blocks in rounds) against
+    dbf_mma2_kernel + pc_fft_kernel on the same cube: same arithmetic in the same order, so beam and pulse-compressed
+    cubes must be bit identical; ragged shapes (cluster sizes 2 / 3 / 5, a partial last TMA tile, channel counts that
+    are not a multiple of 4) included.  The fused result is also checked against the oracle."""
+    import os
+    config, cfar_params, cluster_params = rsp.default_config(channel_num=C, beam_num=B, prtNum=P, point_PRT=N)
+    pd = rsp.build_precomputed_data(config)
+    ocfg = o.shaped_config(C, B, P, N)
+    opre = o.build_precomputed(ocfg)
+    tg = [o.Target(900.0, 0.1 * opre["v_max"], -5.0, 25.0), o.Target(3000.0, -0.1 * opre["v_max"], 8.0, 20.0),
+          o.Target(6000.0, 0.05 * opre["v_max"], 12.0, 20.0)]
+    raw = o.add_noise(o.synthesize_echo(tg, ocfg, opre), 3).astype(np.complex64)
+    out = {}
+    for fused in ("1", "0"):
+        os.environ["RSP_FUSE_DBF_PC"] = fused
+        try:
+            chain = rsp.RadarChain(config, cfar_params, pd)
+            chain.process_cpi(raw)
+            out[fused] = (chain.get_beam(), chain.get_pc(), chain.get_rdm(), chain.info()["kernels_per_cpi"])
+            chain.close()
+        finally:
+            os.environ.pop("RSP_FUSE_DBF_PC", None)
+    assert out["1"][3] < out["0"][3], "the fused kernel was not selected for this shape"
+    for a, b, what in zip(out["1"][:3], out["0"][:3], ("beam", "pc", "rdm")):
+        assert np.array_equal(a, b), what
+    res = o.process_cube(raw.astype(np.complex128), ocfg, opre, workers=-1)
+    assert rel_errors(out["1"][0], res.beam)[0] <= 5e-6
+    assert rel_errors(out["1"][1], res.pc)[0] <= 1e-5
+    assert rel_errors(out["1"][2], res.rdm)[0] <= RDM_REL_TOL
 
 
 def test_batched_frames_equal_one_at_a_time():
