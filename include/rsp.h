@@ -145,12 +145,16 @@ int rsp_process_cpi(rsp_ctx* ctx, const void* raw, rsp_layout layout, rsp_dtype 
 /* ---- device-resident CPI stream (throughput path; no host<->device traffic, asynchronous) ----
  * Processes n_cpi cubes: cube i is read from raw_dev + (i % raw_pool) * C*N*P complex64 (RSP_LAYOUT_PCN),
  * its RDM is written to rdm_dev + (i % rdm_pool) * B*G*P complex64, its detections to slot
- * (first_slot + i) of the context's device detection ring.  Returns after enqueueing. */
+ * (first_slot + i) of the context's device detection ring.  Returns after enqueueing.
+ * Consecutive CPIs run concurrently on the context's lanes (rsp_info.lanes), so a caller ring must hold at least that many
+ * maps, and a multiple of it when n_cpi > rdm_pool (else RSP_ERR_INVALID_ARG); rdm_dev = NULL keeps one map per lane. */
 int rsp_stream_enqueue(rsp_ctx* ctx, const void* raw_dev, int32_t raw_pool, void* rdm_dev, int32_t rdm_pool,
                        int32_t n_cpi, int32_t first_slot);
 /* Pipelined host-input path: enqueue the host->device copy of one PCN complex64 cube (pinned host memory
  * for true overlap) and its chain on lane (slot % lanes), and return at once; the copy of cube i+1 then
  * overlaps the kernels of cube i.  Collect with rsp_stream_fetch(ctx, slot, ...), which waits for that slot. */
+/* Submit / fetch pairing: a slot must be fetched (rsp_stream_fetch / rsp_fetch_targets) before it is submitted again;
+ * resubmitting an unfetched slot returns RSP_ERR_INVALID_ARG (its host cube / target block may still be in flight). */
 int rsp_submit_cpi(rsp_ctx* ctx, const void* raw_host, void* rdm_dev /* may be NULL */, int32_t slot);
 int rsp_stream_slots(const rsp_ctx* ctx);                 /* capacity of the detection ring (CPIs) */
 /* Raw device pointers to the ring: counts[slot] (int32) and records[slot][max_detections] (unsorted). */

@@ -163,7 +163,7 @@ extern "C" void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
     for (size_t k = 0; k < K; ++k) {
         const double R = mxGetScalar(field_at(targets, k, "Range")), V = mxGetScalar(field_at(targets, k, "Velocity"));
         const double El = mxGetScalar(field_at(targets, k, "ElevationAngle")), snr = mxGetScalar(field_at(targets, k, "SNR_dB"));
-        const long d = matlab_round(2.0 * R / c0 * fs);                                   // fsf:55-56
+        const long d = matlab_round((2.0 * R / c0) / (1.0 / fs));                          // fsf:18,55-56: round(delay / ts)
         if (!(d > 0 && d < (long)N)) continue;                                            // fsf:66
         const size_t len = std::min(tx.size(), N - (size_t)d);                            // fsf:67
         const double amp = std::sqrt(std::pow(10.0, snr / 10.0) / p_sig);                 // fsf:61-63

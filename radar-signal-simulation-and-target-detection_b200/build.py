@@ -18,7 +18,7 @@ EMUL = os.path.join(LIB_DIR, "librsp_emul.so")
 
 CUDA_SOURCES = ["rsp_api.cu"]
 CXX_SOURCES = ["rsp_cluster.cpp"]
-HEADERS = ["rsp_math.cuh", "rsp_phases.cuh", "rsp_kernels.cuh", "rsp_fused.cuh", "rsp_plan.hpp", "rsp_dft_big.cuh"]
+HEADERS = ["rsp_math.cuh", "rsp_phases.cuh", "rsp_kernels.cuh", "rsp_fused.cuh", "rsp_dbf_tc.cuh", "rsp_plan.hpp", "rsp_dft_big.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -53,5 +53,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A/B build of the same ABI with extra -D flags: lib/variants/librsp_<name>.so (select with RSP_LIBRARY)."""
+    out_dir = os.path.join(LIB_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"librsp_{name}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + [
+        "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out]
+    cmd += [os.path.join(CSRC, f) for f in CUDA_SOURCES + CXX_SOURCES]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")], verbose="--verbose" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

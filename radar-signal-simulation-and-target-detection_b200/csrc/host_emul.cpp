@@ -25,35 +25,7 @@ template <class Cfg> static void run_mtd_tile(cf* s, const cf* tw, const cf* src
         for (int t = 0; t < RSP_MTD_THREADS; ++t) mtd_passes_phase<Cfg>(s, tw, t, pass);
 }
 
-template <class Cfg> static void run_pc2_block(const PcBlockArgs& a, cf* s) {
-    for (int t = 0; t < Cfg::T; ++t) pc2_phase_a<Cfg>(a, s, t);
-    for (int t = 0; t < Cfg::T; ++t) pc2_phase_b<Cfg>(a, s, t);
-    for (int t = 0; t < Cfg::T; ++t) pc2_phase_c<Cfg>(a, s, t);
-}
-
 extern "C" {
-
-// the two-pass (N x N) overlap-save blocks
-int emul_pc2_segment(const float* line, int N, int seg_start0, int gate0, int ngates, const double* taps_ri, int ntaps, int L,
-                     float* out_line, int* nblk_used) {
-    std::vector<zc> taps(ntaps);
-    for (int i = 0; i < ntaps; ++i) taps[i] = zc(taps_ri[2 * i], taps_ri[2 * i + 1]);
-    PcPlan pl;
-    if (!make_pc2_plan(pl, L, taps.data(), ntaps, seg_start0, gate0, ngates)) return -1;
-    std::vector<cf> smem((size_t)L + 2 * 64 + 16);
-    for (int blk = 0; blk < pl.nblk; ++blk) {
-        PcBlockArgs a;
-        a.line = reinterpret_cast<const cf*>(line);
-        a.out_line = reinterpret_cast<cf*>(out_line);
-        a.tw1 = pl.tw1.data(); a.tw2 = nullptr; a.Hmid = pl.Hmid.data();
-        a.in_lo = seg_start0; a.in_hi = N; a.seg_start0 = seg_start0; a.taps = ntaps;
-        a.g0 = gate0 + blk * pl.valid; a.g_end = gate0 + ngates;
-        if (L == 4096) run_pc2_block<Pc2Cfg<4096, 64>>(a, smem.data());
-        else run_pc2_block<Pc2Cfg<1024, 32>>(a, smem.data());
-    }
-    if (nblk_used) *nblk_used = pl.nblk;
-    return 0;
-}
 
 int emul_small_dft(int R, int sign, float* v) {
     cf* c = reinterpret_cast<cf*>(v);

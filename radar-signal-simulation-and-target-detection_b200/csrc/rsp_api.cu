@@ -11,11 +11,21 @@
 #include "rsp.h"
 #include "rsp_kernels.cuh"
 #include "rsp_fused.cuh"
+#include "rsp_dbf_tc.cuh"
 #include "rsp_plan.hpp"
 
 using namespace rsp;
 
 static thread_local std::string g_create_error;
+
+// Measurement aids (stage masks, stream priorities, uniform carve-outs, kernels with parts switched off) exist only in a
+// library built with -DRSP_PROBES (build.py --variant probes -DRSP_PROBES; tools/stage_probe.py picks it up): the shipped
+// library cannot be told by its environment to skip stages or to produce wrong results.
+#ifdef RSP_PROBES
+static int probe_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+static int probe_env(const char*, int dflt) { return dflt; }
+#endif
 
 struct rsp_ctx {
     rsp_params prm{};
@@ -63,17 +73,26 @@ struct rsp_ctx {
     float2* d_W = nullptr;
     float4* d_Wfrag = nullptr;            // tensor-core DBF weight fragments
     float4* d_Wfrag_wa = nullptr;         // same for dbf_mma2_kernel (weights as the A operand)
-    bool pc_one_launch = false;           // RSP_PC_ONE_LAUNCH=1: the mixed PC plan in one multi-role launch instead of two launches
-    size_t pc_multi_smem = 0;
     int pc_group_bar = 1;                 // RSP_PC_GROUP_BAR at rsp_create: per-group named barriers in pc_fft_kernel
     // S5 + S6 in one launch (dbf_pc_kernel, rsp_fused.cuh): cluster per pulse, TMA-fed DBF, beam lines in shared memory
     bool dbf_pc_ok = false;               // the shape and block plan fit the fused kernel (else: dbf + pc_fft launches)
-    bool dbf_pc_enabled = true;           // RSP_FUSE_DBF_PC=0: two-kernel path (A/B measurements)
+    bool dbf_pc_enabled = false;          // RSP_FUSE_DBF_PC=1 selects the fused cluster kernel
     bool keep_beam = false;               // single-CPI path: the fused kernel also writes the beam cube for rsp_get_beam
     DbfPcArgs dbf_pc{};                   // everything but the per-launch pointers
     size_t dbf_pc_smem = 0;
     int dbf_pc_tma_rank4 = 1;
-    struct TmapEntry { const void* ptr; CUtensorMap map; };
+    // tcgen05 DBF (dbf_tc_kernel, rsp_dbf_tc.cuh)
+    bool dbf_tc = false;                  // selected for this shape (RSP_DBF=tc forces it on, any other RSP_DBF value off)
+    float* d_Bw_tc = nullptr;             // [2][Npad * Kpad] weight operands, canonical K-major core-matrix layout
+    DbfTcArgs dbf_tc_args{};
+    size_t dbf_tc_smem = 0;
+    int dbf_tc_grid = 0;
+    bool dbf_tma2 = false;                // RSP_DBF=tma2: stand-alone TMA-tensor-fed DBF (dbf_tma2_kernel)
+    int dbf_tma2_tiles = 8;               // tiles per CTA (RSP_DBF_TMA2_TILES)
+    const float2* exp_raw = nullptr;      // RSP_EXP_MERGE experiment: the cube whose DBF rides inside the PC launch
+    float2* exp_beam = nullptr;
+    int dbf_pc_clusters = 0;              // cudaOccupancyMaxActiveClusters of the fused kernel
+    struct TmapEntry { const void* ptr; int mode; CUtensorMap map; };
     std::vector<TmapEntry> tmaps;         // tensor maps of the raw cubes seen so far (keyed by device pointer)
     long long* d_fused_dbg = nullptr;     // RSP_FUSED_DEBUG: phase timestamps of the last dbf_pc launch [grid][8]
     int fused_dbg_flags = -1;
@@ -82,13 +101,9 @@ struct rsp_ctx {
     int stages = 15;                      // RSP_STAGES at rsp_create (measurement aid, see enqueue_chain)
     bool dbf_wa = true;                   // RSP_DBF=mma selects the older data-as-A kernel
     int dbf_nt = 0, dbf_ks = 0;           // 0 = FFMA kernel
-    bool dbf_tma = false;                 // TMA-fed persistent variant
-    bool dbf_tma1 = false;                // TMA-fed one-tile-per-CTA variant (bulk loads and bulk stores)
-    int dbf_tma_ctas = 0;
     float* d_fir = nullptr;
     int n_fir = 0;
     PcPlan med, lng;
-    bool pc_two_pass = false;             // Pc2Cfg plans (64x64 / 32x32), RSP_PC=r64
     // stage-2 (process_stage2_mtd) plans: one per gated segment, own tables
     struct S2Seg { PcPlan pl; float2 *tw1 = nullptr, *tw2 = nullptr, *H = nullptr; int lo = 0, hi = 0; };
     S2Seg s2[3];
@@ -108,7 +123,7 @@ struct rsp_ctx {
     float* d_win = nullptr;
     std::vector<float> h_win, h_s2_win;   // host copies: the register MTD kernel takes the window as an argument
     bool cfar_pad = true;                 // conflict-free CFAR tile pitches (P <= 64)
-    int mtd_mode = 2;                     // RSP_MTD: 0 = tile (generic), 1 = reg (one thread per Doppler line, P = 32 / 64), 2 = p64 (specialised tile; default when P = 64)
+    int mtd_mode = 2;                     // RSP_MTD: 0 = tile (generic), 2 = p64 (specialised tile; default when P = 64)
     bool mtd_approx_sqrt = false;         // RSP_MTD_SQRT=approx
     double *d_range_axis = nullptr, *d_vel_axis = nullptr, *d_beam_angles = nullptr, *d_k_slopes = nullptr;
     double delta_r = 0, delta_v = 0;
@@ -198,7 +213,7 @@ template <typename T> static cudaError_t upload(T** dptr, const std::vector<T>& 
 // shared memory), so that an SM never has to drain to change its carve-out between kernels of different lanes.  Measured:
 // it does not make the kernels of different streams overlap any better (DBF + PC together still cost the sum of their
 // times) and the smaller L1 slows both (DBF 15.3 -> 21.0 us, PC 21.8 -> 24.2 us), profiles/r1_overlap_probe.txt.
-static int carveout_pct() { static const int v = [] { const char* e = getenv("RSP_CARVEOUT"); return e ? atoi(e) : 0; }(); return v == 1 ? 100 : v; }
+static int carveout_pct() { static const int v = probe_env("RSP_CARVEOUT", 0); return v == 1 ? 100 : v; }
 template <typename KernelT> static void prefer_max_smem(KernelT kern) {
     if (carveout_pct() > 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct());
 }
@@ -230,14 +245,6 @@ template <class A, class B> static size_t pc_smem_pair() { return smem_for_occup
 // X(long plan, medium plan)
 #define RSP_FOR_EACH_PC_PAIR(X) X(Pc1024, Pc1024) X(Pc2048, Pc1024) X(Pc4096, Pc1024) X(Pc1024, Pc2048) X(Pc2048, Pc2048) \
     X(Pc4096, Pc2048) X(Pc1024, Pc4096) X(Pc2048, Pc4096) X(Pc4096, Pc4096)
-
-typedef Pc2Cfg<4096, 64> Pc2L;
-typedef Pc2Cfg<1024, 32> Pc2S;
-template <class Cfg> static size_t pc2_smem_bytes() {
-    return (size_t)(RSP_PC2_THREADS / Cfg::T) * Cfg::SMEM_ELEMS * sizeof(float2) + 256 * sizeof(float);
-}
-template <class A, class B> static size_t pc2_smem_pair() { return std::max(pc2_smem_bytes<A>(), pc2_smem_bytes<B>()); }
-#define RSP_FOR_EACH_PC2_PAIR(X) X(Pc2L, Pc2L) X(Pc2L, Pc2S) X(Pc2S, Pc2L) X(Pc2S, Pc2S)
 
 // generic Doppler DFT kernel: (tile gates, power-of-two factor R of P)
 // (tile gates, power-of-two factor R of P, output bins per work item KT)
@@ -282,6 +289,7 @@ static cudaError_t mtd_opt_in(int P, size_t bytes) {
 }
 
 static void plan_dbf_pc(rsp_ctx* c);
+static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k);
 
 extern "C" {
 
@@ -305,7 +313,7 @@ void rsp_destroy(rsp_ctx* c) {
         if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
     }
     if (c->fork) cudaEventDestroy(c->fork);
-    cudaFree(c->d_rawdet); cudaFree(c->d_fused_dbg);
+    cudaFree(c->d_rawdet); cudaFree(c->d_fused_dbg); cudaFree(c->d_Bw_tc);
     cudaFree(c->d_tx); cudaFree(c->d_tg); cudaFree(c->d_tg_ring);
     if (c->h_tg_ring) cudaFreeHost(c->h_tg_ring);
     for (auto& sg : c->s2) { cudaFree(sg.tw1); cudaFree(sg.tw2); cudaFree(sg.H); }
@@ -372,12 +380,12 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     // RSP_STREAM_PRIO=high: the context's own streams get the greatest priority (measurement aid, tools/overlap_probe.py)
     int prio_lo = 0, prio_hi = 0;
     CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    { const char* e = getenv("RSP_STREAM_PRIO"); if (!(e && !strcmp(e, "high"))) prio_hi = prio_lo > 0 ? 0 : prio_lo; }
+    if (!probe_env("RSP_STREAM_PRIO_HIGH", 0)) prio_hi = prio_lo > 0 ? 0 : prio_lo;
     CUC(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     const size_t PBG = (size_t)c->P * c->B * c->G;
     CUC(dev_alloc(&c->d_raw, (size_t)c->P * c->C * c->N));
     CUC(dev_alloc(&c->d_rdm, PBG));
-    { const char* e = getenv("RSP_STAGES"); c->stages = e ? atoi(e) : 15; }
+    c->stages = probe_env("RSP_STAGES", 15);
     { const char* e = getenv("RSP_FUSE_SYNTH"); c->fuse_synth = !(e && atoi(e) == 0); }
     { const char* e = getenv("RSP_PC_GROUP_BAR"); c->pc_group_bar = e ? atoi(e) : 1; }
     const char* el = getenv("RSP_LANES");
@@ -461,30 +469,8 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             CU(c, upload(&c->d_Wfrag, make_dbf_fragments(reinterpret_cast<const double*>(k->dbf_weights), B, C, c->dbf_nt, c->dbf_ks)));
             CU(c, upload(&c->d_Wfrag_wa, make_dbf_fragments_wa(reinterpret_cast<const double*>(k->dbf_weights), B, C, (B + 7) / 8, c->dbf_ks)));
             c->dbf_wa = !(e && std::string(e) == "mma");
-            c->dbf_tma = e && std::string(e) == "tma";             // RSP_DBF=tma: persistent cp.async.bulk-fed variant
-            c->dbf_tma1 = e && std::string(e) == "tma1";           // RSP_DBF=tma1: one tile per CTA, bulk loads + bulk stores
-            if (c->dbf_tma1) {
-                const size_t sm1 = (size_t)(C + B) * RSP_DBF_TMA_ROWB;
-                switch (c->dbf_nt * 10 + c->dbf_ks) {
-#define CASE(nt, ks) case nt * 10 + ks: CU(c, opt_in_smem(dbf_tma1_kernel<nt, ks>, sm1)); break;
-                    CASE(1, 4) CASE(2, 4) CASE(3, 4) CASE(4, 4) CASE(1, 8) CASE(2, 8) CASE(3, 8) CASE(4, 8)
-#undef CASE
-                }
-            }
-            if (c->dbf_tma) {
-                const size_t sm = (size_t)RSP_DBF_TMA_STAGES * C * RSP_DBF_TMA_ROWB;
-                int nsm = 148;
-                cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->prm.device);
-                const char* ec = getenv("RSP_DBF_CTAS_PER_SM");
-                const int per_sm = ec ? std::max(1, atoi(ec)) : (sm <= 72 * 1024 ? 2 : 1);
-                c->dbf_tma_ctas = nsm * per_sm;
-                const int key = c->dbf_nt * 10 + c->dbf_ks;
-                switch (key) {
-#define CASE(nt, ks) case nt * 10 + ks: CU(c, opt_in_smem(dbf_tma_kernel<nt, ks>, sm)); break;
-                    CASE(1, 4) CASE(2, 4) CASE(3, 4) CASE(4, 4) CASE(1, 8) CASE(2, 8) CASE(3, 8) CASE(4, 8)
-#undef CASE
-                }
-            }
+            c->dbf_tma2 = e && std::string(e) == "tma2";
+            { const char* et = getenv("RSP_DBF_TMA2_TILES"); c->dbf_tma2_tiles = et ? std::max(1, atoi(et)) : 8; }
         }
     }
     std::vector<float> fir(k->n_fir);
@@ -503,17 +489,10 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         int L = choose_pc_len(nt, ng);
         const char* e = getenv(env);
         if (e && atoi(e) > 0) L = atoi(e);
-        if (c->pc_two_pass) {                        // only 1024 (32 x 32) and 4096 (64 x 64) exist in this plan
-            const int L2 = (nt - 1 < 512 && (ng + 1024 - nt) / (1024 - (nt - 1)) <= 2) ? 1024 : 4096;
-            if (!make_pc2_plan(pl, L2, t.data(), nt, seg_start1 - 1, gate0, ng))
-                return fail(c, RSP_ERR_UNSUPPORTED, "no two-pass block plan for %d taps", nt);
-            return RSP_OK;
-        }
         if (!make_pc_plan(pl, L, t.data(), nt, seg_start1 - 1, gate0, ng))
             return fail(c, RSP_ERR_UNSUPPORTED, "no block plan for %d taps (L=%d)", nt, L);
         return RSP_OK;
     };
-    { const char* e = getenv("RSP_PC"); c->pc_two_pass = e && std::string(e) == "r64"; }
     int rc = plan_seg(c->med, k->mf_medium, k->n_mf_medium, c->prm.seg_start[1], g1, g2, "RSP_PC_LEN_MEDIUM");
     if (rc) return rc;
     rc = plan_seg(c->lng, k->mf_long, k->n_mf_long, c->prm.seg_start[2], g1 + g2, g3, "RSP_PC_LEN_LONG");
@@ -525,7 +504,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         int counts[3];
         const int nt = k->n_mf_long;
         const int mix_pts = (g3 > 0 && nt >= 1 && nt <= 1024) ? choose_pc_mix(nt, g3, counts) : 0;
-        if (!(em && atoi(em) == 0) && !(el && atoi(el) > 0) && !c->pc_two_pass && c->lng.L && mix_pts > 0 &&
+        if (!(em && atoi(em) == 0) && !(el && atoi(el) > 0) && c->lng.L && mix_pts > 0 &&
             mix_pts < c->lng.nblk * c->lng.L) {
             std::vector<zc> t(nt);
             for (int i = 0; i < nt; ++i) t[i] = zc(k->mf_long[i].re, k->mf_long[i].im);
@@ -543,16 +522,8 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             }
         }
     }
-    { const char* e = getenv("RSP_PC_ONE_LAUNCH"); c->pc_one_launch = e && atoi(e) != 0; }
-    c->pc_multi_smem = smem_for_occupancy(std::max(std::max(pc_smem_bytes<Pc1024>(), pc_smem_bytes<Pc2048>()), pc_smem_bytes<Pc4096>()), pc_occ_cap());
-    CU(c, opt_in_smem(pc_fft_multi_kernel, c->pc_multi_smem));
     for (int i = 0; i < 2; ++i)
         if (c->lngx[i].L) { CU(c, upload(&c->d_lngx_tw1[i], c->lngx[i].tw1)); CU(c, upload(&c->d_lngx_tw2[i], c->lngx[i].tw2)); CU(c, upload(&c->d_lngx_H[i], c->lngx[i].Hmid)); }
-    if (c->pc_two_pass) {
-#define X2(A, B) CU(c, opt_in_smem(pc2_fft_kernel<A, B>, pc2_smem_pair<A, B>()));
-        RSP_FOR_EACH_PC2_PAIR(X2)
-#undef X2
-    }
     if (c->med.L) { CU(c, upload(&c->d_med_tw1, c->med.tw1)); CU(c, upload(&c->d_med_tw2, c->med.tw2)); CU(c, upload(&c->d_med_H, c->med.Hmid)); }
     if (c->lng.L) { CU(c, upload(&c->d_lng_tw1, c->lng.tw1)); CU(c, upload(&c->d_lng_tw2, c->lng.tw2)); CU(c, upload(&c->d_lng_H, c->lng.Hmid)); }
 #define X(A, B) CU(c, opt_in_smem(pc_fft_kernel<A, B>, pc_smem_pair<A, B>()));
@@ -589,7 +560,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     }
     CU(c, upload(&c->d_win, win));
     c->h_win = win;
-    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 2 : !strcmp(e, "tile") ? 0 : !strcmp(e, "reg") ? 1 : 2; }
+    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 2 : !strcmp(e, "tile") ? 0 : 2; }
     { const char* e = getenv("RSP_MTD_SQRT"); c->mtd_approx_sqrt = e && !strcmp(e, "approx"); }
     {   // CFAR tile height: the largest of {64,32,16} whose shared arrays let three CTAs share an SM
         const int mR = c->prm.guard_r + c->prm.ref_r;
@@ -632,6 +603,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     c->delta_r = k->delta_r;
     c->delta_v = k->delta_v;
     plan_dbf_pc(c);
+    if (int rc_tc = plan_dbf_tc(c, k)) return rc_tc;
     c->have_constants = true;
     return RSP_OK;
 }
@@ -673,11 +645,12 @@ static EncodeTiledFn encode_tiled_fn() {
 // N/16 groups, P pulses} with box {32, C, 8, 1}: ONE copy lands a [8 groups][C][16 samples] tile, the layout in which the
 // MMA fragment loads (4 channels x 8 sample pairs per warp instruction) are 512 contiguous bytes.  rank2 (fallback should a
 // driver reject the non-monotonic strides): {2 N floats, C P rows} with box {32, C}, eight copies per tile.
-static bool encode_raw_tmap(const rsp_ctx* c, const void* raw, bool rank4, CUtensorMap* out) {
+enum { TMAP_GROUPS_2D = 0, TMAP_GROUPS_4D = 1, TMAP_ROWS_2D = 2 };   // TMAP_ROWS_2D: box {256 floats, C rows} = [C][128 samples] (dbf_tc_kernel)
+static bool encode_raw_tmap(const rsp_ctx* c, const void* raw, int mode, CUtensorMap* out) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
     const cuuint64_t N = (cuuint64_t)c->N, C = (cuuint64_t)c->C, P = (cuuint64_t)c->P;
-    if (rank4) {
+    if (mode == TMAP_GROUPS_4D) {
         const cuuint64_t dims[4] = {32, C, N / 16, P};
         const cuuint64_t strides[3] = {N * 8, 128, C * N * 8};
         const cuuint32_t box[4] = {32, (cuuint32_t)C, RSP_FUSED_TILE / 16, 1};
@@ -687,7 +660,7 @@ static bool encode_raw_tmap(const rsp_ctx* c, const void* raw, bool rank4, CUten
     }
     const cuuint64_t dims[2] = {2 * N, C * P};
     const cuuint64_t strides[1] = {N * 8};
-    const cuuint32_t box[2] = {32, (cuuint32_t)C};
+    const cuuint32_t box[2] = {mode == TMAP_ROWS_2D ? 256u : 32u, (cuuint32_t)C};
     const cuuint32_t es[2] = {1, 1};
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(raw), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -701,8 +674,14 @@ static int pc_smem_elems(int L) { return L + L / 16 + 16; }
 // rounds of 8 warps.  Called at the end of rsp_upload_constants.
 static void plan_dbf_pc(rsp_ctx* c) {
     c->dbf_pc_ok = false;
-    { const char* e = getenv("RSP_FUSE_DBF_PC"); c->dbf_pc_enabled = !(e && atoi(e) == 0); }
-    if (!c->dbf_pc_enabled || !c->dbf_nt || !c->dbf_wa || c->dbf_tma || c->dbf_tma1 || c->pc_two_pass) return;
+    c->tmaps.clear();
+    if (encode_tiled_fn() && c->N % 16 == 0) {   // tensor-map form: probe the single-copy rank-4 map once (any 16-byte aligned address will do)
+        const char* e = getenv("RSP_FUSED_TMA");
+        CUtensorMap probe;
+        c->dbf_pc_tma_rank4 = !(e && !strcmp(e, "2d")) && encode_raw_tmap(c, c->d_raw, TMAP_GROUPS_4D, &probe);
+    }
+    { const char* e = getenv("RSP_FUSE_DBF_PC"); c->dbf_pc_enabled = e && atoi(e) != 0; }   // opt-in: measured slower than dbf_tc + pc_fft
+    if (!c->dbf_pc_enabled || !c->dbf_nt || !c->dbf_wa || c->dbf_tma2) return;
     if (c->B > 8 || c->C > 16 || c->N % 16 != 0 || c->N > 8192 || (c->ldb & 1) || !encode_tiled_fn()) return;
     const bool narrow = c->prm.n_gates[0] > 0;
     if (narrow && !c->med.L) return;                   // the narrow FIR rides on the medium group
@@ -762,36 +741,36 @@ static void plan_dbf_pc(rsp_ctx* c) {
     a.tiles = (c->N + RSP_FUSED_TILE - 1) / RSP_FUSED_TILE;
     a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
     a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
-    {   // tensor-map form: probe the single-copy rank-4 map once (any 16-byte aligned address will do for the encoder)
-        const char* e = getenv("RSP_FUSED_TMA");
-        CUtensorMap probe;
-        c->dbf_pc_tma_rank4 = !(e && !strcmp(e, "2d")) && encode_raw_tmap(c, c->d_raw, true, &probe);
-        if (!c->dbf_pc_tma_rank4 && !encode_raw_tmap(c, c->d_raw, false, &probe)) return;
-    }
+    { CUtensorMap probe; if (!c->dbf_pc_tma_rank4 && !encode_raw_tmap(c, c->d_raw, TMAP_GROUPS_2D, &probe)) return; }
     a.tma_rank4 = c->dbf_pc_tma_rank4;
     if (cudaFuncSetAttribute(dbf_pc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dbf_pc_smem) != cudaSuccess) { cudaGetLastError(); return; }
     cudaFuncSetAttribute(dbf_pc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaGetLastError();
-    c->tmaps.clear();
+    {   // clusters that can be resident at once = pulses per wave; a CTA prefetches the slice of the pulse one wave ahead
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(c->P * c->B)); cfg.blockDim = dim3(RSP_FUSED_THREADS); cfg.dynamicSmemBytes = c->dbf_pc_smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)c->B; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, dbf_pc_kernel<4>, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+        const char* e = getenv("RSP_FUSED_PREFETCH");
+        a.prefetch_ahead = e ? atoi(e) : nc;
+        c->dbf_pc_clusters = nc;
+    }
     if (const char* e = getenv("RSP_FUSED_DEBUG")) {   // measurement aid (tools/fused_diag.py): per-CTA phase timestamps
-        c->fused_dbg_flags = atoi(e);
+        c->fused_dbg_flags = probe_env("RSP_FUSED_DEBUG", 0);
+        (void)e;
         if (!c->d_fused_dbg && cudaMalloc(reinterpret_cast<void**>(&c->d_fused_dbg), (size_t)c->P * c->B * 8 * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); c->d_fused_dbg = nullptr; }
     }
     c->dbf_pc_ok = true;
 }
 
+static const CUtensorMap* raw_tmap(rsp_ctx* c, const float2* raw, int mode = -1);
 static int launch_dbf_pc(rsp_ctx* c, const float2* raw, int* det_count) {
-    const CUtensorMap* map = nullptr;
-    for (auto& e : c->tmaps) if (e.ptr == raw) { map = &e.map; break; }
-    if (!map) {
-        if (c->tmaps.size() >= 64) c->tmaps.erase(c->tmaps.begin());
-        rsp_ctx::TmapEntry e;
-        e.ptr = raw;
-        if ((reinterpret_cast<uintptr_t>(raw) & 15) || !encode_raw_tmap(c, raw, c->dbf_pc_tma_rank4 != 0, &e.map))
-            return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
-        c->tmaps.push_back(e);
-        map = &c->tmaps.back().map;
-    }
+    const CUtensorMap* map = raw_tmap(c, raw);
+    if (!map) return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
     DbfPcArgs a = c->dbf_pc;
     a.pc = c->cur->pc;
     a.beam_out = c->keep_beam ? c->cur->beam : nullptr;
@@ -813,6 +792,116 @@ static int launch_dbf_pc(rsp_ctx* c, const float2* raw, int* det_count) {
     return RSP_OK;
 }
 
+static const CUtensorMap* raw_tmap(rsp_ctx* c, const float2* raw, int mode) {
+    if (mode < 0) mode = c->dbf_pc_tma_rank4 ? TMAP_GROUPS_4D : TMAP_GROUPS_2D;
+    for (auto& e : c->tmaps) if (e.ptr == raw && e.mode == mode) return &e.map;
+    if (c->tmaps.size() >= 64) c->tmaps.erase(c->tmaps.begin());
+    rsp_ctx::TmapEntry e;
+    e.ptr = raw;
+    e.mode = mode;
+    if ((reinterpret_cast<uintptr_t>(raw) & 15) || !encode_raw_tmap(c, raw, mode, &e.map)) return nullptr;
+    c->tmaps.push_back(e);
+    return &c->tmaps.back().map;
+}
+
+static int launch_dbf_tma2(rsp_ctx* c, const float2* raw, int* det_count) {
+    const CUtensorMap* map = raw_tmap(c, raw);
+    if (!map) return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
+    DbfTmaArgs a;
+    a.beam = c->cur->beam; a.Wa = c->d_Wfrag_wa; a.det_count = det_count;
+    a.C = c->C; a.B = c->B; a.N = c->N; a.ldb = c->ldb;
+    a.tiles = (c->N + RSP_FUSED_TILE - 1) / RSP_FUSED_TILE;
+    a.tiles_per_cta = c->dbf_tma2_tiles;
+    a.tma_rank4 = c->dbf_pc_tma_rank4;
+    a.dead = dead_amp(c);
+    const size_t sm = (size_t)RSP_DBFT_STAGES * (RSP_FUSED_TILE / 16) * c->C * 128;
+    static bool once = false;
+    if (!once) { cudaFuncSetAttribute(dbf_tma2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); once = true; }
+    dim3 grid((a.tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, c->P);
+    Timed t(c, K_DBF);
+    dbf_tma2_kernel<4><<<grid, RSP_FUSED_THREADS, sm, c->cur->s>>>(*map, a);
+    return RSP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// dbf_tc_kernel (rsp_dbf_tc.cuh): weight operands, shared-memory budget, launch
+// ------------------------------------------------------------------------------------------
+static std::vector<float> make_dbf_tc_weights(const double* W_ri /* [B][C][2] */, int B, int C, int Npad, int Cpad) {
+    const int K = 2 * Cpad;
+    std::vector<float> out((size_t)2 * Npad * K, 0.f);
+    for (int n = 0; n < Npad; ++n)
+        for (int kk = 0; kk < K; ++kk) {
+            const int b = n >> 1, ro = n & 1, ch = kk >> 1, ri = kk & 1;
+            float v = 0.f;
+            if (b < B && ch < C) {
+                const float wr = (float)W_ri[((size_t)b * C + ch) * 2], wi = (float)W_ri[((size_t)b * C + ch) * 2 + 1];
+                v = ro == 0 ? (ri == 0 ? wr : wi) : (ri == 0 ? -wi : wr);      // x * conj(W), fsf:95
+            }
+            const size_t off = ((size_t)(kk / 4) * (Npad / 8) * 128 + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(kk % 4) * 4) / 4;
+            const float hi = host_tf32(v);
+            out[off] = hi;
+            out[(size_t)Npad * K + off] = host_tf32(v - hi);
+        }
+    return out;
+}
+
+static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
+    c->dbf_tc = false;
+    const char* e = getenv("RSP_DBF");
+    if (e && strcmp(e, "tc")) return RSP_OK;                      // another DBF kernel was asked for
+    if (c->B > 16 || c->C > 32 || (c->N & 1) || !encode_tiled_fn()) return RSP_OK;
+    { CUtensorMap probe; if (!encode_raw_tmap(c, c->d_raw, TMAP_ROWS_2D, &probe)) return RSP_OK; }
+    DbfTcArgs& a = c->dbf_tc_args;
+    a = DbfTcArgs{};
+    a.C = c->C; a.B = c->B; a.P = c->P; a.N = c->N; a.ldb = c->ldb;
+    a.Cpad = c->C <= 8 ? 8 : c->C <= 16 ? 16 : 32;
+    a.Npad = 2 * c->B <= 16 ? 16 : 32;
+    a.tiles_per_pulse = (c->N + RSP_TC_TILE - 1) / RSP_TC_TILE;
+    const size_t raw_stage = (size_t)c->C * 1024, b_bytes = (size_t)a.Npad * 2 * a.Cpad * 4;
+    const size_t fixed = 2 * b_bytes + (2 * RSP_TC_MAX_STAGES + 6) * 8 + 16;
+    // Three stages and, for the small shapes, CTAs of 16 tiles: measured best inside the chain (a deep ring or one long-lived
+    // CTA per SM is faster alone but keeps the other lanes' kernels off the SM; profiles/r2_tc_probe.txt)
+    int ns = 3;
+    if (const char* es = getenv("RSP_TC_STAGES")) ns = std::max(2, std::min(RSP_TC_MAX_STAGES, atoi(es)));
+    a.chunk = c->C <= 16 ? 16 : 0;
+    while (ns > 2 && fixed + ns * raw_stage > 220 * 1024) --ns;
+    if (fixed + ns * raw_stage > 227 * 1024) return RSP_OK;
+    a.stages = ns;
+    a.dbg = probe_env("RSP_TC_DEBUG", 0);
+    c->dbf_tc_smem = fixed + ns * raw_stage;
+    CU(c, upload(&c->d_Bw_tc, make_dbf_tc_weights(reinterpret_cast<const double*>(k->dbf_weights), c->B, c->C, a.Npad, a.Cpad)));
+    a.Bw = c->d_Bw_tc;
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->prm.device);
+    int per_sm = 1;
+    if (const char* ep = getenv("RSP_TC_CTAS_PER_SM")) per_sm = std::max(1, atoi(ep));
+    c->dbf_tc_grid = std::min(nsm * per_sm, c->P * a.tiles_per_pulse);
+    if (const char* ec = getenv("RSP_TC_CHUNK")) a.chunk = std::max(0, atoi(ec));
+    if (a.chunk > 0) c->dbf_tc_grid = (c->P * a.tiles_per_pulse + a.chunk - 1) / a.chunk;
+    cudaError_t err = cudaErrorInvalidValue;
+#define RSP_TC_CASE(NP, CP) if (a.Npad == NP && a.Cpad == CP) err = cudaFuncSetAttribute(dbf_tc_kernel<NP, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dbf_tc_smem);
+    RSP_TC_CASE(16, 8) RSP_TC_CASE(16, 16) RSP_TC_CASE(16, 32) RSP_TC_CASE(32, 8) RSP_TC_CASE(32, 16) RSP_TC_CASE(32, 32)
+#undef RSP_TC_CASE
+    if (err != cudaSuccess) { cudaGetLastError(); return RSP_OK; }
+    c->dbf_tc = true;
+    return RSP_OK;
+}
+
+static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count) {
+    const CUtensorMap* map = raw_tmap(c, raw, TMAP_ROWS_2D);
+    if (!map) return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
+    DbfTcArgs a = c->dbf_tc_args;
+    a.beam = c->cur->beam;
+    a.det_count = det_count;
+    a.dead = dead_amp(c);
+    Timed t(c, K_DBF);
+#define RSP_TC_CASE(NP, CP) if (a.Npad == NP && a.Cpad == CP) dbf_tc_kernel<NP, CP><<<c->dbf_tc_grid, RSP_TC_THREADS, c->dbf_tc_smem, c->cur->s>>>(*map, a);
+    RSP_TC_CASE(16, 8) RSP_TC_CASE(16, 16) RSP_TC_CASE(16, 32) RSP_TC_CASE(32, 8) RSP_TC_CASE(32, 16) RSP_TC_CASE(32, 32)
+#undef RSP_TC_CASE
+    return RSP_OK;
+}
+
 template <int NB> static void launch_dbf(rsp_ctx* c, const float2* raw, int* det_count) {
     constexpr int SPT = 2, CU_ = 4;
     Timed t(c, K_DBF);
@@ -825,46 +914,11 @@ template <int NT, int KS> static void launch_dbf_mma(rsp_ctx* c, const float2* r
     const int per_cta = (RSP_DBF_MMA_THREADS / 32) * 32;
     dim3 grid((c->N + per_cta - 1) / per_cta, c->P);
     const bool vec = (c->N % 2 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
-    if (vec && c->dbf_tma1) {
-        const size_t sm = (size_t)(c->C + c->B) * RSP_DBF_TMA_ROWB;
-        dim3 g1((c->N + RSP_DBF_TMA_TILE - 1) / RSP_DBF_TMA_TILE, c->P);
-        dbf_tma1_kernel<NT, KS><<<g1, RSP_DBF_T1_THREADS, sm, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
-        return;
-    }
-    if (vec && c->dbf_tma) {
-        const size_t sm = (size_t)RSP_DBF_TMA_STAGES * c->C * RSP_DBF_TMA_ROWB;
-        const int n_tiles = c->P * ((c->N + RSP_DBF_TMA_TILE - 1) / RSP_DBF_TMA_TILE);
-        const int nctas = std::min(n_tiles, c->dbf_tma_ctas);
-        dbf_tma_kernel<NT, KS><<<nctas, RSP_DBF_TMA_THREADS, sm, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, c->P, det_count, dead_amp(c));
-        return;
-    }
     if (vec && c->dbf_wa) {
         constexpr int MT = (NT + 1) / 2;       // NT = ceil(B / 4) n-tiles of the old kernel  ->  ceil(B / 8) m-tiles
-        // RSP_DBF_IT = tiles per warp (1, 4, 8); negative = software-pipelined loads (two tiles in registers)
-        static const int it_env = [] { const char* e = getenv("RSP_DBF_IT"); return e ? atoi(e) : 1; }();
-        constexpr bool kPipe = (KS <= 4 && MT == 1);      // two tiles of loads in registers: 64 for C <= 16, too many beyond
-        const int it = std::abs(it_env);
-        // RSP_OCC_DBF caps the DBF CTAs per SM (dynamic shared-memory padding the kernel never touches)
-        static const size_t dbf_pad = [] { const char* e = getenv("RSP_OCC_DBF"); return e && atoi(e) > 0 ? smem_for_occupancy(0, atoi(e)) : (size_t)0; }();
-        static const int dbf_ld = [] { const char* e = getenv("RSP_DBF_LD"); return e ? atoi(e) : 0; }();   // 1: L1::no_allocate loads
         constexpr int NQ = (KS <= 4 && MT == 1) ? 2 : 1;  // 16-sample warp tiles for the big shapes (registers)
-        // RSP_DBF_SPLIT = n: the pulses of a CPI go out in n launches (experiment: shorter kernels interleave better
-        // across the lanes; the mixed PC plan as two launches beats the same work in one launch by 5 % of the chain)
-        static const int dbf_split = [] { const char* e = getenv("RSP_DBF_SPLIT"); return e ? std::max(1, atoi(e)) : 1; }();
-#define RSP_DBF2(ITV, PIPEV) do { const int span = ITV * per_cta * NQ / 2;                                                              \
-            { static const bool once = (prefer_max_smem(dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ>), true); (void)once; }                \
-            if (dbf_pad > 48 * 1024) cudaFuncSetAttribute(dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dbf_pad); \
-            const int ns = std::min(dbf_split, c->P);                                                                                \
-            for (int part = 0; part < ns; ++part) {                                                                                  \
-                const int pa = (int)((long)c->P * part / ns), pb = (int)((long)c->P * (part + 1) / ns);                              \
-                dim3 gg((c->N + span - 1) / span, pb - pa);                                                                          \
-                if (part) c->launches++;                                                                                            \
-                dbf_mma2_kernel<MT, KS, ITV, PIPEV, NQ><<<gg, RSP_DBF_MMA_THREADS, dbf_pad, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, \
-                    c->N, c->ldb, part ? nullptr : det_count, part ? DiscardArgs{nullptr, 0} : dead_amp(c), dbf_ld, pa); } } while (0)
-        if (it >= 8 && c->N >= 8 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(8, kPipe); else RSP_DBF2(8, false); }
-        else if (it >= 4 && c->N >= 4 * per_cta) { if (it_env < 0 && kPipe) RSP_DBF2(4, kPipe); else RSP_DBF2(4, false); }
-        else RSP_DBF2(1, false);
-#undef RSP_DBF2
+        dim3 gg((c->N + per_cta * NQ / 2 - 1) / (per_cta * NQ / 2), c->P);
+        dbf_mma2_kernel<MT, KS, NQ><<<gg, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag_wa, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
         return;
     }
     if (vec) dbf_mma_kernel<NT, KS, true><<<grid, RSP_DBF_MMA_THREADS, 0, c->cur->s>>>(raw, c->cur->beam, c->d_Wfrag, c->C, c->B, c->N, c->ldb, det_count, dead_amp(c));
@@ -880,7 +934,7 @@ template <int MT, int KS> static void launch_dbf_synth(rsp_ctx* c, int* det_coun
 }
 
 static bool fused_synth_possible(const rsp_ctx* c, int n_tg) {
-    return c->fuse_synth && c->dbf_nt && c->dbf_wa && !c->dbf_tma && !c->dbf_tma1 && (c->N % 2 == 0) && n_tg <= RSP_SYNTH_GATHER_T &&
+    return c->fuse_synth && c->dbf_nt && c->dbf_wa && (c->N % 2 == 0) && n_tg <= RSP_SYNTH_FUSED_T &&
            c->C <= 4 * c->dbf_ks;
 }
 
@@ -894,6 +948,13 @@ static int launch_dbf_any(rsp_ctx* c, const float2* raw, int* det_count) {
         }
         return fail(c, RSP_ERR_UNSUPPORTED, "no fused synthesis kernel for %d beams / %d channels", c->B, c->C);
     }
+    // A context that synthesises its own echoes (rsp_set_waveform) takes the mma.sync DBF on every path: the fused S4 + S5
+    // kernel of the pipelined frame path is built on that arithmetic, so a frame gives the same bits whether it goes
+    // through rsp_process_targets, rsp_submit_targets or rsp_synthesize + rsp_process_cpi.
+    const bool frame_mma = c->have_waveform && c->dbf_nt && c->dbf_wa && (c->N % 2 == 0);
+    if (c->dbf_tc && !frame_mma && !(reinterpret_cast<uintptr_t>(raw) & 15)) return launch_dbf_tc(c, raw, det_count);
+    if (c->dbf_tma2 && c->dbf_nt && c->B <= 8 && c->C <= 16 && c->N % 16 == 0 && !(c->ldb & 1) && encode_tiled_fn())
+        return launch_dbf_tma2(c, raw, det_count);
     if (c->dbf_nt) {
         const int key = c->dbf_nt * 10 + c->dbf_ks;
         switch (key) {
@@ -917,7 +978,7 @@ static void fill_seg(const rsp_ctx* c, PcSegArgs& sg, const PcPlan& pl, const fl
     sg.seg_start0 = pl.seg_start0; sg.in_lo = pl.seg_start0; sg.in_hi = c->N; sg.taps = pl.taps; sg.gate0 = pl.gate0; sg.g_end = pl.gate0 + pl.ngates; sg.valid = pl.valid;
     sg.nblk = pl.nblk;
     sg.n_items = pl.L ? c->P * c->B * pl.nblk : 0;
-    const int ng = pl.L ? (c->pc_two_pass ? RSP_PC2_THREADS : RSP_PC_THREADS) / pl.T : 1;
+    const int ng = pl.L ? RSP_PC_THREADS / pl.T : 1;
     sg.n_ctas = (sg.n_items + ng - 1) / ng;
 }
 
@@ -942,36 +1003,24 @@ static void launch_pc(rsp_ctx* c) {
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
     const int la = c->lng.L ? c->lng.L : 1024, lb = c->med.L ? c->med.L : 1024;
     Timed t(c, K_PC);
-    if (c->pc_two_pass) {
-#define X2(A, B) if (la == A::L && lb == B::L) pc2_fft_kernel<A, B><<<nctas, RSP_PC2_THREADS, pc2_smem_pair<A, B>(), c->cur->s>>>(a);
-        RSP_FOR_EACH_PC2_PAIR(X2)
-#undef X2
-        return;
-    }
-    if (c->lngx[0].L && c->pc_one_launch) {      // mixed plan: every role in one launch, longest blocks first
-        PcMultiArgs m;
-        m.k = a;
-        const PcPlan* pl[4] = {&c->lng, &c->lngx[0], &c->lngx[1], &c->med};
-        const float2* tw1[4] = {c->d_lng_tw1, c->d_lngx_tw1[0], c->d_lngx_tw1[1], c->d_med_tw1};
-        const float2* tw2[4] = {c->d_lng_tw2, c->d_lngx_tw2[0], c->d_lngx_tw2[1], c->d_med_tw2};
-        const float2* H[4] = {c->d_lng_H, c->d_lngx_H[0], c->d_lngx_H[1], c->d_med_H};
-        int order[4] = {0, 1, 2, 3};                 // roles sorted by block length, descending (stable)
-        std::stable_sort(order, order + 4, [&](int x, int y) { return pl[x]->L > pl[y]->L; });
-        int total = 0;
-        m.narrow_role = -1;
-        for (int r = 0; r < 4; ++r) {
-            const int i = order[r];
-            fill_seg(c, m.seg[r], *pl[i], tw1[i], tw2[i], H[i]);
-            m.len[r] = pl[i]->L;
-            if (i == 3 && pl[i]->L) m.narrow_role = r;
-            total += m.seg[r].n_ctas;
-        }
-        pc_fft_multi_kernel<<<total, RSP_PC_THREADS, c->pc_multi_smem, c->cur->s>>>(m);
-        return;
-    }
+#ifdef RSP_PROBES
+    static const int exp_merge = probe_env("RSP_EXP_MERGE", 0);
+    if (exp_merge && la == 4096 && lb == 1024 && c->exp_raw && c->B <= 8 && c->C <= 16) {   // experiment: DBF CTAs interleaved with the PC CTAs
+        if (!c->exp_beam) cudaMalloc(reinterpret_cast<void**>(&c->exp_beam), (size_t)c->P * c->B * c->ldb * sizeof(float2));
+        MergeDbfArgs d;
+        d.raw = c->exp_raw; d.beam = c->exp_beam; d.Wa = c->d_Wfrag_wa; d.C = c->C; d.NB = c->B; d.N = c->N; d.ldb = c->ldb; d.P = c->P;
+        d.n_dbf = c->P * ((c->N + 255) / 256) / (exp_merge > 1 ? exp_merge : 1);
+        d.n_total = nctas + d.n_dbf;
+        static bool once = false;
+        if (!once) { opt_in_smem(pc_dbf_merge_kernel<Pc4096, Pc1024>, pc_smem_pair<Pc4096, Pc1024>()); once = true; }
+        pc_dbf_merge_kernel<Pc4096, Pc1024><<<d.n_total, RSP_PC_THREADS, pc_smem_pair<Pc4096, Pc1024>(), c->cur->s>>>(a, d);
+    } else
+#endif
+    {
 #define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
     RSP_FOR_EACH_PC_PAIR(X)
 #undef X
+    }
     if (c->lngx[0].L) {            // the shorter blocks of a mixed long-segment plan
         fill_seg(c, a.seg[0], c->lngx[0], c->d_lngx_tw1[0], c->d_lngx_tw2[0], c->d_lngx_H[0]);
         fill_seg(c, a.seg[1], c->lngx[1], c->d_lngx_tw1[1], c->d_lngx_tw2[1], c->d_lngx_H[1]);
@@ -1001,15 +1050,6 @@ static void launch_mtd(rsp_ctx* c, float2* rdm) {
         { static const bool once = (prefer_max_smem(mtd64_kernel<true>), prefer_max_smem(mtd64_kernel<false>), true); (void)once; }
         if (c->mtd_approx_sqrt) mtd64_kernel<true><<<sgrid, 256, 0, c->cur->s>>>(r);
         else mtd64_kernel<false><<<sgrid, 256, 0, c->cur->s>>>(r);
-        return;
-    }
-    if (c->pow2_doppler && c->mtd_mode == 1 && (c->P == 32 || c->P == 64) && (int)c->h_win.size() == c->P) {
-        MtdRegArgs r;
-        r.m = a;
-        for (int p = 0; p < 64; ++p) r.win[p] = p < c->P ? c->h_win[p] : 0.f;
-        dim3 rgrid((c->G + RSP_MTD_REG_THREADS - 1) / RSP_MTD_REG_THREADS, c->B);
-        if (c->P == 64) mtd_reg_kernel<64><<<rgrid, RSP_MTD_REG_THREADS, 0, c->cur->s>>>(r);
-        else mtd_reg_kernel<32><<<rgrid, RSP_MTD_REG_THREADS, 0, c->cur->s>>>(r);
         return;
     }
     if (c->pow2_doppler) {
@@ -1065,7 +1105,7 @@ static void launch_refine(rsp_ctx* c, int first, int n, cudaStream_t st) {
 
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
-    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + ((c->lngx[0].L && !c->pc_one_launch) ? 1 : 0) + 1 /*mtd*/;
+    int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + (c->lngx[0].L ? 1 : 0) + 1 /*mtd*/;
     if (c->dbf_pc_ok) n = 1 /*dbf_pc*/ + 1 /*mtd*/;
     if (cfar_testable(c)) n += 1;   // cfar (S9 is one refine launch per batch, not per CPI)
     return n;
@@ -1074,6 +1114,7 @@ static int kernels_per_cpi(const rsp_ctx* c) {
 // enqueue S5..S9 for one device-resident PCN cube on lane `lane`
 static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, int lane) {
     c->cur = &c->lanes[lane];
+    c->exp_raw = raw;
     // RSP_STAGES (bit mask 1 = DBF, 2 = PC, 4 = MTD, 8 = CFAR) is a measurement aid for tools/stage_probe.py: it
     // leaves stages out so that the steady-state cost of each kernel on the lanes can be timed in isolation.
     const int stages = c->stages;
@@ -1092,6 +1133,15 @@ static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, i
     CU(c, cudaGetLastError());
     return RSP_OK;
 }
+
+// RDM buffer of a lane for the pipelined paths: concurrent lanes must not share one
+static float2* lane_rdm(rsp_ctx* c, int l) {
+    if (l == 0) return c->d_rdm;
+    rsp_ctx::Lane& ln = c->lanes[l];
+    if (!ln.rdm && cudaMalloc(reinterpret_cast<void**>(&ln.rdm), (size_t)c->P * c->B * c->G * sizeof(float2)) != cudaSuccess) return nullptr;
+    return ln.rdm;
+}
+
 
 static bool det_less(const rsp_detection& a, const rsp_detection& b) {
     if (a.pair_idx != b.pair_idx) return a.pair_idx < b.pair_idx;
@@ -1132,6 +1182,14 @@ static int stage_input(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype
     }
     CU(c, cudaGetLastError());
     *out = c->d_raw;
+    return RSP_OK;
+}
+
+// A slot whose previous pipelined submission has not been fetched must not be reused: its pinned descriptor block /
+// host cube may still be read by the asynchronous copy of that submission, and its counts and records would be replaced.
+static int check_slot_free(rsp_ctx* c, int slot) {
+    if (!c->slot_prefetched.empty() && c->slot_prefetched[slot])
+        return fail(c, RSP_ERR_INVALID_ARG, "slot %d was submitted and not fetched yet (pair every submit with a fetch)", slot);
     return RSP_OK;
 }
 
@@ -1219,6 +1277,12 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
     CU(c, cudaSetDevice(c->prm.device));
     const size_t in_elems = (size_t)c->P * c->C * c->N, out_elems = (size_t)c->P * c->B * c->G;
     const int nl = std::min(c->n_lanes, std::max(n_cpi, 1));
+    // Up to nl CPIs are in flight at once, one per lane: their range-Doppler maps must not share a buffer (MTD of CPI i + 1
+    // would race with MTD and CFAR of CPI i).  A caller ring needs at least nl buffers, n_cpi > rdm_pool needs
+    // rdm_pool % nl == 0 (CPI i goes to lane i % nl and to buffer i % rdm_pool); without a ring every lane uses its own map.
+    const bool own_rdm = !(rdm_dev && rdm_pool > 0);
+    if (!own_rdm && nl > 1 && (rdm_pool < nl || (n_cpi > rdm_pool && rdm_pool % nl != 0)))
+        return fail(c, RSP_ERR_INVALID_ARG, "rdm_pool %d cannot serve %d concurrent lanes (need rdm_pool >= lanes, and a multiple of lanes when n_cpi > rdm_pool)", rdm_pool, nl);
     { const char* e = getenv("RSP_L2_DISCARD"); c->discard = !(e && atoi(e) == 0); }
     if (nl > 1) {                                    // fork: the extra lanes wait for work already on the caller's stream
         CU(c, cudaEventRecord(c->fork, c->stream));
@@ -1226,7 +1290,8 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
     }
     for (int i = 0; i < n_cpi; ++i) {
         const float2* in = static_cast<const float2*>(raw_dev) + (size_t)(i % raw_pool) * in_elems;
-        float2* rdm = (rdm_dev && rdm_pool > 0) ? static_cast<float2*>(rdm_dev) + (size_t)(i % rdm_pool) * out_elems : c->d_rdm;
+        float2* rdm = own_rdm ? lane_rdm(c, i % nl) : static_cast<float2*>(rdm_dev) + (size_t)(i % rdm_pool) * out_elems;
+        if (!rdm) return fail(c, RSP_ERR_CUDA, "out of device memory for the lane's RDM");
         int rc = enqueue_chain(c, in, rdm, first_slot + i, i % nl);
         if (rc) return rc;
         c->slot_lane[first_slot + i] = -1;
@@ -1252,18 +1317,11 @@ static int lane_fork(rsp_ctx* c, int l) {
     return RSP_OK;
 }
 
-// RDM buffer of a lane for the pipelined paths: concurrent lanes must not share one
-static float2* lane_rdm(rsp_ctx* c, int l) {
-    if (l == 0) return c->d_rdm;
-    rsp_ctx::Lane& ln = c->lanes[l];
-    if (!ln.rdm && cudaMalloc(reinterpret_cast<void**>(&ln.rdm), (size_t)c->P * c->B * c->G * sizeof(float2)) != cudaSuccess) return nullptr;
-    return ln.rdm;
-}
-
 int rsp_submit_cpi(rsp_ctx* c, const void* raw_host, void* rdm_dev, int32_t slot) {
     if (!c || !raw_host || slot < 0 || slot >= c->slots) return fail(c, RSP_ERR_INVALID_ARG, "bad submit arguments");
     if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
     CU(c, cudaSetDevice(c->prm.device));
+    if (int rcs = check_slot_free(c, slot)) return rcs;
     const int l = slot % c->n_lanes;
     rsp_ctx::Lane& ln = c->lanes[l];
     const size_t bytes = (size_t)c->P * c->C * c->N * sizeof(float2);
@@ -1388,7 +1446,7 @@ int rsp_stage2_configure(rsp_ctx* c, const rsp_stage2_config* cfg) {
     }
     CU(c, upload(&c->d_s2_win, win));
     c->h_s2_win = win;
-    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 2 : !strcmp(e, "tile") ? 0 : !strcmp(e, "reg") ? 1 : 2; }
+    { const char* e = getenv("RSP_MTD"); c->mtd_mode = !e ? 2 : !strcmp(e, "tile") ? 0 : 2; }
     { const char* e = getenv("RSP_MTD_SQRT"); c->mtd_approx_sqrt = e && !strcmp(e, "approx"); }
     if (c->pow2_doppler) {
         CU(c, upload(&c->d_dop_tw, c->dop.tw));
@@ -1540,7 +1598,8 @@ static int make_synth_targets(const rsp_ctx* c, const rsp_target_in* targets, in
     const double kPiD = 3.14159265358979323846;
     int n = 0;
     for (int i = 0; i < n_targets; ++i) {
-        const long d = matlab_round(2.0 * targets[i].range / c->wf.c * c->wf.fs);                       // fsf:55-56
+        const double ts = 1.0 / c->wf.fs;                                                               // fsf:18
+        const long d = matlab_round((2.0 * targets[i].range / c->wf.c) / ts);                           // fsf:55-56: round(delay / ts)
         if (!(d > 0 && d < c->N)) continue;                                                              // fsf:66
         SynthTarget t;
         t.delay = (int)d;
@@ -1610,6 +1669,7 @@ int rsp_submit_targets(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targe
     if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
     if (!c->have_waveform) return fail(c, RSP_ERR_NOT_READY, "rsp_set_waveform has not been called");
     CU(c, cudaSetDevice(c->prm.device));
+    if (int rcs = check_slot_free(c, slot)) return rcs;
     if (!c->d_tg_ring) {
         CU(c, dev_alloc(&c->d_tg_ring, (size_t)c->slots * RSP_MAX_FRAME_TARGETS));
         CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_tg_ring), (size_t)c->slots * RSP_MAX_FRAME_TARGETS * sizeof(SynthTarget)));
@@ -1638,6 +1698,7 @@ int rsp_submit_targets(rsp_ctx* c, const rsp_target_in* targets, int32_t n_targe
     }
     if (rc) return rc;
     launch_refine(c, slot, 1, ln.s);
+    if (l == 0) { c->ran = true; c->rdm_in_ctx = true; }     // lane 0 works in the context's own buffers (rsp_get_beam / rsp_get_rdm)
     return finish_submit(c, slot, l);
 }
 
@@ -1694,7 +1755,7 @@ int rsp_set_profiling(rsp_ctx* c, int enable) {
 int rsp_get_kernel_times(rsp_ctx* c, rsp_kernel_times* out) {
     if (!c || !out) return RSP_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->prm.device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    if (int rcs = rsp_synchronize(c)) return rcs;       // spans of the pipelined paths sit on the other lanes' streams
     std::memset(out, 0, sizeof *out);
     out->n = K_NCLASS;
     for (int i = 0; i < K_NCLASS; ++i) out->name[i] = kKernelNames[i];

@@ -60,6 +60,8 @@ struct DbfPcArgs {
     DiscardArgs dead;
     long long* dbg;          // optional [grid][8] phase timestamps (globaltimer ns) + SM id, tools/fused_diag.py; nullptr in production
     int dbg_flags;           // measurement aid: 1 = skip the DSMEM stores (results are wrong)
+    int prefetch_ahead;      // > 0: during its PC phase a CTA prefetches its slice of pulse p + prefetch_ahead into L2 (the
+                             // cluster that will take that pulse when this wave retires then streams from L2, not HBM)
 };
 
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -250,6 +252,16 @@ __global__ void __launch_bounds__(RSP_FUSED_THREADS, 2) dbf_pc_kernel(const __gr
         const float4* src = reinterpret_cast<const float4*>(line);
         for (int i = tid; i < N / 2; i += RSP_FUSED_THREADS) dst[i] = src[i];
     }
+    if (tid == 0 && k.prefetch_ahead > 0 && p + k.prefetch_ahead < k.P) {
+        const int pn = p + k.prefetch_ahead;
+#pragma unroll 1
+        for (int i = 0; i < n_my; ++i) {
+            const int grp0 = (t_lo + i) * (RSP_FUSED_TILE / 16);
+            if (k.tma_rank4) tma_prefetch_4d(&tmap, 0, 0, grp0, pn);
+            else
+                for (int j = 0; j < RSP_FUSED_TILE / 16; ++j) tma_prefetch_2d(&tmap, 32 * (grp0 + j), pn * C);
+        }
+    }
     float2* out_line = k.pc + line_id * k.ldg;
 #pragma unroll 1
     for (int r = 0; r < k.n_rounds; ++r) {
@@ -264,5 +276,177 @@ __global__ void __launch_bounds__(RSP_FUSED_THREADS, 2) dbf_pc_kernel(const __gr
         if (dbg && tid == 0 && r < 3) dbg[4 + r] = global_ns();       // thread 0's group only
     }
 }
+
+
+// ------------------------------------------------------------------------------------------
+// S5 alone, fed by TMA tensor copies (the DBF phase of dbf_pc_kernel as its own kernel; shapes the fused kernel does not
+// cover, and the two-kernel A/B path): CTA = 8 warps, one slice of `tiles_per_cta` consecutive 128-sample tiles of one
+// pulse, NS-stage ring, one [8 groups][C][16 samples] tile per copy, fragment loads conflict free (4 wavefronts per
+// 512 B instead of the 16 a fragment-order ld.global costs), beam rows written as 64-byte pieces like dbf_mma2_kernel.
+// ------------------------------------------------------------------------------------------
+#define RSP_DBFT_STAGES 3
+struct DbfTmaArgs {
+    float2* beam;
+    const float4* Wa;
+    int* det_count;
+    int C, B, N, ldb, tiles, tiles_per_cta, tma_rank4;
+    DiscardArgs dead;
+};
+template <int KS>
+__global__ void __launch_bounds__(RSP_FUSED_THREADS, 4) dbf_tma2_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        const __grid_constant__ DbfTmaArgs k) {
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    __shared__ __align__(8) unsigned long long bars[RSP_DBFT_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int C = k.C, B = k.B, N = k.N, p = blockIdx.y;
+    if (k.det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *k.det_count = 0;
+    if (tid == 0) {
+        for (int s = 0; s < RSP_DBFT_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int t_lo = blockIdx.x * k.tiles_per_cta, t_hi = min(k.tiles, t_lo + k.tiles_per_cta), n_my = t_hi - t_lo;
+    const uint32_t stage_bytes = (uint32_t)(RSP_FUSED_TILE / 16) * C * 128u;
+    auto issue = [&](int i) {
+        const int s = i % RSP_DBFT_STAGES;
+        const uint32_t full = smem_u32(&bars[s]);
+        const uint32_t dst = smem_u32(tsm) + (uint32_t)s * stage_bytes;
+        const int grp0 = (t_lo + i) * (RSP_FUSED_TILE / 16);
+        mbar_expect_tx(full, stage_bytes);
+        if (k.tma_rank4) tma_load_4d(dst, &tmap, 0, 0, grp0, p, full);
+        else
+            for (int j = 0; j < RSP_FUSED_TILE / 16; ++j) tma_load_2d(dst + (uint32_t)j * C * 128u, &tmap, 32 * (grp0 + j), p * C, full);
+    };
+    if (tid == 0)
+        for (int i = 0; i < RSP_DBFT_STAGES && i < n_my; ++i) issue(i);
+    l2_discard(k.dead);
+    const int sg_ = (g & 1) ? g + 7 : g;
+    float4 ah[KS], al[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        ah[s] = __ldg(k.Wa + (s * 2 + 0) * 32 + lane);
+        al[s] = __ldg(k.Wa + (s * 2 + 1) * 32 + lane);
+    }
+    float2* const brow = k.beam + ((size_t)p * B + g) * k.ldb;
+#pragma unroll 1
+    for (int i = 0; i < n_my; ++i) {
+        const int s = i % RSP_DBFT_STAGES;
+        mbar_wait(smem_u32(&bars[s]), (uint32_t)(i / RSP_DBFT_STAGES) & 1u);
+        const unsigned char* st = tsm + (size_t)s * stage_bytes + (size_t)w * C * 128;
+        float4 x[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int c = 4 * ks + t;
+            x[ks] = c < C ? *reinterpret_cast<const float4*>(st + c * 128 + sg_ * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        unsigned dep = 0u;                              // see dbf_pc_kernel: the loads must have returned before the refill
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            dep |= __float_as_uint(x[ks].x) | __float_as_uint(x[ks].y) | __float_as_uint(x[ks].z) | __float_as_uint(x[ks].w);
+        __syncthreads_or(dep == 0x7FB1C0DEu);
+        if (tid == 0 && i + RSP_DBFT_STAGES < n_my) issue(i + RSP_DBFT_STAGES);
+        float E[4] = {0.f, 0.f, 0.f, 0.f}, O[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const float v[4] = {x[ks].x, x[ks].y, x[ks].z, x[ks].w};
+            uint32_t bh[4], bl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bh[j] = __float_as_uint(v[j]) & 0xFFFFE000u;
+                bl[j] = __float_as_uint(v[j] - __uint_as_float(bh[j])) & 0xFFFFE000u;
+            }
+            mma_tf32_wa(E, al[ks], bh[0], bh[1]);
+            mma_tf32_wa(E, ah[ks], bl[0], bl[1]);
+            mma_tf32_wa(E, ah[ks], bh[0], bh[1]);
+            mma_tf32_wa(O, al[ks], bh[2], bh[3]);
+            mma_tf32_wa(O, ah[ks], bl[2], bl[3]);
+            mma_tf32_wa(O, ah[ks], bh[2], bh[3]);
+        }
+        const int n = (t_lo + i) * RSP_FUSED_TILE + w * 16 + 2 * t;
+        if (g < B) {
+            if (n < N) *reinterpret_cast<float4*>(brow + n) = make_float4(E[0], E[2], O[0], O[2]);
+            if (n + 8 < N) *reinterpret_cast<float4*>(brow + n + 8) = make_float4(E[1], E[3], O[1], O[3]);
+        }
+    }
+}
+
+
+#ifdef RSP_PROBES
+// ------------------------------------------------------------------------------------------
+// Experiment (RSP_EXP_MERGE=1, tools/stage_probe.py): do a memory-bound and an issue-bound stage overlap when their CTAs
+// are guaranteed to share SMs?  One launch holds the CTAs of pc_fft_kernel AND CTAs that run the DBF of dbf_mma2_kernel
+// (256 samples of one pulse each) on a scratch beam buffer, interleaved evenly in block-index order.
+// ------------------------------------------------------------------------------------------
+struct MergeDbfArgs {
+    const float2* raw;
+    float2* beam;
+    const float4* Wa;
+    int C, NB, N, ldb, P;
+    int n_dbf, n_total;      // DBF CTAs / all CTAs of the launch
+};
+template <int KS>
+__device__ __forceinline__ void dbf_role_256(const MergeDbfArgs& k, int idx) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int per_pulse = (k.N + 255) / 256;
+    const int p = idx / per_pulse, n_base = (idx - p * per_pulse) * 256 + w * 32;
+    if (p >= k.P || n_base >= k.N) return;
+    const int sg = (g & 1) ? g + 7 : g;
+    const float2* rp = k.raw + (size_t)p * k.C * k.N + sg + (unsigned)(t * k.N);
+    float4 x[KS][2];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * s + t < k.C && n_base + 16 * q + sg < k.N) x[s][q] = __ldcs(reinterpret_cast<const float4*>(rp + s * 4u * (unsigned)k.N + n_base + 16 * q));
+        }
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float v[4] = {x[s][q].x, x[s][q].y, x[s][q].z, x[s][q].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t hi = __float_as_uint(v[i]) & 0xFFFFE000u;
+                bh[2 * q + (i >> 1)][i & 1] = hi;
+                bl[2 * q + (i >> 1)][i & 1] = __float_as_uint(v[i] - __uint_as_float(hi)) & 0xFFFFE000u;
+            }
+        }
+        const float4 ah = __ldg(k.Wa + (s * 2 + 0) * 32 + lane), al = __ldg(k.Wa + (s * 2 + 1) * 32 + lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mma_tf32_wa(acc[j], al, bh[j][0], bh[j][1]);
+            mma_tf32_wa(acc[j], ah, bl[j][0], bl[j][1]);
+            mma_tf32_wa(acc[j], ah, bh[j][0], bh[j][1]);
+        }
+    }
+    if (g < k.NB) {
+        float2* row = k.beam + ((size_t)p * k.NB + g) * k.ldb + 2 * t + n_base;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int n = n_base + 16 * q + 2 * t;
+            if (n < k.N) *reinterpret_cast<float4*>(row + 16 * q) = make_float4(acc[2 * q][0], acc[2 * q][2], acc[2 * q + 1][0], acc[2 * q + 1][2]);
+            if (n + 8 < k.N) *reinterpret_cast<float4*>(row + 16 * q + 8) = make_float4(acc[2 * q][1], acc[2 * q][3], acc[2 * q + 1][1], acc[2 * q + 1][3]);
+        }
+    }
+}
+template <class CfgA, class CfgB>
+__global__ void __launch_bounds__(RSP_PC_THREADS, 3) pc_dbf_merge_kernel(const PcKernelArgs k, const MergeDbfArgs d) {
+    extern __shared__ float2 pc_smem[];
+    const long i = blockIdx.x;
+    const int before = (int)(i * d.n_dbf / d.n_total), after = (int)((i + 1) * d.n_dbf / d.n_total);
+    if (after > before) { dbf_role_256<4>(d, before); return; }
+    const int cta = (int)i - before;
+    if (cta < k.seg[0].n_ctas) pc_role<CfgA>(k, k.seg[0], cta, pc_smem, false);
+    else pc_role<CfgB>(k, k.seg[1], cta - k.seg[0].n_ctas, pc_smem, k.do_narrow != 0);
+}
+
+#endif  // RSP_PROBES
 
 }  // namespace rsp

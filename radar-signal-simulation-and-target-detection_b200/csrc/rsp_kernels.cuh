@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256) synth_kernel(const __grid_constant__ Synt
 // third of the line does) and only then gathers tx_pulse -- which is zero between the pulses, so no
 // per-stretch test is needed.  Targets are added in index order, like the staged kernel.
 #define RSP_SYNTH_GATHER_T 8
+#define RSP_SYNTH_FUSED_T 64             // targets per frame of the fused S4 + S5 kernel = RSP_MAX_FRAME_TARGETS (BASELINE config 4)
 #define RSP_SYNTH_GATHER_CHUNK 8192
 // Samples n0 (even) and n0 + 1 of line `line_id` = pulse * C + channel: Philox noise, then the targets in index order.
 // ph[t * ph_stride] is target t's phasor for this (pulse, channel).  Statement for statement the per-pair body of
@@ -527,131 +528,84 @@ __device__ __forceinline__ void mma_tf32_wa(float (&d)[4], const float4& a, uint
                    "r"(b0), "r"(b1));
 }
 
-// IT = consecutive 32-sample tiles per warp.  IT > 1 software-pipelines the warp: the loads of tile j + 1 are in
-// flight while tile j goes through the tensor cores, so a warp always has 4 KB of reads outstanding instead of
-// alternating between a load phase and a compute phase (the IT = 1 kernel spends 56 % of its warp-cycles waiting
-// at the first MMA, profiles/r1b_*), and the grid is a single resident wave of long-lived CTAs.
-// streaming 16-byte load that does not allocate in L1 (RSP_DBF_LD=1; experiment against ld.global.cs)
-__device__ __forceinline__ float4 ld_stream_noalloc(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
 // NQ = 16-sample groups per warp tile (2: 32 samples; 1 for the big shapes, C > 16 or B > 8, whose 32-sample tile would
-// need 64 registers of loads + 32 accumulators: 178 registers and 8 warps per SM at config 3).
-template <int MT, int KS, int IT, bool PIPE, int NQ>
-__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, (IT > 1 ? 4 : ((MT == 1 && KS <= 4) || NQ == 1 ? (MT * KS * NQ <= 8 ? 8 : 5) : 1))) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
+// need 64 registers of loads + 32 accumulators: 178 registers and 8 warps per SM at config 3).  One tile per warp: software
+// pipelining, several tiles per warp, split launches and L1::no_allocate loads were all measured neutral or slower
+// (profiles/README.md) and are gone.
+template <int MT, int KS, int NQ>
+__global__ void __launch_bounds__(RSP_DBF_MMA_THREADS, ((MT == 1 && KS <= 4) || NQ == 1 ? (MT * KS * NQ <= 8 ? 8 : 5) : 1)) dbf_mma2_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
                                                                        const float4* __restrict__ Wa /* [KS][MT][2][32] */,
                                                                        int C, int NB, int N, int ldb,
-                                                                       int* __restrict__ det_count, const DiscardArgs dead, int ld_mode,
-                                                                       int p0 /* first pulse of this launch */) {
+                                                                       int* __restrict__ det_count, const DiscardArgs dead) {
     const int tid = threadIdx.x;
     l2_discard(dead);
     if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;   // first kernel of the CPI
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int p = blockIdx.y + p0;
-    const int n_first = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (16 * NQ * IT);  // IT tiles of 16 NQ samples per warp
-    if (n_first >= N) return;
+    const int p = blockIdx.y;
+    const int n_base = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (16 * NQ);
+    if (n_base >= N) return;
     // column g of the even n-tile of a 16-sample group <-> sample sg = g (g even) or g + 7 (g odd), odd n-tile: sg + 1.
     // With this order the D fragments of lane t are samples 2t, 2t+1 and 2t+8, 2t+9, so each of the two 16-byte stores
     // of a quad is 64 contiguous bytes (full 32-byte sectors) instead of four 16-byte pieces 32 bytes apart.
     const int sg = (g & 1) ? g + 7 : g;
     const float2* rp = raw + (size_t)p * C * N + sg + (unsigned)(t * N);                 // channel t of k-step 0
     const unsigned cstep = 4u * (unsigned)N;                                           // k-step s: channel 4s + t
-    float2* const brow = beam + (size_t)p * NB * ldb + 2 * t;
-
-    auto load_tile = [&](float4 (&x)[KS][NQ], int n_base) {
+    float4 x[KS][NQ];
 #pragma unroll
-        for (int s = 0; s < KS; ++s) {
+    for (int s = 0; s < KS; ++s) {
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (4 * s + t < C && n_base + 16 * q + sg < N) {
-                    const float4* src = reinterpret_cast<const float4*>(rp + s * cstep + n_base + 16 * q);
-                    x[s][q] = ld_mode ? ld_stream_noalloc(src) : __ldcs(src);
-                }
-            }
+        for (int q = 0; q < NQ; ++q) {
+            x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * s + t < C && n_base + 16 * q + sg < N) x[s][q] = __ldcs(reinterpret_cast<const float4*>(rp + s * cstep + n_base + 16 * q));
         }
-    };
-    auto compute_store = [&](const float4 (&x)[KS][NQ], int n_base) {
-        float acc[MT][2 * NQ][4];
+    }
+    float acc[MT][2 * NQ][4];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int j = 0; j < 2 * NQ; ++j)
+        for (int j = 0; j < 2 * NQ; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+            for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
 #pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            // n-tile j = 2q + parity: {b0, b1} = (re, im) of sample 16q + sg + parity
-            uint32_t bh[2 * NQ][2], bl[2 * NQ][2];
+    for (int s = 0; s < KS; ++s) {
+        // n-tile j = 2q + parity: {b0, b1} = (re, im) of sample 16q + sg + parity
+        uint32_t bh[2 * NQ][2], bl[2 * NQ][2];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const float v[4] = {x[s][q].x, x[s][q].y, x[s][q].z, x[s][q].w};
+        for (int q = 0; q < NQ; ++q) {
+            const float v[4] = {x[s][q].x, x[s][q].y, x[s][q].z, x[s][q].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t hi = __float_as_uint(v[i]) & 0xFFFFE000u;
-                    bh[2 * q + (i >> 1)][i & 1] = hi;
-                    bl[2 * q + (i >> 1)][i & 1] = __float_as_uint(v[i] - __uint_as_float(hi)) & 0xFFFFE000u;
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const float4 ah = __ldg(Wa + ((s * MT + mt) * 2 + 0) * 32 + lane);
-                const float4 al = __ldg(Wa + ((s * MT + mt) * 2 + 1) * 32 + lane);
-#pragma unroll
-                for (int j = 0; j < 2 * NQ; ++j) {
-                    mma_tf32_wa(acc[mt][j], al, bh[j][0], bh[j][1]);
-                    mma_tf32_wa(acc[mt][j], ah, bl[j][0], bl[j][1]);
-                    mma_tf32_wa(acc[mt][j], ah, bh[j][0], bh[j][1]);
-                }
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t hi = __float_as_uint(v[i]) & 0xFFFFE000u;
+                bh[2 * q + (i >> 1)][i & 1] = hi;
+                bl[2 * q + (i >> 1)][i & 1] = __float_as_uint(v[i] - __uint_as_float(hi)) & 0xFFFFE000u;
             }
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-            const int b = 8 * mt + g;
-            if (b < NB) {
-                float2* row = brow + (size_t)b * ldb + n_base;
+            const float4 ah = __ldg(Wa + ((s * MT + mt) * 2 + 0) * 32 + lane);
+            const float4 al = __ldg(Wa + ((s * MT + mt) * 2 + 1) * 32 + lane);
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const float(&E)[4] = acc[mt][2 * q];
-                    const float(&O)[4] = acc[mt][2 * q + 1];
-                    const int n = n_base + 16 * q + 2 * t;
-                    if (n < N) *reinterpret_cast<float4*>(row + 16 * q) = make_float4(E[0], E[2], O[0], O[2]);
-                    if (n + 8 < N) *reinterpret_cast<float4*>(row + 16 * q + 8) = make_float4(E[1], E[3], O[1], O[3]);
-                }
+            for (int j = 0; j < 2 * NQ; ++j) {
+                mma_tf32_wa(acc[mt][j], al, bh[j][0], bh[j][1]);
+                mma_tf32_wa(acc[mt][j], ah, bl[j][0], bl[j][1]);
+                mma_tf32_wa(acc[mt][j], ah, bh[j][0], bh[j][1]);
             }
         }
-    };
-
-    if (IT == 1) {
-        float4 x[KS][NQ];
-        load_tile(x, n_first);
-        compute_store(x, n_first);
-    } else if (!PIPE) {
-        // several tiles per warp, one after the other: the weight fragments stay in registers, the CTA lives longer
-#pragma unroll 1
-        for (int j = 0; j < IT; ++j) {
-            const int n0 = n_first + 16 * NQ * j;
-            if (n0 >= N) break;
-            float4 x[KS][NQ];
-            load_tile(x, n0);
-            compute_store(x, n0);
-        }
-    } else {
-        float4 xa[KS][NQ], xb[KS][NQ];
-        load_tile(xa, n_first);
-#pragma unroll 1
-        for (int j = 0; j < IT; j += 2) {
-            const int n0 = n_first + 16 * NQ * j;
-            if (n0 >= N) break;
-            if (j + 1 < IT && n0 + 16 * NQ < N) load_tile(xb, n0 + 16 * NQ);
-            compute_store(xa, n0);
-            if (j + 1 >= IT || n0 + 16 * NQ >= N) break;
-            if (j + 2 < IT && n0 + 32 * NQ < N) load_tile(xa, n0 + 32 * NQ);
-            compute_store(xb, n0 + 16 * NQ);
+    }
+    float2* const brow = beam + (size_t)p * NB * ldb + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int b = 8 * mt + g;
+        if (b < NB) {
+            float2* row = brow + (size_t)b * ldb + n_base;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float(&E)[4] = acc[mt][2 * q];
+                const float(&O)[4] = acc[mt][2 * q + 1];
+                const int n = n_base + 16 * q + 2 * t;
+                if (n < N) *reinterpret_cast<float4*>(row + 16 * q) = make_float4(E[0], E[2], O[0], O[2]);
+                if (n + 8 < N) *reinterpret_cast<float4*>(row + 16 * q + 8) = make_float4(E[1], E[3], O[1], O[3]);
+            }
         }
     }
 }
@@ -669,8 +623,8 @@ template <int MT, int KS, int NQ>
 __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_synth_kernel(const __grid_constant__ SynthArgs k, float2* __restrict__ beam,
                                                                         const float4* __restrict__ Wa /* [KS][MT][2][32] */,
                                                                         int NB, int ldb, int* __restrict__ det_count, const DiscardArgs dead) {
-    __shared__ float2 s_ph[RSP_SYNTH_GATHER_T * 4 * KS];      // [target][channel], channel stride 4 KS >= C
-    __shared__ int s_delay[RSP_SYNTH_GATHER_T];
+    __shared__ float2 s_ph[RSP_SYNTH_FUSED_T * 4 * KS];       // [target][channel], channel stride 4 KS >= C
+    __shared__ int s_delay[RSP_SYNTH_FUSED_T];
     const int tid = threadIdx.x;
     const int C = k.C, N = k.N;
     l2_discard(dead);
@@ -749,14 +703,7 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_synth_kernel(const __
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// S5, TMA-fed variant: a persistent CTA (4 MMA warps + 1 producer warp) streams [C channels x 128
-// samples] tiles of the raw cube through a 4-stage shared-memory ring with cp.async.bulk (one 1-D bulk
-// copy per channel row, completion counted on an mbarrier), so the bytes in flight per SM are set by
-// the ring (4 x 16.5 KB per CTA), not by registers or occupancy.  Rows are padded by 32 bytes so that
-// the float4 A-fragment reads (4 channels x 2 row groups per quarter warp) hit 8 distinct bank groups.
-// MMA math, fragment mapping and the stores are those of dbf_mma_kernel<.., VEC = true>.
-// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy helpers of the TMA-fed kernels (rsp_fused.cuh, rsp_dbf_tc.cuh)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -773,210 +720,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-#define RSP_DBF_TMA_TILE 128                    // samples per tile (32 per MMA warp)
-#define RSP_DBF_TMA_STAGES 4
-#define RSP_DBF_TMA_ROWB (RSP_DBF_TMA_TILE * 8 + 32)
-#define RSP_DBF_TMA_THREADS 160                 // 4 consumer warps + 1 producer warp
-template <int NT, int KS>
-__global__ void __launch_bounds__(RSP_DBF_TMA_THREADS) dbf_tma_kernel(const float2* __restrict__ raw,
-                                                                      float2* __restrict__ beam,
-                                                                      const float4* __restrict__ Wfrag /* [KS][NT][32] */,
-                                                                      int C, int NB, int N, int ldb, int P,
-                                                                      int* __restrict__ det_count, const DiscardArgs dead) {
-    extern __shared__ __align__(128) unsigned char dbf_smem[];
-    l2_discard(dead);
-    __shared__ float4 sW[KS * NT * 32];
-    __shared__ __align__(8) unsigned long long bars[2 * RSP_DBF_TMA_STAGES];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int stage_bytes = C * RSP_DBF_TMA_ROWB;
-    const int tiles_per_pulse = (N + RSP_DBF_TMA_TILE - 1) / RSP_DBF_TMA_TILE;
-    const int n_tiles = P * tiles_per_pulse;
-    if (det_count && blockIdx.x == 0 && tid == 0) *det_count = 0;          // first kernel of the CPI
-    for (int i = tid; i < KS * NT * 32; i += RSP_DBF_TMA_THREADS) sW[i] = Wfrag[i];
-    if (tid == 0) {
-        for (int s = 0; s < RSP_DBF_TMA_STAGES; ++s) {
-            mbar_init(smem_u32(&bars[s]), 1);                               // full: the producer's expect_tx arrive
-            mbar_init(smem_u32(&bars[RSP_DBF_TMA_STAGES + s]), 4);          // empty: one arrive per consumer warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (w == 4) {
-        // ------------------------------ producer ------------------------------
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int s = it % RSP_DBF_TMA_STAGES, round = it / RSP_DBF_TMA_STAGES;
-                if (round > 0) mbar_wait(smem_u32(&bars[RSP_DBF_TMA_STAGES + s]), (round - 1) & 1);
-                const int p = tile / tiles_per_pulse, n0 = (tile - p * tiles_per_pulse) * RSP_DBF_TMA_TILE;
-                const uint32_t row_bytes = (uint32_t)min(RSP_DBF_TMA_TILE, N - n0) * 8u;
-                const uint32_t full = smem_u32(&bars[s]);
-                mbar_expect_tx(full, row_bytes * (uint32_t)C);
-                const float2* src = raw + (size_t)p * C * N + n0;
-                const uint32_t dst = smem_u32(dbf_smem) + (uint32_t)s * stage_bytes;
-                for (int c = 0; c < C; ++c) bulk_g2s(dst + c * RSP_DBF_TMA_ROWB, src + (size_t)c * N, row_bytes, full);
-            }
-        }
-        return;
-    }
-    // ------------------------------ consumers ------------------------------
-    const int g = lane >> 2, t = lane & 3;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % RSP_DBF_TMA_STAGES, round = it / RSP_DBF_TMA_STAGES;
-        const int p = tile / tiles_per_pulse, n0 = (tile - p * tiles_per_pulse) * RSP_DBF_TMA_TILE;
-        mbar_wait(smem_u32(&bars[s]), round & 1);
-        const unsigned char* st = dbf_smem + (size_t)s * stage_bytes;
-        float4 x[KS][2];
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int c = 4 * ks + t;
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-                x[ks][m] = c < C ? *reinterpret_cast<const float4*>(st + c * RSP_DBF_TMA_ROWB + (32 * w + 16 * m + 2 * g) * 8)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[RSP_DBF_TMA_STAGES + s]));   // stage may be refilled
-        float acc[2][NT][4];
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            uint32_t ah[2][4], al[2][4];
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const float v[4] = {x[ks][m].x, x[ks][m].z, x[ks][m].y, x[ks][m].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    ah[m][i] = __float_as_uint(v[i]) & 0xFFFFE000u;
-                    al[m][i] = __float_as_uint(v[i] - __uint_as_float(ah[m][i])) & 0xFFFFE000u;
-                }
-            }
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const float4 wf = sW[(ks * NT + nt) * 32 + lane];
-                const uint32_t b0h = __float_as_uint(wf.x), b1h = __float_as_uint(wf.y);
-                const uint32_t b0l = __float_as_uint(wf.z), b1l = __float_as_uint(wf.w);
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    mma_tf32(acc[m][nt], al[m], b0h, b1h);
-                    mma_tf32(acc[m][nt], ah[m], b0l, b1l);
-                    mma_tf32(acc[m][nt], ah[m], b0h, b1h);
-                }
-            }
-        }
-        const int n_base = n0 + 32 * w;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int b = 4 * nt + t;
-            if (b < NB) {
-                float2* row = beam + ((size_t)p * NB + b) * ldb;
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    const int n = n_base + 16 * m + 2 * g;
-                    if (n < N)
-                        *reinterpret_cast<float4*>(row + n) = make_float4(acc[m][nt][0], acc[m][nt][1], acc[m][nt][2], acc[m][nt][3]);
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// S5, one-tile-per-CTA TMA variant: like dbf_mma_kernel (one CTA per 128-sample tile, no persistence, many
-// CTAs per SM hide latency) but the tile arrives by cp.async.bulk (no LSU data-pipe wavefronts for the
-// 64 KB/line-strided input: a streaming L1 miss costs the LSU one wavefront per 32-byte sector, a bulk copy
-// none) and leaves by cp.async.bulk stores from a shared-memory staging tile.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-#define RSP_DBF_T1_THREADS 128
-template <int NT, int KS>
-__global__ void __launch_bounds__(RSP_DBF_T1_THREADS) dbf_tma1_kernel(const float2* __restrict__ raw, float2* __restrict__ beam,
-                                                                      const float4* __restrict__ Wfrag, int C, int NB, int N,
-                                                                      int ldb, int* __restrict__ det_count, const DiscardArgs dead) {
-    extern __shared__ __align__(128) unsigned char t1_smem[];          // [C rows x ROWB] input | [NB rows x ROWB] output
-    __shared__ __align__(8) unsigned long long bar;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    l2_discard(dead);
-    if (det_count && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *det_count = 0;
-    const int p = blockIdx.y, n0 = blockIdx.x * RSP_DBF_TMA_TILE;
-    const uint32_t row_bytes = (uint32_t)min(RSP_DBF_TMA_TILE, N - n0) * 8u;
-    unsigned char* out_tile = t1_smem + (size_t)C * RSP_DBF_TMA_ROWB;
-    if (tid == 0) {
-        mbar_init(smem_u32(&bar), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(smem_u32(&bar), row_bytes * (uint32_t)C);
-        const float2* src = raw + (size_t)p * C * N + n0;
-        for (int c = 0; c < C; ++c) bulk_g2s(smem_u32(t1_smem) + c * RSP_DBF_TMA_ROWB, src + (size_t)c * N, row_bytes, smem_u32(&bar));
-    }
-    __syncthreads();                                   // barrier initialised and armed before anyone waits
-    mbar_wait(smem_u32(&bar), 0);
-    float acc[2][NT][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-        const int c = 4 * ks + t;
-        uint32_t ah[2][4], al[2][4];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            const float4 x = c < C ? *reinterpret_cast<const float4*>(t1_smem + c * RSP_DBF_TMA_ROWB + (32 * w + 16 * m + 2 * g) * 8)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float v[4] = {x.x, x.z, x.y, x.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ah[m][i] = __float_as_uint(v[i]) & 0xFFFFE000u;
-                al[m][i] = __float_as_uint(v[i] - __uint_as_float(ah[m][i]));
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const float4 wf = __ldg(Wfrag + (ks * NT + nt) * 32 + lane);
-            const uint32_t b0h = __float_as_uint(wf.x), b1h = __float_as_uint(wf.y);
-            const uint32_t b0l = __float_as_uint(wf.z), b1l = __float_as_uint(wf.w);
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                mma_tf32(acc[m][nt], al[m], b0h, b1h);
-                mma_tf32(acc[m][nt], ah[m], b0l, b1l);
-                mma_tf32(acc[m][nt], ah[m], b0h, b1h);
-            }
-        }
-    }
-    // stage the beam tile [NB rows][128 samples] in shared memory, then one bulk store per beam row
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        const int b = 4 * nt + t;
-        if (b < NB) {
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-                *reinterpret_cast<float4*>(out_tile + b * RSP_DBF_TMA_ROWB + (32 * w + 16 * m + 2 * g) * 8) =
-                    make_float4(acc[m][nt][0], acc[m][nt][1], acc[m][nt][2], acc[m][nt][3]);
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copy
-    __syncthreads();
-    if (tid < NB) {
-        bulk_s2g(beam + ((size_t)p * NB + tid) * ldb + n0, smem_u32(out_tile) + tid * RSP_DBF_TMA_ROWB, row_bytes);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until read
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1066,93 +809,22 @@ __device__ __forceinline__ void pc_role(const PcKernelArgs& k, const PcSegArgs& 
 
 // CfgA = block plan of role 0 (the long segment), CfgB = role 1 (the medium segment + narrow FIR).
 // The short role-1 CTAs have the highest block indices, so they fill the tail of the long ones.
+// Register budget of the pulse-compression kernel: RSP_PC_NREG caps the registers per thread (the kernel compiles without
+// spills down to 56), which sets how many 256-thread CTAs share an SM (80 -> 3, 64 -> 4) and how much of the register file
+// is left for the co-resident tcgen05 DBF of another lane's CPI.
+#ifndef RSP_PC_NREG
+#define RSP_PC_NREG 0
+#endif
+#if RSP_PC_NREG > 0
+#define RSP_PC_BOUNDS __maxnreg__(RSP_PC_NREG)
+#else
+#define RSP_PC_BOUNDS __launch_bounds__(RSP_PC_THREADS, 3)
+#endif
 template <class CfgA, class CfgB>
-__global__ void __launch_bounds__(RSP_PC_THREADS, 3) pc_fft_kernel(const PcKernelArgs k) {
+__global__ void RSP_PC_BOUNDS pc_fft_kernel(const PcKernelArgs k) {
     extern __shared__ float2 pc_smem[];
     if ((int)blockIdx.x < k.seg[0].n_ctas) pc_role<CfgA>(k, k.seg[0], blockIdx.x, pc_smem, false);
     else pc_role<CfgB>(k, k.seg[1], blockIdx.x - k.seg[0].n_ctas, pc_smem, k.do_narrow != 0);
-}
-
-// Any mix of block lengths in ONE launch: up to four roles, each a (segment, block length) pair, CTAs of the roles laid
-// end to end (longest blocks first, so the short ones fill the tail).  Used for the mixed long-segment plan, where the
-// 4096-, 2048- and 1024-point blocks of the long filter and the 1024-point medium block (+ narrow FIR) are independent.
-struct PcMultiArgs {
-    PcKernelArgs k;              // k.seg[] unused here; beam / pc / pitches / FIR / barrier mode as in pc_fft_kernel
-    PcSegArgs seg[4];
-    int len[4];                  // block length of the role (4096 / 2048 / 1024), 0 = role absent
-    int narrow_role;             // role whose groups also compute the narrow-pulse gates, or -1
-};
-
-__global__ void __launch_bounds__(RSP_PC_THREADS, 3) pc_fft_multi_kernel(const __grid_constant__ PcMultiArgs m) {
-    extern __shared__ float2 pc_smem[];
-    int cta = blockIdx.x;
-#pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
-        if (m.len[r] == 0) continue;
-        if (cta < m.seg[r].n_ctas) {
-            const bool narrow = r == m.narrow_role && m.k.do_narrow != 0;
-            if (m.len[r] == 4096) pc_role<PcCfg<4096, 16, 16, 16>>(m.k, m.seg[r], cta, pc_smem, narrow);
-            else if (m.len[r] == 2048) pc_role<PcCfg<2048, 8, 16, 16>>(m.k, m.seg[r], cta, pc_smem, narrow);
-            else pc_role<PcCfg<1024, 16, 16, 4>>(m.k, m.seg[r], cta, pc_smem, narrow);
-            return;
-        }
-        cta -= m.seg[r].n_ctas;
-    }
-}
-
-// Two-pass variant (Pc2Cfg: 64 x 64 = 4096-point and 32 x 32 = 1024-point blocks, N threads per block,
-// N points per thread in registers).  Same roles and work list as pc_fft_kernel.
-#define RSP_PC2_THREADS 128
-#ifndef RSP_PC2_MINB
-#define RSP_PC2_MINB 2
-#endif
-template <class Cfg>
-__device__ __forceinline__ void pc2_role(const PcKernelArgs& k, const PcSegArgs& sg, int cta, float2* smem, bool narrow) {
-    constexpr int NG = RSP_PC2_THREADS / Cfg::T;
-    float* sfir = reinterpret_cast<float*>(smem + NG * Cfg::SMEM_ELEMS);
-    if (narrow)
-        for (int i = threadIdx.x; i < k.nfir; i += RSP_PC2_THREADS) sfir[i] = k.fir[i];
-    const int grp = threadIdx.x / Cfg::T, t = threadIdx.x - grp * Cfg::T;
-    const int item = cta * NG + grp;
-    const bool active = item < sg.n_items;
-    const int line = active ? item / sg.nblk : 0, blk = active ? item - line * sg.nblk : 0;
-    float2* s = smem + grp * Cfg::SMEM_ELEMS;
-    PcBlockArgs a;
-    a.line = k.beam + (size_t)line * k.ldb;
-    a.out_line = k.pc + (size_t)line * k.ldg;
-    a.tw1 = sg.tw1;
-    a.tw2 = nullptr;
-    a.Hmid = sg.Hmid;
-    a.in_lo = sg.in_lo;
-    a.in_hi = sg.in_hi;
-    a.seg_start0 = sg.seg_start0;
-    a.taps = sg.taps;
-    a.g0 = sg.gate0 + blk * sg.valid;
-    a.g_end = sg.g_end;
-    if (active) pc2_phase_a<Cfg>(a, s, t);
-    __syncthreads();
-    if (active) pc2_phase_b<Cfg>(a, s, t);
-    __syncthreads();
-    if (active) pc2_phase_c<Cfg>(a, s, t);
-    if (narrow) {                                   // uniform over the CTA
-        const int need = k.narrow_gates + k.fir_delay;
-        const bool fast = need <= k.N - k.narrow_start0 && need <= Cfg::SMEM_ELEMS;
-        __syncthreads();
-        if (active && blk == 0 && fast)
-            for (int i = t; i < need; i += Cfg::T) s[i] = a.line[k.narrow_start0 + i];
-        __syncthreads();
-        if (active && blk == 0)
-            for (int g = t; g < k.narrow_gates; g += Cfg::T)
-                a.out_line[g] = fast ? pc_narrow_gate_smem(s, sfir, k.nfir, k.fir_delay, g)
-                                     : pc_narrow_gate(a.line, k.N, k.narrow_start0, sfir, k.nfir, k.fir_delay, g);
-    }
-}
-
-template <class CfgA, class CfgB>
-__global__ void __launch_bounds__(RSP_PC2_THREADS, RSP_PC2_MINB) pc2_fft_kernel(const PcKernelArgs k) {
-    extern __shared__ float2 pc_smem[];
-    if ((int)blockIdx.x < k.seg[0].n_ctas) pc2_role<CfgA>(k, k.seg[0], blockIdx.x, pc_smem, false);
-    else pc2_role<CfgB>(k, k.seg[1], blockIdx.x - k.seg[0].n_ctas, pc_smem, k.do_narrow != 0);
 }
 
 __global__ void __launch_bounds__(256) pc_narrow_kernel(const float2* __restrict__ beam, float2* __restrict__ pc,
@@ -1213,59 +885,11 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
     }
 }
 
-// S7, register variant (P = 32 or 64): one thread owns one (beam, gate) Doppler line.  Its P pulses arrive
-// with P independent coalesced loads (lanes = consecutive gates), the whole windowed FFT is straight-line
-// code on registers (generated SmallDft<32/64>, every twiddle an immediate, the window read from the
-// constant bank because it sits in the kernel arguments), and shared memory is used once, for the corner
-// turn: a warp-private [32 gates][32 rows + 1] tile, so only __syncwarp() is ever needed.  Against the tiled
-// kernel this removes two shared-memory round trips per point and all run-time butterfly addressing
-// (84 -> ~45 instructions per point; on sm_100a an integer instruction costs an issue slot just like an FFMA,
-// tools/ubench/opcost.cu).  Opt-in (RSP_MTD=reg): a CPI has only 46 k Doppler lines = 1444 warps, ~10 per SM at 159
-// registers, so there is nothing to hide the load and store latency with -- 16.9 us alone against 14.7 us tiled.
+// Arguments of the P = 64 specialisation: the window sits in the kernel arguments (constant bank).
 struct MtdRegArgs {
     MtdArgs m;
     float win[64];          // kaiser(P) * (-1)^p  (fftshift folded in), fun_process_single_frame.m:134-135
 };
-#define RSP_MTD_REG_THREADS 128
-template <int P>
-__global__ void __launch_bounds__(RSP_MTD_REG_THREADS, (P > 32 ? 3 : 4)) mtd_reg_kernel(const __grid_constant__ MtdRegArgs k) {
-    static_assert(P == 32 || P == 64, "register MTD exists for P = 32 and 64");
-    constexpr int H = 32, PITCH = H + 1;
-    __shared__ float2 tiles[(RSP_MTD_REG_THREADS / 32) * 32 * PITCH];
-    l2_discard(k.m.dead);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b = blockIdx.y, G = k.m.G;
-    const int gw = blockIdx.x * RSP_MTD_REG_THREADS + w * 32;      // first gate of this warp
-    if (gw >= G) return;                                           // whole warp out of range (no CTA-wide barrier below)
-    const int g = gw + lane;
-    const unsigned pstride = (unsigned)k.m.B * (unsigned)k.m.ldg;
-    const float2* src = k.m.pc + (size_t)b * k.m.ldg + (g < G ? g : G - 1);
-    cf v[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) v[p] = src[p * pstride];
-#pragma unroll
-    for (int p = 0; p < P; ++p) v[p] = cscale(v[p], k.win[p]);
-    SmallDft<P, -1>::run(v);
-    float2* tile = tiles + w * 32 * PITCH;
-    const int rows = G - gw < 32 ? G - gw : 32;                    // gates of this warp that exist
-    float2* rdm_w = k.m.rdm + ((size_t)b * G + gw) * P + lane;
-    float* amp_w = k.m.amp + ((size_t)b * G + gw) * P + lane;
-#pragma unroll
-    for (int h = 0; h < P / H; ++h) {
-        if (h) __syncwarp();
-#pragma unroll
-        for (int i = 0; i < H; ++i) tile[lane * PITCH + i] = v[h * H + i];
-        __syncwarp();
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            if (r < rows) {
-                const float2 x = tile[r * PITCH + lane];
-                __stcs(rdm_w + r * P + h * H, x);
-                amp_w[r * P + h * H] = sqrtf(fmaf(x.x, x.x, x.y * x.y));
-            }
-        }
-    }
-}
 
 // S7, P = 64 specialisation of the tiled kernel (8 x 8 Cooley-Tukey, every index a compile-time constant).
 //   phase 1, thread (q = warp, gl = lane): pulses p = q + 8m of gate gl -> window -> DFT-8 over m -> . W64^(q k1) -> S1[k1][q][gl]

@@ -202,85 +202,6 @@ RSP_HD cf pc_narrow_gate_smem(const cf* ys, const float* fir, int nfir, int fir_
     return acc;
 }
 
-// =============================================================================================
-// Pulse compression, two-pass variant: L = N x N (64 x 64 = 4096, 32 x 32 = 1024), a block is handled by
-// N threads and every thread keeps N points in registers, so a block crosses shared memory only twice
-// (2 writes + 2 reads per point instead of 4 + 4) and needs two barriers instead of four:
-//   A (thread j2):  x[s0 + j2 + N m] -> DFT_N -> . W_L^{j2 k1} -> s[k1][j2]
-//   B (thread k1):  s[k1][.] -> DFT_N -> . H -> IDFT_N -> s[k1][.]            (frequency f = k1 + N k2)
-//   C (thread j2):  s[.][j2] . conj(W_L^{j2 k1}) -> IDFT_N -> c[j2 + N m] -> valid gates
-// Row pitch N + 1 keeps both the row-wise (B) and the column-wise (A, C) accesses conflict free.
-// =============================================================================================
-template <int L_, int N_> struct Pc2Cfg {
-    static constexpr int L = L_, N = N_, T = N_, PITCH = N_ + 1;
-    static constexpr int SMEM_ELEMS = N_ * (N_ + 1);
-    static_assert(N_ * N_ == L_, "two-pass plan needs a square factorisation");
-};
-// PcBlockArgs is reused: tw1 = [(k1-1)*N + j2] = e^{-2 pi i j2 k1 / L}, Hmid = Hq[k2*N + k1] = H[k1 + N k2] / L
-
-template <class Cfg> RSP_HD void pc2_phase_a(const PcBlockArgs& a, cf* s, int j2) {
-    constexpr int N = Cfg::N;
-    const int s0 = a.seg_start0 + a.g0 - (a.taps - 1);
-    const bool interior = s0 >= a.in_lo && s0 + Cfg::L <= a.in_hi;
-    cf v[N];
-    if (interior) {
-        const cf* src = a.line + s0 + j2;
-#pragma unroll
-        for (int m = 0; m < N; ++m) v[m] = src[m * N];
-    } else {
-#pragma unroll
-        for (int m = 0; m < N; ++m) {
-            const int idx = s0 + j2 + m * N;
-            v[m] = (idx >= a.in_lo && idx < a.in_hi) ? a.line[idx] : make_float2(0.f, 0.f);
-        }
-    }
-    SmallDft<N, -1>::run(v);
-    cf* col = s + j2;
-    const cf* tw = a.tw1 + j2;
-    col[0] = v[0];
-#pragma unroll
-    for (int k1 = 1; k1 < N; ++k1) {
-        const cf w = tw[(k1 - 1) * N];
-        col[k1 * Cfg::PITCH] = mul_tw<-1>(v[k1], w.x, w.y);
-    }
-}
-
-template <class Cfg> RSP_HD void pc2_phase_b(const PcBlockArgs& a, cf* s, int k1) {
-    constexpr int N = Cfg::N;
-    cf* row = s + k1 * Cfg::PITCH;
-    const cf* h = a.Hmid + k1;
-    cf v[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) v[j] = row[j];
-    SmallDft<N, -1>::run(v);
-#pragma unroll
-    for (int k2 = 0; k2 < N; ++k2) v[k2] = cmul(v[k2], h[k2 * N]);
-    SmallDft<N, +1>::run(v);
-#pragma unroll
-    for (int j = 0; j < N; ++j) row[j] = v[j];
-}
-
-template <class Cfg> RSP_HD void pc2_phase_c(const PcBlockArgs& a, const cf* s, int j2) {
-    constexpr int N = Cfg::N;
-    const bool full = a.g0 + Cfg::L - (a.taps - 1) <= a.g_end;
-    const cf* col = s + j2;
-    const cf* tw = a.tw1 + j2;
-    cf v[N];
-    v[0] = col[0];
-#pragma unroll
-    for (int k1 = 1; k1 < N; ++k1) {
-        const cf w = tw[(k1 - 1) * N];
-        v[k1] = mul_tw<+1>(col[k1 * Cfg::PITCH], w.x, w.y);
-    }
-    SmallDft<N, +1>::run(v);
-    cf* dst = a.out_line + a.g0 + j2 - (a.taps - 1);
-#pragma unroll
-    for (int m = 0; m < N; ++m) {
-        const int io = j2 + m * N;
-        if (io >= a.taps - 1 && (full || a.g0 + io - (a.taps - 1) < a.g_end)) dst[m * N] = v[m];
-    }
-}
-
 // Narrow-pulse FIR + circshift (fun_process_single_frame.m:111-112,123):
 //   u = filter(fir, 1, y(seg_start:end));  piece1(g) = u((g + fir_delay) mod Lseg)
 RSP_HD cf pc_narrow_gate(const cf* line, int N, int seg_start0, const float* fir, int nfir, int fir_delay, int g) {

@@ -94,28 +94,6 @@ inline bool make_pc_plan(PcPlan& pl, int L, const zc* taps, int ntaps, int seg_s
     return true;
 }
 
-// Two-pass (N x N) plan: tw1[(k1-1)*N + j2] = W_L^{j2 k1}; Hmid := Hq[k2*N + k1] = H[k1 + N k2] / L.
-inline bool make_pc2_plan(PcPlan& pl, int L, const zc* taps, int ntaps, int seg_start0, int gate0, int ngates) {
-    const int N = L == 4096 ? 64 : (L == 1024 ? 32 : 0);
-    if (!N || ntaps < 1 || ntaps > L) return false;
-    pl = PcPlan();
-    pl.L = L; pl.R1 = N; pl.R2 = N; pl.R3 = 1; pl.T = N;
-    pl.taps = ntaps; pl.valid = L - (ntaps - 1);
-    pl.seg_start0 = seg_start0; pl.gate0 = gate0; pl.ngates = ngates;
-    pl.nblk = (ngates + pl.valid - 1) / pl.valid;
-    pl.tw1 = make_twiddles(L, N);                       // [(k1-1)*(L/N) + j2], L/N == N
-    std::vector<zc> h((size_t)L, zc(0, 0));
-    for (int i = 0; i < ntaps; ++i) h[i] = taps[i];
-    host_fft(h);
-    pl.Hmid.assign((size_t)L, make_float2(0, 0));
-    for (int k1 = 0; k1 < N; ++k1)
-        for (int k2 = 0; k2 < N; ++k2) {
-            const zc v = h[(size_t)k1 + (size_t)N * k2] / (double)L;
-            pl.Hmid[(size_t)k2 * N + k1] = make_float2((float)v.real(), (float)v.imag());
-        }
-    return true;
-}
-
 // Cost model used to pick the block length: every pass keeps all threads busy, so the work is
 // proportional to the points transformed; longer blocks waste less on the (taps-1) overlap.
 inline double pc_plan_cost(int L, int ntaps, int ngates) {

@@ -367,7 +367,8 @@ def synthesize_echo(targets: Sequence, config, precomputed_data) -> np.ndarray:
     raw = np.zeros((P, Cn, N), dtype=np.complex128)
     m = np.arange(P)
     for t in targets:
-        delay_samples = _matlab_round(2 * float(_field(t, "Range")) / c0 * fs)
+        ts = 1.0 / fs                                                  # fsf:18
+        delay_samples = _matlab_round((2 * float(_field(t, "Range")) / c0) / ts)   # fsf:55-56: round(delay / ts), not delay * fs
         doppler = np.exp(1j * 2 * np.pi * (2 * float(_field(t, "Velocity")) / lam) * m * prt)
         amplitude = math.sqrt(10 ** (float(_field(t, "SNR_dB")) / 10) / p_sig)
         base = np.zeros(N, dtype=np.complex128)
@@ -389,6 +390,43 @@ def add_noise(raw: np.ndarray, rng: np.random.Generator, P_noise_floor: float = 
 _chain_cache = {}
 
 
+def _context_key(config, cfar_params, precomputed_data, device: int):
+    """What defines a device context: shape, CFAR parameters, device and the CONTENT of every uploaded table.  The reference
+    re-reads its structs on every call, so a caller may change T_CFAR or swap a filter between two calls with the same
+    objects; keying the cache on id() would silently reuse a stale context (and ids are recycled after garbage collection)."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    sc = _field(config, "Sig_Config")
+    for name in ("prtNum", "point_PRT", "channel_num", "beam_num", "fs", "c", "wavelength", "prt"):
+        h.update(repr((name, _field(sc, name))).encode())
+    h.update(repr(tuple(_field(sc, "point_prt_segments"))).encode())
+    h.update(repr(float(_field(_field(config, "Array"), "element_spacing"))).encode())
+    for name in ("T_CFAR", "guardCells_R", "guardCells_V", "refCells_R", "refCells_V"):
+        h.update(repr((name, _field(cfar_params, name))).encode())
+    for name in sorted(_fields_of(precomputed_data)):
+        v = _field(precomputed_data, name)
+        h.update(name.encode())
+        h.update(np.ascontiguousarray(np.asarray(v)).tobytes() if not isinstance(v, (str, bytes)) else str(v).encode())
+    return (int(device), h.hexdigest())
+
+
+def _fields_of(obj):
+    if isinstance(obj, dict):
+        return list(obj.keys())
+    return [k for k in vars(obj) if not k.startswith("_")]
+
+
+def _cached_chain(config, cfar_params, precomputed_data, device: int):
+    key = _context_key(config, cfar_params, precomputed_data, device)
+    chain = _chain_cache.get(key)
+    if chain is None:
+        for old in _chain_cache.values():
+            old.close()
+        _chain_cache.clear()
+        chain = _chain_cache[key] = RadarChain(config, cfar_params, precomputed_data, device=device)
+    return chain
+
+
 def fun_process_single_frame(targets, config, cfar_params, cluster_params, precomputed_data, frame_idx=1, *,
                              rng: Optional[np.random.Generator] = None, noise: bool = True,
                              chain: Optional[RadarChain] = None, device: int = 0, host_synthesis: bool = False) -> List[dict]:
@@ -399,14 +437,8 @@ def fun_process_single_frame(targets, config, cfar_params, cluster_params, preco
     crosses the bus; the noise comes from the device Philox generator seeded from ``rng`` (the reference
     draws from MATLAB's global randn stream, which cannot be reproduced).  ``host_synthesis=True`` builds
     the cube with NumPy (``rng`` noise) and hands it to the device chain instead."""
-    own = chain is None
-    if own:
-        key = id(precomputed_data)
-        chain = _chain_cache.get(key)
-        if chain is None:
-            chain = RadarChain(config, cfar_params, precomputed_data, device=device)
-            _chain_cache.clear()
-            _chain_cache[key] = chain
+    if chain is None:
+        chain = _cached_chain(config, cfar_params, precomputed_data, device)
     if host_synthesis:
         raw = synthesize_echo(targets, config, precomputed_data)
         if noise:
@@ -430,12 +462,7 @@ def fun_process_frames(target_lists, config, cfar_params, cluster_params, precom
     same per-frame results as calling fun_process_single_frame frame by frame with the same ``rng`` (one seed
     is drawn per frame, in order), but the frames are pipelined over the device lanes."""
     if chain is None:
-        key = id(precomputed_data)
-        chain = _chain_cache.get(key)
-        if chain is None:
-            chain = RadarChain(config, cfar_params, precomputed_data, device=device)
-            _chain_cache.clear()
-            _chain_cache[key] = chain
+        chain = _cached_chain(config, cfar_params, precomputed_data, device)
     if not getattr(chain, "_has_waveform", False):
         chain.set_waveform(config, precomputed_data)
     rng = rng if rng is not None else np.random.default_rng()

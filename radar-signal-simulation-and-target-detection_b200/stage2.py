@@ -104,10 +104,32 @@ _cache = {}
 def process_stage2_mtd(iq_data, angle, config, device: int = 0):
     """Drop-in for process_stage2_mtd.m:1.  ``angle`` is accepted and unused, like the reference
     (process_stage2_mtd.m:26)."""
-    key = id(config)
+    key = (int(device), _config_digest(config))      # content, not id(): the reference re-reads config on every call
     ch = _cache.get(key)
     if ch is None:
-        ch = Stage2Chain(config, device=device)
+        for old in _cache.values():
+            old.close()
         _cache.clear()
-        _cache[key] = ch
+        ch = _cache[key] = Stage2Chain(config, device=device)
     return ch(np.asarray(iq_data))
+
+
+def _config_digest(obj) -> str:
+    """Stable digest of a (nested) struct of scalars / sequences / arrays."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+
+    def walk(x):
+        if isinstance(x, dict):
+            for k in sorted(x.keys()):
+                h.update(str(k).encode())
+                walk(x[k])
+        elif isinstance(x, (list, tuple)):
+            for v in x:
+                walk(v)
+        elif isinstance(x, np.ndarray):
+            h.update(np.ascontiguousarray(x).tobytes())
+        else:
+            h.update(repr(x).encode())
+    walk(obj)
+    return h.hexdigest()

@@ -18,7 +18,7 @@ def rel_errors(got: np.ndarray, ref: np.ndarray):
     return float(np.abs(d).max() / np.abs(ref).max()), float(np.linalg.norm(d) / np.linalg.norm(ref))
 
 
-def compare_detections(dets, ref_rows, margin, ref_par, pre, tol_angle=ANGLE_TOL_DEG):
+def compare_detections(dets, ref_rows, margin, ref_par, pre, tol_angle=ANGLE_TOL_DEG, tol_power=1e-5):
     """dets: structured device table; ref_rows: oracle rows [v, r, pair, amp] (1-based);
     margin[pair, g, v]: |S - T*noise|/(T*noise); ref_par: oracle rows [R, V, A, P, pair].
     Returns a dict of statistics; raises AssertionError on a parity violation."""
@@ -49,7 +49,7 @@ def compare_detections(dets, ref_rows, margin, ref_par, pre, tol_angle=ANGLE_TOL
             n_step += 1
             assert er <= dR / 8 * 1.0001 + 1e-9 and ev <= dV / 4 * 1.0001 + 1e-9, (key, er, ev)
     assert max_da <= tol_angle, f"angle differs by {max_da} deg"
-    assert max_dp <= 1e-5, f"detection power differs by {max_dp} relative"
+    assert max_dp <= tol_power, f"detection power differs by {max_dp} relative"
     assert n_step <= max(1, n_common // 50), f"{n_step} of {n_common} spline peaks moved by a grid step"
     return dict(n_ref=len(want), n_dev=len(got), n_common=n_common, only_dev=len(only_got), only_ref=len(only_want),
                 max_angle_err=max_da, max_power_rel=max_dp, spline_step_moves=n_step)

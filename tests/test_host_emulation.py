@@ -125,29 +125,6 @@ def test_cfar_pitch_is_conflict_free_across_rows(lib):
         assert p >= need and p % 4 == 0 and p % 32 == 8 and p - need < 32
 
 
-@pytest.mark.parametrize("seg,L", [("medium", 1024), ("medium", 4096), ("long", 4096), ("long", 1024)])
-def test_pc_two_pass_blocks_match_reference(lib, cfg1, seg, L):
-    """The N x N register-resident plan (64 x 64, 32 x 32) of pc2_fft_kernel."""
-    cfg, pre, beam, pc = cfg1
-    N, G = cfg.point_PRT, cfg.n_gates
-    g1, g2 = pre["N_gate_narrow"], pre["N_gate_medium"]
-    if seg == "medium":
-        ss, gate0, ng, taps = pre["seg_start_medium"] - 1, g1, g2, pre["MF_medium_win"]
-    else:
-        ss, gate0, ng, taps = pre["seg_start_long"] - 1, g1 + g2, G - g1 - g2, pre["MF_long_win"]
-    t = np.ascontiguousarray(np.stack([taps.real, taps.imag], -1))
-    for (p, b) in ((3, 2), (31, 0)):
-        line = np.ascontiguousarray(beam[p, b].astype(np.complex64))
-        out = np.zeros(G, np.complex64)
-        nb = ctypes.c_int()
-        rc = lib.emul_pc2_segment(line.ctypes.data_as(fp), N, int(ss), int(gate0), int(ng), t.ctypes.data_as(dp), len(taps), L,
-                                  out.ctypes.data_as(fp), ctypes.byref(nb))
-        assert rc == 0
-        ref = pc[p, b, gate0:gate0 + ng]
-        assert np.abs(out[gate0:gate0 + ng] - ref).max() <= 2e-6 * np.abs(ref).max()
-        assert not out[:gate0].any() and not out[gate0 + ng:].any()
-
-
 def test_pc_narrow_fir(lib, cfg1):
     cfg, pre, beam, pc = cfg1
     g1 = pre["N_gate_narrow"]

@@ -63,3 +63,9 @@ def trace_report(flags):
 
 for flags in (0, 1):
     trace_report(flags)
+
+for pf in ("0",):
+    os.environ["RSP_FUSED_PREFETCH"] = pf
+    print("prefetch_ahead =", pf)
+    trace_report(0)
+    os.environ.pop("RSP_FUSED_PREFETCH")

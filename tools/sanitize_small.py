@@ -26,7 +26,7 @@ def run(cfgname, **shape):
 
 run("cfg1")                                                         # P=32, vectorised CFAR (5,4,2), pow2 MTD
 run("odd", channel_num=16, beam_num=5, prtNum=20, point_PRT=4097)   # odd N, generic DFT MTD, generic CFAR window
-for dbf in ("ffma", "tma", "tma1"):
+for dbf in ("ffma", "mma2", "tma2", "tc"):
     os.environ["RSP_DBF"] = dbf
     run("cfg1-" + dbf, channel_num=16, beam_num=13, prtNum=32, point_PRT=4096)
 os.environ.pop("RSP_DBF")
