@@ -810,10 +810,10 @@ __device__ __forceinline__ void pc_role(const PcKernelArgs& k, const PcSegArgs& 
 // CfgA = block plan of role 0 (the long segment), CfgB = role 1 (the medium segment + narrow FIR).
 // The short role-1 CTAs have the highest block indices, so they fill the tail of the long ones.
 // Register budget of the pulse-compression kernel: RSP_PC_NREG caps the registers per thread (the kernel compiles without
-// spills down to 56), which sets how many 256-thread CTAs share an SM (80 -> 3, 64 -> 4) and how much of the register file
-// is left for the co-resident tcgen05 DBF of another lane's CPI.
+// spills down to 56), which sets how many 256-thread CTAs share an SM: 64 registers -> 4 CTAs = 32 warps per SM, measured
+// 20.1 -> 18.9 us per CPI against the 80 registers / 3 CTAs that __launch_bounds__(256, 3) gave (profiles/r2_pc_regs.txt).
 #ifndef RSP_PC_NREG
-#define RSP_PC_NREG 0
+#define RSP_PC_NREG 64
 #endif
 #if RSP_PC_NREG > 0
 #define RSP_PC_BOUNDS __maxnreg__(RSP_PC_NREG)
