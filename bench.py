@@ -155,7 +155,7 @@ def run_reference_runtime(exe: str, name: str, n_frames: int):
     ref_dir = os.environ.get("RSP_REFERENCE_DIR", "/root/reference/Simulation")
     if not os.path.isdir(ref_dir):
         return None
-    script = f"addpath('{os.path.join(ROOT, 'tools')}'); ref_golden('{ref_dir}', '', '{name}', {n_frames});"
+    script = f"addpath('{os.path.join(ROOT, 'tools', 'ref_golden')}'); ref_golden('{ref_dir}', '', '{name}', {n_frames});"
     cmd = [exe, "--no-gui", "--eval", script] if "octave" in os.path.basename(exe) else [exe, "-batch", script]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=900).stdout

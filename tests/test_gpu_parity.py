@@ -666,3 +666,36 @@ def test_stream_ring_smaller_than_the_lanes_is_refused():
         chain.submit_cpi(pinned, 5)
     chain.stream_fetch(5)
     chain.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2", "native"])
+def test_cufft_cross_check_of_pulse_compression_and_mtd(name):
+    """north_star: "cuFFT is used only as a cross-check".  An independent third opinion on S6 and S7 that shares no FFT code
+    with the kernels (hand-written Stockham passes) or with the oracle (SciPy pocketfft): the reference's own recipe --
+    ifft(fft(seg, N_fft) .* MF_fft) per segment (fsf:115-120) and fftshift(fft(pc .* win)) over the pulses (fsf:134-135) --
+    evaluated by torch.fft (cuFFT) in complex128 on the DEVICE's beam cube, against the device's pulse-compressed cube and
+    range-Doppler map.  Lives in tests/ only; the product never calls cuFFT."""
+    import torch
+    chain, config, cfar_params, cluster_params, pd = _device_chain(name)
+    cfg, pre, raw = o.make_cube(name, 6)
+    chain.process_cpi(raw)
+    beam = torch.from_numpy(chain.get_beam()).cuda().to(torch.complex128)            # [P, B, N]
+    pc_dev, rdm_dev = chain.get_pc(), chain.get_rdm()
+    g1, g2, G = pre["N_gate_narrow"], pre["N_gate_medium"], pre["N_total_gate"]
+    nm, nl = int(pre["N_fft_med"]), int(pre["N_fft_long"])
+    s_m, s_l = pre["seg_start_medium"] - 1, pre["seg_start_long"] - 1
+    Hm = torch.from_numpy(np.asarray(pre["MF_medium_fft"])).cuda()
+    Hl = torch.from_numpy(np.asarray(pre["MF_long_fft"])).cuda()
+    med = torch.fft.ifft(torch.fft.fft(beam[..., s_m:], n=nm, dim=-1) * Hm, n=nm, dim=-1)[..., g1:g1 + g2]
+    lng = torch.fft.ifft(torch.fft.fft(beam[..., s_l:], n=nl, dim=-1) * Hl, n=nl, dim=-1)[..., g1 + g2:G]
+    e_med = rel_errors(pc_dev[..., g1:g1 + g2], med.cpu().numpy())
+    e_lng = rel_errors(pc_dev[..., g1 + g2:G], lng.cpu().numpy())
+    assert e_med[0] <= 1e-5 and e_lng[0] <= 1e-5, (e_med, e_lng)
+    # S7 from the device's own pulse-compressed cube (all three segments), so that only the Doppler stage is compared
+    pc = torch.from_numpy(pc_dev).cuda().to(torch.complex128)                        # [P, B, G]
+    win = torch.from_numpy(np.asarray(pre["MTD_win"], dtype=np.float64)).cuda()
+    r = torch.fft.fftshift(torch.fft.fft(pc * win[:, None, None], dim=0), dim=0).permute(1, 2, 0)      # [B, G, P]
+    e_rdm = rel_errors(rdm_dev, r.cpu().numpy())
+    assert e_rdm[0] <= RDM_REL_TOL and e_rdm[1] <= RDM_REL_TOL, e_rdm
+    print(name, "cuFFT cross-check: pc medium", e_med, "pc long", e_lng, "rdm", e_rdm)
+    chain.close()
