@@ -198,6 +198,26 @@ typedef struct {
 int rsp_stage2_configure(rsp_ctx* ctx, const rsp_stage2_config* cfg);
 int rsp_stage2_mtd(rsp_ctx* ctx, const void* iq, rsp_dtype dtype, rsp_c128* mtd_out, rsp_c128* pc_out);
 
+/* ---- the per-segment 1-D range CFAR of the real-data path (debug_simulated_data_processing_v2.m:419-511:
+ * local_execute_cfar / executeCFAR_2D / Function_CFAR1D_sub) ----
+ * Each of the three pulse segments of a beam's Doppler map is detected on its own along range: two reference windows of
+ * `ref_cells` gates `save_cells` away from the cell, a window that leaves the segment is replaced by the other one,
+ * level = greater (method 0, GOCA) or smaller (method 1, SOCA) of the two means, flag = amplitude >= level * t_cfar;
+ * Doppler rows within +-zero_vel_bins of row round(V/2)+1 are not tested (flag 0, threshold 0).
+ * Arrays are [beam][gate][Doppler], Doppler fastest == MATLAB (Doppler, gate) maps per beam. */
+typedef struct {
+    int32_t ref_cells, save_cells;   /* config.cfar.refCells_R, saveCells_R */
+    int32_t method;                  /* config.cfar.CFARmethod_R: 0 = greatest-of, 1 = smallest-of */
+    int32_t zero_vel_bins;           /* config.cfar.MTD_0v_num */
+    float   t_cfar;                  /* config.cfar.T_CFAR */
+    int32_t seg_len[3];              /* gates of the narrow / medium / long segment (config.Sig_Config.point_prt(2:4)) */
+} rsp_cfar1d_params;
+/* Any amplitude map(s) in host memory (mtd_amplitude_map = abs(MTD) of n_beams beams). */
+int rsp_cfar1d(int32_t device, const float* amp_host, int32_t n_doppler, int32_t n_gates, int32_t n_beams,
+               const rsp_cfar1d_params* p, uint8_t* flags_host, float* thresholds_host /* may be NULL */);
+/* The Doppler maps the last rsp_stage2_mtd left in the context (all beams, |MTD| computed on the device). */
+int rsp_stage2_cfar(rsp_ctx* ctx, const rsp_cfar1d_params* p, uint8_t* flags_host, float* thresholds_host /* may be NULL */);
+
 /* ---- S4 + S4.1 on the device (fun_process_single_frame.m:47-88): echo synthesis + noise ----
  * Fills a device-resident PCN complex64 cube: for every target the delayed transmit pulse scaled by the
  * SNR amplitude, the pulse-to-pulse Doppler phasor and the per-channel steering phasor (fsf:55-74), plus

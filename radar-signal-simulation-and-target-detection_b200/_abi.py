@@ -72,6 +72,11 @@ class rsp_stage2_config(C.Structure):
                 ("zero_vel_bins", C.c_int32)]
 
 
+class rsp_cfar1d_params(C.Structure):
+    _fields_ = [("ref_cells", C.c_int32), ("save_cells", C.c_int32), ("method", C.c_int32), ("zero_vel_bins", C.c_int32),
+                ("t_cfar", C.c_float), ("seg_len", C.c_int32 * 3)]
+
+
 class rsp_kernel_times(C.Structure):
     _fields_ = [("n", C.c_int32), ("name", C.c_char_p * 12), ("total_ms", C.c_double * 12), ("launches", C.c_int64 * 12)]
 
@@ -109,6 +114,8 @@ SYMBOLS = [
                                     C.POINTER(C.c_int32)]),
     ("rsp_stage2_configure", C.c_int, [_P, C.POINTER(rsp_stage2_config)]),
     ("rsp_stage2_mtd", C.c_int, [_P, _P, C.c_int, _P, _P]),
+    ("rsp_cfar1d", C.c_int, [C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(rsp_cfar1d_params), _P, _P]),
+    ("rsp_stage2_cfar", C.c_int, [_P, C.POINTER(rsp_cfar1d_params), _P, _P]),
     ("rsp_set_waveform", C.c_int, [_P, C.POINTER(rsp_waveform)]),
     ("rsp_synthesize", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, _P]),
     ("rsp_process_targets", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, C.POINTER(rsp_cluster_params), _P, C.c_int32,

@@ -18,7 +18,7 @@ EMUL = os.path.join(LIB_DIR, "librsp_emul.so")
 
 CUDA_SOURCES = ["rsp_api.cu"]
 CXX_SOURCES = ["rsp_cluster.cpp"]
-HEADERS = ["rsp_math.cuh", "rsp_phases.cuh", "rsp_kernels.cuh", "rsp_fused.cuh", "rsp_dbf_tc.cuh", "rsp_plan.hpp", "rsp_dft_big.cuh"]
+HEADERS = ["rsp_math.cuh", "rsp_phases.cuh", "rsp_kernels.cuh", "rsp_fused.cuh", "rsp_dbf_tc.cuh", "rsp_cfar1d.cuh", "rsp_plan.hpp", "rsp_dft_big.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 

@@ -12,6 +12,7 @@
 #include "rsp_kernels.cuh"
 #include "rsp_fused.cuh"
 #include "rsp_dbf_tc.cuh"
+#include "rsp_cfar1d.cuh"
 #include "rsp_plan.hpp"
 
 using namespace rsp;
@@ -1557,6 +1558,82 @@ int rsp_stage2_mtd(rsp_ctx* c, const void* iq, rsp_dtype dtype, rsp_c128* mtd_ou
     CU(c, cudaGetLastError());
     c->ran = true;
     c->rdm_in_ctx = true;
+    return RSP_OK;
+}
+
+static int cfar1d_fill(rsp_ctx* c, Cfar1dArgs& a, const rsp_cfar1d_params* p, int V, int R, int B) {
+    if (!p || p->ref_cells < 1 || p->save_cells < 0 || p->ref_cells + p->save_cells > RSP_CFAR1D_MAXW || (p->method != 0 && p->method != 1))
+        return fail(c, RSP_ERR_INVALID_ARG, "1-D CFAR: need ref >= 1, save >= 0, ref + save <= %d, method 0 or 1", RSP_CFAR1D_MAXW);
+    const int W = p->ref_cells + p->save_cells;
+    int g = 0;
+    for (int s = 0; s < 3; ++s) {
+        if (p->seg_len[s] < 0 || (p->seg_len[s] > 0 && p->seg_len[s] < 2 * W))       // every cell needs one window inside its segment
+            return fail(c, RSP_ERR_UNSUPPORTED, "1-D CFAR: segment %d has %d gates, fewer than 2 (ref + save) = %d", s, p->seg_len[s], 2 * W);
+        a.seg_lo[s] = g; g += p->seg_len[s]; a.seg_hi[s] = g;
+    }
+    if (g != R) return fail(c, RSP_ERR_INVALID_ARG, "1-D CFAR: segments add up to %d gates, the map has %d", g, R);
+    a.V = V; a.R = R; a.B = B;
+    a.ref = p->ref_cells; a.save = p->save_cells; a.method = p->method; a.t_cfar = p->t_cfar;
+    const long center = (long)std::floor(V / 2.0 + 0.5) + 1;                         // round(V/2) + 1, 1-based (:446)
+    const int n0 = p->zero_vel_bins < 0 ? 0 : p->zero_vel_bins;
+    a.notch_lo = (int)std::max(1L, center - n0) - 1;
+    a.notch_hi = (int)std::min((long)V, center + n0) - 1;
+    return RSP_OK;
+}
+
+static void cfar1d_launch(const Cfar1dArgs& a, cudaStream_t s) {
+    dim3 grid((a.V + 31) / 32, (a.R + RSP_CFAR1D_TG - 1) / RSP_CFAR1D_TG, a.B);
+    cfar1d_kernel<<<grid, 256, 0, s>>>(a);
+}
+
+int rsp_cfar1d(int32_t device, const float* amp_host, int32_t V, int32_t R, int32_t B, const rsp_cfar1d_params* p,
+               uint8_t* flags_host, float* thr_host) {
+    if (!amp_host || !flags_host || V < 1 || R < 1 || B < 1) return fail(nullptr, RSP_ERR_INVALID_ARG, "1-D CFAR: null or empty map");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(nullptr, RSP_ERR_NO_DEVICE, "no CUDA device visible; librsp has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(nullptr, RSP_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+    Cfar1dArgs a{};
+    if (int rc = cfar1d_fill(nullptr, a, p, V, R, B)) return rc;
+    CU(nullptr, cudaSetDevice(device));
+    const size_t n = (size_t)V * R * B;
+    float *d_amp = nullptr, *d_thr = nullptr;
+    unsigned char* d_flags = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_amp), n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_flags), n);
+    if (e == cudaSuccess && thr_host) e = cudaMalloc(reinterpret_cast<void**>(&d_thr), n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_amp, amp_host, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        a.amp = d_amp; a.rdm = nullptr; a.flags = d_flags; a.thr = d_thr;
+        cfar1d_launch(a, nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(flags_host, d_flags, n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && thr_host) e = cudaMemcpy(thr_host, d_thr, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_amp); cudaFree(d_flags); cudaFree(d_thr);
+    if (e != cudaSuccess) return fail(nullptr, RSP_ERR_CUDA, "1-D CFAR failed: %s", cudaGetErrorString(e));
+    return RSP_OK;
+}
+
+int rsp_stage2_cfar(rsp_ctx* c, const rsp_cfar1d_params* p, uint8_t* flags_host, float* thr_host) {
+    if (!c || !flags_host) return fail(c, RSP_ERR_INVALID_ARG, "null argument");
+    if (!c->s2_ready || !c->ran || !c->rdm_in_ctx) return fail(c, RSP_ERR_NOT_READY, "rsp_stage2_mtd has not produced a Doppler map in this context");
+    Cfar1dArgs a{};
+    if (int rc = cfar1d_fill(c, a, p, c->P, c->G, c->B)) return rc;
+    CU(c, cudaSetDevice(c->prm.device));
+    const size_t n = (size_t)c->P * c->G * c->B;
+    unsigned char* d_flags = nullptr;
+    float* d_thr = nullptr;
+    CU(c, cudaMalloc(reinterpret_cast<void**>(&d_flags), n));
+    if (thr_host && cudaMalloc(reinterpret_cast<void**>(&d_thr), n * sizeof(float)) != cudaSuccess) { cudaFree(d_flags); return fail(c, RSP_ERR_CUDA, "out of device memory"); }
+    a.amp = nullptr; a.rdm = c->d_rdm; a.flags = d_flags; a.thr = d_thr;
+    cfar1d_launch(a, c->stream);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flags_host, d_flags, n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && thr_host) e = cudaMemcpyAsync(thr_host, d_thr, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_flags); cudaFree(d_thr);
+    if (e != cudaSuccess) return fail(c, RSP_ERR_CUDA, "1-D CFAR failed: %s", cudaGetErrorString(e));
     return RSP_OK;
 }
 

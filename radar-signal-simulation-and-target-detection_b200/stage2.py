@@ -47,6 +47,7 @@ class Stage2Chain:
     def __init__(self, config, device: int = 0, mtd_win=None):
         self._lib = _abi.load()
         self._ctx = C.c_void_p()
+        self._config = config
         sc = _field(config, "Sig_Config")
         mtd = config["mtd"] if "mtd" in config else sc
         self.P = int(_field(sc, "prtNum"))
@@ -86,6 +87,17 @@ class Stage2Chain:
                                             C.c_void_p(mtd.ctypes.data), C.c_void_p(pc.ctypes.data)), self._ctx)
         return mtd, pc
 
+    def cfar(self, config=None):
+        """The 1-D range CFAR (local_execute_cfar) on the Doppler maps the last call left on the device, all beams at once,
+        without a host round trip of the maps.  Returns (cfar_flag, threshold_matrix) as [P, G, B] float64."""
+        cfgd = config if config is not None else self._config
+        p = _cfar1d_params(cfgd["cfar"], self.gates)
+        flags = np.empty((self.B, self.G, self.P), np.uint8)
+        thr = np.empty((self.B, self.G, self.P), np.float32)
+        _abi.check(self._lib.rsp_stage2_cfar(self._ctx, C.byref(p), C.c_void_p(flags.ctypes.data), C.c_void_p(thr.ctypes.data)),
+                   self._ctx)
+        return np.transpose(flags, (2, 1, 0)).astype(np.float64), np.transpose(thr, (2, 1, 0)).astype(np.float64)
+
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
             self._lib.rsp_destroy(self._ctx)
@@ -96,6 +108,40 @@ class Stage2Chain:
             self.close()
         except Exception:
             pass
+
+
+def _cfar1d_params(cfar, seg_len):
+    p = _abi.rsp_cfar1d_params()
+    p.ref_cells, p.save_cells = int(cfar["refCells_R"]), int(cfar["saveCells_R"])
+    p.method = int(cfar["CFARmethod_R"]) if "CFARmethod_R" in cfar else 0
+    p.zero_vel_bins = int(cfar["MTD_0v_num"]) if "MTD_0v_num" in cfar else 0
+    p.t_cfar = float(cfar["T_CFAR"])
+    p.seg_len[:] = [int(x) for x in seg_len]
+    return p
+
+
+def local_execute_cfar(mtd_amplitude_map, cfar_params, config, device: int = 0):
+    """Drop-in for local_execute_cfar, debug_simulated_data_processing_v2.m:419: per-segment 1-D range GOCA / SOCA CFAR
+    with the zero-velocity rows left out.  ``mtd_amplitude_map``: [V, R] (one beam) or [V, R, B]; ``config.cfar`` holds
+    refCells_R, saveCells_R, T_CFAR, CFARmethod_R, MTD_0v_num and ``config.Sig_Config.point_prt`` = [total, narrow, medium,
+    long] gates; like the reference, ``cfar_params`` is accepted and config.cfar is what is read (:427-429).
+    Returns (cfar_flag, threshold_matrix), float64 arrays shaped like the input."""
+    amp = np.asarray(mtd_amplitude_map)
+    one = amp.ndim == 2
+    if one:
+        amp = amp[:, :, None]
+    V, R, B = amp.shape
+    seg = list(config["Sig_Config"]["point_prt"])[1:4]
+    p = _cfar1d_params(config["cfar"], seg)
+    dev_amp = np.ascontiguousarray(np.transpose(amp, (2, 1, 0)), dtype=np.float32)          # [B][R][V]
+    flags = np.empty((B, R, V), np.uint8)
+    thr = np.empty((B, R, V), np.float32)
+    lib = _abi.load()
+    _abi.check(lib.rsp_cfar1d(int(device), C.c_void_p(dev_amp.ctypes.data), V, R, B, C.byref(p), C.c_void_p(flags.ctypes.data),
+                              C.c_void_p(thr.ctypes.data)))
+    f = np.transpose(flags, (2, 1, 0)).astype(np.float64)
+    t = np.transpose(thr, (2, 1, 0)).astype(np.float64)
+    return (f[:, :, 0], t[:, :, 0]) if one else (f, t)
 
 
 _cache = {}

@@ -699,3 +699,57 @@ def test_cufft_cross_check_of_pulse_compression_and_mtd(name):
     assert e_rdm[0] <= RDM_REL_TOL and e_rdm[1] <= RDM_REL_TOL, e_rdm
     print(name, "cuFFT cross-check: pc medium", e_med, "pc long", e_lng, "rdm", e_rdm)
     chain.close()
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_range_cfar_1d_matches_the_literal_reference_loops(method):
+    """f-3: per-segment 1-D range GOCA / SOCA CFAR with the zero-velocity rows masked, edge fallback and >= compare
+    (debug_simulated_data_processing_v2.m:419-511) -- cfar1d_kernel against the oracle's literal loops on the same maps:
+    identical flags (cells whose amplitude is within 1e-6 of the threshold excepted) and thresholds within 1e-6."""
+    gates = [228, 723, 2453]
+    P, B = 64, 3
+    rng = np.random.default_rng(40 + method)
+    amp = np.abs(rng.standard_normal((P, sum(gates), B)) + 1j * rng.standard_normal((P, sum(gates), B)))
+    for (v, g, b) in ((10, 5, 0), (20, 229, 1), (33, 950, 1), (40, 3403, 2), (50, 1500, 0), (32, 2000, 2)):
+        amp[v, g, b] += 40.0
+    amp = amp.astype(np.float32).astype(np.float64)                 # the device takes fp32 maps
+    config = rsp.Struct(Sig_Config=rsp.Struct(point_prt=[sum(gates)] + gates),
+                        cfar=rsp.Struct(refCells_R=5, saveCells_R=14, T_CFAR=3.0, CFARmethod_R=method, MTD_0v_num=3))
+    flag, thr = rsp.local_execute_cfar(amp, config.cfar, config)
+    assert flag.shape == thr.shape == amp.shape
+    n_flag = 0
+    for b in range(B):
+        f_ref, t_ref = o.local_execute_cfar(amp[:, :, b], gates, 3, 5, 14, 3.0, method)
+        assert np.allclose(thr[:, :, b], t_ref, rtol=1e-6, atol=0)
+        diff = flag[:, :, b] != f_ref
+        assert np.all(np.abs(amp[:, :, b][diff] - t_ref[diff]) <= 1e-6 * t_ref[diff])
+        n_flag += int(f_ref.sum())
+    assert n_flag >= 5
+    ctr = round(P / 2) + 1
+    assert not flag[ctr - 1 - 3: ctr + 3].any() and not thr[ctr - 1 - 3: ctr + 3].any()
+    one_f, one_t = rsp.local_execute_cfar(amp[:, :, 1], config.cfar, config)           # the reference's 2-D call shape
+    assert np.array_equal(one_f, flag[:, :, 1]) and np.array_equal(one_t, thr[:, :, 1])
+
+
+def test_stage2_chain_range_cfar_on_the_device_maps():
+    """process_stage2_mtd followed by the 1-D range CFAR on the Doppler maps still on the device (rsp_stage2_cfar): equals
+    local_execute_cfar applied to abs() of the returned maps."""
+    gates = [228, 723, 2453]
+    P, B = 64, 2
+    config = rsp.Struct(Sig_Config=rsp.Struct(fs=25e6, prtNum=P, tao=[0.16e-6, 8e-6, 28e-6], B=20e6, point_prt=[sum(gates)] + gates),
+                        mtd=rsp.Struct(beam_num=B), cfar=rsp.Struct(MTD_0v_num=3, refCells_R=5, saveCells_R=14, T_CFAR=6.0, CFARmethod_R=0))
+    rng = np.random.default_rng(8)
+    iq = (rng.standard_normal((P, sum(gates), B)) + 1j * rng.standard_normal((P, sum(gates), B))) * np.sqrt(0.5)
+    pulses = o.stage2_reference_pulses()
+    dop = np.exp(2j * np.pi * 0.2 * np.arange(P))
+    iq[:, 1500:1500 + 700, 0] += 3.0 * dop[:, None] * pulses[2][None, :]
+    ch = rsp.Stage2Chain(config)
+    mtd, pc = ch(iq)
+    flag, thr = ch.cfar()
+    for b in range(B):
+        f_ref, t_ref = o.local_execute_cfar(np.abs(mtd[:, :, b]), gates, 3, 5, 14, 6.0, 0)
+        assert np.allclose(thr[:, :, b], t_ref, rtol=2e-6, atol=1e-6 * np.abs(mtd).max())
+        diff = flag[:, :, b] != f_ref
+        assert diff.sum() <= 2 and np.all(np.abs(np.abs(mtd[:, :, b])[diff] - t_ref[diff]) <= 1e-5 * t_ref[diff])
+    assert flag[:, 1500, 0].any()
+    ch.close()

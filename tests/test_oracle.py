@@ -138,3 +138,29 @@ def test_stage2_specification_is_a_per_segment_correlation():
     assert not mtd[P // 2 - 2: P // 2 + 3].any()
     keep = np.r_[0:P // 2 - 2, P // 2 + 3:P]
     assert np.allclose(mtd[keep], full[keep])
+
+
+def test_range_cfar_1d_literal_restatement_properties():
+    """f-3 (debug_simulated_data_processing_v2.m:419-511): hand-checkable facts of the literal restatement."""
+    V, seg = 12, [40, 44, 60]
+    R = sum(seg)
+    amp = np.ones((V, R))
+    amp[3, 20] = 50.0            # narrow segment
+    amp[8, 40 + 2] = 50.0        # third column of the medium segment: the left window leaves the segment
+    amp[9, R - 1] = 50.0         # last gate of the long segment: the right window leaves the segment
+    amp[6, 100] = 50.0           # on the zero-velocity row round(12/2)+1 = 7 (1-based) -> never tested
+    flag, thr = o.local_execute_cfar(amp, seg, 1, 5, 14, 3.0, 0)
+    assert flag[3, 20] == 1 and flag[8, 42] == 1 and flag[9, R - 1] == 1
+    assert flag[5:8].sum() == 0 and thr[5:8].sum() == 0          # rows 6..8 (1-based) are masked for MTD_0v_num = 1
+    assert flag.sum() == 3
+    assert np.all(thr[0] == 3.0) and thr[3, 0] == 3.0 and thr[3, 20] == 3.0
+    # a strong cell raises the threshold of exactly the cells whose windows contain it: columns 20 +- (15..19) in its segment
+    hit = np.flatnonzero(thr[3, :seg[0]] > 3.0)
+    assert set(hit) == {1, 2, 3, 4, 5, 35, 36, 37, 38, 39}
+    assert np.allclose(thr[3, hit], 3.0 * (4 * 1.0 + 50.0) / 5)
+    # smallest-of ignores it where the other window is clean (columns 35..39); at columns 1..5 the left window leaves the
+    # segment and is REPLACED by the right one (:481-485), so both hold the strong cell and the level stays raised
+    _, thr_so = o.local_execute_cfar(amp, seg, 1, 5, 14, 3.0, 1)
+    assert np.all(thr_so[3, 35:40] == 3.0) and np.allclose(thr_so[3, 1:6], 32.4) and np.all(thr_so[3, 6:35] == 3.0)
+    with pytest.raises(IndexError):                                  # the reference would index outside a 30-gate segment
+        o.local_execute_cfar(np.ones((4, 30)), [30, 0, 0], 0, 5, 14, 3.0, 0)
