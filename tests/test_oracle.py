@@ -142,15 +142,15 @@ def test_stage2_specification_is_a_per_segment_correlation():
 
 def test_range_cfar_1d_literal_restatement_properties():
     """f-3 (debug_simulated_data_processing_v2.m:419-511): hand-checkable facts of the literal restatement."""
-    V, seg = 12, [40, 44, 60]
+    V, seg = 12, [80, 44, 60]
     R = sum(seg)
     amp = np.ones((V, R))
     amp[3, 20] = 50.0            # narrow segment
-    amp[8, 40 + 2] = 50.0        # third column of the medium segment: the left window leaves the segment
+    amp[8, 80 + 2] = 50.0        # third column of the medium segment: the left window leaves the segment
     amp[9, R - 1] = 50.0         # last gate of the long segment: the right window leaves the segment
-    amp[6, 100] = 50.0           # on the zero-velocity row round(12/2)+1 = 7 (1-based) -> never tested
+    amp[6, 150] = 50.0           # on the zero-velocity row round(12/2)+1 = 7 (1-based) -> never tested
     flag, thr = o.local_execute_cfar(amp, seg, 1, 5, 14, 3.0, 0)
-    assert flag[3, 20] == 1 and flag[8, 42] == 1 and flag[9, R - 1] == 1
+    assert flag[3, 20] == 1 and flag[8, 82] == 1 and flag[9, R - 1] == 1
     assert flag[5:8].sum() == 0 and thr[5:8].sum() == 0          # rows 6..8 (1-based) are masked for MTD_0v_num = 1
     assert flag.sum() == 3
     assert np.all(thr[0] == 3.0) and thr[3, 0] == 3.0 and thr[3, 20] == 3.0
