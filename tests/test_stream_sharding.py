@@ -71,3 +71,55 @@ def test_gather_detections_world_size_2_gloo():
 def test_pack_overflow_is_an_error():
     with pytest.raises(OverflowError):
         stream.pack_detections([_fake_detections(1, 40)], slots=1, cap=32)
+
+
+def _async_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    slots, cap, maxdet = 8, 16, 32
+    ok = True
+    # the device ring as CPU tensors: counts [slots] int32 as bytes, records [slots, maxdet * 40] bytes
+    lists = [[_fake_detections(1000 * rank + 10 * b + i, 3 + i + b) for i in range(4)] for b in range(2)]     # two batches of 4 CPIs
+    counts = torch.zeros(slots, dtype=torch.int32)
+    recs = torch.zeros((slots, maxdet * stream.REC_BYTES), dtype=torch.uint8)
+    for b in range(2):
+        c, r = stream.pack_detections(lists[b], slots=4, cap=maxdet)
+        counts[4 * b:4 * b + 4] = c
+        recs[4 * b:4 * b + 4] = r
+    gat = stream.AsyncDetectionGather(counts.view(torch.uint8), recs, batch_slots=4, cap=cap)
+    h0 = gat.launch(0)
+    h1 = gat.launch(4)
+    out0, out1 = gat.wait(h0), gat.wait(h1)
+    for b, out in enumerate((out0, out1)):
+        for r in range(world):
+            for i in range(4):
+                want = rsp.sort_detections(_fake_detections(1000 * r + 10 * b + i, 3 + i + b))
+                ok &= bool(np.array_equal(out[r][i], want))
+    # more detections than the message holds: an error on every rank, never a truncated list
+    counts[0] = cap + 1
+    h = gat.launch(0)
+    try:
+        gat.wait(h)
+        ok = False
+    except OverflowError:
+        pass
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_async_packed_gather_world_size_2_gloo():
+    """stream.AsyncDetectionGather (one packed all_gather per batch: count header + records) over gloo on CPU tensors."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_async_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]

@@ -60,3 +60,43 @@ def test_frame_loop_tags_frames_and_azimuth():
     dpf = 6 * 6.0 * 332 * 232.76e-6                                                              # v8_3:94-95
     assert log[0]["iAntAngle"] == pytest.approx(dpf) and log[1]["iAntAngle"] == pytest.approx(3 * dpf)
     assert len(tracks) == 1 and tracks[0]["NumPoints"] == 3 and tracks[0]["Power"] == 5.0
+
+
+def test_tracker_against_the_oracle_statement():
+    """f-4: the product's FIFO search (tracker.inter_frame_cluster, v8_3:272-336) against the oracle's independent
+    statement (connected components of the 5-D gate graph) on random logs with chains, ties and isolated points; the
+    kinematics (init_tracks / evolve, v8_3:103-117, :210-224) against the oracle's closed form."""
+    from conftest import oracle as o
+    rng = np.random.default_rng(12)
+    cfg = rsp.default_scan_and_track_config(dict(max_range_sep=30.0, max_vel_sep=0.4, max_angle_sep=5.0))
+    ifc = cfg["inter_frame_cluster"]
+    for trial in range(6):
+        log = []
+        for k in range(int(rng.integers(3, 9))):                 # a few true tracks: slow drift over frames, some frames missing
+            R0, V0, El0 = rng.uniform(2000, 9000), rng.uniform(-20, 20), rng.uniform(0, 40)
+            for fr in range(1, 13):
+                if rng.random() < 0.25:
+                    continue
+                log.append(dict(Range=R0 - 4.0 * fr + rng.normal(0, 3), Velocity=V0 + rng.normal(0, 0.05), Angle=El0 + rng.normal(0, 0.3),
+                                Power=float(rng.uniform(1, 100)), iFrame=fr, iAntAngle=2.8 * fr))
+        for _ in range(10):                                        # clutter
+            log.append(dict(Range=rng.uniform(500, 12000), Velocity=rng.uniform(-30, 30), Angle=rng.uniform(-10, 60),
+                            Power=float(rng.uniform(1, 100)), iFrame=int(rng.integers(1, 13)), iAntAngle=float(rng.uniform(0, 40))))
+        log.append(dict(log[0]))                                   # an exact duplicate: a tie in power, first maximum wins
+        rng.shuffle(log)
+        got = rsp.inter_frame_cluster(log, cfg)
+        want = o.inter_frame_tracks(log, ifc["Gate_R"], ifc["Gate_V"], ifc["Gate_Az"], ifc["Gate_El"], ifc["Max_Frame_Gap"])
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            for key in ("Range", "Velocity", "Angle", "Power"):
+                assert a[key] == b[key], (trial, key)
+            assert abs(a["Azimuth"] - b["Azimuth"]) <= 1e-12 * max(1.0, abs(b["Azimuth"]))
+            assert (a["FirstFrame"], a["LastFrame"], a["NumPoints"]) == (b["FirstFrame"], b["LastFrame"], b["NumPoints"])
+    T_frame = 332 * 232.76e-6
+    tg = [dict(Range=3000.0, Velocity=20.0, ElevationAngle=10.0, SNR_dB=10.0), dict(Range=10000.0, Velocity=25.0, ElevationAngle=10.0, SNR_dB=15.0)]
+    tracks = rsp.init_tracks(tg)
+    for n in range(1, 41):
+        cur = rsp.evolve(tracks, T_frame)
+        for t, c in zip(tg, cur):
+            R, El, Vr = o.track_state_after(o.Target(t["Range"], t["Velocity"], t["ElevationAngle"], t["SNR_dB"]), n, T_frame)
+            assert abs(c["Range"] - R) <= 1e-9 * R and abs(c["ElevationAngle"] - El) <= 1e-10 and abs(c["Velocity"] - Vr) <= 1e-10
