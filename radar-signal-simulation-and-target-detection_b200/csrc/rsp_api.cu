@@ -88,6 +88,13 @@ struct rsp_ctx {
     DbfTcArgs dbf_tc_args{};
     size_t dbf_tc_smem = 0;
     int dbf_tc_grid = 0;
+    // Range-blocked chain (shapes whose beam + pulse-compressed cubes do not fit L2, e.g. config 3): the CPI is processed in
+    // chunks of one overlap-save block's gates, DBF -> PC -> MTD -> CFAR per chunk, so every intermediate is consumed while
+    // it is still in L2 instead of making a round trip through HBM
+    struct Chunk { int tile_lo, tile_hi; int part, blk; bool medium; int g_lo, g_hi; int cut_lo, cut_hi; };
+    std::vector<Chunk> chunks;
+    bool blocked = false;
+    int block_lanes = 1;
     bool dbf_tma2 = false;                // RSP_DBF=tma2: stand-alone TMA-tensor-fed DBF (dbf_tma2_kernel)
     int dbf_tma2_tiles = 8;               // tiles per CTA (RSP_DBF_TMA2_TILES)
     const float2* exp_raw = nullptr;      // RSP_EXP_MERGE experiment: the cube whose DBF rides inside the PC launch
@@ -291,6 +298,7 @@ static cudaError_t mtd_opt_in(int P, size_t bytes) {
 
 static void plan_dbf_pc(rsp_ctx* c);
 static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k);
+static void plan_blocking(rsp_ctx* c);
 
 extern "C" {
 
@@ -605,6 +613,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
     c->delta_v = k->delta_v;
     plan_dbf_pc(c);
     if (int rc_tc = plan_dbf_tc(c, k)) return rc_tc;
+    plan_blocking(c);
     c->have_constants = true;
     return RSP_OK;
 }
@@ -889,15 +898,23 @@ static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
     return RSP_OK;
 }
 
-static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count) {
+static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile_lo = 0, int tile_hi = -1) {
     const CUtensorMap* map = raw_tmap(c, raw, TMAP_ROWS_2D);
     if (!map) return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
     DbfTcArgs a = c->dbf_tc_args;
     a.beam = c->cur->beam;
     a.det_count = det_count;
     a.dead = dead_amp(c);
+    a.tile_lo = tile_lo; a.tile_hi = tile_hi < 0 ? a.tiles_per_pulse : tile_hi;
+    a.p_lo = 0; a.p_hi = c->P;
+    int grid = c->dbf_tc_grid;
+    if (tile_hi >= 0) {                        // a chunk of the range-blocked path
+        const int n_tiles = c->P * (a.tile_hi - a.tile_lo);
+        a.dead = DiscardArgs{nullptr, 0};
+        grid = a.chunk > 0 ? (n_tiles + a.chunk - 1) / a.chunk : std::min(grid, n_tiles);
+    }
     Timed t(c, K_DBF);
-#define RSP_TC_CASE(NP, CP) if (a.Npad == NP && a.Cpad == CP) dbf_tc_kernel<NP, CP><<<c->dbf_tc_grid, RSP_TC_THREADS, c->dbf_tc_smem, c->cur->s>>>(*map, a);
+#define RSP_TC_CASE(NP, CP) if (a.Npad == NP && a.Cpad == CP) dbf_tc_kernel<NP, CP><<<grid, RSP_TC_THREADS, c->dbf_tc_smem, c->cur->s>>>(*map, a);
     RSP_TC_CASE(16, 8) RSP_TC_CASE(16, 16) RSP_TC_CASE(16, 32) RSP_TC_CASE(32, 8) RSP_TC_CASE(32, 16) RSP_TC_CASE(32, 32)
 #undef RSP_TC_CASE
     return RSP_OK;
@@ -1035,19 +1052,21 @@ static void launch_pc(rsp_ctx* c) {
     }
 }
 
-static void launch_mtd(rsp_ctx* c, float2* rdm) {
+static void launch_mtd(rsp_ctx* c, float2* rdm, int g_lo = 0, int g_hi = -1) {
     MtdArgs a;
     a.pc = c->cur->pc; a.rdm = rdm; a.amp = c->cur->amp; a.win = c->d_win; a.tw = c->d_dop_tw; a.perm = c->d_dop_perm;
     a.P = c->P; a.B = c->B; a.G = c->G; a.ldg = c->ldg;
-    a.dead = dead_beam(c);
+    a.dead = g_hi < 0 ? dead_beam(c) : DiscardArgs{nullptr, 0};
+    a.g_lo = g_lo; a.g_hi = g_hi < 0 ? c->G : g_hi;
+    const int ng = a.g_hi - a.g_lo;
     const int tg = c->mtd_tg;
-    dim3 grid((c->G + tg - 1) / tg, c->B);
+    dim3 grid((ng + tg - 1) / tg, c->B);
     Timed t(c, K_MTD);
     if (c->pow2_doppler && c->mtd_mode == 2 && c->P == 64 && (int)c->h_win.size() == c->P) {
         MtdRegArgs r;
         r.m = a;
         for (int p = 0; p < 64; ++p) r.win[p] = c->h_win[p];
-        dim3 sgrid((c->G + 31) / 32, c->B);
+        dim3 sgrid((ng + 31) / 32, c->B);
         { static const bool once = (prefer_max_smem(mtd64_kernel<true>), prefer_max_smem(mtd64_kernel<false>), true); (void)once; }
         if (c->mtd_approx_sqrt) mtd64_kernel<true><<<sgrid, 256, 0, c->cur->s>>>(r);
         else mtd64_kernel<false><<<sgrid, 256, 0, c->cur->s>>>(r);
@@ -1071,7 +1090,7 @@ static bool cfar_testable(const rsp_ctx* c) {
     return c->G - 2 * mR > 0 && c->P - 2 * mV > 0;      // else fsf:192-193 loop ranges are empty
 }
 
-static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
+static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot, int cut_lo = -1, int cut_hi = -1) {
     if (!cfar_testable(c)) return;
     CfarArgs a;
     a.amp = c->cur->amp; a.rdm = rdm;
@@ -1081,9 +1100,12 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot) {
     a.raw = c->d_rawdet + (size_t)slot * c->prm.max_detections;
     a.cap = c->prm.max_detections;
     a.complex_mode = c->prm.monopulse_complex;
-    a.dead = dead_pc(c);
+    a.dead = cut_lo < 0 ? dead_pc(c) : DiscardArgs{nullptr, 0};
     const int mR = c->prm.guard_r + c->prm.ref_r;
-    const int ncut = c->G - 2 * mR, tg = c->cfar_tg;
+    a.cut_lo = cut_lo < 0 ? mR : cut_lo;
+    a.cut_hi = cut_hi < 0 ? c->G - mR : cut_hi;
+    if (a.cut_hi <= a.cut_lo) return;
+    const int ncut = a.cut_hi - a.cut_lo, tg = c->cfar_tg;
     dim3 grid((ncut + tg - 1) / tg, c->B - 1);
     Timed t(c, K_CFAR);
 #define LAUNCH(K) K<<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->cur->s>>>(a);
@@ -1104,10 +1126,126 @@ static void launch_refine(rsp_ctx* c, int first, int n, cudaStream_t st) {
     refine_kernel<<<dim3(4, n), 128, 0, st>>>(r);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Range-blocked chain.  Chunk 0 = narrow + medium segments (gates [0, g1 + g2)); then one chunk per overlap-save block of
+// the long segment, in gate order.  Per chunk: DBF of the 128-sample tiles the block reads, the block's FFT . H . IFFT over
+// all lines, the Doppler FFT of its gates, and the CFAR of the cells whose range windows are complete (they trail the
+// Doppler stage by guard + ref gates).  The beam / pc / amplitude buffers keep their full size; only the chunk's part of
+// each is touched between two HBM-bound stages, so it is still in L2 when the next kernel reads it.
+// ------------------------------------------------------------------------------------------
+static void plan_blocking(rsp_ctx* c) {
+    c->blocked = false;
+    c->chunks.clear();
+    // Opt-in (RSP_BLOCK=1): measured at config 3, where beam + pc cubes are 500 MB, the chunked chain is SLOWER than the
+    // whole-CPI kernels (631 vs 526 us per CPI on one lane, 541 on three; profiles/r2_block_cfg3.txt): every stage loses
+    // more to its five short launches than it gains from reading its input out of L2.  Kept because it is exact
+    // (bit-identical, tested) and is the scaffolding a fused per-chunk kernel would need.
+    const char* e = getenv("RSP_BLOCK");
+    const bool want = e && atoi(e) != 0;
+    if (!want || !c->dbf_tc || c->dbf_pc_ok || !c->lng.L) return;
+    { const char* el = getenv("RSP_BLOCK_LANES"); c->block_lanes = el ? std::max(1, std::min(8, atoi(el))) : 1; }
+    const int mR = c->prm.guard_r + c->prm.ref_r;
+    const int g12 = c->prm.n_gates[0] + c->prm.n_gates[1];
+    auto tiles_of = [&](int s_lo, int s_hi, int& tl, int& th) {
+        tl = std::max(0, s_lo) / RSP_TC_TILE;
+        th = std::min((std::min(s_hi, c->N) + RSP_TC_TILE - 1) / RSP_TC_TILE, c->dbf_tc_args.tiles_per_pulse);
+    };
+    int cut = mR;
+    auto push = [&](rsp_ctx::Chunk ch) {
+        ch.cut_lo = cut;
+        ch.cut_hi = std::max(cut, std::min(ch.g_hi == c->G ? c->G - mR : ch.g_hi - mR, c->G - mR));
+        cut = ch.cut_hi;
+        c->chunks.push_back(ch);
+    };
+    if (g12 > 0) {                                                          // narrow FIR + medium block(s)
+        rsp_ctx::Chunk ch{};
+        int s_hi = c->prm.seg_start[0] - 1 + c->prm.n_gates[0] + c->prm.fir_delay + c->n_fir;
+        if (c->med.L) s_hi = std::max(s_hi, c->med.seg_start0 + c->med.gate0 - (c->med.taps - 1) + (c->med.nblk - 1) * c->med.valid + c->med.L);
+        tiles_of(0, s_hi, ch.tile_lo, ch.tile_hi);
+        ch.medium = true; ch.part = -1; ch.blk = 0; ch.g_lo = 0; ch.g_hi = g12;
+        push(ch);
+    }
+    const PcPlan* parts[3] = {&c->lng, &c->lngx[0], &c->lngx[1]};
+    for (int q = 0; q < 3; ++q) {
+        const PcPlan& pl = *parts[q];
+        if (!pl.L) continue;
+        for (int b = 0; b < pl.nblk; ++b) {
+            rsp_ctx::Chunk ch{};
+            const int g0 = pl.gate0 + b * pl.valid;
+            const int s0 = pl.seg_start0 + g0 - (pl.taps - 1);
+            tiles_of(s0, s0 + pl.L, ch.tile_lo, ch.tile_hi);
+            ch.medium = false; ch.part = q; ch.blk = b;
+            ch.g_lo = g0; ch.g_hi = std::min(g0 + pl.valid, pl.gate0 + pl.ngates);
+            push(ch);
+        }
+    }
+    if (c->chunks.empty() || c->chunks.back().g_hi != c->G) { c->chunks.clear(); return; }
+    c->blocked = true;
+}
+
+static void launch_pc_chunk(rsp_ctx* c, const rsp_ctx::Chunk& ch) {
+    PcKernelArgs a;
+    a.beam = c->cur->beam; a.pc = c->cur->pc; a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
+    a.group_bar = c->pc_group_bar;
+    a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
+    a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
+    PcPlan none;
+    int la = 1024, lb = 1024;
+    if (ch.medium) {
+        const bool narrow = c->prm.n_gates[0] > 0;
+        if (narrow && !c->med.L) {
+            Timed t(c, K_PC_NARROW);
+            pc_narrow_kernel<<<c->P * c->B, 256, 0, c->cur->s>>>(c->cur->beam, c->cur->pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
+                                                                 c->ldb, c->ldg, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
+            return;
+        }
+        if (!c->med.L) return;
+        fill_seg(c, a.seg[0], none, nullptr, nullptr, nullptr);
+        fill_seg(c, a.seg[1], c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H);
+        a.do_narrow = narrow ? 1 : 0;
+        lb = c->med.L;
+    } else {
+        const PcPlan* parts[3] = {&c->lng, &c->lngx[0], &c->lngx[1]};
+        const float2* tw1[3] = {c->d_lng_tw1, c->d_lngx_tw1[0], c->d_lngx_tw1[1]};
+        const float2* tw2[3] = {c->d_lng_tw2, c->d_lngx_tw2[0], c->d_lngx_tw2[1]};
+        const float2* H[3] = {c->d_lng_H, c->d_lngx_H[0], c->d_lngx_H[1]};
+        const PcPlan& pl = *parts[ch.part];
+        fill_seg(c, a.seg[0], pl, tw1[ch.part], tw2[ch.part], H[ch.part]);
+        // one block of every line: block index 0 of a segment that starts at this block's first gate
+        a.seg[0].gate0 = pl.gate0 + ch.blk * pl.valid;
+        a.seg[0].nblk = 1;
+        a.seg[0].n_items = c->P * c->B;
+        a.seg[0].n_ctas = (a.seg[0].n_items + RSP_PC_THREADS / pl.T - 1) / (RSP_PC_THREADS / pl.T);
+        fill_seg(c, a.seg[1], none, nullptr, nullptr, nullptr);
+        a.do_narrow = 0;
+        la = pl.L;
+    }
+    const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
+    if (nctas == 0) return;
+    Timed t(c, K_PC);
+#define X(A, B) if (la == A::L && lb == B::L) pc_fft_kernel<A, B><<<nctas, RSP_PC_THREADS, pc_smem_pair<A, B>(), c->cur->s>>>(a);
+    RSP_FOR_EACH_PC_PAIR(X)
+#undef X
+}
+
+static int enqueue_chain_blocked(rsp_ctx* c, const float2* raw, float2* rdm, int slot) {
+    bool first = true;
+    for (const rsp_ctx::Chunk& ch : c->chunks) {
+        if (int rc = launch_dbf_tc(c, raw, first ? c->d_counts + slot : nullptr, ch.tile_lo, ch.tile_hi)) return rc;
+        first = false;
+        launch_pc_chunk(c, ch);
+        launch_mtd(c, rdm, ch.g_lo, ch.g_hi);
+        if (cfar_testable(c)) launch_cfar(c, rdm, slot, ch.cut_lo, ch.cut_hi);
+    }
+    return RSP_OK;
+}
+
 static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
     int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + (c->lngx[0].L ? 1 : 0) + 1 /*mtd*/;
     if (c->dbf_pc_ok) n = 1 /*dbf_pc*/ + 1 /*mtd*/;
+    if (c->blocked) return (int)c->chunks.size() * (cfar_testable(c) ? 4 : 3);
     if (cfar_testable(c)) n += 1;   // cfar (S9 is one refine launch per batch, not per CPI)
     return n;
 }
@@ -1120,6 +1258,14 @@ static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, i
     // leaves stages out so that the steady-state cost of each kernel on the lanes can be timed in isolation.
     const int stages = c->stages;
     int rc = RSP_OK;
+    const bool frame_ctx = c->have_waveform && c->dbf_nt && c->dbf_wa && (c->N % 2 == 0);      // see launch_dbf_any
+    if (c->blocked && !c->fused && !frame_ctx && stages == 15 && !c->keep_beam && !(reinterpret_cast<uintptr_t>(raw) & 15)) {
+        rc = enqueue_chain_blocked(c, raw, rdm, slot);
+        c->cur = &c->lanes[0];
+        if (rc) return rc;
+        CU(c, cudaGetLastError());
+        return RSP_OK;
+    }
     if (c->dbf_pc_ok && !c->fused && (stages & 3) == 3) {
         rc = launch_dbf_pc(c, raw, c->d_counts + slot);                   // S5 + S6 in one launch; zeroes the slot's counter
         if (rc) return rc;
@@ -1277,7 +1423,7 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
         return fail(c, RSP_ERR_INVALID_ARG, "slots [%d,%d) exceed the ring of %d", first_slot, first_slot + n_cpi, c->slots);
     CU(c, cudaSetDevice(c->prm.device));
     const size_t in_elems = (size_t)c->P * c->C * c->N, out_elems = (size_t)c->P * c->B * c->G;
-    const int nl = std::min(c->n_lanes, std::max(n_cpi, 1));
+    const int nl = std::min(c->blocked ? std::min(c->n_lanes, c->block_lanes) : c->n_lanes, std::max(n_cpi, 1));
     // Up to nl CPIs are in flight at once, one per lane: their range-Doppler maps must not share a buffer (MTD of CPI i + 1
     // would race with MTD and CFAR of CPI i).  A caller ring needs at least nl buffers, n_cpi > rdm_pool needs
     // rdm_pool % nl == 0 (CPI i goes to lane i % nl and to buffer i % rdm_pool); without a ring every lane uses its own map.

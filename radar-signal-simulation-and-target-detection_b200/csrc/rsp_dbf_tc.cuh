@@ -39,6 +39,8 @@ struct DbfTcArgs {
     int stages;              // ring depth
     int tiles_per_pulse;     // ceil(N / 128)
     int chunk;               // > 0: CTA j owns the contiguous tiles [j chunk, (j + 1) chunk); 0: persistent, tile = j + i gridDim
+    int tile_lo, tile_hi;    // tiles [tile_lo, tile_hi) of every pulse (the whole line: 0, tiles_per_pulse; range-blocked path: a chunk)
+    int p_lo, p_hi;          // pulses [p_lo, p_hi)
     int dbg;                 // RSP_TC_DEBUG measurement aid (results wrong): 1 no MMAs, 2 no beam stores, 4 no conversion, 8 no proxy fence, 16 one MMA term
     DiscardArgs dead;
 };
@@ -153,7 +155,8 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    const int n_tiles = k.P * k.tiles_per_pulse;
+    const int tpp = k.tile_hi - k.tile_lo;                                   // tiles per pulse of this launch
+    const int n_tiles = (k.p_hi - k.p_lo) * tpp;
     const int first = k.chunk > 0 ? blockIdx.x * k.chunk : blockIdx.x, step = k.chunk > 0 ? 1 : gridDim.x;
     const int n_my = first >= n_tiles ? 0 : k.chunk > 0 ? min(k.chunk, n_tiles - first) : (n_tiles - first + step - 1) / step;
 
@@ -164,7 +167,7 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
                 const int s = i % NS, round = i / NS;
                 if (round > 0) mbar_wait(BAR(NS + s), (uint32_t)(round - 1) & 1u);
                 const int tile = first + i * step;
-                const int p = tile / k.tiles_per_pulse, n0 = (tile - p * k.tiles_per_pulse) * RSP_TC_TILE;
+                const int pr = tile / tpp, p = k.p_lo + pr, n0 = (k.tile_lo + tile - pr * tpp) * RSP_TC_TILE;
                 mbar_expect_tx(BAR(s), raw_stage);
                 tma_load_2d(smem_u32(s_raw) + (uint32_t)s * raw_stage, &tmap, 2 * n0, p * C, BAR(s));
             }
@@ -209,7 +212,7 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
         l2_discard(k.dead);
         auto epilogue = [&](int i) {
             const int tile = first + i * step;
-            const int p = tile / k.tiles_per_pulse, n = (tile - p * k.tiles_per_pulse) * RSP_TC_TILE + m;
+            const int pr = tile / tpp, p = k.p_lo + pr, n = (k.tile_lo + tile - pr * tpp) * RSP_TC_TILE + m;
             float2* dst = k.beam + (size_t)p * k.B * k.ldb + n;
 #pragma unroll
             for (int h = 0; h < NPAD / 16; ++h) {                        // 16 accumulator columns = 8 beams at a time

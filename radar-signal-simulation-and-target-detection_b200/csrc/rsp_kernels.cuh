@@ -854,6 +854,7 @@ struct MtdArgs {
     const int* perm;       // pow2 only: iperm[pos] = pulse stored at position pos
     int P;
     int B, G, ldg;
+    int g_lo, g_hi;        // gates [g_lo, g_hi) of this launch (the whole map: 0, G; range-blocked path: one chunk)
     DiscardArgs dead;      // buffer whose last reader has finished (the beam cube), or {nullptr, 0}
 };
 
@@ -866,9 +867,9 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
     float2* stw = mtd_smem + P * (TG + 1);         // [Cfg::TW_COUNT]
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < Cfg::TW_COUNT; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
-    const int g0 = blockIdx.x * TG, b = blockIdx.y;
+    const int g0 = k.g_lo + blockIdx.x * TG, b = blockIdx.y;
     // innermost pass straight from global memory
-    mtd_first_pass_t<Cfg>(tile, k.pc + (size_t)b * k.ldg + g0, (size_t)k.B * k.ldg, k.win, g0 + lane < k.G, tid);
+    mtd_first_pass_t<Cfg>(tile, k.pc + (size_t)b * k.ldg + g0, (size_t)k.B * k.ldg, k.win, g0 + lane < k.g_hi, tid);
     __syncthreads();
     if (MtdInner<Cfg>::PASS < 1 && Cfg::R1 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 1); __syncthreads(); }
     if (MtdInner<Cfg>::PASS < 2) { mtd_passes_phase<Cfg>(tile, stw, tid, 2); __syncthreads(); }
@@ -876,7 +877,7 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
 #pragma unroll 4
     for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {
         const int gl = e / P, row = e - gl * P;          // P is a compile-time power of two
-        if (g0 + gl < k.G) {
+        if (g0 + gl < k.g_hi) {
             const float2 v = tile[row * (TG + 1) + gl];
             const size_t o = ((size_t)b * k.G + g0 + gl) * P + row;
             __stcs(k.rdm + o, v);
@@ -948,11 +949,11 @@ __global__ void __launch_bounds__(256, 8) mtd64_kernel(const __grid_constant__ M
     float2* const S1 = S2;
     l2_discard(k.m.dead);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b = blockIdx.y, G = k.m.G, g0 = blockIdx.x * 32;
+    const int b = blockIdx.y, G = k.m.G, g0 = k.m.g_lo + blockIdx.x * 32, g_hi = k.m.g_hi;
     {   // phase 1: the warp index picks the compile-time instance, so window and twiddles are immediates
         const int g = g0 + lane;
         const unsigned pstride = (unsigned)k.m.B * (unsigned)k.m.ldg;
-        const float2* src = k.m.pc + (size_t)b * k.m.ldg + (g < G ? g : G - 1) + (size_t)w * pstride;
+        const float2* src = k.m.pc + (size_t)b * k.m.ldg + (g < g_hi ? g : g_hi - 1) + (size_t)w * pstride;
         switch (w) {
             case 0: mtd64_phase1<0>(k, src, pstride, S1, lane); break;
             case 1: mtd64_phase1<1>(k, src, pstride, S1, lane); break;
@@ -980,7 +981,7 @@ __global__ void __launch_bounds__(256, 8) mtd64_kernel(const __grid_constant__ M
         const size_t o = ((size_t)b * G + g0) * 64 + threadIdx.x;
         float2* rdm = k.m.rdm + o;
         float* amp = k.m.amp + o;
-        const int rows = G - g0;                 // gates of this tile that exist (>= 1)
+        const int rows = g_hi - g0;              // gates of this tile that exist (>= 1)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int gl = glb + 4 * i;
@@ -1009,11 +1010,11 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_c
     float2* stw = xout + (size_t)P * (TG + 1);
     const int tid = threadIdx.x;
     for (int i = tid; i < P; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
-    const int g0 = blockIdx.x * TG, b = blockIdx.y;
+    const int g0 = k.g_lo + blockIdx.x * TG, b = blockIdx.y;
     for (int e = tid; e < P * TG; e += RSP_MTD_THREADS) {
         const int p = e / TG, gl = e - p * TG, g = g0 + gl;
         float2 x = make_float2(0.f, 0.f);
-        if (g < k.G) x = k.pc[((size_t)p * k.B + b) * k.ldg + g];
+        if (g < k.g_hi) x = k.pc[((size_t)p * k.B + b) * k.ldg + g];
         xin[p * (TG + 1) + gl] = cscale(x, k.win[p]);
     }
     __syncthreads();
@@ -1032,7 +1033,7 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_c
     __syncthreads();
     for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {
         const int gl = e / P, row = e - gl * P, g = g0 + gl;
-        if (g < k.G) {
+        if (g < k.g_hi) {
             const float2 v = xout[row * (TG + 1) + gl];
             const size_t o = ((size_t)b * k.G + g) * P + row;
             __stcs(k.rdm + o, v);
@@ -1073,6 +1074,7 @@ struct CfarArgs {
     RawDet* raw;                 // raw records of this CPI slot
     int cap;
     int complex_mode;
+    int cut_lo, cut_hi;          // cells under test: gates [cut_lo, cut_hi) (the whole map: mR, G - mR; range-blocked path: a chunk)
     DiscardArgs dead;            // the pc cube (its last reader, mtd_kernel, has finished)
 };
 
@@ -1109,7 +1111,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k
     float* R5 = S + rows * P;
     float* D5 = R5 + cfar_r5_rows(k.c, TG) * P;
     const int pair = blockIdx.y;
-    const int g_first = mR + blockIdx.x * TG;
+    const int g_first = k.cut_lo + blockIdx.x * TG;
     const int tid = threadIdx.x;
     const float* A = k.amp + (size_t)pair * G * P;
     const float* Bm = A + (size_t)G * P;
@@ -1122,7 +1124,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS) cfar_kernel(const CfarArgs k
     const int nv = P - 2 * mV;                       // CUT columns [mV, P - mV)
     for (int e = tid; e < TG * nv; e += RSP_CFAR_THREADS) {
         const int gl = e / nv, v = mV + (e - gl * nv), g = g_first + gl;
-        if (g >= G - mR) break;
+        if (g >= k.cut_hi) break;
         float cut;
         if (cfar_decide(S, R5, D5, k.c, gl, v, &cut)) cfar_emit(k, S + (gl + mR) * P, P, v, g, pair, cut);
     }
@@ -1143,7 +1145,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(
     float* S = cfar_smem;                       // [rows][PP]
     float* R5 = S + g.rows * g.PP;              // [r5_rows][RP]
     const int pair = blockIdx.y;
-    const int g_first = mR + blockIdx.x * TG;
+    const int g_first = k.cut_lo + blockIdx.x * TG;
     const int tid = threadIdx.x;
     const float4* A4 = reinterpret_cast<const float4*>(k.amp + ((size_t)pair * G + (g_first - mR)) * P);
     const float4* B4 = A4 + (size_t)G * g.P4;
@@ -1182,7 +1184,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(
     cfar4_r5_phase<RR>(S, R5, k.c, g, tid, RSP_CFAR_THREADS);
     __syncthreads();
     const int c_lo = mV / 4, nq = (P - mV - 1) / 4 - c_lo + 1;            // quads holding at least one CUT
-    const int gl_end = min(TG, G - mR - g_first);
+    const int gl_end = min(TG, k.cut_hi - g_first);
     for (int idx = tid; idx < gl_end * nq; idx += RSP_CFAR_THREADS) {
         const int gl = idx / nq, c4 = c_lo + (idx - gl * nq);
         float cut[4];

@@ -753,3 +753,35 @@ def test_stage2_chain_range_cfar_on_the_device_maps():
         assert diff.sum() <= 2 and np.all(np.abs(np.abs(mtd[:, :, b])[diff] - t_ref[diff]) <= 1e-5 * t_ref[diff])
     assert flag[:, 1500, 0].any()
     ch.close()
+
+
+@pytest.mark.parametrize("name,force", [("cfg3", "1"), ("cfg2", "1"), ("cfg1", "1")])
+def test_range_blocked_stream_equals_the_whole_cpi_chain(name, force):
+    """RSP_BLOCK=1 runs the stream path in range chunks -- DBF tiles, one overlap-save block, the Doppler FFT and the CFAR of
+    that block's gates per chunk -- so that every intermediate is consumed out of L2 (opt-in: measured slower than the
+    whole-CPI kernels).  Same kernels on sub-ranges: detections and range-Doppler map must equal the whole-CPI
+    chain (rsp_process_cpi) bit for bit on config 3, config 2 (mixed block plan: 4096 + 2048 + 1024) and config 1."""
+    import os
+    import torch
+    if force:
+        os.environ["RSP_BLOCK"] = force
+    try:
+        chain, config, cfar_params, cluster_params, pd = _device_chain(name)
+    finally:
+        os.environ.pop("RSP_BLOCK", None)
+    cubes = [o.make_cube(name, s)[2] for s in (0, 1)]
+    single, maps = [], []
+    for c in cubes:
+        single.append(chain.process_cpi(c))
+        maps.append(chain.get_rdm())
+    lanes = chain.info()["lanes"]
+    assert chain.info()["kernels_per_cpi"] > 6, "the range-blocked plan was not selected"
+    pool = torch.from_numpy(np.stack(cubes)).cuda()
+    rdm = torch.empty((lanes, chain.B, chain.G, chain.P), dtype=torch.complex64, device="cuda")
+    chain.stream_enqueue(pool.data_ptr(), 2, rdm.data_ptr(), lanes, lanes, 0)
+    chain.synchronize()
+    for i in range(lanes):
+        assert np.array_equal(chain.stream_fetch(i), single[i % 2]), i
+        assert np.array_equal(rdm[i].cpu().numpy(), maps[i % 2]), i
+    assert len(single[0]) >= 50
+    chain.close()
