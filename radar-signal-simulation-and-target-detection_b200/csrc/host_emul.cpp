@@ -317,6 +317,47 @@ int emul_cfar4_map(const float* S, int G, int P, int guard_r, int guard_v, int r
     return 0;
 }
 
+// Marching CFAR (cfar5_kernel): uninitialised pad columns (NaN here), chunk-major items, range test first, queued Doppler test.
+int emul_cfar5_map(const float* S, int G, int P, int guard_r, int guard_v, int ref_r, int ref_v, float t_cfar, int TG,
+                   unsigned char* det /* [G][P] */) {
+    const int p4 = P / 4;
+    if (P % 4 || (p4 & (p4 - 1)) || ref_r != 5 || !((ref_v == 5 && guard_v == 10) || (ref_v == 4 && guard_v == 2))) return -1;
+    CfarParams c;
+    c.P = P; c.G = G; c.guard_r = guard_r; c.guard_v = guard_v; c.ref_r = ref_r; c.ref_v = ref_v; c.t_cfar = t_cfar;
+    constexpr int CR = RSP_CFAR5_CR;
+    const int mR = guard_r + ref_r, mV = guard_v + ref_v, rows = TG + 2 * mR;
+    const int pitch = cfar5_pitch(P, mV), nq = cfar5_nq(P, mV), c_lo = mV / 4;
+    if (((CR * (pitch / 4) - nq) & 7) || pitch < P + 2 * RSP_CFAR5_HALO) return -2;
+    std::memset(det, 0, (size_t)G * P);
+    std::vector<float> tile((size_t)rows * pitch);
+    for (int g_first = mR; g_first < G - mR; g_first += TG) {
+        std::fill(tile.begin(), tile.end(), std::nanf(""));
+        for (int row = 0; row < rows; ++row) {
+            const int gg = g_first - mR + row;
+            for (int v = 0; v < P; ++v) tile[(size_t)row * pitch + RSP_CFAR5_HALO + v] = gg < G ? S[(size_t)gg * P + v] : 0.f;
+        }
+        const int gl_end = std::min(TG, G - mR - g_first);
+        const int n_items = ((gl_end + CR - 1) / CR) * nq;
+        std::vector<unsigned> queue;
+        for (int it = 0; it < n_items; ++it) {
+            const int ch = it / nq, c4 = c_lo + (it - ch * nq), gl0 = ch * CR;
+            auto hit = [&](int s, unsigned m) { queue.push_back(((unsigned)(gl0 + s) << 16) | ((unsigned)c4 << 4) | m); };
+            if (ref_v == 5) cfar5_march<5, 15, CR>(tile.data(), pitch, c, gl0, std::min(CR, gl_end - gl0), c4, hit);
+            else cfar5_march<5, 6, CR>(tile.data(), pitch, c, gl0, std::min(CR, gl_end - gl0), c4, hit);
+        }
+        const float kv = t_cfar / (float)ref_v;
+        for (unsigned w : queue) {
+            const int gl = (int)(w >> 16), c4 = (int)((w >> 4) & 0xFFFu);
+            const float* row0 = tile.data() + (size_t)(gl + mR) * pitch + RSP_CFAR5_HALO;
+            float4 cq;
+            const unsigned m = ref_v == 5 ? cfar5_doppler<5, 10>(row0 + 4 * c4, kv, w & 15u, &cq) : cfar5_doppler<4, 2>(row0 + 4 * c4, kv, w & 15u, &cq);
+            for (int j = 0; j < 4; ++j)
+                if (m & (1u << j)) det[(size_t)(g_first + gl) * P + 4 * c4 + j] = 1;
+        }
+    }
+    return 0;
+}
+
 double emul_spline5_peak(const double* y, int os) { return rsp_spline5_peak(y, os); }
 
 int emul_digit_reverse(int f, int L, const int* radices, int nrad) { return rsp_digit_reverse(f, L, radices, nrad); }

@@ -99,6 +99,7 @@ struct rsp_ctx {
     int dbf_tma2_tiles = 8;               // tiles per CTA (RSP_DBF_TMA2_TILES)
     const float2* exp_raw = nullptr;      // RSP_EXP_MERGE experiment: the cube whose DBF rides inside the PC launch
     float2* exp_beam = nullptr;
+    long exp_multi_count = 0;             // RSP_EXP_DBF_MULTI experiment
     int dbf_pc_clusters = 0;              // cudaOccupancyMaxActiveClusters of the fused kernel
     struct TmapEntry { const void* ptr; int mode; CUtensorMap map; };
     std::vector<TmapEntry> tmaps;         // tensor maps of the raw cubes seen so far (keyed by device pointer)
@@ -160,6 +161,7 @@ struct rsp_ctx {
     std::vector<char> slot_prefetched;
     int mtd_tg = 32, mtd_r = 1, mtd_kt = 1, cfar_tg = 32, cfar_variant = 0;
     bool cfar_vec = false;
+    bool cfar5 = false;                   // cfar5_kernel (marching) instead of cfar4_kernel
     size_t mtd_smem = 0, cfar_smem = 0;
     // per-kernel event timing (rsp_set_profiling)
     bool profiling = false;
@@ -235,7 +237,9 @@ template <typename KernelT> static cudaError_t opt_in_smem(KernelT kern, size_t 
 // of other lanes then keep their share of the SM (measured: CFAR at 4 CTAs/SM costs the chain 10 %).
 static size_t smem_for_occupancy(size_t needed, int max_ctas_per_sm) {
     if (max_ctas_per_sm <= 0) return needed;
-    const size_t per_sm = 227 * 1024;
+    // RSP_SMEM_RESERVE_KB: shared memory left free beside the capped CTAs (room for a co-resident kernel of another stream)
+    static const size_t reserve = [] { const char* e = getenv("RSP_SMEM_RESERVE_KB"); return (size_t)(e ? atoi(e) : 0) * 1024; }();
+    const size_t per_sm = 227 * 1024 - reserve;
     size_t pad_to = per_sm / (size_t)(max_ctas_per_sm + 1) + 1024;               // max_ctas + 1 no longer fit
     pad_to = std::min(pad_to, per_sm / (size_t)max_ctas_per_sm - 2048);          // ... but max_ctas still do
     return std::max(needed, pad_to);                                             // never below what the kernel uses
@@ -598,8 +602,28 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         else if (c->cfar_variant == 1) { ACTION((cfar4_kernel<TGV, 5, 5, 10>)) }                \
         else if (c->cfar_variant == 2) { ACTION((cfar4_kernel<TGV, 5, 4, 2>)) }                 \
         else { ACTION((cfar4_kernel<TGV, 0, 0, 0>)) }
+#define RSP_CFAR5_CASE(TGV, ACTION)                                                             \
+        if (c->cfar_tg == TGV) {                                                                \
+            if (c->cfar_variant == 1) { ACTION((cfar5_kernel<TGV, 5, 5, 10>)) }                     \
+            else { ACTION((cfar5_kernel<TGV, 5, 4, 2>)) }                                           \
+        }
+#define RSP_CFAR5_DISPATCH(ACTION) RSP_CFAR5_CASE(40, ACTION) RSP_CFAR5_CASE(80, ACTION) RSP_CFAR5_CASE(120, ACTION)
 #define OPTIN(K) CU(c, opt_in_smem(K, c->cfar_smem));
-        if (c->cfar_tg == 64) { RSP_CFAR_DISPATCH(64, OPTIN) }
+        // marching kernel (cfar5_kernel): compile-time windows, P / 4 a power of two; RSP_CFAR=quad keeps cfar4_kernel
+        const int p4 = P / 4;
+        { const char* e = getenv("RSP_CFAR"); c->cfar5 = c->cfar_vec && c->cfar_variant != 0 && p4 >= 1 && p4 <= RSP_CFAR_THREADS && (p4 & (p4 - 1)) == 0 && !(e && !strcmp(e, "quad")); }
+        if (c->cfar5) {
+            const int mV = c->prm.guard_v + c->prm.ref_v;
+            auto smem5 = [&](int tg) { return ((size_t)(tg + 2 * mR) * cfar5_pitch(P, mV) + 1 + (size_t)tg * cfar5_nq(P, mV)) * sizeof(float); };
+            c->cfar_tg = 40;
+            for (int tg : {120, 80, 40})          // measured at config 2: 120 > 80 > 40 (profiles/r2d_cfar5_ab.txt)
+                if (smem5(tg) <= 72 * 1024) { c->cfar_tg = tg; break; }
+            if (const char* e = getenv("RSP_CFAR5_TG")) { const int v = atoi(e); if (v == 40 || v == 80 || v == 120) c->cfar_tg = v; }
+            c->cfar_smem = smem5(c->cfar_tg);
+            if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
+            RSP_CFAR5_DISPATCH(OPTIN)
+        }
+        else if (c->cfar_tg == 64) { RSP_CFAR_DISPATCH(64, OPTIN) }
         else if (c->cfar_tg == 32) { RSP_CFAR_DISPATCH(32, OPTIN) }
         else { RSP_CFAR_DISPATCH(16, OPTIN) }
 #undef OPTIN
@@ -890,7 +914,7 @@ static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
     if (const char* ec = getenv("RSP_TC_CHUNK")) a.chunk = std::max(0, atoi(ec));
     if (a.chunk > 0) c->dbf_tc_grid = (c->P * a.tiles_per_pulse + a.chunk - 1) / a.chunk;
     cudaError_t err = cudaErrorInvalidValue;
-#define RSP_TC_CASE(NP, CP) if (a.Npad == NP && a.Cpad == CP) err = cudaFuncSetAttribute(dbf_tc_kernel<NP, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dbf_tc_smem);
+#define RSP_TC_CASE(NP, CP) if (a.Npad == NP && a.Cpad == CP) { prefer_max_smem(dbf_tc_kernel<NP, CP>); err = cudaFuncSetAttribute(dbf_tc_kernel<NP, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dbf_tc_smem); }
     RSP_TC_CASE(16, 8) RSP_TC_CASE(16, 16) RSP_TC_CASE(16, 32) RSP_TC_CASE(32, 8) RSP_TC_CASE(32, 16) RSP_TC_CASE(32, 32)
 #undef RSP_TC_CASE
     if (err != cudaSuccess) { cudaGetLastError(); return RSP_OK; }
@@ -913,6 +937,33 @@ static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile
         a.dead = DiscardArgs{nullptr, 0};
         grid = a.chunk > 0 ? (n_tiles + a.chunk - 1) / a.chunk : std::min(grid, n_tiles);
     }
+#ifdef RSP_PROBES
+    // Experiment RSP_EXP_DBF_MULTI=K (tools/overlap_probe.py): ONE persistent launch forms the beams of K consecutive cubes of
+    // the input pool (the launches of the other K - 1 CPIs are skipped), writing into a two-deep scratch ring, so that the
+    // DBF CTAs stay resident while the kernels of another context come and go: do they share the SMs?
+    static const int exp_multi = probe_env("RSP_EXP_DBF_MULTI", 0);
+    static CUtensorMap multi_map;
+    if (exp_multi > 1 && tile_hi < 0) {
+        if ((c->exp_multi_count++ % exp_multi) != 0) return RSP_OK;
+        const cuuint64_t dims[2] = {2 * (cuuint64_t)c->N, (cuuint64_t)c->C * c->P * exp_multi};
+        const cuuint64_t strides[1] = {(cuuint64_t)c->N * 8};
+        const cuuint32_t box[2] = {256u, (cuuint32_t)c->C};
+        const cuuint32_t es[2] = {1, 1};
+        if (encode_tiled_fn()(&multi_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(raw), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(c, RSP_ERR_CUDA, "multi-CPI tensor map");
+        map = &multi_map;
+        if (!c->exp_beam) cudaMalloc(reinterpret_cast<void**>(&c->exp_beam), (size_t)2 * c->P * c->B * c->ldb * sizeof(float2));
+        a.beam = c->exp_beam;
+        a.p_hi = c->P * exp_multi;
+        a.p_wrap = 2 * c->P;
+        a.chunk = 0;
+        a.dead = DiscardArgs{nullptr, 0};
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->prm.device);
+        grid = nsm;
+    }
+#endif
     Timed t(c, K_DBF);
 #define RSP_TC_CASE(NP, CP) if (a.Npad == NP && a.Cpad == CP) dbf_tc_kernel<NP, CP><<<grid, RSP_TC_THREADS, c->dbf_tc_smem, c->cur->s>>>(*map, a);
     RSP_TC_CASE(16, 8) RSP_TC_CASE(16, 16) RSP_TC_CASE(16, 32) RSP_TC_CASE(32, 8) RSP_TC_CASE(32, 16) RSP_TC_CASE(32, 32)
@@ -1109,7 +1160,8 @@ static void launch_cfar(rsp_ctx* c, const float2* rdm, int slot, int cut_lo = -1
     dim3 grid((ncut + tg - 1) / tg, c->B - 1);
     Timed t(c, K_CFAR);
 #define LAUNCH(K) K<<<grid, RSP_CFAR_THREADS, c->cfar_smem, c->cur->s>>>(a);
-    if (tg == 64) { RSP_CFAR_DISPATCH(64, LAUNCH) }
+    if (c->cfar5) { RSP_CFAR5_DISPATCH(LAUNCH) }
+    else if (tg == 64) { RSP_CFAR_DISPATCH(64, LAUNCH) }
     else if (tg == 32) { RSP_CFAR_DISPATCH(32, LAUNCH) }
     else { RSP_CFAR_DISPATCH(16, LAUNCH) }
 #undef LAUNCH

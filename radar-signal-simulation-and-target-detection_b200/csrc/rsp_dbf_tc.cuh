@@ -41,6 +41,7 @@ struct DbfTcArgs {
     int chunk;               // > 0: CTA j owns the contiguous tiles [j chunk, (j + 1) chunk); 0: persistent, tile = j + i gridDim
     int tile_lo, tile_hi;    // tiles [tile_lo, tile_hi) of every pulse (the whole line: 0, tiles_per_pulse; range-blocked path: a chunk)
     int p_lo, p_hi;          // pulses [p_lo, p_hi)
+    int p_wrap;              // RSP_PROBES builds: > 0 writes pulse p to beam row p % p_wrap (multi-CPI experiment)
     int dbg;                 // RSP_TC_DEBUG measurement aid (results wrong): 1 no MMAs, 2 no beam stores, 4 no conversion, 8 no proxy fence, 16 one MMA term
     DiscardArgs dead;
 };
@@ -213,7 +214,11 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
         auto epilogue = [&](int i) {
             const int tile = first + i * step;
             const int pr = tile / tpp, p = k.p_lo + pr, n = (k.tile_lo + tile - pr * tpp) * RSP_TC_TILE + m;
+#ifdef RSP_PROBES
+            float2* dst = k.beam + (size_t)(k.p_wrap > 0 ? p % k.p_wrap : p) * k.B * k.ldb + n;
+#else
             float2* dst = k.beam + (size_t)p * k.B * k.ldb + n;
+#endif
 #pragma unroll
             for (int h = 0; h < NPAD / 16; ++h) {                        // 16 accumulator columns = 8 beams at a time
                 float v[16];

@@ -1197,6 +1197,74 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(
     }
 }
 
+// Marching variant (cfar5_* in rsp_phases.cuh): the default for compile-time windows and P / 4 a power of two <= 256.
+// Tile = gates [g_first - mR, g_first + TG + mR) of the pair's sum map; thread (quad q, row group) fills it with two
+// 16-byte loads per row (the tile is one contiguous block of each amplitude map); then work item (chunk of CR gates,
+// CUT quad) walks down its gates.
+template <int TG, int RR, int RV, int GV>
+__global__ void __launch_bounds__(RSP_CFAR_THREADS, 3) cfar5_kernel(const CfarArgs k) {
+    extern __shared__ float cfar_smem[];
+    l2_discard(k.dead);
+    constexpr int CR = RSP_CFAR5_CR;
+    const int P = k.c.P, G = k.c.G, P4 = P >> 2;
+    const int mR = k.c.guard_r + RR, mV = GV + RV;
+    const int pitch = cfar5_pitch(P, mV), pitch4 = pitch >> 2, rows = TG + 2 * mR;
+    const int sh = 31 - __clz(P4);                                        // P4 is a power of two (checked by the host)
+    const int pair = blockIdx.y, g_first = k.cut_lo + blockIdx.x * TG, tid = threadIdx.x;
+    float* S = cfar_smem;
+    {
+        const int q = tid & (P4 - 1), r0 = tid >> sh, rstep = RSP_CFAR_THREADS >> sh;
+        const float4* A4 = reinterpret_cast<const float4*>(k.amp + ((size_t)pair * G + (g_first - mR)) * P) + q;
+        const float4* B4 = A4 + (size_t)G * P4;
+        float4* Sq = reinterpret_cast<float4*>(S + RSP_CFAR5_HALO) + q;
+        const int rows_valid = min(rows, G - (g_first - mR));
+        constexpr int U = 3;
+        for (int r = r0; r < rows; r += U * rstep) {
+            float4 a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = r + u * rstep;
+                a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                b[u] = a[u];
+                if (rr < rows_valid) { a[u] = A4[(size_t)rr * P4]; b[u] = B4[(size_t)rr * P4]; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = r + u * rstep;
+                if (rr < rows) Sq[rr * pitch4] = f4add(a[u], b[u]);
+            }
+        }
+    }
+    unsigned* queue = reinterpret_cast<unsigned*>(S + rows * pitch);      // [1 + TG * nq]: count, then (gl << 16 | c4 << 4 | mask)
+    if (tid == 0) queue[0] = 0;
+    __syncthreads();
+    const int nq = cfar5_nq(P, mV), c_lo = mV / 4;
+    const int gl_end = min(TG, k.cut_hi - g_first);
+    const int n_items = ((gl_end + CR - 1) / CR) * nq;
+    for (int it = tid; it < n_items; it += RSP_CFAR_THREADS) {
+        const int ch = it / nq, c4 = c_lo + (it - ch * nq), gl0 = ch * CR;
+        cfar5_march<RR, GV + RV, CR>(S, pitch, k.c, gl0, min(CR, gl_end - gl0), c4, [&](int s, unsigned m) {
+            queue[1 + atomicAdd(queue, 1u)] = ((unsigned)(gl0 + s) << 16) | ((unsigned)c4 << 4) | m;
+        });
+    }
+    __syncthreads();
+    const int n_hit = (int)queue[0];                                      // quads above the range threshold: Doppler test, then emit
+    const float kv = k.c.t_cfar / (float)RV;
+    for (int e = tid; e < n_hit; e += RSP_CFAR_THREADS) {
+        const unsigned w = queue[1 + e];
+        const int gl = (int)(w >> 16), c4 = (int)((w >> 4) & 0xFFFu);
+        const float* row0 = S + (gl + mR) * pitch + RSP_CFAR5_HALO;
+        float4 cq;
+        unsigned m = cfar5_doppler<RV, GV>(row0 + 4 * c4, kv, w & 15u, &cq);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float cut = j == 0 ? cq.x : j == 1 ? cq.y : j == 2 ? cq.z : cq.w;
+            cfar_emit(k, row0, pitch, 4 * c4 + j, g_first + gl, pair, cut);
+        }
+    }
+}
+
 // S9 (fun_process_single_frame.m:241-298) for every raw record of slots [first_slot, first_slot + n_slots):
 // spline peak search on the fp32 sum-map neighbours the detector saw, monopulse ratio from the two
 // beams at the integer cell.  One launch per batch; blockIdx.y = slot.

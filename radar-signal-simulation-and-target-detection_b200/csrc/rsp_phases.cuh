@@ -553,3 +553,83 @@ RSP_HD unsigned cfar4_decide_quad(const float* S, const float* R5, const CfarPar
     }
     return mask;
 }
+
+// =============================================================================================
+// CFAR, marching variant (cfar5_kernel; P / 4 a power of two, compile-time windows).  Same cells as cfar4_*, about a
+// third of the instructions:
+//   * no range-sum array: a work item owns one CUT quad (4 Doppler bins) of CR consecutive gates and walks down them
+//     with the rows of its leading and trailing range windows in registers (one new row of each per gate; the sums are
+//     re-added left to right for every gate, exactly like the reference's mean(), no subtractive updates);
+//   * range test first: the Doppler windows are only summed for quads with a cell above the range threshold
+//     (cut > T max(noise_R, noise_V)  <=>  cut > T noise_R  and  cut > T noise_V, fun_process_single_frame.m:196-209);
+//   * the tile keeps 4 (not 8) pad floats on each side of a row and they are never initialised: every window that
+//     touches them belongs to a Doppler bin outside [mV, P - mV), which the decision masks.
+// Row pitch: items are numbered chunk-major (it = chunk * nq + quad), so consecutive lanes read consecutive 16-byte
+// groups only if a chunk's offset CR * pitch / 4 is congruent to nq (mod 8): cfar5_pitch picks the smallest such pitch.
+// =============================================================================================
+#define RSP_CFAR5_HALO 4
+#define RSP_CFAR5_CR 5
+
+RSP_HD int cfar5_nq(int P, int mV) { return (P - mV - 1) / 4 - mV / 4 + 1; }          // quads holding at least one CUT
+RSP_HD int cfar5_pitch(int P, int mV) {
+    const int nq = cfar5_nq(P, mV);
+    int p4 = (P + 2 * RSP_CFAR5_HALO) / 4;
+    while (((RSP_CFAR5_CR * p4 - nq) & 7) != 0) ++p4;                                 // CR is odd: a solution every 8 steps
+    return 4 * p4;
+}
+
+RSP_HD float4 cfar5_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// Doppler test of a quad that passed the range test: clears the bits of the cells at or below T * noise_V.
+// row = S(CUT row, 4 c4).
+template <int RV, int GV>
+RSP_HD unsigned cfar5_doppler(const float* row, float kv, unsigned m, float4* cq_out) {
+    float lead[4], trail[4];
+    cfar4_window4<RV, -(GV + RV)>(row, lead);
+    cfar4_window4<RV, GV + 1>(row, trail);
+    const float4 cq = cfar5_ld4(row);
+    const float cu[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (!(cu[j] > kv * fmaxf(lead[j], trail[j]))) m &= ~(1u << j);
+    *cq_out = cq;
+    return m;
+}
+
+// Rows [gl0, gl0 + n_rows) of CUT quad c4 (n_rows <= CR).  S = tile base (row 0 = gate g_first - mR), pitch in floats.
+// hit(s, mask) is called for every row gl0 + s with cells above the RANGE threshold (bit j of mask = Doppler bin
+// 4 c4 + j); the caller queues them for cfar5_doppler (rare, so the marching loop stays lean in registers).
+template <int RR, int GV_PLUS_RV, int CR, class Hit>
+RSP_HD void cfar5_march(const float* S, int pitch, const CfarParams& c, int gl0, int n_rows, int c4, Hit&& hit) {
+    const int mR = c.guard_r + RR, mV = GV_PLUS_RV;
+    const int v0 = 4 * c4;
+    unsigned vmask = 0;                                                   // Doppler bins of the quad that are cells under test
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (v0 + j >= mV && v0 + j < c.P - mV) vmask |= 1u << j;
+    const float* pl = S + RSP_CFAR5_HALO + v0 + (size_t)gl0 * pitch;      // next leading-window row: S(gl0 + i, v0)
+    const float* pt = pl + (mR + c.guard_r + 1) * pitch;                  // next trailing-window row
+    const float* pc = pl + mR * pitch;                                    // CUT row
+    const float kr = c.t_cfar / (float)RR;                                // T * mean == (T / ref) * sum
+    float4 L[RR], T[RR];                                                  // rings: window row i of step s lives in slot (s + i) % RR
+#pragma unroll
+    for (int i = 0; i < RR - 1; ++i) {
+        L[i] = cfar5_ld4(pl); pl += pitch;
+        T[i] = cfar5_ld4(pt); pt += pitch;
+    }
+#pragma unroll
+    for (int s = 0; s < CR; ++s) {
+        if (s < n_rows) {
+            L[(s + RR - 1) % RR] = cfar5_ld4(pl); pl += pitch;
+            T[(s + RR - 1) % RR] = cfar5_ld4(pt); pt += pitch;
+            const float4 cq = cfar5_ld4(pc); pc += pitch;
+            float4 ls = L[s % RR], ts = T[s % RR];
+#pragma unroll
+            for (int i = 1; i < RR; ++i) { ls = f4add(ls, L[(s + i) % RR]); ts = f4add(ts, T[(s + i) % RR]); }
+            unsigned m = (cq.x > kr * fmaxf(ls.x, ts.x) ? 1u : 0u) | (cq.y > kr * fmaxf(ls.y, ts.y) ? 2u : 0u) |
+                         (cq.z > kr * fmaxf(ls.z, ts.z) ? 4u : 0u) | (cq.w > kr * fmaxf(ls.w, ts.w) ? 8u : 0u);
+            m &= vmask;
+            if (m) hit(s, m);
+        }
+    }
+}

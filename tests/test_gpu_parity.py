@@ -373,7 +373,8 @@ def test_config2_kernel_variants_agree():
     mma2, fused = {"RSP_DBF": "mma2"}, {"RSP_FUSE_DBF_PC": "1"}
     variants = [{}, mma2, fused, dict(fused, RSP_FUSED_TMA="2d"), {"RSP_MTD": "tile"}, {"RSP_MTD_SQRT": "approx"}, {"RSP_PC_MIX": "0"},
                 {"RSP_CFAR_PAD": "0"}, {"RSP_DBF": "tma2"}, {"RSP_DBF": "mma"}, {"RSP_DBF": "ffma"}, {"RSP_PC_GROUP_BAR": "0"},
-                {"RSP_TC_CHUNK": "0", "RSP_TC_STAGES": "6"}, dict(fused, RSP_PC_MIX="0")]
+                {"RSP_TC_CHUNK": "0", "RSP_TC_STAGES": "6"}, dict(fused, RSP_PC_MIX="0"),
+                {"RSP_CFAR": "quad"}, {"RSP_CFAR5_TG": "40"}, {"RSP_CFAR5_TG": "80"}]      # default CFAR: cfar5_kernel, 120-gate tiles
     results = []
     for env in variants:
         os.environ.update(env)
@@ -403,6 +404,8 @@ def test_config2_kernel_variants_agree():
         b = set(map(tuple, ref_d[["v_idx", "r_idx", "pair_idx"]].tolist()))
         # different roundings of the beams (tensor-core accumulation order) or of the amplitudes may flip a cell that sits on the threshold
         assert len(a ^ b) <= 2, (env, len(a ^ b))
+        if all(k.startswith("RSP_CFAR") for k in env):      # same amplitude map, same sums in the same order: identical cells
+            assert a == b and np.array_equal(r, ref_r), env
 
 
 @pytest.mark.parametrize("C,B,P,N", [(16, 8, 8, 8192), (12, 5, 6, 4112), (16, 2, 8, 4096), (7, 3, 6, 6000)])

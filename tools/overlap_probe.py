@@ -14,10 +14,17 @@ ma, mb = int(sys.argv[1]), int(sys.argv[2])
 config, cfar_params, _ = rsp.named_config("cfg2")
 pd = rsp.build_precomputed_data(config)
 os.environ["RSP_STAGES"] = str(ma)
+# per-context environment: A:KEY=VAL / B:KEY=VAL arguments (read at rsp_create)
+envA = dict(a[2:].split("=", 1) for a in sys.argv[3:] if a.startswith("A:"))
+envB = dict(a[2:].split("=", 1) for a in sys.argv[3:] if a.startswith("B:"))
+os.environ.update(envA)
 if "--a-high" in sys.argv:
     os.environ["RSP_STREAM_PRIO"] = "high"      # context A's streams get the greatest priority
 A = rsp.RadarChain(config, cfar_params, pd)
 os.environ.pop("RSP_STREAM_PRIO", None)
+for k_ in envA:
+    os.environ.pop(k_, None)
+os.environ.update(envB)
 os.environ["RSP_STAGES"] = str(mb)
 B = rsp.RadarChain(config, cfar_params, pd)
 g = torch.Generator(device="cuda").manual_seed(0)
