@@ -258,7 +258,7 @@ typedef struct {
     int64_t algorithmic_bytes_per_cpi;   /* 8*P*N*C + 8*B*P*G */
     int64_t launches_total;       /* kernels launched by this context so far */
     int32_t lanes;                /* concurrent CPI lanes of the stream / pipelined paths (RSP_LANES) */
-    int32_t reserved_;
+    int32_t graph_launches;       /* rsp_stream_enqueue batches replayed as one CUDA graph (launches_total counts their kernels) */
 } rsp_info;
 int rsp_get_info(const rsp_ctx* ctx, rsp_info* info);
 /* Measurement aid of the fused DBF + pulse-compression kernel: when the context was created under RSP_FUSED_DEBUG=<flags>,

@@ -65,6 +65,13 @@ struct rsp_ctx {
     // pipelined submission orders its lane behind the caller's stream only when the lane has not seen the
     // current epoch -- doing it per submission would serialise lane l behind everything queued on lane 0.
     unsigned long long caller_epoch = 1;
+    struct GraphEntry {                   // one captured rsp_stream_enqueue batch (stream_enqueue_graphed)
+        const void* raw; void* rdm; int raw_pool, rdm_pool, n_cpi, first_slot, flags;
+        cudaGraphExec_t exec; bool failed; long launches;
+    };
+    std::vector<GraphEntry> graphs;
+    unsigned long long graph_epoch = 0;
+    long graph_launches = 0;
     Lane* cur = nullptr;                  // lane the launch helpers enqueue on
     bool discard = false;                 // stream path: drop dead intermediates from L2 (see l2_discard)
     cudaEvent_t fork = nullptr;
@@ -316,9 +323,11 @@ int rsp_device_count(void) {
 
 const char* rsp_last_error(const rsp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+static void drop_graphs(rsp_ctx* c);
 void rsp_destroy(rsp_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->prm.device);
+    drop_graphs(c);
     cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_rdm);
     for (auto& ln : c->lanes) {
         cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp); cudaFree(ln.raw); cudaFree(ln.rdm);
@@ -402,7 +411,11 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
     { const char* e = getenv("RSP_FUSE_SYNTH"); c->fuse_synth = !(e && atoi(e) == 0); }
     { const char* e = getenv("RSP_PC_GROUP_BAR"); c->pc_group_bar = e ? atoi(e) : 1; }
     const char* el = getenv("RSP_LANES");
-    c->n_lanes = el ? std::min(8, std::max(1, atoi(el))) : 3;
+    // Default: six lanes while a lane's intermediates (beam + pulse-compressed + amplitude cubes) stay under 128 MB, else three.
+    // Measured (profiles/r2e_graph_lanes_ab.txt): config 1 52 k -> 68 k CPI/s and config 2 50.3 -> 49.0 us per CPI from 3 to 6
+    // lanes (more kernels to fill each other's ramps and tails); config 3 and the native shape do not care.
+    const size_t lane_bytes = ((size_t)c->P * c->B * (c->ldb + c->ldg)) * sizeof(float2) + PBG * sizeof(float);
+    c->n_lanes = el ? std::min(8, std::max(1, atoi(el))) : (lane_bytes < ((size_t)128 << 20) ? 6 : 3);
     CUC(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
     for (int i = 0; i < c->n_lanes; ++i) {
         rsp_ctx::Lane& ln = c->lanes[i];
@@ -1467,22 +1480,11 @@ int rsp_process_cpi(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dt
     return fetch_slot(c, 0, dets, det_cap, n_dets);
 }
 
-int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* rdm_dev, int32_t rdm_pool, int32_t n_cpi,
-                       int32_t first_slot) {
-    if (!c || !raw_dev || raw_pool < 1 || n_cpi < 0) return fail(c, RSP_ERR_INVALID_ARG, "bad stream arguments");
-    if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
-    if (first_slot < 0 || first_slot + n_cpi > c->slots)
-        return fail(c, RSP_ERR_INVALID_ARG, "slots [%d,%d) exceed the ring of %d", first_slot, first_slot + n_cpi, c->slots);
-    CU(c, cudaSetDevice(c->prm.device));
+// The launches of one rsp_stream_enqueue call: fork the lanes from the caller's stream, deal the CPIs round-robin, join,
+// one S9 launch for the batch.
+static int stream_enqueue_body(rsp_ctx* c, const void* raw_dev, int raw_pool, void* rdm_dev, int rdm_pool, int n_cpi, int first_slot, int nl) {
     const size_t in_elems = (size_t)c->P * c->C * c->N, out_elems = (size_t)c->P * c->B * c->G;
-    const int nl = std::min(c->blocked ? std::min(c->n_lanes, c->block_lanes) : c->n_lanes, std::max(n_cpi, 1));
-    // Up to nl CPIs are in flight at once, one per lane: their range-Doppler maps must not share a buffer (MTD of CPI i + 1
-    // would race with MTD and CFAR of CPI i).  A caller ring needs at least nl buffers, n_cpi > rdm_pool needs
-    // rdm_pool % nl == 0 (CPI i goes to lane i % nl and to buffer i % rdm_pool); without a ring every lane uses its own map.
     const bool own_rdm = !(rdm_dev && rdm_pool > 0);
-    if (!own_rdm && nl > 1 && (rdm_pool < nl || (n_cpi > rdm_pool && rdm_pool % nl != 0)))
-        return fail(c, RSP_ERR_INVALID_ARG, "rdm_pool %d cannot serve %d concurrent lanes (need rdm_pool >= lanes, and a multiple of lanes when n_cpi > rdm_pool)", rdm_pool, nl);
-    { const char* e = getenv("RSP_L2_DISCARD"); c->discard = !(e && atoi(e) == 0); }
     if (nl > 1) {                                    // fork: the extra lanes wait for work already on the caller's stream
         CU(c, cudaEventRecord(c->fork, c->stream));
         for (int l = 1; l < nl; ++l) CU(c, cudaStreamWaitEvent(c->lanes[l].s, c->fork, 0));
@@ -1493,16 +1495,98 @@ int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* 
         if (!rdm) return fail(c, RSP_ERR_CUDA, "out of device memory for the lane's RDM");
         int rc = enqueue_chain(c, in, rdm, first_slot + i, i % nl);
         if (rc) return rc;
-        c->slot_lane[first_slot + i] = -1;
-        if (!c->slot_prefetched.empty()) c->slot_prefetched[first_slot + i] = 0;
     }
-    c->discard = false;
     for (int l = 1; l < nl; ++l) {                   // join
         CU(c, cudaEventRecord(c->lanes[l].done, c->lanes[l].s));
         CU(c, cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
     }
     launch_refine(c, first_slot, n_cpi, c->stream);  // S9 for the whole batch
     CU(c, cudaGetLastError());
+    return RSP_OK;
+}
+
+// CUDA graph per batch.  A steady stream calls rsp_stream_enqueue with the same few argument sets over and over (pool
+// pointers, ring slots); the second time a set is seen its launches are captured (stream capture of the very same code,
+// lanes included) and from then on one cudaGraphLaunch replaces n_cpi x kernels_per_cpi launches plus the fork / join
+// events: host cost per CPI drops from ~16 us to under 2 us (tools/enqueue_cost.py), which is what bounds the small
+// shapes (config 1: ~20 us of device time per CPI).  Keyed on everything the kernel arguments depend on; any change of
+// constants, stream or profiling state (caller_epoch) drops the cache.  RSP_GRAPH=0 keeps the direct launches.
+static void drop_graphs(rsp_ctx* c) {
+    for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+static int stream_enqueue_graphed(rsp_ctx* c, const void* raw_dev, int raw_pool, void* rdm_dev, int rdm_pool, int n_cpi, int first_slot, int nl) {
+    static const bool enabled = [] { const char* e = getenv("RSP_GRAPH"); return !(e && atoi(e) == 0); }();
+    if (!enabled || c->profiling || n_cpi < 2)
+        return stream_enqueue_body(c, raw_dev, raw_pool, rdm_dev, rdm_pool, n_cpi, first_slot, nl);
+    if (c->graph_epoch != c->caller_epoch) { drop_graphs(c); c->graph_epoch = c->caller_epoch; }
+    rsp_ctx::GraphEntry key{};
+    key.raw = raw_dev; key.rdm = rdm_dev; key.raw_pool = raw_pool; key.rdm_pool = rdm_pool; key.n_cpi = n_cpi; key.first_slot = first_slot;
+    key.flags = (c->discard ? 1 : 0) | (c->keep_beam ? 2 : 0) | (nl << 8);
+    rsp_ctx::GraphEntry* hit = nullptr;
+    for (auto& g : c->graphs)
+        if (g.raw == key.raw && g.rdm == key.rdm && g.raw_pool == key.raw_pool && g.rdm_pool == key.rdm_pool && g.n_cpi == key.n_cpi &&
+            g.first_slot == key.first_slot && g.flags == key.flags) { hit = &g; break; }
+    if (!hit) {                                      // first sight: remember the set, launch directly
+        if (c->graphs.size() >= 16) { if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+        c->graphs.push_back(key);
+        return stream_enqueue_body(c, raw_dev, raw_pool, rdm_dev, rdm_pool, n_cpi, first_slot, nl);
+    }
+    if (!hit->exec && !hit->failed) {                // second sight: capture
+        const long before = c->launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            if (getenv("RSP_GRAPH_DEBUG")) fprintf(stderr, "librsp: cudaStreamBeginCapture failed: %s\n", cudaGetErrorString(cudaPeekAtLastError()));
+            cudaGetLastError();
+            hit->failed = true;
+        }
+        else {
+            const int rc = stream_enqueue_body(c, raw_dev, raw_pool, rdm_dev, rdm_pool, n_cpi, first_slot, nl);
+            const cudaError_t ee = cudaStreamEndCapture(c->stream, &graph);
+            hit->launches = c->launches - before;
+            c->launches = before;
+            cudaError_t ei = cudaSuccess;
+            if (rc != RSP_OK || ee != cudaSuccess || !graph || (ei = cudaGraphInstantiate(&hit->exec, graph, 0)) != cudaSuccess) {
+                if (getenv("RSP_GRAPH_DEBUG")) fprintf(stderr, "librsp: graph capture failed: rc %d (%s), end-capture %s, instantiate %s\n", rc, c->err.c_str(), cudaGetErrorString(ee), cudaGetErrorString(ei));
+                cudaGetLastError();
+                hit->exec = nullptr;
+                hit->failed = true;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+    }
+    if (!hit->exec) return stream_enqueue_body(c, raw_dev, raw_pool, rdm_dev, rdm_pool, n_cpi, first_slot, nl);
+    CU(c, cudaGraphLaunch(hit->exec, c->stream));
+    c->launches += hit->launches;
+    c->graph_launches++;
+    return RSP_OK;
+}
+
+int rsp_stream_enqueue(rsp_ctx* c, const void* raw_dev, int32_t raw_pool, void* rdm_dev, int32_t rdm_pool, int32_t n_cpi,
+                       int32_t first_slot) {
+    if (!c || !raw_dev || raw_pool < 1 || n_cpi < 0) return fail(c, RSP_ERR_INVALID_ARG, "bad stream arguments");
+    if (!c->have_constants) return fail(c, RSP_ERR_NOT_READY, "rsp_upload_constants has not been called");
+    if (first_slot < 0 || first_slot + n_cpi > c->slots)
+        return fail(c, RSP_ERR_INVALID_ARG, "slots [%d,%d) exceed the ring of %d", first_slot, first_slot + n_cpi, c->slots);
+    CU(c, cudaSetDevice(c->prm.device));
+    const int nl = std::min(c->blocked ? std::min(c->n_lanes, c->block_lanes) : c->n_lanes, std::max(n_cpi, 1));
+    // Up to nl CPIs are in flight at once, one per lane: their range-Doppler maps must not share a buffer (MTD of CPI i + 1
+    // would race with MTD and CFAR of CPI i).  A caller ring needs at least nl buffers, n_cpi > rdm_pool needs
+    // rdm_pool % nl == 0 (CPI i goes to lane i % nl and to buffer i % rdm_pool); without a ring every lane uses its own map.
+    const bool own_rdm = !(rdm_dev && rdm_pool > 0);
+    if (!own_rdm && nl > 1 && (rdm_pool < nl || (n_cpi > rdm_pool && rdm_pool % nl != 0)))
+        return fail(c, RSP_ERR_INVALID_ARG, "rdm_pool %d cannot serve %d concurrent lanes (need rdm_pool >= lanes, and a multiple of lanes when n_cpi > rdm_pool)", rdm_pool, nl);
+    { const char* e = getenv("RSP_L2_DISCARD"); c->discard = !(e && atoi(e) == 0); }
+    if (own_rdm)                                     // allocate before a capture could be open
+        for (int l = 0; l < nl; ++l)
+            if (!lane_rdm(c, l)) return fail(c, RSP_ERR_CUDA, "out of device memory for the lane's RDM");
+    int rc = stream_enqueue_graphed(c, raw_dev, raw_pool, rdm_dev, rdm_pool, n_cpi, first_slot, nl);
+    c->discard = false;
+    if (rc) return rc;
+    for (int i = 0; i < n_cpi; ++i) {
+        c->slot_lane[first_slot + i] = -1;
+        if (!c->slot_prefetched.empty()) c->slot_prefetched[first_slot + i] = 0;
+    }
     return RSP_OK;
 }
 
@@ -2067,7 +2151,7 @@ int rsp_get_info(const rsp_ctx* c, rsp_info* info) {
     info->algorithmic_bytes_per_cpi = 8LL * c->P * c->N * c->C + 8LL * c->B * c->P * c->G;
     info->launches_total = c->launches;
     info->lanes = c->n_lanes;
-    info->reserved_ = 0;
+    info->graph_launches = (int32_t)c->graph_launches;
     return RSP_OK;
 }
 

@@ -187,6 +187,41 @@ def test_stream_path_equals_single_cpi_path():
     chain.close()
 
 
+def test_stream_batches_replayed_as_cuda_graphs_equal_direct_launches():
+    """rsp_stream_enqueue captures a batch the second time it sees the same arguments and replays it as one CUDA graph from
+    then on (stream_enqueue_graphed): the replays must leave exactly what the direct launches left -- detection slots and
+    range-Doppler maps -- and a change of arguments must not reuse a stale graph."""
+    import torch
+    chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
+    lanes = chain.info()["lanes"]
+    cubes = [o.make_cube("cfg1", s)[2] for s in (0, 1, 2)]
+    single = [chain.process_cpi(c) for c in cubes]
+    pool = torch.from_numpy(np.stack(cubes)).cuda()
+    n = 2 * lanes
+    rdm = torch.zeros((lanes, chain.B, chain.G, chain.P), dtype=torch.complex64, device="cuda")
+    maps = []
+    for rep in range(4):                                    # direct, capture + launch, replay, replay
+        rdm.zero_()
+        chain.stream_enqueue(pool.data_ptr(), 3, rdm.data_ptr(), lanes, n, 0)
+        chain.synchronize()
+        for i in range(n):
+            assert np.array_equal(chain.stream_fetch(i), single[i % 3]), (rep, i)
+        maps.append(rdm.cpu().numpy().copy())
+        assert np.array_equal(maps[rep], maps[0]), rep
+    assert chain.info()["graph_launches"] == 3
+    launches_per_batch = chain.info()["kernels_per_cpi"] * n + 1
+    before = chain.info()["launches_total"]
+    chain.stream_enqueue(pool.data_ptr(), 3, rdm.data_ptr(), lanes, n, 0)
+    assert chain.info()["launches_total"] - before == launches_per_batch      # a replay counts its kernels
+    # other arguments (a shifted pool, other slots): first sight is launched directly, results follow the new arguments
+    chain.stream_enqueue(pool.data_ptr() + pool[0].numel() * 8, 2, rdm.data_ptr(), lanes, n, n)
+    chain.synchronize()
+    for i in range(n):
+        assert np.array_equal(chain.stream_fetch(n + i), single[1 + i % 2]), i
+    assert chain.info()["graph_launches"] == 4
+    chain.close()
+
+
 def test_detection_overflow_is_an_error_not_truncation():
     chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1", max_detections=8)
     cfg, pre, raw = o.make_cube("cfg1", 0)
