@@ -168,6 +168,7 @@ struct rsp_ctx {
     std::vector<char> slot_prefetched;
     int mtd_tg = 32, mtd_r = 1, mtd_kt = 1, cfar_tg = 32, cfar_variant = 0;
     bool cfar_vec = false;
+    int pulse_block = 0;                  // > 0: pulses per group of the pulse-blocked S5 -> S6 path (enqueue_chain)
     bool cfar5 = false;                   // cfar5_kernel (marching) instead of cfar4_kernel
     size_t mtd_smem = 0, cfar_smem = 0;
     // per-kernel event timing (rsp_set_profiling)
@@ -895,6 +896,7 @@ static std::vector<float> make_dbf_tc_weights(const double* W_ri /* [B][C][2] */
 
 static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
     c->dbf_tc = false;
+    c->pulse_block = 0;
     const char* e = getenv("RSP_DBF");
     if (e && strcmp(e, "tc")) return RSP_OK;                      // another DBF kernel was asked for
     if (c->B > 16 || c->C > 32 || (c->N & 1) || !encode_tiled_fn()) return RSP_OK;
@@ -932,10 +934,13 @@ static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
 #undef RSP_TC_CASE
     if (err != cudaSuccess) { cudaGetLastError(); return RSP_OK; }
     c->dbf_tc = true;
+    // RSP_PULSE_BLOCK=n: opt-in pulse-blocked S5 -> S6 (enqueue_chain).  Measured slower at config 3 (470 us per CPI whole-cube,
+    // 493 with groups of 16 pulses, 511 with 8: profiles/r2f_pulse_block_cfg3.txt), like the range-blocked chain.
+    if (const char* e = getenv("RSP_PULSE_BLOCK")) c->pulse_block = std::max(0, atoi(e));
     return RSP_OK;
 }
 
-static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile_lo = 0, int tile_hi = -1) {
+static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile_lo = 0, int tile_hi = -1, int p_lo = 0, int p_hi = -1) {
     const CUtensorMap* map = raw_tmap(c, raw, TMAP_ROWS_2D);
     if (!map) return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
     DbfTcArgs a = c->dbf_tc_args;
@@ -943,11 +948,11 @@ static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile
     a.det_count = det_count;
     a.dead = dead_amp(c);
     a.tile_lo = tile_lo; a.tile_hi = tile_hi < 0 ? a.tiles_per_pulse : tile_hi;
-    a.p_lo = 0; a.p_hi = c->P;
+    a.p_lo = p_lo; a.p_hi = p_hi < 0 ? c->P : p_hi;
     int grid = c->dbf_tc_grid;
-    if (tile_hi >= 0) {                        // a chunk of the range-blocked path
-        const int n_tiles = c->P * (a.tile_hi - a.tile_lo);
-        a.dead = DiscardArgs{nullptr, 0};
+    if (tile_hi >= 0 || p_hi >= 0) {           // a chunk of the range-blocked path / a pulse group of the pulse-blocked path
+        const int n_tiles = (a.p_hi - a.p_lo) * (a.tile_hi - a.tile_lo);
+        if (!det_count) a.dead = DiscardArgs{nullptr, 0};
         grid = a.chunk > 0 ? (n_tiles + a.chunk - 1) / a.chunk : std::min(grid, n_tiles);
     }
 #ifdef RSP_PROBES
@@ -1055,29 +1060,34 @@ static int launch_dbf_any(rsp_ctx* c, const float2* raw, int* det_count) {
     return RSP_OK;
 }
 
-static void fill_seg(const rsp_ctx* c, PcSegArgs& sg, const PcPlan& pl, const float2* tw1, const float2* tw2, const float2* H) {
+static void fill_seg(const rsp_ctx* c, PcSegArgs& sg, const PcPlan& pl, const float2* tw1, const float2* tw2, const float2* H, int n_lines = -1) {
     sg.tw1 = tw1; sg.tw2 = tw2; sg.Hmid = H;
     sg.seg_start0 = pl.seg_start0; sg.in_lo = pl.seg_start0; sg.in_hi = c->N; sg.taps = pl.taps; sg.gate0 = pl.gate0; sg.g_end = pl.gate0 + pl.ngates; sg.valid = pl.valid;
     sg.nblk = pl.nblk;
-    sg.n_items = pl.L ? c->P * c->B * pl.nblk : 0;
+    sg.n_items = pl.L ? (n_lines < 0 ? c->P * c->B : n_lines) * pl.nblk : 0;
     const int ng = pl.L ? RSP_PC_THREADS / pl.T : 1;
     sg.n_ctas = (sg.n_items + ng - 1) / ng;
 }
 
 // One launch covers the long segment (role 0), the medium segment and the narrow FIR (role 1).
-static void launch_pc(rsp_ctx* c) {
+// p_hi >= 0: only the lines of pulses [p_lo, p_hi) (pulse-blocked path; lines are [pulse][beam], so a pulse group is a
+// contiguous run of lines of both cubes).
+static void launch_pc(rsp_ctx* c, int p_lo = 0, int p_hi = -1) {
     const bool narrow = c->prm.n_gates[0] > 0;
     const bool fold = narrow && c->med.L > 0;        // the medium groups compute the narrow gates too
+    const int line0 = p_lo * c->B, n_lines = ((p_hi < 0 ? c->P : p_hi) - p_lo) * c->B;
+    const float2* beam = c->cur->beam + (size_t)line0 * c->ldb;
+    float2* pc = c->cur->pc + (size_t)line0 * c->ldg;
     if (narrow && !fold) {
         Timed t(c, K_PC_NARROW);
-        pc_narrow_kernel<<<c->P * c->B, 256, 0, c->cur->s>>>(c->cur->beam, c->cur->pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
-                                                             c->ldb, c->ldg, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
+        pc_narrow_kernel<<<n_lines, 256, 0, c->cur->s>>>(beam, pc, c->d_fir, c->n_fir, c->prm.fir_delay, c->N,
+                                                         c->ldb, c->ldg, c->prm.seg_start[0] - 1, c->prm.n_gates[0]);
     }
     if (!c->med.L && !c->lng.L) return;
     PcKernelArgs a;
-    a.beam = c->cur->beam; a.pc = c->cur->pc; a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
-    fill_seg(c, a.seg[0], c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H);
-    fill_seg(c, a.seg[1], c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H);
+    a.beam = beam; a.pc = pc; a.N = c->N; a.ldb = c->ldb; a.ldg = c->ldg;
+    fill_seg(c, a.seg[0], c->lng, c->d_lng_tw1, c->d_lng_tw2, c->d_lng_H, n_lines);
+    fill_seg(c, a.seg[1], c->med, c->d_med_tw1, c->d_med_tw2, c->d_med_H, n_lines);
     a.do_narrow = fold ? 1 : 0;
     a.group_bar = c->pc_group_bar;
     a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
@@ -1104,8 +1114,8 @@ static void launch_pc(rsp_ctx* c) {
 #undef X
     }
     if (c->lngx[0].L) {            // the shorter blocks of a mixed long-segment plan
-        fill_seg(c, a.seg[0], c->lngx[0], c->d_lngx_tw1[0], c->d_lngx_tw2[0], c->d_lngx_H[0]);
-        fill_seg(c, a.seg[1], c->lngx[1], c->d_lngx_tw1[1], c->d_lngx_tw2[1], c->d_lngx_H[1]);
+        fill_seg(c, a.seg[0], c->lngx[0], c->d_lngx_tw1[0], c->d_lngx_tw2[0], c->d_lngx_H[0], n_lines);
+        fill_seg(c, a.seg[1], c->lngx[1], c->d_lngx_tw1[1], c->d_lngx_tw2[1], c->d_lngx_H[1], n_lines);
         a.do_narrow = 0;
         const int n2 = a.seg[0].n_ctas + a.seg[1].n_ctas;
         const int l0 = c->lngx[0].L, l1 = c->lngx[1].L ? c->lngx[1].L : 1024;
@@ -1310,6 +1320,9 @@ static int kernels_per_cpi(const rsp_ctx* c) {
     const bool narrow = c->prm.n_gates[0] > 0;
     int n = 1 /*dbf*/ + (narrow && c->med.L == 0) + ((c->med.L > 0 || c->lng.L > 0) ? 1 : 0) + (c->lngx[0].L ? 1 : 0) + 1 /*mtd*/;
     if (c->dbf_pc_ok) n = 1 /*dbf_pc*/ + 1 /*mtd*/;
+    const bool frame_ctx = c->have_waveform && c->dbf_nt && c->dbf_wa && (c->N % 2 == 0);
+    if (!c->dbf_pc_ok && c->dbf_tc && !frame_ctx && c->pulse_block > 0 && c->pulse_block < c->P)   // pulse groups: each its own DBF + PC launches
+        n = (n - 1) * ((c->P + c->pulse_block - 1) / c->pulse_block) + 1;
     if (c->blocked) return (int)c->chunks.size() * (cfar_testable(c) ? 4 : 3);
     if (cfar_testable(c)) n += 1;   // cfar (S9 is one refine launch per batch, not per CPI)
     return n;
@@ -1335,9 +1348,23 @@ static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, i
         rc = launch_dbf_pc(c, raw, c->d_counts + slot);                   // S5 + S6 in one launch; zeroes the slot's counter
         if (rc) return rc;
     } else {
+        // Opt-in (RSP_PULSE_BLOCK) pulse-blocked S5 -> S6: the beams of a group of pulses are formed and pulse-compressed before
+        // the next group is touched, so that at the big shapes the beam cube is consumed out of L2 instead of costing a DRAM
+        // write + read (config 3: 2 x 268 MB of 2.0 GB per CPI).  Same kernels, bit-identical results -- and slower: the short
+        // launches lose more to ramp-up and tails than the DRAM traffic gives back (see plan_dbf_tc).
+        const bool tc_ok = c->dbf_tc && !frame_ctx && !c->fused && !(reinterpret_cast<uintptr_t>(raw) & 15);
+        if (c->pulse_block > 0 && c->pulse_block < c->P && tc_ok && stages == 15) {
+            for (int p0 = 0; p0 < c->P && !rc; p0 += c->pulse_block) {
+                const int p1 = std::min(c->P, p0 + c->pulse_block);
+                rc = launch_dbf_tc(c, raw, p0 == 0 ? c->d_counts + slot : nullptr, 0, -1, p0, p1);
+                if (!rc) launch_pc(c, p0, p1);
+            }
+            if (rc) return rc;
+        } else {
         if (stages & 1) rc = launch_dbf_any(c, raw, c->d_counts + slot);  // dbf_kernel also zeroes the slot's counter
         if (rc) return rc;
         if (stages & 2) launch_pc(c);
+        }
     }
     if (stages & 4) launch_mtd(c, rdm);
     if ((stages & 8) && cfar_testable(c)) launch_cfar(c, rdm, slot);

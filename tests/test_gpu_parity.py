@@ -478,6 +478,33 @@ def test_fused_dbf_pc_equals_the_two_kernel_path(C, B, P, N):
     assert rel_errors(out["1"][2], res.rdm)[0] <= RDM_REL_TOL
 
 
+@pytest.mark.parametrize("C,B,P,N,pb", [(16, 8, 8, 8192, 3), (32, 16, 8, 4096, 2), (12, 5, 6, 4112, 4)])
+def test_pulse_blocked_dbf_pc_equals_whole_cube_launches(C, B, P, N, pb):
+    """The pulse-blocked S5 -> S6 path of the big shapes (dbf_tc + pc_fft launched per group of pulses so that the beam cube is
+    consumed out of L2; opt-in, RSP_PULSE_BLOCK) runs the same kernels on sub-ranges: beam, pulse-compressed cube, RDM and
+    detections must be bit identical to the whole-cube launches, also with a ragged last group."""
+    import os
+    config, cfar_params, cluster_params = rsp.default_config(channel_num=C, beam_num=B, prtNum=P, point_PRT=N)
+    pd = rsp.build_precomputed_data(config)
+    ocfg = o.shaped_config(C, B, P, N)
+    opre = o.build_precomputed(ocfg)
+    tg = [o.Target(900.0, 0.1 * opre["v_max"], -5.0, 25.0), o.Target(3000.0, -0.1 * opre["v_max"], 8.0, 20.0)]
+    raw = o.add_noise(o.synthesize_echo(tg, ocfg, opre), 5).astype(np.complex64)
+    out = {}
+    for mode in (str(pb), "0"):
+        os.environ["RSP_PULSE_BLOCK"] = mode
+        try:
+            chain = rsp.RadarChain(config, cfar_params, pd)
+            d = chain.process_cpi(raw)
+            out[mode] = (chain.get_beam(), chain.get_pc(), chain.get_rdm(), d, chain.info()["kernels_per_cpi"])
+            chain.close()
+        finally:
+            os.environ.pop("RSP_PULSE_BLOCK", None)
+    assert out[str(pb)][4] > out["0"][4], "the pulse-blocked path was not taken"
+    for a, b, what in zip(out[str(pb)][:4], out["0"][:4], ("beam", "pc", "rdm", "detections")):
+        assert np.array_equal(a, b), what
+
+
 def test_batched_frames_equal_one_at_a_time():
     """process_targets_batch (device synthesis of many frames + multi-lane stream) == process_targets per frame."""
     chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")

@@ -24,15 +24,16 @@ chain = rsp.RadarChain(config, cfar_params, pd)
 g = torch.Generator(device="cuda").manual_seed(0)
 pool = torch.view_as_complex(torch.randn((a.pool, chain.P, chain.C, chain.N, 2), device="cuda", generator=g)
                              * (0.5 ** 0.5)).contiguous()
-rdm = torch.empty((4, chain.B, chain.G, chain.P), dtype=torch.complex64, device="cuda")
+nr = 2 * chain.info()["lanes"]
+rdm = torch.empty((nr, chain.B, chain.G, chain.P), dtype=torch.complex64, device="cuda")
 torch.cuda.synchronize()
 chain.set_stream(torch.cuda.current_stream().cuda_stream)
 if a.range:
-    chain.stream_enqueue(pool.data_ptr(), a.pool, rdm.data_ptr(), 4, a.cpis, 0)      # warm-up outside the range
+    chain.stream_enqueue(pool.data_ptr(), a.pool, rdm.data_ptr(), nr, a.cpis, 0)      # warm-up outside the range
     chain.synchronize()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-chain.stream_enqueue(pool.data_ptr(), a.pool, rdm.data_ptr(), 4, a.cpis, 0)
+chain.stream_enqueue(pool.data_ptr(), a.pool, rdm.data_ptr(), nr, a.cpis, 0)
 chain.synchronize()
 if a.range:
     torch.cuda.synchronize()
