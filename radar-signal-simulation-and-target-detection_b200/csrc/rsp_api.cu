@@ -940,7 +940,8 @@ static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
     return RSP_OK;
 }
 
-static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile_lo = 0, int tile_hi = -1, int p_lo = 0, int p_hi = -1) {
+static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile_lo = 0, int tile_hi = -1, int p_lo = 0, int p_hi = -1,
+                         DiscardArgs dead_group = DiscardArgs{nullptr, 0}) {
     const CUtensorMap* map = raw_tmap(c, raw, TMAP_ROWS_2D);
     if (!map) return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
     DbfTcArgs a = c->dbf_tc_args;
@@ -952,7 +953,7 @@ static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile
     int grid = c->dbf_tc_grid;
     if (tile_hi >= 0 || p_hi >= 0) {           // a chunk of the range-blocked path / a pulse group of the pulse-blocked path
         const int n_tiles = (a.p_hi - a.p_lo) * (a.tile_hi - a.tile_lo);
-        if (!det_count) a.dead = DiscardArgs{nullptr, 0};
+        if (!det_count) a.dead = dead_group;
         grid = a.chunk > 0 ? (n_tiles + a.chunk - 1) / a.chunk : std::min(grid, n_tiles);
     }
 #ifdef RSP_PROBES
@@ -1356,7 +1357,12 @@ static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, i
         if (c->pulse_block > 0 && c->pulse_block < c->P && tc_ok && stages == 15) {
             for (int p0 = 0; p0 < c->P && !rc; p0 += c->pulse_block) {
                 const int p1 = std::min(c->P, p0 + c->pulse_block);
-                rc = launch_dbf_tc(c, raw, p0 == 0 ? c->d_counts + slot : nullptr, 0, -1, p0, p1);
+                // the beams of the previous group have been consumed by its pulse compression: drop their dirty lines from L2
+                // instead of writing them back (the first group discards the previous CPI's amplitude map, like every DBF)
+                const size_t per_pulse = (size_t)c->B * c->ldb * sizeof(float2);
+                const DiscardArgs prev = p0 == 0 ? DiscardArgs{nullptr, 0}
+                    : dead_buf(c, reinterpret_cast<char*>(c->cur->beam) + (size_t)(p0 - c->pulse_block) * per_pulse, (size_t)c->pulse_block * per_pulse);
+                rc = launch_dbf_tc(c, raw, p0 == 0 ? c->d_counts + slot : nullptr, 0, -1, p0, p1, prev);
                 if (!rc) launch_pc(c, p0, p1);
             }
             if (rc) return rc;

@@ -136,6 +136,7 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
     const int B_A_READY = 2 * NS, B_MMA_DONE = 2 * NS + 2, B_D_FREE = 2 * NS + 4;
 
     if (k.det_count && blockIdx.x == 0 && tid == 0) *k.det_count = 0;          // first kernel of the CPI
+    l2_discard(k.dead);                                                        // every thread of the grid takes its share of the lines
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(NS + s), 4); }
         for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_A_READY + b), 4); mbar_init(BAR(B_MMA_DONE + b), 1); mbar_init(BAR(B_D_FREE + b), 4); }
@@ -210,7 +211,6 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
     } else {
         // ------------------------------------------------------------------ converters + epilogue (thread = sample row)
         const int q = w & 3, m = 32 * q + lane;                          // TMEM lanes 32 q .. 32 q + 31 belong to warp q (mod 4)
-        l2_discard(k.dead);
         auto epilogue = [&](int i) {
             const int tile = first + i * step;
             const int pr = tile / tpp, p = k.p_lo + pr, n = (k.tile_lo + tile - pr * tpp) * RSP_TC_TILE + m;
