@@ -320,8 +320,7 @@ int emul_cfar4_map(const float* S, int G, int P, int guard_r, int guard_v, int r
 // Marching CFAR (cfar5_kernel): uninitialised pad columns (NaN here), chunk-major items, range test first, queued Doppler test.
 int emul_cfar5_map(const float* S, int G, int P, int guard_r, int guard_v, int ref_r, int ref_v, float t_cfar, int TG,
                    unsigned char* det /* [G][P] */) {
-    const int p4 = P / 4;
-    if (P % 4 || (p4 & (p4 - 1)) || ref_r != 5 || !((ref_v == 5 && guard_v == 10) || (ref_v == 4 && guard_v == 2))) return -1;
+    if (P % 4 || ref_r != 5 || !((ref_v == 5 && guard_v == 10) || (ref_v == 4 && guard_v == 2))) return -1;
     CfarParams c;
     c.P = P; c.G = G; c.guard_r = guard_r; c.guard_v = guard_v; c.ref_r = ref_r; c.ref_v = ref_v; c.t_cfar = t_cfar;
     constexpr int CR = RSP_CFAR5_CR;

@@ -621,18 +621,18 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             if (c->cfar_variant == 1) { ACTION((cfar5_kernel<TGV, 5, 5, 10>)) }                     \
             else { ACTION((cfar5_kernel<TGV, 5, 4, 2>)) }                                           \
         }
-#define RSP_CFAR5_DISPATCH(ACTION) RSP_CFAR5_CASE(40, ACTION) RSP_CFAR5_CASE(80, ACTION) RSP_CFAR5_CASE(120, ACTION)
+#define RSP_CFAR5_DISPATCH(ACTION) RSP_CFAR5_CASE(20, ACTION) RSP_CFAR5_CASE(40, ACTION) RSP_CFAR5_CASE(80, ACTION) RSP_CFAR5_CASE(120, ACTION)
 #define OPTIN(K) CU(c, opt_in_smem(K, c->cfar_smem));
         // marching kernel (cfar5_kernel): compile-time windows, P / 4 a power of two; RSP_CFAR=quad keeps cfar4_kernel
         const int p4 = P / 4;
-        { const char* e = getenv("RSP_CFAR"); c->cfar5 = c->cfar_vec && c->cfar_variant != 0 && p4 >= 1 && p4 <= RSP_CFAR_THREADS && (p4 & (p4 - 1)) == 0 && !(e && !strcmp(e, "quad")); }
+        { const char* e = getenv("RSP_CFAR"); c->cfar5 = c->cfar_vec && c->cfar_variant != 0 && p4 >= 1 && p4 <= RSP_CFAR_THREADS && !(e && !strcmp(e, "quad")); }
         if (c->cfar5) {
             const int mV = c->prm.guard_v + c->prm.ref_v;
             auto smem5 = [&](int tg) { return ((size_t)(tg + 2 * mR) * cfar5_pitch(P, mV) + 1 + (size_t)tg * cfar5_nq(P, mV)) * sizeof(float); };
-            c->cfar_tg = 40;
-            for (int tg : {120, 80, 40})          // measured at config 2: 120 > 80 > 40 (profiles/r2d_cfar5_ab.txt)
+            c->cfar_tg = 20;
+            for (int tg : {120, 80, 40, 20})      // measured at config 2: 120 > 80 > 40 (profiles/r2d_cfar5_ab.txt)
                 if (smem5(tg) <= 72 * 1024) { c->cfar_tg = tg; break; }
-            if (const char* e = getenv("RSP_CFAR5_TG")) { const int v = atoi(e); if (v == 40 || v == 80 || v == 120) c->cfar_tg = v; }
+            if (const char* e = getenv("RSP_CFAR5_TG")) { const int v = atoi(e); if (v == 20 || v == 40 || v == 80 || v == 120) c->cfar_tg = v; }
             c->cfar_smem = smem5(c->cfar_tg);
             if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
             RSP_CFAR5_DISPATCH(OPTIN)

@@ -1197,7 +1197,7 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, RSP_CFAR_MINB) cfar4_kernel(
     }
 }
 
-// Marching variant (cfar5_* in rsp_phases.cuh): the default for compile-time windows and P / 4 a power of two <= 256.
+// Marching variant (cfar5_* in rsp_phases.cuh): the default for compile-time windows and P % 4 == 0, P <= 1024.
 // Tile = gates [g_first - mR, g_first + TG + mR) of the pair's sum map; thread (quad q, row group) fills it with two
 // 16-byte loads per row (the tile is one contiguous block of each amplitude map); then work item (chunk of CR gates,
 // CUT quad) walks down its gates.
@@ -1209,17 +1209,19 @@ __global__ void __launch_bounds__(RSP_CFAR_THREADS, 3) cfar5_kernel(const CfarAr
     const int P = k.c.P, G = k.c.G, P4 = P >> 2;
     const int mR = k.c.guard_r + RR, mV = GV + RV;
     const int pitch = cfar5_pitch(P, mV), pitch4 = pitch >> 2, rows = TG + 2 * mR;
-    const int sh = 31 - __clz(P4);                                        // P4 is a power of two (checked by the host)
     const int pair = blockIdx.y, g_first = k.cut_lo + blockIdx.x * TG, tid = threadIdx.x;
     float* S = cfar_smem;
     {
-        const int q = tid & (P4 - 1), r0 = tid >> sh, rstep = RSP_CFAR_THREADS >> sh;
+        const int rstep = RSP_CFAR_THREADS / P4, r0 = tid / P4, q = tid - r0 * P4;   // threads beyond rstep * P4 idle (P4 not a power of two)
         const float4* A4 = reinterpret_cast<const float4*>(k.amp + ((size_t)pair * G + (g_first - mR)) * P) + q;
         const float4* B4 = A4 + (size_t)G * P4;
         float4* Sq = reinterpret_cast<float4*>(S + RSP_CFAR5_HALO) + q;
         const int rows_valid = min(rows, G - (g_first - mR));
-        constexpr int U = 3;
-        for (int r = r0; r < rows; r += U * rstep) {
+#ifndef RSP_CFAR5_U
+#define RSP_CFAR5_U 5
+#endif
+        constexpr int U = RSP_CFAR5_U;     // rows in flight per thread (2 x 16-byte loads each)
+        for (int r = r0 < rstep ? r0 : rows; r < rows; r += U * rstep) {
             float4 a[U], b[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {

@@ -230,8 +230,8 @@ def test_cfar_vectorised_quads_match_oracle(lib, shape, tg, use_template):
     assert len(want) >= 4          # including the two corner CUTs
 
 
-@pytest.mark.parametrize("tg", [40, 80, 120])
-@pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (260, 128, 10, 10, 5, 5), (173, 32, 10, 10, 5, 5), (150, 16, 4, 2, 5, 4)])
+@pytest.mark.parametrize("tg", [20, 40, 80, 120])
+@pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (260, 128, 10, 10, 5, 5), (173, 32, 10, 10, 5, 5), (150, 16, 4, 2, 5, 4), (120, 332, 10, 10, 5, 5), (130, 48, 10, 2, 5, 4)])
 def test_cfar_marching_kernel_phases_match_oracle(lib, shape, tg):
     """cfar5_march / cfar5_doppler (the phases of cfar5_kernel) with NaN in the never-initialised pad columns."""
     G, P, gR, gV, rR, rV = shape
