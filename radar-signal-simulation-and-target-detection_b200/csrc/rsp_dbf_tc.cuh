@@ -165,13 +165,20 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
     if (w == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
+#ifdef RSP_TC_EVICT_FIRST
+            const uint64_t pol = l2_policy_evict_first();
+#endif
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % NS, round = i / NS;
                 if (round > 0) mbar_wait(BAR(NS + s), (uint32_t)(round - 1) & 1u);
                 const int tile = first + i * step;
                 const int pr = tile / tpp, p = k.p_lo + pr, n0 = (k.tile_lo + tile - pr * tpp) * RSP_TC_TILE;
                 mbar_expect_tx(BAR(s), raw_stage);
+#ifdef RSP_TC_EVICT_FIRST
+                tma_load_2d_hint(smem_u32(s_raw) + (uint32_t)s * raw_stage, &tmap, 2 * n0, p * C, BAR(s), pol);
+#else
                 tma_load_2d(smem_u32(s_raw) + (uint32_t)s * raw_stage, &tmap, 2 * n0, p * C, BAR(s));
+#endif
             }
         }
     } else if (w == 1) {

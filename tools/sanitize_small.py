@@ -15,7 +15,7 @@ def run(cfgname, **shape):
     cube = torch.empty((2, ch.P, ch.C, ch.N), dtype=torch.complex64, device="cuda")
     ch.synthesize(tg, 1.0, 2, out=cube[0]); ch.synthesize(tg, 1.0, 3, out=cube[1])
     rdm = torch.empty((2, ch.B, ch.G, ch.P), dtype=torch.complex64, device="cuda")
-    ch.stream_enqueue(cube.data_ptr(), 2, rdm.data_ptr(), 2, 5, 0); ch.synchronize()
+    ch.stream_enqueue(cube.data_ptr(), 2, 0, 0, 5, 0); ch.synchronize()                 # no ring: every lane its own map
     n = [len(ch.stream_fetch(i)) for i in range(5)]
     host = cube[0].cpu().numpy()
     a = ch.process_cpi(host); b = ch.process_cpi(np.ascontiguousarray(np.transpose(host, (1, 2, 0)).astype(np.complex128)), layout="matlab")
