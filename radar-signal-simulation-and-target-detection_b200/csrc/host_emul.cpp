@@ -4,6 +4,7 @@
 #include <cstring>
 #include <algorithm>
 #include <vector>
+#include <type_traits>
 #include "rsp_plan.hpp"
 #include "rsp_dft_big.cuh"
 
@@ -247,6 +248,44 @@ int emul_mtd_dft_tile_kt(const float* x /* [P][TG] */, int P, int TG, int KT, co
             RSP_EMUL_KT(4, 11) RSP_EMUL_KT(2, 11) RSP_EMUL_KT(1, 11) RSP_EMUL_KT(4, 6) RSP_EMUL_KT(2, 6) RSP_EMUL_KT(1, 6)
 #undef RSP_EMUL_KT
         }
+    cf* o = reinterpret_cast<cf*>(out);
+    for (int gl = 0; gl < TG; ++gl)
+        for (int row = 0; row < P; ++row) o[(size_t)gl * P + row] = xout[(size_t)row * (TG + 1) + gl];
+    return 0;
+}
+
+// the folded (even / odd) work items of mtd_dft_kernel<TG, R, 100 + KP> for odd Q = P / R
+int emul_mtd_dft_tile_sym(const float* x /* [P][TG] */, int P, int TG, int KP, const float* win, float* out /* [TG][P] */) {
+    const int R = (P % 8 == 0) ? 8 : (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1, Q = P / R;
+    if (R > 4 || !(Q & 1) || !(KP == 3 || KP == 4 || KP == 6)) return -1;
+    const cf* xi = reinterpret_cast<const cf*>(x);
+    std::vector<cf> xin((size_t)P * (TG + 1)), xout((size_t)P * (TG + 1), make_float2(-7.f, -7.f)), stw(P);
+    for (int m = 0; m < P; ++m) {
+        const double ang = -2.0 * kPi * m / P;
+        stw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    for (int p = 0; p < P; ++p)
+        for (int gl = 0; gl < TG; ++gl) xin[(size_t)p * (TG + 1) + gl] = cscale(xi[(size_t)p * TG + gl], win[p]);
+    for (int t = 0; t < RSP_MTD_THREADS; ++t) mtd_dft_fold_phase(xin.data(), P, R, TG, t, RSP_MTD_THREADS);
+    if (TG != 8) return -3;                                   // the row pitch is a template parameter: the test uses tiles of 8 gates
+    // as the in-place kernel runs it: every item computes into its registers, barrier, every item stores over the input tile
+    const int groups = mtd_dft_sym_groups(Q, KP);
+    const bool inplace = mtd_dft_sym_inplace(Q, KP, TG, RSP_MTD_THREADS);
+    cf* dst = inplace ? xin.data() : xout.data();
+    auto run = [&](auto r_tag, auto kp_tag) {
+        constexpr int RR = decltype(r_tag)::value, KK = decltype(kp_tag)::value;
+        struct Regs { cf A[KK][RR], B[KK][RR]; int kk[KK]; };
+        std::vector<Regs> regs((size_t)groups * TG);
+        for (int e = 0; e < groups * TG; ++e)
+            mtd_dft_sym_compute<RR, KK, 9>(xin.data(), stw.data(), P, (e / TG) * KK, e % TG, regs[e].A, regs[e].B, regs[e].kk);
+        for (int e = 0; e < groups * TG; ++e)
+            mtd_dft_sym_store<RR, KK, 9>(dst, stw.data(), P, (e / TG) * KK, e % TG, regs[e].A, regs[e].B, regs[e].kk);
+    };
+#define RSP_EMUL_SYM(r, kp) if (R == r && KP == kp) run(std::integral_constant<int, r>{}, std::integral_constant<int, kp>{});
+    RSP_EMUL_SYM(4, 3) RSP_EMUL_SYM(2, 3) RSP_EMUL_SYM(1, 3) RSP_EMUL_SYM(4, 4) RSP_EMUL_SYM(2, 4) RSP_EMUL_SYM(1, 4)
+    RSP_EMUL_SYM(4, 6) RSP_EMUL_SYM(2, 6) RSP_EMUL_SYM(1, 6)
+#undef RSP_EMUL_SYM
+    if (inplace) xout = xin;
     cf* o = reinterpret_cast<cf*>(out);
     for (int gl = 0; gl < TG; ++gl)
         for (int row = 0; row < P; ++row) o[(size_t)gl * P + row] = xout[(size_t)row * (TG + 1) + gl];

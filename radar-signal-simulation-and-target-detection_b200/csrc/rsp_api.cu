@@ -270,29 +270,39 @@ template <class A, class B> static size_t pc_smem_pair() { return smem_for_occup
 // (tile gates, power-of-two factor R of P, output bins per work item KT)
 #define RSP_FOR_EACH_DFT_TR(X, kt) X(32, 1, kt) X(32, 2, kt) X(32, 4, kt) X(16, 1, kt) X(16, 2, kt) X(16, 4, kt) X(8, 1, kt) X(8, 2, kt) X(8, 4, kt)
 #define RSP_FOR_EACH_DFT(X) RSP_FOR_EACH_DFT_TR(X, 1) RSP_FOR_EACH_DFT_TR(X, 4) RSP_FOR_EACH_DFT_TR(X, 6) RSP_FOR_EACH_DFT_TR(X, 11) \
-    X(32, 8, 1) X(16, 8, 1) X(8, 8, 1) X(32, 8, 4) X(16, 8, 4) X(8, 8, 4)
+    X(32, 8, 1) X(16, 8, 1) X(8, 8, 1) X(32, 8, 4) X(16, 8, 4) X(8, 8, 4)                                                          \
+    RSP_FOR_EACH_DFT_TR(X, 103) RSP_FOR_EACH_DFT_TR(X, 104) RSP_FOR_EACH_DFT_TR(X, 106)      /* odd Q: 3 / 4 / 6 bin pairs per item */
 #define RSP_FOR_EACH_POW2_P(X) X(8, 8, 1, 1) X(16, 16, 1, 1) X(32, 8, 4, 1) X(64, 8, 8, 1) X(128, 16, 8, 1) X(256, 16, 16, 1) X(512, 8, 8, 8)
 // Tile width (gates) and output bins per work item of the generic Doppler DFT kernel.  The kernel's cost per
 // gate is (rounds of the CTA over its work items) x (bins per item) / (tile gates), divided by how many CTAs
 // fit an SM (the load and read-out phases of one tile hide behind the sums of another; measured on the
 // native P = 332 = 4 x 83: (32, 11) 455 us, (16, 6) 376 us, (16, 4) 452 us, (8, 4) 370 us).  Near-ties go to
 // the wider tile (longer contiguous stretches in the pulse-compressed cube).
-static size_t dft_smem_bytes(int P, int tg) { return ((size_t)2 * P * (tg + 1) + P) * sizeof(float2); }
+static size_t dft_smem_bytes(int P, int tg, int R = 1, int kt = 1) {    // input tile + output tile (one tile for the in-place folded form) + twiddles
+    const bool one = kt >= 100 && mtd_dft_sym_inplace(P / R, kt - 100, tg, RSP_MTD_THREADS);
+    return ((size_t)(one ? 1 : 2) * P * (tg + 1) + P) * sizeof(float2);
+}
 static bool choose_dft_plan(int P, int R, int* tg_out, int* kt_out) {
     const int Q = P / R;
     const int tg_env = getenv("RSP_DFT_TG") ? atoi(getenv("RSP_DFT_TG")) : 0;
     const int kt_env = getenv("RSP_DFT_KT") ? atoi(getenv("RSP_DFT_KT")) : 0;
     double best = -1.0;
     for (int tg : {32, 16, 8}) {
-        const size_t sm = dft_smem_bytes(P, tg);
-        if (sm > 200 * 1024 || (tg_env && tg != tg_env)) continue;
-        for (int kt : {1, 4, 6, 11}) {
+        if (tg_env && tg != tg_env) continue;
+        // odd Q >= 7: the folded form (kt = 100 + bin pairs per item) does a quarter of the multiply-adds; RSP_DFT_SYM=0 keeps the direct sums
+        static const bool sym_ok = [] { const char* e = getenv("RSP_DFT_SYM"); return !(e && atoi(e) == 0); }();
+        const bool sym = sym_ok && (Q & 1) && Q >= 7 && R <= 4;
+        for (int kt : {1, 4, 6, 11, 103, 104, 106}) {
+            if ((kt >= 100) != sym && !(kt_env && kt == kt_env && (kt < 100 || ((Q & 1) && R <= 4)))) continue;
             if ((kt > 4 && R > 4) || (kt_env ? kt != kt_env : kt == 1)) continue;     // kt = 1 only on request
-            const int regs = kt == 11 ? 160 : kt == 6 ? 96 : 64;
+            const int kp = kt >= 100 ? kt - 100 : 0;
+            const size_t sm = dft_smem_bytes(P, tg, R, kt);
+            if (sm > 200 * 1024) continue;
+            const int regs = kt >= 100 ? (kp == 6 ? 168 : kp == 4 ? 128 : 96) : kt == 11 ? 160 : kt == 6 ? 96 : 64;
             const int ctas = (int)std::min<size_t>(std::min<size_t>(227 * 1024 / (sm + 1024), 65536 / (regs * RSP_MTD_THREADS)), 3);
-            const long items = (long)((Q + kt - 1) / kt) * tg;
+            const long items = (long)(kt >= 100 ? ((Q - 1) / 2 + 1 + kp - 1) / kp : (Q + kt - 1) / kt) * tg;
             const long rounds = (items + RSP_MTD_THREADS - 1) / RSP_MTD_THREADS;
-            const double cost = (double)rounds * kt / tg / std::max(ctas, 1);
+            const double cost = (double)rounds * (kt >= 100 ? kp : kt) / tg / std::max(ctas, 1);
             if (best < 0 || cost < best * 0.85) { best = cost; *tg_out = tg; *kt_out = kt; }
         }
     }
@@ -580,7 +590,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         c->mtd_tg = 0;
         if (!choose_dft_plan(P, c->mtd_r, &c->mtd_tg, &c->mtd_kt))
             return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
-        c->mtd_smem = dft_smem_bytes(P, c->mtd_tg);
+        c->mtd_smem = dft_smem_bytes(P, c->mtd_tg, c->mtd_r, c->mtd_kt);
 #define X(tg, r, kt) if (c->mtd_tg == tg && c->mtd_r == r && c->mtd_kt == kt) CU(c, opt_in_smem(mtd_dft_kernel<tg, r, kt>, c->mtd_smem));
         RSP_FOR_EACH_DFT(X)
 #undef X
@@ -1781,7 +1791,7 @@ int rsp_stage2_configure(rsp_ctx* c, const rsp_stage2_config* cfg) {
         c->mtd_tg = 0;
         if (!choose_dft_plan(P, c->mtd_r, &c->mtd_tg, &c->mtd_kt))
             return fail(c, RSP_ERR_UNSUPPORTED, "P=%d too large for the generic Doppler DFT kernel", P);
-        c->mtd_smem = dft_smem_bytes(P, c->mtd_tg);
+        c->mtd_smem = dft_smem_bytes(P, c->mtd_tg, c->mtd_r, c->mtd_kt);
 #define X(tg, r, kt) if (c->mtd_tg == tg && c->mtd_r == r && c->mtd_kt == kt) CU(c, opt_in_smem(mtd_dft_kernel<tg, r, kt>, c->mtd_smem));
         RSP_FOR_EACH_DFT(X)
 #undef X

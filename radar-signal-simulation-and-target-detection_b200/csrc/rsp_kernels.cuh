@@ -1005,12 +1005,15 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_c
     extern __shared__ float2 mtd_smem[];
     l2_discard(k.dead);
     const int P = k.P, Q = P / R;
+    constexpr int KP = KT >= 100 ? KT - 100 : 1;
+    const bool inplace = KT >= 100 && mtd_dft_sym_inplace(Q, KP, TG, RSP_MTD_THREADS);
     float2* xin = mtd_smem;
-    float2* xout = xin + (size_t)P * (TG + 1);
+    float2* xout = inplace ? xin : xin + (size_t)P * (TG + 1);
     float2* stw = xout + (size_t)P * (TG + 1);
     const int tid = threadIdx.x;
     for (int i = tid; i < P; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
     const int g0 = k.g_lo + blockIdx.x * TG, b = blockIdx.y;
+#pragma unroll 4
     for (int e = tid; e < P * TG; e += RSP_MTD_THREADS) {
         const int p = e / TG, gl = e - p * TG, g = g0 + gl;
         float2 x = make_float2(0.f, 0.f);
@@ -1018,7 +1021,25 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_c
         xin[p * (TG + 1) + gl] = cscale(x, k.win[p]);
     }
     __syncthreads();
-    if (KT == 1) {
+    if (KT >= 100) {                  // odd Q: even / odd folding, KT - 100 bin pairs per work item (mtd_dft_sym_*)
+        mtd_dft_fold_phase(xin, P, R, TG, tid, RSP_MTD_THREADS);
+        __syncthreads();
+        const int n_items = mtd_dft_sym_groups(Q, KP) * TG;
+        cf A[KP][R], Bm[KP][R];
+        int kk[KP];
+        if (inplace) {
+            const int kg = tid / TG, gl = tid - kg * TG;
+            if (tid < n_items) mtd_dft_sym_compute<R, KP, TG + 1>(xin, stw, P, kg * KP, gl, A, Bm, kk);
+            __syncthreads();          // every item has read the tile
+            if (tid < n_items) mtd_dft_sym_store<R, KP, TG + 1>(xout, stw, P, kg * KP, gl, A, Bm, kk);
+        } else {
+            for (int e = tid; e < n_items; e += RSP_MTD_THREADS) {
+                const int kg = e / TG, gl = e - kg * TG;
+                mtd_dft_sym_compute<R, KP, TG + 1>(xin, stw, P, kg * KP, gl, A, Bm, kk);
+                mtd_dft_sym_store<R, KP, TG + 1>(xout, stw, P, kg * KP, gl, A, Bm, kk);
+            }
+        }
+    } else if (KT == 1) {
         for (int e = tid; e < Q * TG; e += RSP_MTD_THREADS) {
             const int kk = e / TG, gl = e - kk * TG;
             mtd_dft_item<R>(xin, xout, stw, P, TG, kk, gl);
@@ -1027,7 +1048,7 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_c
         const int groups = (Q + KT - 1) / KT;
         for (int e = tid; e < groups * TG; e += RSP_MTD_THREADS) {
             const int kg = e / TG, gl = e - kg * TG;
-            mtd_dft_item_kt<R, (KT > 1 ? KT : 2)>(xin, xout, stw, P, TG, kg * KT, gl);
+            mtd_dft_item_kt<R, (KT > 1 && KT < 100 ? KT : 2)>(xin, xout, stw, P, TG, kg * KT, gl);
         }
     }
     __syncthreads();

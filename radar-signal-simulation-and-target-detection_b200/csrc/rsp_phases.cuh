@@ -376,6 +376,105 @@ template <int R, int KT> RSP_HD void mtd_dft_item_kt(const cf* xin, cf* xout, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Odd sub-length Q (the native P = 332 = 4 x 83): the length-Q DFTs by their even / odd parts.  With
+//   S_n = x[n] + x[Q-n],  D_n = x[n] - x[Q-n]   (n = 1 .. H = (Q-1)/2, formed once per line by mtd_dft_fold_phase),
+//   X[k]   = x[0] + sum_n S_n cos(2 pi n k / Q)  -  i sum_n D_n sin(2 pi n k / Q)
+//   X[Q-k] = x[0] + sum_n S_n cos(...)           +  i sum_n D_n sin(...)
+// a pair of bins costs 4 FMAs per (n, sub-sequence) instead of the 16 of two direct sums: a quarter of the multiply-adds
+// (110 k -> 28 k per line at P = 332), which is what the direct kernel was bound by.  KP bin pairs per work item share the
+// S / D loads; pair 0 is bin 0 alone.  Same radix-R recombination as mtd_dft_item.
+// ---------------------------------------------------------------------------------------------
+RSP_HD void mtd_dft_fold_phase(cf* xin, int P, int R, int TG, int tid, int nthreads) {
+    const int Q = P / R, H = (Q - 1) / 2, ld = TG + 1;
+    const int n_items = R * H * TG;
+    for (int e = tid; e < n_items; e += nthreads) {
+        const int an = e / TG, gl = e - an * TG;
+        const int n = an / R, a = an - n * R;
+        cf* lo = xin + (a + R * (n + 1)) * ld + gl;
+        cf* hi = xin + (a + R * (Q - 1 - n)) * ld + gl;
+        const cf x = *lo, y = *hi;
+        *lo = cadd(x, y);
+        *hi = csub(x, y);
+    }
+}
+
+// LD = TG + 1 (row pitch of the tile) is a template parameter so that every shared-memory offset of the inner loop is an
+// immediate; the twiddle index is kept pre-scaled (stw[R (n k mod Q)] = stw[(n R k) mod P]).
+template <int R, int KP, int LD>
+RSP_HD void mtd_dft_sym_compute(const cf* xin, const cf* stw, int P, int kp0, int gl, cf (&A)[KP][R], cf (&B)[KP][R], int (&kk)[KP]) {
+    const int Q = P / R, H = (Q - 1) / 2;
+    int idx[KP], step[KP];                                  // A = x0 + sum S cos,  B = - sum D sin
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        kk[j] = kp0 + j <= H ? kp0 + j : H;                 // pairs past the end repeat the last one and are not stored
+        idx[j] = 0;
+        step[j] = R * kk[j];
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+            A[j][a] = xin[a * LD + gl];
+            B[j][a] = make_float2(0.f, 0.f);
+        }
+    }
+    const cf* pS = xin + gl + R * LD;                       // row n = 1 of sub-sequence 0
+    const cf* pD = xin + gl + R * (Q - 1) * LD;             // row Q - 1
+    for (int n = 1; n <= H; ++n, pS += R * LD, pD -= R * LD) {
+        cf S[R], D[R];
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+            S[a] = pS[a * LD];
+            D[a] = pD[a * LD];
+        }
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            idx[j] += step[j];
+            if (idx[j] >= P) idx[j] -= P;                   // R (n k_j mod Q)
+            const cf w = stw[idx[j]];                       // (cos, -sin) of 2 pi n k_j / Q
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+                A[j][a].x = fmaf(S[a].x, w.x, A[j][a].x);
+                A[j][a].y = fmaf(S[a].y, w.x, A[j][a].y);
+                B[j][a].x = fmaf(D[a].x, w.y, B[j][a].x);
+                B[j][a].y = fmaf(D[a].y, w.y, B[j][a].y);
+            }
+        }
+    }
+}
+
+template <int R, int KP, int LD>
+RSP_HD void mtd_dft_sym_store(cf* xout, const cf* stw, int P, int kp0, int gl, const cf (&A)[KP][R], const cf (&B)[KP][R], const int (&kk)[KP]) {
+    const int Q = P / R, H = (Q - 1) / 2, half = P / 2;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        if (kp0 + j > H) break;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && kk[j] == 0) break;             // bin 0 has no mirror
+            const int k = side == 0 ? kk[j] : Q - kk[j];
+            cf acc[R];
+#pragma unroll
+            for (int a = 0; a < R; ++a)                     // X[k] = A + i B,  X[Q-k] = A - i B   (B carries the minus of the sine sum)
+                acc[a] = side == 0 ? make_float2(A[j][a].x - B[j][a].y, A[j][a].y + B[j][a].x)
+                                   : make_float2(A[j][a].x + B[j][a].y, A[j][a].y - B[j][a].x);
+#pragma unroll
+            for (int a = 1; a < R; ++a) acc[a] = cmul(acc[a], stw[a * k]);
+            if (R > 1) SmallDft<(R > 1 ? R : 2), -1>::run(acc);
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                int row = k + Q * d + half;
+                if (row >= P) row -= P;
+                xout[row * LD + gl] = acc[d];
+            }
+        }
+    }
+}
+
+// work items of one tile: groups of KP bin pairs x TG gates
+RSP_HD int mtd_dft_sym_groups(int Q, int KP) { return ((Q - 1) / 2 + 1 + KP - 1) / KP; }
+// When one round of the CTA covers all items, the results wait in registers until every item has read the tile and then
+// overwrite it: one tile instead of two in shared memory (twice the CTAs per SM at P = 332).
+RSP_HD bool mtd_dft_sym_inplace(int Q, int KP, int TG, int nthreads) { return mtd_dft_sym_groups(Q, KP) * TG <= nthreads; }
+
 // =============================================================================================
 // CFAR on one (pair, gate tile): S tile rows = gates [g_first - mR, g_first + TG + mR), P columns.
 //   fun_process_single_frame.m:192-213.  Two phases: window sums, then the decision.

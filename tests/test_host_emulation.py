@@ -182,6 +182,22 @@ def test_mtd_generic_dft_tile_k_tiled_is_bit_identical(lib, P, KT):
     assert np.array_equal(one.view(np.uint32), kt.view(np.uint32))
 
 
+@pytest.mark.parametrize("KP", [3, 4, 6])
+@pytest.mark.parametrize("P", [332, 83, 20, 166, 7, 45, 28])
+def test_mtd_generic_dft_tile_folded_form(lib, P, KP):
+    """mtd_dft_kernel<TG, R, 100 + KP> for odd Q = P / R (the native 332 = 4 x 83): even / odd folding (mtd_dft_fold_phase) and
+    bin pairs (mtd_dft_item_sym) against NumPy, every output row written exactly once (a last, partly filled group included)."""
+    TG = 8
+    rng = np.random.default_rng(P + KP)
+    x = (rng.standard_normal((P, TG)) + 1j * rng.standard_normal((P, TG))).astype(np.complex64)
+    win = np.kaiser(P, 4.5).astype(np.float32)
+    out = np.zeros((TG, P), np.complex64)
+    rc = lib.emul_mtd_dft_tile_sym(x.ctypes.data_as(fp), P, TG, KP, win.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert rc == 0
+    ref = np.fft.fftshift(np.fft.fft(x.astype(np.complex128) * win.astype(np.float64)[:, None], axis=0), axes=0).T
+    assert np.abs(out - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("tg", [16, 32, 64])
 @pytest.mark.parametrize("shape", [(300, 64, 10, 10, 5, 5), (200, 32, 10, 2, 5, 4), (150, 48, 3, 4, 2, 3)])
 def test_cfar_tiles_match_oracle(lib, shape, tg):
