@@ -1,7 +1,8 @@
 /* mex.h -- PROTOTYPE SHIM for compile-checking the gateways where MATLAB/Octave is absent.
  * Declares only the subset of the MEX C API (R2018a interleaved-complex flavour) the gateways use.
- * It is never linked: build the real MEX file with `mex -R2018a` (MATLAB) or `mkoctfile --mex`
- * (Octave), which supply the genuine header and library.  See INTEGRATION.md. */
+ * The real MEX file is built with `mex -R2018a` (MATLAB) or `mkoctfile --mex` (Octave), which supply the genuine header
+ * and library.  For the tests, mex_stub_runtime.cpp implements these entry points well enough to LINK the
+ * gateways against librsp.so and RUN them (tests/test_mex_gateway.py). */
 #ifndef RSP_MEX_SHIM_H_
 #define RSP_MEX_SHIM_H_
 #include <stddef.h>
