@@ -59,6 +59,24 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// mbarrier wait of the role warps.  RSP_TC_SLEEP_NS > 0 backs off between polls (__nanosleep): the polls are 40 % of this
+// kernel's executed instructions, which cost nothing while it runs alone but take issue slots from co-resident kernels.
+#ifndef RSP_TC_SLEEP_NS
+#define RSP_TC_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
+#if RSP_TC_SLEEP_NS > 0
+    uint32_t ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(RSP_TC_SLEEP_NS);
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -170,7 +188,7 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
 #endif
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % NS, round = i / NS;
-                if (round > 0) mbar_wait(BAR(NS + s), (uint32_t)(round - 1) & 1u);
+                if (round > 0) tc_wait(BAR(NS + s), (uint32_t)(round - 1) & 1u);
                 const int tile = first + i * step;
                 const int pr = tile / tpp, p = k.p_lo + pr, n0 = (k.tile_lo + tile - pr * tpp) * RSP_TC_TILE;
                 mbar_expect_tx(BAR(s), raw_stage);
@@ -196,8 +214,8 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
             const int first_term = (k.dbg & 1) ? 3 : (k.dbg & 16) ? 2 : 0;
             for (int i = 0; i < n_my; ++i) {
                 const int buf = i & 1;
-                mbar_wait(BAR(B_A_READY + buf), (uint32_t)(i >> 1) & 1u);
-                if (i >= 2) mbar_wait(BAR(B_D_FREE + buf), (uint32_t)((i >> 1) - 1) & 1u);
+                tc_wait(BAR(B_A_READY + buf), (uint32_t)(i >> 1) & 1u);
+                if (i >= 2) tc_wait(BAR(B_D_FREE + buf), (uint32_t)((i >> 1) - 1) & 1u);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(buf * NPAD);
                 const uint32_t a_hi = tmem_base + 64u + (uint32_t)(2 * buf * KCOLS), a_lo = a_hi + (uint32_t)KCOLS;
@@ -244,8 +262,8 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
         };
         for (int i = 0; i < n_my; ++i) {
             const int s = i % NS, buf = i & 1;
-            mbar_wait(BAR(s), (uint32_t)(i / NS) & 1u);
-            if (i >= 2) { mbar_wait(BAR(B_MMA_DONE + buf), (uint32_t)((i >> 1) - 1) & 1u); tc_fence_after(); }   // operand buffer `buf` has been consumed
+            tc_wait(BAR(s), (uint32_t)(i / NS) & 1u);
+            if (i >= 2) { tc_wait(BAR(B_MMA_DONE + buf), (uint32_t)((i >> 1) - 1) & 1u); tc_fence_after(); }   // operand buffer `buf` has been consumed
             const unsigned char* rs = s_raw + (size_t)s * raw_stage + (size_t)m * 8;
             const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + 64u + (uint32_t)(2 * buf * KCOLS);    // hi buffer; lo follows at + KCOLS
             if (!(k.dbg & 4)) {
@@ -272,13 +290,13 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
             __syncwarp();
             if (lane == 0) { mbar_arrive(BAR(B_A_READY + buf)); mbar_arrive(BAR(NS + s)); }
             if (i > 0) {                                                  // epilogue of the previous tile while the tensor core works on this one
-                mbar_wait(BAR(B_MMA_DONE + (buf ^ 1)), (uint32_t)((i - 1) >> 1) & 1u);
+                tc_wait(BAR(B_MMA_DONE + (buf ^ 1)), (uint32_t)((i - 1) >> 1) & 1u);
                 tc_fence_after();
                 epilogue(i - 1);
             }
         }
         if (n_my > 0) {
-            mbar_wait(BAR(B_MMA_DONE + ((n_my - 1) & 1)), (uint32_t)((n_my - 1) >> 1) & 1u);
+            tc_wait(BAR(B_MMA_DONE + ((n_my - 1) & 1)), (uint32_t)((n_my - 1) >> 1) & 1u);
             tc_fence_after();
             epilogue(n_my - 1);
         }
