@@ -60,6 +60,36 @@ template <int SIGN> RSP_HD void dft4(cf& x0, cf& x1, cf& x2, cf& x3) {
     x3 = csub(t1, t3);
 }
 
+// y0 = a + w b, y1 = a - w b with w = (wr, wi) the FORWARD twiddle (SIGN > 0: its conjugate), as 4 + 2 fused multiply-adds:
+// the product goes straight into the sum and the difference is 2 a - y0.  Two instructions fewer than multiply, add, subtract.
+#ifndef RSP_FFT_FMA
+#define RSP_FFT_FMA 1
+#endif
+template <int SIGN> RSP_HD void fma_pm(cf a, cf b, float wr, float wi, cf& y0, cf& y1) {
+    if (SIGN < 0) {
+        y0.x = fmaf(b.x, wr, fmaf(-b.y, wi, a.x));
+        y0.y = fmaf(b.x, wi, fmaf(b.y, wr, a.y));
+    } else {
+        y0.x = fmaf(b.x, wr, fmaf(b.y, wi, a.x));
+        y0.y = fmaf(b.y, wr, fmaf(-b.x, wi, a.y));
+    }
+    y1.x = fmaf(2.f, a.x, -y0.x);
+    y1.y = fmaf(2.f, a.y, -y0.y);
+}
+// DFT-4 of (x0, w1 x1, w2 x2, w3 x3); T0 = false: x0 is multiplied by w0 as well
+template <int SIGN, bool T0> RSP_HD void dft4_tw(cf& x0, cf& x1, cf& x2, cf& x3, cf w0, cf w1, cf w2, cf w3) {
+    const cf a0 = T0 ? x0 : mul_tw<SIGN>(x0, w0.x, w0.y);
+    cf t0, t1, t2, t3;
+    fma_pm<SIGN>(a0, x2, w2.x, w2.y, t0, t1);
+    const cf u = mul_tw<SIGN>(x1, w1.x, w1.y);
+    fma_pm<SIGN>(u, x3, w3.x, w3.y, t2, t3);
+    t3 = mul_quarter<SIGN>(t3);
+    x0 = cadd(t0, t2);
+    x1 = cadd(t1, t3);
+    x2 = csub(t0, t2);
+    x3 = csub(t1, t3);
+}
+
 template <int R, int SIGN> struct SmallDft;
 
 template <int SIGN> struct SmallDft<2, SIGN> {
@@ -92,7 +122,40 @@ template <int SIGN> struct SmallDft<16, SIGN> {
     static RSP_HD void run(cf* v) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) dft4<SIGN>(v[b], v[4 + b], v[8 + b], v[12 + b]);   // t[b][c] at v[4c+b]
-        // t[b][c] *= W16^{bc}
+        run_second_stage(v);
+    }
+    // t[b][c] *= W16^{bc}, then for every c a DFT-4 over b
+    static RSP_HD void run_second_stage(cf* v) {
+#if RSP_FFT_FMA
+        cf o[16];
+        {   // c = 0: no twiddles
+            cf a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+            dft4<SIGN>(a0, a1, a2, a3);
+            o[0] = a0; o[4] = a1; o[8] = a2; o[12] = a3;
+        }
+        {   // c = 1: W16^1, W16^2, W16^3 folded into the butterfly
+            cf a0 = v[4], a1 = v[5], a2 = v[6], a3 = v[7];
+            dft4_tw<SIGN, true>(a0, a1, a2, a3, make_float2(1.f, 0.f), make_float2(RSP_COS_PI_8, -RSP_SIN_PI_8),
+                                make_float2(RSP_SQRT1_2, -RSP_SQRT1_2), make_float2(RSP_SIN_PI_8, -RSP_COS_PI_8));
+            o[1] = a0; o[5] = a1; o[9] = a2; o[13] = a3;
+        }
+        {   // c = 2: W16^2, W16^4 = -i (free), W16^6
+            cf a0 = v[8], a2 = mul_quarter<SIGN>(v[10]);
+            const cf u = mul_tw<SIGN>(v[9], RSP_SQRT1_2, -RSP_SQRT1_2);
+            cf t0 = cadd(a0, a2), t1 = csub(a0, a2), t2, t3;
+            fma_pm<SIGN>(u, v[11], -RSP_SQRT1_2, -RSP_SQRT1_2, t2, t3);
+            t3 = mul_quarter<SIGN>(t3);
+            o[2] = cadd(t0, t2); o[6] = cadd(t1, t3); o[10] = csub(t0, t2); o[14] = csub(t1, t3);
+        }
+        {   // c = 3: W16^3, W16^6, W16^9
+            cf a0 = v[12], a1 = v[13], a2 = v[14], a3 = v[15];
+            dft4_tw<SIGN, true>(a0, a1, a2, a3, make_float2(1.f, 0.f), make_float2(RSP_SIN_PI_8, -RSP_COS_PI_8),
+                                make_float2(-RSP_SQRT1_2, -RSP_SQRT1_2), make_float2(-RSP_COS_PI_8, RSP_SIN_PI_8));
+            o[3] = a0; o[7] = a1; o[11] = a2; o[15] = a3;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = o[i];
+#else
         v[4 * 1 + 1] = mul_tw<SIGN>(v[4 * 1 + 1], RSP_COS_PI_8, -RSP_SIN_PI_8);      // e=1
         v[4 * 1 + 2] = mul_tw<SIGN>(v[4 * 1 + 2], RSP_SQRT1_2, -RSP_SQRT1_2);        // e=2
         v[4 * 1 + 3] = mul_tw<SIGN>(v[4 * 1 + 3], RSP_SIN_PI_8, -RSP_COS_PI_8);      // e=3
@@ -111,6 +174,20 @@ template <int SIGN> struct SmallDft<16, SIGN> {
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = o[i];
+#endif
+    }
+    // the same transform of (v[0], w[1] v[1], ..., w[15] v[15]): the input twiddles of a DIT pass folded into the first stage
+    static RSP_HD void run_twiddled(cf* v, const cf* w) {
+#if RSP_FFT_FMA
+        dft4_tw<SIGN, true>(v[0], v[4], v[8], v[12], make_float2(1.f, 0.f), w[4], w[8], w[12]);
+#pragma unroll
+        for (int b = 1; b < 4; ++b) dft4_tw<SIGN, false>(v[b], v[4 + b], v[8 + b], v[12 + b], w[b], w[4 + b], w[8 + b], w[12 + b]);
+        run_second_stage(v);
+#else
+#pragma unroll
+        for (int k = 1; k < 16; ++k) v[k] = mul_tw<SIGN>(v[k], w[k].x, w[k].y);
+        run(v);
+#endif
     }
 };
 

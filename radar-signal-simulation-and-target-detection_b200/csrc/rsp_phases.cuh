@@ -123,12 +123,18 @@ template <class Cfg, int SIGN, bool DIF> RSP_HD void pc_pass2_butterfly(cf* s, c
         for (int k = 1; k < R; ++k) sb[RSP_POFF(k * SPAN)] = mul_tw<SIGN>(v[k], w[k].x, w[k].y);
     } else {
         v[0] = sb[0];
+        if (R == 16) {                                   // input twiddles folded into the first butterfly stage (fma_pm)
 #pragma unroll
-        for (int k = 1; k < R; ++k) {
-            const cf x = sb[RSP_POFF(k * SPAN)];
-            v[k] = mul_tw<SIGN>(x, w[k].x, w[k].y);
+            for (int k = 1; k < R; ++k) v[k] = sb[RSP_POFF(k * SPAN)];
+            SmallDft<16, SIGN>::run_twiddled(v, w);
+        } else {
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                const cf x = sb[RSP_POFF(k * SPAN)];
+                v[k] = mul_tw<SIGN>(x, w[k].x, w[k].y);
+            }
+            SmallDft<R, SIGN>::run(v);
         }
-        SmallDft<R, SIGN>::run(v);
 #pragma unroll
         for (int m = 0; m < R; ++m) sb[RSP_POFF(m * SPAN)] = v[m];
     }
@@ -173,12 +179,18 @@ template <class Cfg> RSP_HD void pc_phase_ipass1_store(const PcBlockArgs& a, con
         cf v[Cfg::R1], w[Cfg::R1];
         pc_twiddles<Cfg::R1>(a.tw1 + q, Cfg::SPAN1, w);
         v[0] = sb[0];
+        if (Cfg::R1 == 16) {
 #pragma unroll
-        for (int k = 1; k < Cfg::R1; ++k) {
-            const cf x = sb[RSP_POFF(k * Cfg::SPAN1)];
-            v[k] = mul_tw<+1>(x, w[k].x, w[k].y);
+            for (int k = 1; k < Cfg::R1; ++k) v[k] = sb[RSP_POFF(k * Cfg::SPAN1)];
+            SmallDft<16, +1>::run_twiddled(v, w);
+        } else {
+#pragma unroll
+            for (int k = 1; k < Cfg::R1; ++k) {
+                const cf x = sb[RSP_POFF(k * Cfg::SPAN1)];
+                v[k] = mul_tw<+1>(x, w[k].x, w[k].y);
+            }
+            SmallDft<Cfg::R1, +1>::run(v);
         }
-        SmallDft<Cfg::R1, +1>::run(v);
         cf* dst = a.out_line + a.g0 + q - (a.taps - 1);
 #pragma unroll
         for (int m = 0; m < Cfg::R1; ++m) {
