@@ -162,6 +162,9 @@ struct rsp_ctx {
     // pipelined paths (rsp_submit_cpi / rsp_submit_targets): the count and the first prefetch_k records of a slot
     // are copied to pinned memory behind the slot's kernels, so the fetch is one event wait and no round trip
     int prefetch_k = 0;
+    std::vector<std::pair<uint64_t, int>> sort_keys;      // scratch of sort_detections_inplace
+    std::vector<rsp_detection> sort_tmp;
+    cudaStream_t fetch_stream = nullptr;  // late records of dense frames (fetch_slot)
     int* h_slot_count = nullptr;          // pinned [slots]
     rsp_detection* h_slot_recs = nullptr; // pinned [slots][prefetch_k]
     std::vector<cudaEvent_t> slot_done;   // recorded behind the prefetch copies
@@ -346,6 +349,7 @@ void rsp_destroy(rsp_ctx* c) {
         if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
     }
     if (c->fork) cudaEventDestroy(c->fork);
+    if (c->fetch_stream) cudaStreamDestroy(c->fetch_stream);
     cudaFree(c->d_rawdet); cudaFree(c->d_fused_dbg); cudaFree(c->d_Bw_tc);
     cudaFree(c->d_tx); cudaFree(c->d_tg); cudaFree(c->d_tg_ring);
     if (c->h_tg_ring) cudaFreeHost(c->h_tg_ring);
@@ -1404,6 +1408,20 @@ static bool det_less(const rsp_detection& a, const rsp_detection& b) {
     return a.v_idx < b.v_idx;
 }
 
+// The reference's order (pair, then range, then Doppler: MATLAB find, fsf:215-221).  Dense frames (1600 records of 40 bytes)
+// are sorted through one 64-bit key per record and gathered once; comparing and swapping whole records cost three times as much.
+static void sort_detections_inplace(rsp_ctx* c, rsp_detection* dets, int n) {
+    if (n < 64) { std::sort(dets, dets + n, det_less); return; }
+    std::vector<std::pair<uint64_t, int>>& keys = c->sort_keys;
+    keys.resize((size_t)n);
+    for (int i = 0; i < n; ++i)
+        keys[i] = {((uint64_t)(uint32_t)dets[i].pair_idx << 48) | ((uint64_t)(uint32_t)dets[i].r_idx << 24) | (uint64_t)(uint32_t)dets[i].v_idx, i};
+    std::sort(keys.begin(), keys.end());
+    std::vector<rsp_detection>& tmp = c->sort_tmp;
+    tmp.assign(dets, dets + n);
+    for (int i = 0; i < n; ++i) dets[i] = tmp[(size_t)keys[i].second];
+}
+
 // bring the input cube to device PCN complex64; returns the device pointer to use
 static int stage_input(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem mem, const float2** out) {
     const size_t n = (size_t)c->P * c->C * c->N;
@@ -1452,7 +1470,8 @@ static int check_slot_free(rsp_ctx* c, int slot) {
 static int finish_submit(rsp_ctx* c, int slot, int l) {
     cudaStream_t s = c->lanes[l].s;
     if (!c->h_slot_count) {
-        c->prefetch_k = std::min(512, c->prm.max_detections);
+        c->prefetch_k = std::min(1024, c->prm.max_detections);
+        CU(c, cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking));
         CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_slot_count), (size_t)c->slots * sizeof(int)));
         CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_slot_recs), (size_t)c->slots * c->prefetch_k * sizeof(rsp_detection)));
         c->slot_done.resize((size_t)c->slots);
@@ -1488,13 +1507,22 @@ static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap
     if (n > 0) {
         if (pre && n <= c->prefetch_k) {
             std::memcpy(dets, c->h_slot_recs + (size_t)slot * c->prefetch_k, (size_t)n * sizeof(rsp_detection));
+        } else if (pre) {
+            // a dense frame: the records beyond the prefetched block come over on a stream of their own (the slot's kernels
+            // have finished -- slot_done --, and the lanes' streams already hold the work of later frames)
+            const size_t k0 = (size_t)c->prefetch_k;
+            CU(c, cudaMemcpyAsync(c->h_recs, c->d_recs + (size_t)slot * c->prm.max_detections + k0, ((size_t)n - k0) * sizeof(rsp_detection),
+                                  cudaMemcpyDeviceToHost, c->fetch_stream));
+            std::memcpy(dets, c->h_slot_recs + (size_t)slot * k0, k0 * sizeof(rsp_detection));
+            CU(c, cudaStreamSynchronize(c->fetch_stream));
+            std::memcpy(dets + k0, c->h_recs, ((size_t)n - k0) * sizeof(rsp_detection));
         } else {
             CU(c, cudaMemcpyAsync(c->h_recs, c->d_recs + (size_t)slot * c->prm.max_detections, (size_t)n * sizeof(rsp_detection),
                                   cudaMemcpyDeviceToHost, c->stream));
             CU(c, cudaStreamSynchronize(c->stream));
             std::memcpy(dets, c->h_recs, (size_t)n * sizeof(rsp_detection));
         }
-        std::sort(dets, dets + n, det_less);
+        sort_detections_inplace(c, dets, n);
     }
     return RSP_OK;
 }

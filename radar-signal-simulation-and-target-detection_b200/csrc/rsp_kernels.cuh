@@ -242,7 +242,11 @@ __global__ void __launch_bounds__(256) synth_kernel(const __grid_constant__ Synt
 // Samples n0 (even) and n0 + 1 of line `line_id` = pulse * C + channel: Philox noise, then the targets in index order.
 // ph[t * ph_stride] is target t's phasor for this (pulse, channel).  Statement for statement the per-pair body of
 // synth_gather_kernel (kept in its measured form above), used by the fused dbf_synth_kernel.
-__device__ __forceinline__ float4 synth_pair(const SynthArgs& k, const float2* ph, int ph_stride, const int* delay, int n0, size_t line_id) {
+// act0 / act1: bit t (t + 32) set = target t can reach the caller's sample range (dbf_synth_kernel culls per warp: with 64
+// targets only the ~11 % whose non-zero pulse stretches overlap the warp's 16-32 samples are visited; a culled target would
+// have added exact zeros, so the result is the same).
+__device__ __forceinline__ float4 synth_pair(const SynthArgs& k, const float2* ph, int ph_stride, const int* delay, int n0, size_t line_id,
+                                             unsigned act0 = 0xFFFFFFFFu, unsigned act1 = 0xFFFFFFFFu) {
     float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k.noise_sigma > 0.f) {
         const uint4 r = philox4x32_10(make_uint4((unsigned)(n0 / 2), (unsigned)line_id, (unsigned)(line_id >> 32), 0u), k.round_key);
@@ -250,19 +254,26 @@ __device__ __forceinline__ float4 synth_pair(const SynthArgs& k, const float2* p
         z = make_float4(z0.x * k.noise_sigma, z0.y * k.noise_sigma, z1.x * k.noise_sigma, z1.y * k.noise_sigma);
     }
     const unsigned span = (unsigned)(k.tx_hi - k.tx_lo);
-    for (int t = 0; t < k.n_targets; ++t) {
-        const int j = n0 - delay[t] - k.tx_lo;                          // tx index of sample n0, relative to the hull
-        if ((unsigned)(j + 1) <= span) {                                // sample n0 or n0 + 1 is inside the delayed hull
-            const float2 p = ph[t * ph_stride];
-            if ((unsigned)j < span) {
-                const float2 x = k.tx[j + k.tx_lo];
-                z.x += x.x * p.x - x.y * p.y;
-                z.y += x.x * p.y + x.y * p.x;
-            }
-            if ((unsigned)(j + 1) < span) {
-                const float2 x = k.tx[j + 1 + k.tx_lo];
-                z.z += x.x * p.x - x.y * p.y;
-                z.w += x.x * p.y + x.y * p.x;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        unsigned m = h == 0 ? act0 : act1;
+        if (h == 0 ? k.n_targets < 32 : k.n_targets < 64) m &= (1u << (k.n_targets - 32 * h > 0 ? k.n_targets - 32 * h : 0)) - 1u;
+        while (m) {                                                         // ascending target index, like the plain loop
+            const int t = 32 * h + __ffs(m) - 1;
+            m &= m - 1;
+            const int j = n0 - delay[t] - k.tx_lo;                          // tx index of sample n0, relative to the hull
+            if ((unsigned)(j + 1) <= span) {                                // sample n0 or n0 + 1 is inside the delayed hull
+                const float2 p = ph[t * ph_stride];
+                if ((unsigned)j < span) {
+                    const float2 x = k.tx[j + k.tx_lo];
+                    z.x += x.x * p.x - x.y * p.y;
+                    z.y += x.x * p.y + x.y * p.x;
+                }
+                if ((unsigned)(j + 1) < span) {
+                    const float2 x = k.tx[j + 1 + k.tx_lo];
+                    z.z += x.x * p.x - x.y * p.y;
+                    z.w += x.x * p.y + x.y * p.x;
+                }
             }
         }
     }
@@ -642,6 +653,19 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_synth_kernel(const __
     const int n_base = (blockIdx.x * (RSP_DBF_MMA_THREADS / 32) + w) * (16 * NQ);
     if (n_base >= N) return;
     const int sg = (g & 1) ? g + 7 : g;                                  // even: a float4 is one (n0, n0 + 1) pair of a line
+    unsigned act[2];                                                     // targets with a non-zero stretch inside the warp's samples
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int tt = lane + 32 * h;
+        bool a = false;
+        if (tt < k.n_targets) {
+            const int d = s_delay[tt];
+#pragma unroll
+            for (int sgm = 0; sgm < 3; ++sgm)
+                a = a || (k.seg_hi[sgm] > k.seg_lo[sgm] && d + k.seg_lo[sgm] < n_base + 16 * NQ && d + k.seg_hi[sgm] > n_base);
+        }
+        act[h] = __ballot_sync(0xFFFFFFFFu, a);
+    }
     float4 x[KS][NQ];
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
@@ -650,7 +674,7 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_synth_kernel(const __
         for (int q = 0; q < NQ; ++q) {
             const int n0 = n_base + 16 * q + sg;
             x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < C && n0 < N) x[s][q] = synth_pair(k, s_ph + c, 4 * KS, s_delay, n0, (size_t)p * C + c);
+            if (c < C && n0 < N) x[s][q] = synth_pair(k, s_ph + c, 4 * KS, s_delay, n0, (size_t)p * C + c, act[0], act[1]);
         }
     }
     float acc[MT][2 * NQ][4];

@@ -144,6 +144,43 @@ def test_clustering_equals_the_literal_bfs_on_random_scenes(seed):
         assert np.allclose(m, want, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("case", ["equal_keys", "zero_sep", "nan_range", "dense_1600", "wide_sep"])
+def test_clustering_cell_sweep_degenerate_scenes(case):
+    """The cell sweep of rsp_cluster (cells a quarter of max_range_sep wide) against the literal search where the cell
+    arithmetic degenerates: one cell, zero-width gate, a non-finite key, a dense 64-target frame, a gate wider than the scene."""
+    rng = np.random.default_rng(11)
+    cfg = o.Config()
+    n = 1600 if case == "dense_1600" else 120
+    d = np.zeros(n, dtype=rsp.DETECTION_DTYPE)
+    centres = rng.uniform(4000, 34000, size=64 if case == "dense_1600" else 6)
+    which = rng.integers(0, len(centres), n)
+    d["range"] = centres[which] + np.round(rng.uniform(-14, 14, n) / 6.0) * 6.0
+    d["velocity"] = (which % 7) * 3.0 + rng.choice([0.0, 2.4], n) + rng.normal(0, 0.05, n)
+    d["angle"] = (which % 5) * 4.0 + rng.normal(0, 0.5, n)
+    d["power"] = rng.uniform(1, 1e4, n).astype(np.float32)
+    sep = cfg.max_range_sep
+    if case == "equal_keys":
+        d["range"] = 5000.0
+    elif case == "zero_sep":
+        sep = 0.0
+    elif case == "nan_range":
+        d["range"][7] = np.nan
+        d["range"][31] = np.inf
+    elif case == "wide_sep":
+        sep = 1e6
+    cfg.max_range_sep = sep
+    cp = rsp.Struct(max_range_sep=sep, max_vel_sep=cfg.max_vel_sep, max_angle_sep=cfg.max_angle_sep)
+    s1, fin = rsp.cluster(d, cp)
+    par = np.stack([d["range"], d["velocity"], d["angle"], d["power"].astype(np.float64), np.ones(n)], 1)
+    with np.errstate(invalid="ignore"):
+        ref1 = o.cluster_stage1(par, cfg)
+        ref2 = o.cluster_stage2(ref1, cfg)
+    assert len(s1) == len(ref1) and len(fin) == len(ref2)
+    for got, want in ((s1, ref1), (fin, ref2)):
+        m = np.stack([got["range"], got["velocity"], got["angle"], got["power"]], 1)
+        assert np.allclose(m, want, rtol=1e-12, atol=0, equal_nan=True)
+
+
 def test_product_precompute_equals_oracle_precompute():
     for name in ("native", "cfg1", "cfg2", "cfg3"):
         config, cfar_params, _ = rsp.named_config(name)
