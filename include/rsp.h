@@ -259,8 +259,6 @@ typedef struct {
     int64_t launches_total;       /* kernels launched by this context so far */
     int32_t lanes;                /* concurrent CPI lanes of the stream / pipelined paths (RSP_LANES) */
     int32_t graph_launches;       /* rsp_stream_enqueue batches replayed as one CUDA graph (launches_total counts their kernels) */
-    int32_t coupled_launches;     /* CPIs enqueued (or captured) with the coupled S5 -> S6 launch: pulse compression as a programmatic
-                                   * dependent of the DBF, consuming each pulse's beams out of L2 as soon as they are stored */
 } rsp_info;
 int rsp_get_info(const rsp_ctx* ctx, rsp_info* info);
 /* Measurement aid of the fused DBF + pulse-compression kernel: when the context was created under RSP_FUSED_DEBUG=<flags>,

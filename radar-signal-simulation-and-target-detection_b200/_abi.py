@@ -55,7 +55,7 @@ class rsp_info(C.Structure):
     _fields_ = [("n_gates_total", C.c_int32), ("fft_len_medium", C.c_int32), ("fft_len_long", C.c_int32),
                 ("blocks_medium", C.c_int32), ("blocks_long", C.c_int32), ("kernels_per_cpi", C.c_int32),
                 ("algorithmic_bytes_per_cpi", C.c_int64), ("launches_total", C.c_int64), ("lanes", C.c_int32),
-                ("graph_launches", C.c_int32), ("coupled_launches", C.c_int32)]
+                ("graph_launches", C.c_int32)]
 
 
 class rsp_target_in(C.Structure):

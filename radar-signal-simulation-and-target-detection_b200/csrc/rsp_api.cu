@@ -55,7 +55,6 @@ struct rsp_ctx {
         float* amp = nullptr;
         float2* raw = nullptr;            // staging cube of the pipelined host-input / frame paths (lazy)
         float2* rdm = nullptr;            // own RDM of those paths when the caller passes none (lazy; lane 0 uses d_rdm)
-        unsigned* ready = nullptr;        // [P] per-pulse counters of the coupled S5 -> S6 launches
         unsigned long long seen_epoch = 0;  // last caller_epoch this lane was ordered behind (pipelined paths)
         cudaEvent_t done = nullptr;
     };
@@ -73,7 +72,6 @@ struct rsp_ctx {
     std::vector<GraphEntry> graphs;
     unsigned long long graph_epoch = 0;
     long graph_launches = 0;
-    long coupled_launches = 0;
     Lane* cur = nullptr;                  // lane the launch helpers enqueue on
     bool discard = false;                 // stream path: drop dead intermediates from L2 (see l2_discard)
     cudaEvent_t fork = nullptr;
@@ -174,8 +172,6 @@ struct rsp_ctx {
     int mtd_tg = 32, mtd_r = 1, mtd_kt = 1, cfar_tg = 32, cfar_variant = 0;
     bool cfar_vec = false;
     int pulse_block = 0;                  // > 0: pulses per group of the pulse-blocked S5 -> S6 path (enqueue_chain)
-    bool couple = false;                  // coupled S5 -> S6: the pulse compression runs behind the DBF pulse by pulse (plan_dbf_tc)
-    int n_sm = 148;
     bool cfar5 = false;                   // cfar5_kernel (marching) instead of cfar4_kernel
     size_t mtd_smem = 0, cfar_smem = 0;
     // per-kernel event timing (rsp_set_profiling)
@@ -348,7 +344,7 @@ void rsp_destroy(rsp_ctx* c) {
     drop_graphs(c);
     cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_rdm);
     for (auto& ln : c->lanes) {
-        cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp); cudaFree(ln.raw); cudaFree(ln.rdm); cudaFree(ln.ready);
+        cudaFree(ln.beam); cudaFree(ln.pc); cudaFree(ln.amp); cudaFree(ln.raw); cudaFree(ln.rdm);
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.s && &ln != &c->lanes[0]) cudaStreamDestroy(ln.s);
     }
@@ -443,8 +439,6 @@ int rsp_create(const rsp_params* p, rsp_ctx** out) {
         CUC(dev_alloc(&ln.beam, (size_t)c->P * c->B * c->ldb));
         CUC(dev_alloc(&ln.pc, (size_t)c->P * c->B * c->ldg));
         CUC(dev_alloc(&ln.amp, PBG));
-        CUC(dev_alloc(&ln.ready, (size_t)c->P));
-        CUC(cudaMemset(ln.ready, 0, (size_t)c->P * sizeof(unsigned)));
         CUC(cudaMemset(ln.beam, 0, (size_t)c->P * c->B * c->ldb * sizeof(float2)));
         CUC(cudaMemset(ln.pc, 0, (size_t)c->P * c->B * c->ldg * sizeof(float2)));
     }
@@ -943,7 +937,6 @@ static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
     a.Bw = c->d_Bw_tc;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->prm.device);
-    c->n_sm = nsm;
     int per_sm = 1;
     if (const char* ep = getenv("RSP_TC_CTAS_PER_SM")) per_sm = std::max(1, atoi(ep));
     c->dbf_tc_grid = std::min(nsm * per_sm, c->P * a.tiles_per_pulse);
@@ -958,15 +951,11 @@ static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
     // RSP_PULSE_BLOCK=n: opt-in pulse-blocked S5 -> S6 (enqueue_chain).  Measured slower at config 3 (470 us per CPI whole-cube,
     // 493 with groups of 16 pulses, 511 with 8: profiles/r2f_pulse_block_cfg3.txt), like the range-blocked chain.
     if (const char* e = getenv("RSP_PULSE_BLOCK")) c->pulse_block = std::max(0, atoi(e));
-    // Coupled S5 -> S6 (enqueue_chain): on by default where the beam cube cannot wait in L2 for a separate pulse-compression
-    // launch (config 3: 268 MB, native: 201 MB), i.e. where it costs a DRAM write and a DRAM read; RSP_COUPLE=0 / 1 overrides.
-    c->couple = false;   // measured slower at config 3 (profiles/r2t_couple_cfg3.txt): opt-in
-    if (const char* e = getenv("RSP_COUPLE")) c->couple = atoi(e) != 0;
     return RSP_OK;
 }
 
 static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile_lo = 0, int tile_hi = -1, int p_lo = 0, int p_hi = -1,
-                         DiscardArgs dead_group = DiscardArgs{nullptr, 0}, unsigned* ready = nullptr) {
+                         DiscardArgs dead_group = DiscardArgs{nullptr, 0}) {
     const CUtensorMap* map = raw_tmap(c, raw, TMAP_ROWS_2D);
     if (!map) return fail(c, RSP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the raw cube at %p", raw);
     DbfTcArgs a = c->dbf_tc_args;
@@ -980,11 +969,6 @@ static int launch_dbf_tc(rsp_ctx* c, const float2* raw, int* det_count, int tile
         const int n_tiles = (a.p_hi - a.p_lo) * (a.tile_hi - a.tile_lo);
         if (!det_count) a.dead = dead_group;
         grid = a.chunk > 0 ? (n_tiles + a.chunk - 1) / a.chunk : std::min(grid, n_tiles);
-    }
-    if (ready) {                               // coupled S5 -> S6: one persistent CTA per SM walks the tiles pulse by pulse
-        a.ready = ready;
-        a.chunk = 0;
-        grid = std::min(c->n_sm, c->P * a.tiles_per_pulse);
     }
 #ifdef RSP_PROBES
     // Experiment RSP_EXP_DBF_MULTI=K (tools/overlap_probe.py): ONE persistent launch forms the beams of K consecutive cubes of
@@ -1103,8 +1087,7 @@ static void fill_seg(const rsp_ctx* c, PcSegArgs& sg, const PcPlan& pl, const fl
 // One launch covers the long segment (role 0), the medium segment and the narrow FIR (role 1).
 // p_hi >= 0: only the lines of pulses [p_lo, p_hi) (pulse-blocked path; lines are [pulse][beam], so a pulse group is a
 // contiguous run of lines of both cubes).
-// ready != nullptr: coupled launch (see launch_coupled) -- the first kernel is a programmatic dependent of the DBF before it.
-static void launch_pc(rsp_ctx* c, int p_lo = 0, int p_hi = -1, const unsigned* ready = nullptr) {
+static void launch_pc(rsp_ctx* c, int p_lo = 0, int p_hi = -1) {
     const bool narrow = c->prm.n_gates[0] > 0;
     const bool fold = narrow && c->med.L > 0;        // the medium groups compute the narrow gates too
     const int line0 = p_lo * c->B, n_lines = ((p_hi < 0 ? c->P : p_hi) - p_lo) * c->B;
@@ -1124,21 +1107,9 @@ static void launch_pc(rsp_ctx* c, int p_lo = 0, int p_hi = -1, const unsigned* r
     a.group_bar = c->pc_group_bar;
     a.fir = c->d_fir; a.nfir = c->n_fir; a.fir_delay = c->prm.fir_delay;
     a.narrow_start0 = c->prm.seg_start[0] - 1; a.narrow_gates = c->prm.n_gates[0];
-    a.ready = ready; a.ready_target = 4u * (unsigned)c->dbf_tc_args.tiles_per_pulse; a.ready_B = c->B;
     const int nctas = a.seg[0].n_ctas + a.seg[1].n_ctas;
     const int la = c->lng.L ? c->lng.L : 1024, lb = c->med.L ? c->med.L : 1024;
     Timed t(c, K_PC);
-    if (ready) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)nctas); cfg.blockDim = dim3(RSP_PC_THREADS); cfg.stream = c->cur->s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-#define X(A, B) if (la == A::L && lb == B::L) { cfg.dynamicSmemBytes = pc_smem_pair<A, B>(); cudaLaunchKernelEx(&cfg, pc_fft_kernel<A, B>, a); }
-        RSP_FOR_EACH_PC_PAIR(X)
-#undef X
-    } else
 #ifdef RSP_PROBES
     static const int exp_merge = probe_env("RSP_EXP_MERGE", 0);
     if (exp_merge && la == 4096 && lb == 1024 && c->exp_raw && c->B <= 8 && c->C <= 16) {   // experiment: DBF CTAs interleaved with the PC CTAs
@@ -1372,13 +1343,6 @@ static int kernels_per_cpi(const rsp_ctx* c) {
     return n;
 }
 
-// the coupled launch needs every reader of the beam cube to sit behind the per-pulse counters: the FFT kernel does, the
-// stand-alone narrow-FIR kernel (shapes without a medium segment) does not
-static bool can_couple(const rsp_ctx* c) {
-    const bool narrow = c->prm.n_gates[0] > 0;
-    return (c->med.L > 0 || c->lng.L > 0) && !(narrow && c->med.L == 0);
-}
-
 // enqueue S5..S9 for one device-resident PCN cube on lane `lane`
 static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, int lane) {
     c->cur = &c->lanes[lane];
@@ -1416,16 +1380,6 @@ static int enqueue_chain(rsp_ctx* c, const float2* raw, float2* rdm, int slot, i
                 if (!rc) launch_pc(c, p0, p1);
             }
             if (rc) return rc;
-        } else if (c->couple && tc_ok && stages == 15 && !c->profiling && can_couple(c)) {
-            // Coupled S5 -> S6: the DBF publishes a counter per pulse, the pulse-compression kernel is launched as its
-            // programmatic dependent (it may start once every DBF CTA is resident) and picks up each pulse's lines as soon as
-            // their tiles are stored -- out of L2, while the DBF streams the later pulses in.  Same kernels, same arithmetic.
-            unsigned* ready = c->cur->ready;
-            CU(c, cudaMemsetAsync(ready, 0, (size_t)c->P * sizeof(unsigned), c->cur->s));
-            rc = launch_dbf_tc(c, raw, c->d_counts + slot, 0, -1, 0, -1, DiscardArgs{nullptr, 0}, ready);
-            if (rc) return rc;
-            launch_pc(c, 0, -1, ready);
-            c->coupled_launches++;
         } else {
         if (stages & 1) rc = launch_dbf_any(c, raw, c->d_counts + slot);  // dbf_kernel also zeroes the slot's counter
         if (rc) return rc;
@@ -2269,7 +2223,6 @@ int rsp_get_info(const rsp_ctx* c, rsp_info* info) {
     info->launches_total = c->launches;
     info->lanes = c->n_lanes;
     info->graph_launches = (int32_t)c->graph_launches;
-    info->coupled_launches = (int32_t)c->coupled_launches;
     return RSP_OK;
 }
 

@@ -44,10 +44,6 @@ struct DbfTcArgs {
     int p_wrap;              // RSP_PROBES builds: > 0 writes pulse p to beam row p % p_wrap (multi-CPI experiment)
     int dbg;                 // RSP_TC_DEBUG measurement aid (results wrong): 1 no MMAs, 2 no beam stores, 4 no conversion, 8 no proxy fence, 16 one MMA term
     DiscardArgs dead;
-    // Coupled S5 -> S6 (rsp_api.cu, launch_coupled): ready[p] counts the epilogue warps that have stored their rows of a tile of
-    // pulse p (4 per tile); the pulse-compression kernel, launched as a programmatic dependent of this one, starts a line of
-    // pulse p when ready[p] == 4 tiles_per_pulse and so reads the beams out of L2 while this kernel is still forming later pulses.
-    unsigned* ready;
 };
 
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -178,8 +174,6 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
-    // every CTA of this (persistent) grid is resident and set up: the dependent pulse-compression grid may be scheduled
-    if (k.ready && tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int tpp = k.tile_hi - k.tile_lo;                                   // tiles per pulse of this launch
     const int n_tiles = (k.p_hi - k.p_lo) * tpp;
@@ -264,10 +258,6 @@ __global__ void RSP_TC_BOUNDS dbf_tc_kernel(const __grid_constant__ CUtensorMap 
                     for (int b = 0; b < 8; ++b)
                         if (8 * h + b < k.B) dst[(size_t)(8 * h + b) * k.ldb] = make_float2(v[2 * b], v[2 * b + 1]);
                 }
-            }
-            if (k.ready) {                                               // this warp's 32 rows of the tile are stored: publish them
-                __syncwarp();
-                if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(k.ready + p) : "memory");
             }
         };
         for (int i = 0; i < n_my; ++i) {

@@ -769,26 +769,7 @@ struct PcKernelArgs {
     const float* fir;
     int nfir, fir_delay, narrow_start0, narrow_gates;
     int group_bar;               // 1: the groups of a CTA synchronise separately (named barriers)
-    // Coupled S5 -> S6: when set, a group waits until ready[line / ready_B] == ready_target (all tiles of its pulse stored by
-    // the DBF kernel this launch programmatically depends on) before it touches its beam line.
-    const unsigned* ready = nullptr;
-    unsigned ready_target = 0;
-    int ready_B = 1;
 };
-
-// Wait of one group (whole warps) for the producer's per-pulse counter: one thread polls with acquire loads, the group's
-// barrier passes the visibility on to the others.
-__device__ __forceinline__ void pc_wait_ready(const unsigned* ready, unsigned target, int pulse, int t, int grp, int nthreads) {
-    if (t == 0) {
-        unsigned v;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + pulse) : "memory");
-            if (v >= target) break;
-            __nanosleep(200);
-        }
-    }
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
-}
 
 // Barrier over one group of T threads (whole warps) that share an overlap-save block: named barrier 1 + grp.
 // The groups of a CTA are independent after the shared tables are loaded, so they need not wait for each other.
@@ -823,7 +804,6 @@ __device__ __forceinline__ void pc_role(const PcKernelArgs& k, const PcSegArgs& 
     a.g0 = sg.gate0 + blk * sg.valid;
     a.g_end = sg.g_end;
     const bool pg = k.group_bar != 0 && Cfg::NG > 1;
-    if (k.ready && active) pc_wait_ready(k.ready, k.ready_target, line / k.ready_B, t, grp, Cfg::T);
     if (active) pc_phase_load_pass1<Cfg>(a, s, t);
     __syncthreads();                                 // also publishes stw2 / sfir, loaded by the whole CTA
     if (active) pc_phase_pass2<Cfg>(a, s, t);

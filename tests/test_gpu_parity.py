@@ -505,49 +505,6 @@ def test_pulse_blocked_dbf_pc_equals_whole_cube_launches(C, B, P, N, pb):
         assert np.array_equal(a, b), what
 
 
-@pytest.mark.parametrize("C,B,P,N", [(32, 16, 8, 4096), (16, 8, 12, 8192), (12, 5, 6, 4112), (16, 13, 20, 5819 + 1)])
-def test_coupled_dbf_pc_equals_separate_launches(C, B, P, N):
-    """Coupled S5 -> S6 (default where the beam cube is larger than L2 can hold, RSP_COUPLE=1 here): the DBF counts the stored
-    tiles of every pulse, the pulse-compression kernel is launched as its programmatic dependent and starts a pulse's lines
-    when the counter is complete.  Same kernels and arithmetic as the separate launches: beam, pulse-compressed cube, RDM
-    and detections must be bit identical -- for one CPI, and for a stream of CPIs over the lanes with CUDA-graph replays."""
-    import os
-    import torch
-    config, cfar_params, cluster_params = rsp.default_config(channel_num=C, beam_num=B, prtNum=P, point_PRT=N)
-    pd = rsp.build_precomputed_data(config)
-    ocfg = o.shaped_config(C, B, P, N)
-    opre = o.build_precomputed(ocfg)
-    tg = [o.Target(900.0, 0.1 * opre["v_max"], -5.0, 25.0), o.Target(3000.0, -0.1 * opre["v_max"], 8.0, 20.0)]
-    cubes = [o.add_noise(o.synthesize_echo(tg, ocfg, opre), 5 + i).astype(np.complex64) for i in range(3)]
-    out = {}
-    for mode in ("1", "0"):
-        os.environ["RSP_COUPLE"] = mode
-        try:
-            chain = rsp.RadarChain(config, cfar_params, pd)
-            single = [(chain.process_cpi(c), chain.get_beam(), chain.get_pc(), chain.get_rdm()) for c in cubes]
-            lanes = chain.info()["lanes"]
-            pool = torch.from_numpy(np.stack(cubes)).cuda()
-            rdm = torch.zeros((lanes, chain.B, chain.G, chain.P), dtype=torch.complex64, device="cuda")
-            n = 2 * lanes + 1
-            streamed = []
-            for rep in range(3):                                # direct launches, capture + launch, replay
-                chain.stream_enqueue(pool.data_ptr(), 3, rdm.data_ptr(), lanes, n, 0)
-                chain.synchronize()
-                streamed.append([chain.stream_fetch(i) for i in range(n)])
-            out[mode] = (single, streamed, chain.info()["coupled_launches"], rdm.cpu().numpy().copy())
-            chain.close()
-        finally:
-            os.environ.pop("RSP_COUPLE", None)
-    assert out["1"][2] > 0 and out["0"][2] == 0, "the coupled path was not taken / not switched off"
-    for (d1, b1, p1, r1), (d0, b0, p0, r0) in zip(out["1"][0], out["0"][0]):
-        assert np.array_equal(b1, b0) and np.array_equal(p1, p0) and np.array_equal(r1, r0) and np.array_equal(d1, d0)
-    assert np.abs(out["1"][0][0][3]).max() > 0
-    for rep in range(3):
-        for i, d in enumerate(out["1"][1][rep]):
-            assert np.array_equal(d, out["0"][0][i % 3][0]), (rep, i)
-    assert np.array_equal(out["1"][3], out["0"][3])
-
-
 def test_batched_frames_equal_one_at_a_time():
     """process_targets_batch (device synthesis of many frames + multi-lane stream) == process_targets per frame."""
     chain, config, cfar_params, cluster_params, pd = _device_chain("cfg1")
