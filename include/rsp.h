@@ -250,6 +250,19 @@ int rsp_submit_targets(rsp_ctx* ctx, const rsp_target_in* targets, int32_t n_tar
 int rsp_fetch_targets(rsp_ctx* ctx, int32_t slot, const rsp_cluster_params* cp, rsp_target* final_targets, int32_t cap,
                       int32_t* n_final, rsp_detection* dets /* may be NULL */, int32_t det_cap, int32_t* n_dets /* may be NULL */);
 
+/* A whole block of independent frames (Monte-Carlo trials, the frame loop of main_simulate_echoes_with_array_v8_3.m:200-248)
+ * in one call: frame i = targets[sum(n_targets[0..i)) ...], seeds[i]; frames are submitted `depth` ahead of the fetch
+ * (0 = 2 x lanes) on the ring slots i % slots, and the host half of every frame -- sorting its detections into the reference's
+ * find order, S10 / S11 clustering (fsf:302-407) -- runs on `host_threads` worker threads (0 = 4), so dense frames do not hold
+ * the GPU back.  Results per frame as from rsp_fetch_targets: final_targets[i * cap ...], n_final[i]; optionally every frame's
+ * sorted detections packed back to back in dets[det_offsets[i] .. det_offsets[i + 1]) (dets NULL: not returned).  More targets
+ * than cap in a frame, or more detections than det_cap_total in all, is RSP_ERR_OVERFLOW.  No pipelined submission of this
+ * context may be outstanding when it is called. */
+int rsp_process_frames(rsp_ctx* ctx, const rsp_target_in* targets, const int32_t* n_targets, int32_t n_frames, double noise_power,
+                       const uint64_t* seeds, const rsp_cluster_params* cp, int32_t depth, int32_t host_threads,
+                       rsp_target* final_targets, int32_t cap, int32_t* n_final,
+                       rsp_detection* dets /* may be NULL */, int64_t det_cap_total, int64_t* det_offsets /* [n_frames + 1] when dets */);
+
 /* ---- introspection ---- */
 typedef struct {
     int32_t n_gates_total;        /* G */

@@ -121,6 +121,8 @@ SYMBOLS = [
     ("rsp_process_targets", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, C.POINTER(rsp_cluster_params), _P, C.c_int32,
                                       C.POINTER(C.c_int32), _P, C.c_int32, C.POINTER(C.c_int32)]),
     ("rsp_submit_targets", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_uint64, C.c_int32]),
+    ("rsp_process_frames", C.c_int, [_P, _P, _P, C.c_int32, C.c_double, _P, C.POINTER(rsp_cluster_params), C.c_int32, C.c_int32,
+                                     _P, C.c_int32, _P, _P, C.c_int64, _P]),
     ("rsp_fetch_targets", C.c_int, [_P, C.c_int32, C.POINTER(rsp_cluster_params), _P, C.c_int32, C.POINTER(C.c_int32), _P, C.c_int32,
                                     C.POINTER(C.c_int32)]),
     ("rsp_get_info", C.c_int, [_P, C.POINTER(rsp_info)]),

@@ -5,7 +5,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rsp.h"
@@ -1410,17 +1414,16 @@ static bool det_less(const rsp_detection& a, const rsp_detection& b) {
 
 // The reference's order (pair, then range, then Doppler: MATLAB find, fsf:215-221).  Dense frames (1600 records of 40 bytes)
 // are sorted through one 64-bit key per record and gathered once; comparing and swapping whole records cost three times as much.
-static void sort_detections_inplace(rsp_ctx* c, rsp_detection* dets, int n) {
+static void sort_detections_keyed(rsp_detection* dets, int n, std::vector<std::pair<uint64_t, int>>& keys, std::vector<rsp_detection>& tmp) {
     if (n < 64) { std::sort(dets, dets + n, det_less); return; }
-    std::vector<std::pair<uint64_t, int>>& keys = c->sort_keys;
     keys.resize((size_t)n);
     for (int i = 0; i < n; ++i)
         keys[i] = {((uint64_t)(uint32_t)dets[i].pair_idx << 48) | ((uint64_t)(uint32_t)dets[i].r_idx << 24) | (uint64_t)(uint32_t)dets[i].v_idx, i};
     std::sort(keys.begin(), keys.end());
-    std::vector<rsp_detection>& tmp = c->sort_tmp;
     tmp.assign(dets, dets + n);
     for (int i = 0; i < n; ++i) dets[i] = tmp[(size_t)keys[i].second];
 }
+static void sort_detections_inplace(rsp_ctx* c, rsp_detection* dets, int n) { sort_detections_keyed(dets, n, c->sort_keys, c->sort_tmp); }
 
 // bring the input cube to device PCN complex64; returns the device pointer to use
 static int stage_input(rsp_ctx* c, const void* raw, rsp_layout layout, rsp_dtype dtype, rsp_mem mem, const float2** out) {
@@ -1487,7 +1490,7 @@ static int finish_submit(rsp_ctx* c, int slot, int l) {
     return RSP_OK;
 }
 
-static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets) {
+static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap, int32_t* n_dets, bool sort = true) {
     const bool pre = !c->slot_prefetched.empty() && c->slot_prefetched[slot];
     int n;
     if (pre) {                            // pipelined submission: its result is already on its way to pinned memory
@@ -1522,7 +1525,7 @@ static int fetch_slot(rsp_ctx* c, int slot, rsp_detection* dets, int32_t det_cap
             CU(c, cudaStreamSynchronize(c->stream));
             std::memcpy(dets, c->h_recs, (size_t)n * sizeof(rsp_detection));
         }
-        sort_detections_inplace(c, dets, n);
+        if (sort) sort_detections_inplace(c, dets, n);
     }
     return RSP_OK;
 }
@@ -2150,6 +2153,115 @@ int rsp_fetch_targets(rsp_ctx* c, int32_t slot, const rsp_cluster_params* cp, rs
     if (nf > cap) return fail(c, RSP_ERR_OVERFLOW, "%d targets exceed the caller's capacity %d", nf, cap);
     if (nf > 0 && !final_targets) return fail(c, RSP_ERR_INVALID_ARG, "null output");
     if (nf > 0) std::memcpy(final_targets, fin.data(), (size_t)nf * sizeof(rsp_target));
+    return RSP_OK;
+}
+
+// Many independent frames through the pipelined frame path with the host half of each frame (sorting the detection list
+// into the reference's find order, S10 / S11 clustering) on a pool of worker threads: the submitting thread only enqueues
+// frames `depth` ahead and copies finished detection lists out of pinned memory, so dense frames (64 targets: ~1600
+// detections, 110 us of clustering each) no longer hold the GPU back.
+int rsp_process_frames(rsp_ctx* c, const rsp_target_in* targets, const int32_t* n_targets, int32_t n_frames, double noise_power,
+                       const uint64_t* seeds, const rsp_cluster_params* cp, int32_t depth, int32_t host_threads,
+                       rsp_target* final_targets, int32_t cap, int32_t* n_final,
+                       rsp_detection* dets, int64_t det_cap_total, int64_t* det_offsets) {
+    if (!c || !cp || !n_targets || !seeds || !n_final || n_frames < 0 || cap < 0 || (cap > 0 && !final_targets) || (dets && !det_offsets))
+        return fail(c, RSP_ERR_INVALID_ARG, "bad rsp_process_frames arguments");
+    if (n_frames == 0) { if (det_offsets) det_offsets[0] = 0; return RSP_OK; }
+    CU(c, cudaSetDevice(c->prm.device));
+    depth = std::max(1, std::min(depth > 0 ? depth : 2 * c->n_lanes, c->slots));
+    const int n_workers = std::max(1, std::min({host_threads > 0 ? host_threads : 4, 32, (n_frames + 3) / 4}));
+    std::vector<int64_t> tg_off((size_t)n_frames + 1, 0);
+    for (int i = 0; i < n_frames; ++i) {
+        if (n_targets[i] < 0 || (n_targets[i] > 0 && !targets)) return fail(c, RSP_ERR_INVALID_ARG, "bad target count of frame %d", i);
+        tg_off[i + 1] = tg_off[i] + n_targets[i];
+    }
+    struct Job { int frame; rsp_detection* d; int n; std::vector<rsp_detection> own; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job> queue;
+    bool closed = false;
+    int worker_rc = RSP_OK, worker_frame = -1, worker_nf = 0;
+    auto work = [&]() {
+        std::vector<std::pair<uint64_t, int>> keys;
+        std::vector<rsp_detection> tmp;
+        std::vector<rsp_target> fin;
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return closed || !queue.empty(); });
+                if (queue.empty()) return;
+                job = std::move(queue.front());
+                queue.pop_front();
+            }
+            rsp_detection* d = job.d ? job.d : job.own.data();
+            sort_detections_keyed(d, job.n, keys, tmp);
+            fin.resize((size_t)std::max(job.n, 1));
+            int32_t nf = 0, n1 = 0;
+            int rc = rsp_cluster(d, job.n, cp, nullptr, &n1, fin.data(), &nf);
+            n_final[job.frame] = nf;
+            if (!rc && nf > cap) rc = RSP_ERR_OVERFLOW;
+            if (!rc && nf > 0) std::memcpy(final_targets + (size_t)job.frame * cap, fin.data(), (size_t)nf * sizeof(rsp_target));
+            if (rc) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!worker_rc) { worker_rc = rc; worker_frame = job.frame; worker_nf = nf; }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < n_workers; ++w) pool.emplace_back(work);
+    int rc = RSP_OK, submitted = 0, fetched = 0;
+    int64_t off = 0;
+    if (det_offsets) det_offsets[0] = 0;
+    for (int i = 0; i < n_frames + depth && !rc; ++i) {
+        if (i >= depth) {
+            const int j = i - depth;
+            Job job;
+            job.frame = j; job.d = nullptr; job.n = 0;
+            int32_t n = 0;
+            // peek at the count first (the slot's event has to be waited for anyway), then copy into the caller's flat buffer or
+            // into a vector of the job's own
+            CU(c, cudaEventSynchronize(c->slot_done[j % c->slots]));
+            n = c->h_slot_count[j % c->slots];
+            if (n > c->prm.max_detections) { rc = fail(c, RSP_ERR_OVERFLOW, "frame %d: %d detections exceed max_detections=%d", j, n, c->prm.max_detections); ++fetched; break; }
+            if (dets) {
+                if (off + n > det_cap_total) { rc = fail(c, RSP_ERR_OVERFLOW, "frame %d: detections exceed the caller's capacity %lld", j, (long long)det_cap_total); ++fetched; break; }
+                job.d = dets + off;
+            } else {
+                job.own.resize((size_t)std::max(n, 1));
+            }
+            rc = fetch_slot(c, j % c->slots, job.d ? job.d : job.own.data(), std::max(n, 1), &n, false);
+            ++fetched;
+            if (rc) break;
+            job.n = n;
+            off += n;
+            if (det_offsets) det_offsets[j + 1] = off;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                queue.push_back(std::move(job));
+            }
+            cv.notify_one();
+        }
+        if (i < n_frames) {
+            rc = rsp_submit_targets(c, targets ? targets + tg_off[i] : nullptr, n_targets[i], noise_power, seeds[i], i % c->slots);
+            if (!rc) ++submitted;
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        closed = true;
+    }
+    cv.notify_all();
+    for (auto& t : pool) t.join();
+    if (rc) {                                     // keep the submit / fetch pairing of the ring intact for the next caller
+        const std::string msg = c->err;
+        std::vector<rsp_detection> sink((size_t)c->prm.max_detections);
+        for (int j = fetched; j < submitted; ++j) { int32_t n = 0; fetch_slot(c, j % c->slots, sink.data(), (int32_t)sink.size(), &n, false); }
+        c->err = msg;
+        return rc;
+    }
+    if (worker_rc == RSP_ERR_OVERFLOW) return fail(c, worker_rc, "frame %d: %d targets exceed the caller's capacity %d", worker_frame, worker_nf, cap);
+    if (worker_rc) return fail(c, worker_rc, "clustering failed for frame %d", worker_frame);
     return RSP_OK;
 }
 

@@ -14,6 +14,7 @@ import ctypes as C
 import math
 from typing import Iterable, List, Optional, Sequence
 
+import os
 import numpy as np
 
 from . import _abi
@@ -251,12 +252,21 @@ class RadarChain:
             b = self._res_buf = (fin, dets, C.c_void_p(fin.ctypes.data), C.c_void_p(dets.ctypes.data))
         return b
 
-    def process_targets_batch(self, target_lists, cluster_params, noise_power: float = 1.0, seeds=None, depth: int = 0):
+    def process_targets_batch(self, target_lists, cluster_params, noise_power: float = 1.0, seeds=None, depth: int = 0,
+                              host_threads: int = 0, return_detections: bool = True, native: bool = True):
         """Many independent frames (Monte-Carlo trials, a block of a frame stream), pipelined `depth` deep over
         the lanes: frame i+1 is synthesised on the GPU while frame i runs S5..S9, and only target lists go in
-        and detection lists come back.  Returns [(final targets, detections), ...] in input order."""
+        and detection lists come back.  Returns [(final targets, detections), ...] in input order (detections None
+        with ``return_detections=False`` -- the reference function returns final_targets only).
+
+        ``native`` (default): one rsp_process_frames call per block of 256 frames -- submission, fetch and a pool of
+        ``host_threads`` workers for sorting + clustering all inside librsp, so the host half of a dense frame does
+        not hold the GPU back.  ``native=False``: the same pipeline driven frame by frame from Python
+        (rsp_submit_targets / rsp_fetch_targets)."""
         n = len(target_lists)
         seeds = list(range(n)) if seeds is None else list(seeds)
+        if native:
+            return self._process_frames_native(target_lists, cluster_params, noise_power, seeds, depth, host_threads, return_detections)
         slots = self.stream_slots()
         depth = min(depth or 2 * max(self.info()["lanes"], 1), slots)
         out = []
@@ -266,6 +276,48 @@ class RadarChain:
             if i < n:
                 self.submit_targets(target_lists[i], i % slots, noise_power, seeds[i])
         return out[:n]
+
+    _FRAME_BLOCK = 256           # frames per rsp_process_frames call
+    _FRAME_TARGET_CAP = 512      # final targets per frame
+    _FRAME_DET_CAP = 4096        # detections per frame the flat buffer is sized for (on average)
+
+    def _process_frames_native(self, target_lists, cluster_params, noise_power, seeds, depth, host_threads, return_detections):
+        cp = _abi.rsp_cluster_params(float(_field(cluster_params, "max_range_sep")), float(_field(cluster_params, "max_vel_sep")),
+                                     float(_field(cluster_params, "max_angle_sep")))
+        if host_threads <= 0:
+            host_threads = max(2, min(8, (os.cpu_count() or 4) - 1))
+        out = []
+        packed = {}                                   # a list object that appears many times (one scene, many noise seeds) is packed once
+        for b0 in range(0, len(target_lists), self._FRAME_BLOCK):
+            lists = target_lists[b0:b0 + self._FRAME_BLOCK]
+            nb = len(lists)
+            rows = []
+            for tl in lists:
+                r = packed.get(id(tl))
+                if r is None:
+                    r = np.array([(float(_field(t, "Range")), float(_field(t, "Velocity")), float(_field(t, "ElevationAngle")),
+                                   float(_field(t, "SNR_dB"))) for t in tl], dtype=np.float64).reshape(len(tl), 4)
+                    packed[id(tl)] = r
+                rows.append(r)
+            n_tg = np.array([len(r) for r in rows], dtype=np.int32)
+            tg = np.ascontiguousarray(np.concatenate(rows, axis=0)) if n_tg.sum() else np.zeros((1, 4), dtype=np.float64)
+            sd = np.array([int(x) & (2 ** 64 - 1) for x in seeds[b0:b0 + nb]], dtype=np.uint64)
+            fin = np.empty((nb, self._FRAME_TARGET_CAP), dtype=TARGET_DTYPE)
+            n_fin = np.zeros(nb, dtype=np.int32)
+            if return_detections:
+                cap_total = nb * min(self.max_detections, self._FRAME_DET_CAP)
+                dets = np.empty(cap_total, dtype=DETECTION_DTYPE)
+                offs = np.zeros(nb + 1, dtype=np.int64)
+                pd_, po = C.c_void_p(dets.ctypes.data), C.c_void_p(offs.ctypes.data)
+            else:
+                cap_total, dets, offs, pd_, po = 0, None, None, C.c_void_p(), C.c_void_p()
+            _abi.check(self._lib.rsp_process_frames(self._ctx, C.c_void_p(tg.ctypes.data), C.c_void_p(n_tg.ctypes.data), nb,
+                                                    float(noise_power), C.c_void_p(sd.ctypes.data), C.byref(cp), int(depth),
+                                                    int(host_threads), C.c_void_p(fin.ctypes.data), self._FRAME_TARGET_CAP,
+                                                    C.c_void_p(n_fin.ctypes.data), pd_, cap_total, po), self._ctx)
+            for i in range(nb):
+                out.append((fin[i, :n_fin[i]].copy(), dets[offs[i]:offs[i + 1]].copy() if return_detections else None))
+        return out
 
     # -- device-resident stream -----------------------------------------------------------------
     def stream_slots(self) -> int:

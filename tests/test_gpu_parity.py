@@ -525,6 +525,17 @@ def test_batched_frames_equal_one_at_a_time():
         assert np.array_equal(one[i % 5][1], d2) and np.array_equal(one[i % 5][0], f2)
     with pytest.raises(rsp.RspError):
         chain.submit_targets([lists[0][0]] * 65, 0)
+    # the native block call (rsp_process_frames: worker threads sort and cluster) against the frame-by-frame Python pipeline
+    py = chain.process_targets_batch(lists2, cluster_params, 1.0, seeds2, depth=4, native=False)
+    for (f1, d1), (f2, d2) in zip(py, many2):
+        assert np.array_equal(d1, d2) and np.array_equal(f1, f2)
+    only_targets = chain.process_targets_batch(lists2, cluster_params, 1.0, seeds2, host_threads=3, return_detections=False)
+    assert all(d is None for _, d in only_targets) and all(np.array_equal(f, g) for (f, _), (g, _) in zip(only_targets, many2))
+    with pytest.raises(rsp.RspError):                                        # a bad frame inside a block: error, ring left usable
+        chain.process_targets_batch(lists + [[lists[0][0]] * 65] + lists, cluster_params, 1.0, list(range(13)))
+    again = chain.process_targets_batch(lists, cluster_params, 1.0, seeds)
+    for (f1, d1), (f2, d2) in zip(one, again):
+        assert np.array_equal(d1, d2) and np.array_equal(f1, f2)
     chain.close()
 
 

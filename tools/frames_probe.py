@@ -37,12 +37,19 @@ out["kernel_ms_per_frame_sync"] = {k: round(v[0] / 8, 5) for k, v in chain.kerne
 chain.set_profiling(False)
 n = a.frames
 for depth in (1, 2, 3, 6, 12):
-    chain.process_targets_batch([tl] * 8, cluster_params, 1.0, list(range(8)), depth=depth)
+    chain.process_targets_batch([tl] * 8, cluster_params, 1.0, list(range(8)), depth=depth, native=False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    chain.process_targets_batch([tl] * n, cluster_params, 1.0, list(range(n)), depth=depth)
+    chain.process_targets_batch([tl] * n, cluster_params, 1.0, list(range(n)), depth=depth, native=False)
     torch.cuda.synchronize()
     out[f"frames_per_s_depth{depth}"] = round(n / (time.perf_counter() - t0), 1)
+# rsp_process_frames: submission, fetch and a pool of sorting + clustering threads inside librsp
+for threads in (1, 2, 4, 8):
+    for ret in (True, False):
+        chain.process_targets_batch([tl] * 16, cluster_params, 1.0, list(range(16)), host_threads=threads, return_detections=ret)
+        t0 = time.perf_counter()
+        chain.process_targets_batch([tl] * (4 * n), cluster_params, 1.0, list(range(4 * n)), host_threads=threads, return_detections=ret)
+        out[f"native_frames_per_s_threads{threads}" + ("" if ret else "_targets_only")] = round(4 * n / (time.perf_counter() - t0), 1)
 # host side only: submit everything, wait, then time the fetch + sort + cluster of finished slots
 slots = min(chain.stream_slots(), 96)
 for i in range(slots):
