@@ -440,7 +440,7 @@ def main():
                      "note": "SURVEY 8(d) flop count with this build's block plan / device time per CPI / (SMs x 128 lanes x 2 x SM clock)"}
 
     e2e = e2e_targets_rec = config4 = stream_cfg3 = None
-    d2h = 4 + 40 * min(512, chain.max_detections)      # the count and the first 512 records are prefetched to pinned memory
+    d2h = 4 + 40 * min(1024, chain.max_detections)     # the count and the first 1024 records are prefetched to pinned memory
     if not args.no_extras:
         # end to end through the C ABI with HOST buffers: per CPI a 67 MB H2D copy of the pinned cube and a D2H read of its
         # sorted detection list, both inside the timed region.  rsp_submit_cpi pipelines the copy of cube i+1 under the
@@ -451,16 +451,32 @@ def main():
         e2e_n = max(args.e2e_cpis, 2)
         depth = 3
 
+        host_us = {"submit": 0.0, "fetch_wait": 0.0}
+
         def e2e_pass(n):
             nd = 0
             for i in range(n + depth):
                 if i < n:
+                    t1 = time.perf_counter()
                     chain.submit_cpi(cubes[i % len(cubes)], i % slots)
+                    host_us["submit"] += time.perf_counter() - t1
                 if i >= depth:
+                    t1 = time.perf_counter()
                     nd += len(chain.stream_fetch((i - depth) % slots))
+                    host_us["fetch_wait"] += time.perf_counter() - t1
             return nd
-        e2e_pass(4)
+        e2e_pass(4 * info["lanes"])                       # every lane has its staging cube and its RDM before the clock starts
+        # the link's own rate in this process, same pinned cubes, one cudaMemcpyAsync per cube: the ceiling of this path
+        dev_cube = torch.empty(pinned[0].shape, dtype=pinned.dtype, device="cuda")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(32):
+            dev_cube.copy_(pinned[i % len(cubes)], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_cubes_per_s = 32 / (time.perf_counter() - t0)
+        del dev_cube
         barrier()
+        host_us["submit"] = host_us["fetch_wait"] = 0.0
         t0 = time.perf_counter()
         e2e_pass(e2e_n)
         torch.cuda.synchronize()
@@ -469,7 +485,9 @@ def main():
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * e2e_n / float(t_e.item()), "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h,
-               "cpis": e2e_n, "note": "C ABI with host buffers: rsp_submit_cpi (pinned cube H2D + chain, pipelined 3 deep) and "
+               "cpis": e2e_n, "h2d_copy_ceiling_cpis_per_sec": world * h2d_cubes_per_s,
+               "host_submit_us_per_cpi": host_us["submit"] / e2e_n * 1e6, "host_fetch_wait_us_per_cpi": host_us["fetch_wait"] / e2e_n * 1e6,
+               "note": "C ABI with host buffers: rsp_submit_cpi (pinned cube H2D + chain, pipelined 3 deep) and "
                                       "rsp_stream_fetch (sorted detection list D2H) per CPI; PCIe-bound"}
 
         # the reference's own signature: fun_process_single_frame(targets, ...) -> final_targets.  Only the target list goes
