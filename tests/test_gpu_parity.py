@@ -536,6 +536,22 @@ def test_batched_frames_equal_one_at_a_time():
     again = chain.process_targets_batch(lists, cluster_params, 1.0, seeds)
     for (f1, d1), (f2, d2) in zip(one, again):
         assert np.array_equal(d1, d2) and np.array_equal(f1, f2)
+    # capacity of one target per frame through the C ABI itself: a frame with two final targets is an overflow error, not a
+    # truncation; zero frames is a no-op; afterwards the ring is usable
+    import ctypes as C
+    from rsp_b200 import _abi
+    two = [t for t in lists[1]]
+    assert len(one[1][0]) == 2
+    tg = np.array([(t["Range"], t["Velocity"], t["ElevationAngle"], t["SNR_dB"]) for t in two], dtype=np.float64)
+    n_tg, sd = np.array([len(two)], dtype=np.int32), np.array([seeds[1]], dtype=np.uint64)
+    fin, n_fin = np.zeros(1, dtype=rsp.frame.TARGET_DTYPE), np.zeros(1, dtype=np.int32)
+    cp = _abi.rsp_cluster_params(float(cluster_params.max_range_sep), float(cluster_params.max_vel_sep), float(cluster_params.max_angle_sep))
+    args = lambda nfr: (chain._ctx, C.c_void_p(tg.ctypes.data), C.c_void_p(n_tg.ctypes.data), nfr, 1.0, C.c_void_p(sd.ctypes.data), C.byref(cp),
+                        0, 2, C.c_void_p(fin.ctypes.data), 1, C.c_void_p(n_fin.ctypes.data), C.c_void_p(), 0, C.c_void_p())
+    assert chain._lib.rsp_process_frames(*args(0)) == 0
+    assert chain._lib.rsp_process_frames(*args(1)) == -5 and n_fin[0] == 2          # RSP_ERR_OVERFLOW
+    f3, d3 = chain.process_targets(lists[1], cluster_params, 1.0, seeds[1])
+    assert np.array_equal(f3, one[1][0]) and np.array_equal(d3, one[1][1])
     chain.close()
 
 
