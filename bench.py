@@ -90,19 +90,23 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                try:
+                    pw.append(float(r[2]))
+                except Exception:
+                    pass
                 for nm, val in zip(names, r[3:7]):
                     if val.lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(pw)) if pw else None}
 
 
 def make_pool(rsp, config, pd, n_cubes: int, seed0: int):
@@ -254,6 +258,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=list(CONFIG_DESC))
     ap.add_argument("--cpis-per-step", type=int, default=0, help="CPIs per step (a step is `batches` stream batches)")
+    ap.add_argument("--cpis-per-batch", type=int, default=0, help="CPIs per rsp_stream_enqueue batch (at most half the ring slots)")
     ap.add_argument("--pool", type=int, default=0, help="distinct input CPIs resident in HBM")
     ap.add_argument("--rdm-pool", type=int, default=0, help="distinct RDM output buffers")
     ap.add_argument("--e2e-cpis", type=int, default=256)
@@ -379,7 +384,7 @@ def main():
     cps_default = {"cfg1": 64, "cfg2": 64, "cfg3": 8, "native": 16}[name]
     per_step_default = {"cfg1": 2560, "cfg2": 1024, "cfg3": 96, "native": 96}[name]     # >= 1 s of device time in 20 steps
     per_step = args.cpis_per_step or per_step_default
-    cps = min(cps_default, per_step)
+    cps = min(args.cpis_per_batch or cps_default, per_step)
     batches = max(1, per_step // cps)
     r = stream_bench(name, args.steps, args.warmup, cps, batches, args.pool, args.rdm_pool, clocks=True)
     chain, config, cfar_params, cluster_params, pd, info = r["chain"], r["config"], r["cfar_params"], r["cluster_params"], r["pd"], r["info"]
