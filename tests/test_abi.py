@@ -76,6 +76,21 @@ def test_create_rejects_bad_arguments():
     assert b"channels" in lib.rsp_last_error(None)
 
 
+def test_entry_points_reject_a_null_context_without_touching_a_device():
+    """Every entry point of the frame / stream paths answers a NULL context with RSP_ERR_INVALID_ARG (no crash, no device
+    call) -- what a host binding sees when rsp_create failed and its return code was ignored."""
+    lib = _abi.load()
+    cp = _abi.rsp_cluster_params(30.0, 0.4, 5.0)
+    n = C.c_int32(0)
+    null = C.c_void_p()
+    assert lib.rsp_process_frames(null, null, null, 1, 1.0, null, C.byref(cp), 0, 0, null, 0, null, null, 0, null) == _abi.RSP_ERR_INVALID_ARG
+    assert lib.rsp_submit_targets(null, null, 0, 1.0, 0, 0) == _abi.RSP_ERR_INVALID_ARG
+    assert lib.rsp_fetch_targets(null, 0, C.byref(cp), null, 0, C.byref(n), null, 0, C.byref(n)) == _abi.RSP_ERR_INVALID_ARG
+    assert lib.rsp_stream_fetch(null, 0, null, 0, C.byref(n)) == _abi.RSP_ERR_INVALID_ARG
+    assert lib.rsp_submit_cpi(null, null, null, 0) == _abi.RSP_ERR_INVALID_ARG
+    assert lib.rsp_stream_enqueue(null, null, 0, null, 0, 0, 0) == _abi.RSP_ERR_INVALID_ARG
+
+
 def test_sort_is_reference_find_order():
     rng = np.random.default_rng(0)
     d = np.zeros(500, dtype=rsp.DETECTION_DTYPE)
