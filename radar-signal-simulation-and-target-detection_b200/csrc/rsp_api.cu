@@ -1149,6 +1149,7 @@ static void launch_mtd(rsp_ctx* c, float2* rdm, int g_lo = 0, int g_hi = -1) {
     MtdArgs a;
     a.pc = c->cur->pc; a.rdm = rdm; a.amp = c->cur->amp; a.win = c->d_win; a.tw = c->d_dop_tw; a.perm = c->d_dop_perm;
     a.P = c->P; a.B = c->B; a.G = c->G; a.ldg = c->ldg;
+    a.p_magic = (unsigned)((1ull << 32) / (unsigned)c->P + 1ull);
     a.dead = g_hi < 0 ? dead_beam(c) : DiscardArgs{nullptr, 0};
     a.g_lo = g_lo; a.g_hi = g_hi < 0 ? c->G : g_hi;
     const int ng = a.g_hi - a.g_lo;

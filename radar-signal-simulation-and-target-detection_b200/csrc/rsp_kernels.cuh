@@ -877,6 +877,7 @@ struct MtdArgs {
     const float2* tw;      // pow2: per-pass twiddles; dft: e^{-2 pi i m/P}, m < P
     const int* perm;       // pow2 only: iperm[pos] = pulse stored at position pos
     int P;
+    unsigned p_magic;      // 2^32 / P + 1: e / P == __umulhi(e, p_magic) for e < 64 P (the read-out of the generic-P kernel)
     int B, G, ldg;
     int g_lo, g_hi;        // gates [g_lo, g_hi) of this launch (the whole map: 0, G; range-blocked path: one chunk)
     DiscardArgs dead;      // buffer whose last reader has finished (the beam cube), or {nullptr, 0}
@@ -1037,11 +1038,14 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_c
     const int tid = threadIdx.x;
     for (int i = tid; i < P; i += RSP_MTD_THREADS) stw[i] = k.tw[i];
     const int g0 = k.g_lo + blockIdx.x * TG, b = blockIdx.y;
+    const float2* const src = k.pc + (size_t)b * k.ldg + g0;                 // element (p, gl) of the tile: src[p * B * ldg + gl]
+    const unsigned pstride = (unsigned)k.B * (unsigned)k.ldg;
+    const int gl_end = k.g_hi - g0;
 #pragma unroll 4
     for (int e = tid; e < P * TG; e += RSP_MTD_THREADS) {
-        const int p = e / TG, gl = e - p * TG, g = g0 + gl;
+        const int p = e / TG, gl = e - p * TG;
         float2 x = make_float2(0.f, 0.f);
-        if (g < k.g_hi) x = k.pc[((size_t)p * k.B + b) * k.ldg + g];
+        if (gl < gl_end) x = src[(size_t)((unsigned)p * pstride + (unsigned)gl)];
         xin[p * (TG + 1) + gl] = cscale(x, k.win[p]);
     }
     __syncthreads();
@@ -1076,14 +1080,19 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_dft_kernel(const __grid_c
         }
     }
     __syncthreads();
-    for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {
-        const int gl = e / P, row = e - gl * P, g = g0 + gl;
-        if (g < k.g_hi) {
-            const float2 v = xout[row * (TG + 1) + gl];
-            const size_t o = ((size_t)b * k.G + g) * P + row;
-            __stcs(k.rdm + o, v);
-            k.amp[o] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
-        }
+    // read-out, Doppler-contiguous: element e = gl * P + row of the tile is element e of the tile's block of rdm[b][g0..][.]
+    // (one base pointer, no 64-bit index arithmetic per element; the division by the run-time P is a multiply-high)
+    static_assert(TG <= 64, "p_magic is exact for e < 64 P");
+    const size_t o0 = ((size_t)b * k.G + g0) * P;
+    float2* const rdm = k.rdm + o0;
+    float* const amp = k.amp + o0;
+    const int e_end = min(TG, k.g_hi - g0) * P;
+#pragma unroll 4
+    for (int e = tid; e < e_end; e += RSP_MTD_THREADS) {
+        const int gl = (int)__umulhi((unsigned)e, k.p_magic), row = e - gl * P;
+        const float2 v = xout[row * (TG + 1) + gl];
+        __stcs(rdm + e, v);
+        amp[e] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
     }
 }
 
