@@ -898,16 +898,18 @@ __global__ void __launch_bounds__(RSP_MTD_THREADS) mtd_kernel(const MtdArgs k) {
     __syncthreads();
     if (MtdInner<Cfg>::PASS < 1 && Cfg::R1 > 1) { mtd_passes_phase<Cfg>(tile, stw, tid, 1); __syncthreads(); }
     if (MtdInner<Cfg>::PASS < 2) { mtd_passes_phase<Cfg>(tile, stw, tid, 2); __syncthreads(); }
-    // transposed read-out: consecutive threads take consecutive Doppler rows of one gate
+    // transposed read-out: consecutive threads take consecutive Doppler rows of one gate; element e = gl * P + row of the
+    // tile is element e of the tile's contiguous block of rdm[b][g0 ..][.] (one base pointer, immediate offsets)
+    const size_t o0 = ((size_t)b * k.G + g0) * P;
+    float2* const rdm = k.rdm + o0;
+    float* const amp = k.amp + o0;
+    const int e_end = min(TG, k.g_hi - g0) * P;
 #pragma unroll 4
-    for (int e = tid; e < TG * P; e += RSP_MTD_THREADS) {
+    for (int e = tid; e < e_end; e += RSP_MTD_THREADS) {
         const int gl = e / P, row = e - gl * P;          // P is a compile-time power of two
-        if (g0 + gl < k.g_hi) {
-            const float2 v = tile[row * (TG + 1) + gl];
-            const size_t o = ((size_t)b * k.G + g0 + gl) * P + row;
-            __stcs(k.rdm + o, v);
-            k.amp[o] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
-        }
+        const float2 v = tile[row * (TG + 1) + gl];
+        __stcs(rdm + e, v);
+        amp[e] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
     }
 }
 

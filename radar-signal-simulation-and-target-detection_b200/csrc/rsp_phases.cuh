@@ -285,9 +285,10 @@ RSP_HD void mtd_first_pass_t(cf* s, const cf* src, size_t pstride, const float* 
         const int base = Cfg::R2 > 1 ? (q / Cfg::R1 + Cfg::R0 * (q % Cfg::R1)) : q;
         const cf* col = src + (size_t)base * pstride + gl;
         const float* wq = win + base;
+        const unsigned ps = (unsigned)pstride;                 // P * pstride elements fit 32 bits (the cube is < 16 GB)
         cf v[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) v[k] = gate_ok ? col[(size_t)k * KSTR * pstride] : make_float2(0.f, 0.f);
+        for (int k = 0; k < R; ++k) v[k] = gate_ok ? col[(unsigned)(k * KSTR) * ps] : make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = cscale(v[k], wq[k * KSTR]);
         SmallDft<R, -1>::run(v);
