@@ -445,7 +445,7 @@ def main():
                      "note": "SURVEY 8(d) flop count with this build's block plan / device time per CPI / (SMs x 128 lanes x 2 x SM clock)"}
 
     e2e = e2e_targets_rec = config4 = stream_cfg3 = None
-    d2h = 4 + 40 * min(1024, chain.max_detections)     # the count and the first 1024 records are prefetched to pinned memory
+    d2h = 4 + 40 * min(2048, chain.max_detections)     # the count and the first 2048 records are prefetched to pinned memory
     if not args.no_extras:
         # end to end through the C ABI with HOST buffers: per CPI a 67 MB H2D copy of the pinned cube and a D2H read of its
         # sorted detection list, both inside the timed region.  rsp_submit_cpi pipelines the copy of cube i+1 under the

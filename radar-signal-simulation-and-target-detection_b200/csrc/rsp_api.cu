@@ -1474,7 +1474,7 @@ static int check_slot_free(rsp_ctx* c, int slot) {
 static int finish_submit(rsp_ctx* c, int slot, int l) {
     cudaStream_t s = c->lanes[l].s;
     if (!c->h_slot_count) {
-        c->prefetch_k = std::min(1024, c->prm.max_detections);
+        c->prefetch_k = std::min(2048, c->prm.max_detections);   // a 64-target frame has ~1600 records: no second copy
         CU(c, cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking));
         CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_slot_count), (size_t)c->slots * sizeof(int)));
         CU(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_slot_recs), (size_t)c->slots * c->prefetch_k * sizeof(rsp_detection)));

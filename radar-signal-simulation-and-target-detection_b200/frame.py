@@ -323,8 +323,15 @@ class RadarChain:
                                                     float(noise_power), C.c_void_p(sd.ctypes.data), C.byref(cp), int(depth),
                                                     int(host_threads), C.c_void_p(fin.ctypes.data), self._FRAME_TARGET_CAP,
                                                     C.c_void_p(n_fin.ctypes.data), pd_, cap_total, po), self._ctx)
-            for i in range(nb):
-                out.append((fin[i, :n_fin[i]].copy(), dets[offs[i]:offs[i + 1]].copy() if return_detections else None))
+            # one copy of the block's results out of the reused buffers; the per-frame arrays are views into it
+            nf = n_fin.tolist()
+            fin_b = fin[:nb, :max(nf) if nf else 0].copy()
+            if return_detections:
+                o = offs.tolist()
+                dets_b = dets[:o[nb]].copy()
+                out.extend((fin_b[i, :nf[i]], dets_b[o[i]:o[i + 1]]) for i in range(nb))
+            else:
+                out.extend((fin_b[i, :nf[i]], None) for i in range(nb))
         return out
 
     # -- device-resident stream -----------------------------------------------------------------
