@@ -131,6 +131,14 @@ struct SynthArgs {
     int tx_lo, tx_hi;         // hull of the non-zero stretches
 };
 
+// z += x * p (complex), the one statement every echo-synthesis path accumulates a target with.  Written with rounding-mode
+// intrinsics so that the compiler cannot contract it differently from one kernel to the next: the staged, the gathering and
+// the fused (S4 inside S5) kernels must produce the same bits for the same frame.
+__device__ __forceinline__ void synth_cmac(float& zr, float& zi, const float2 x, const float2 p) {
+    zr = __fadd_rn(zr, __fmaf_rn(x.x, p.x, -__fmul_rn(x.y, p.y)));
+    zi = __fadd_rn(zi, __fmaf_rn(x.x, p.y, __fmul_rn(x.y, p.x)));
+}
+
 // Philox4x32-10 (Salmon et al., SC'11); round_key[r] = key + r * (0x9E3779B9, 0xBB67AE85)
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const uint2 (&round_key)[10]) {
 #pragma unroll
@@ -215,8 +223,7 @@ __global__ void __launch_bounds__(256) synth_kernel(const __grid_constant__ Synt
                 for (int i = lo[sgi] + tid; i < hi[sgi]; i += 256) {
                     const float2 x = k.tx[i];
                     float2 v = s[delay + i - c0];
-                    v.x += x.x * ph.x - x.y * ph.y;
-                    v.y += x.x * ph.y + x.y * ph.x;
+                    synth_cmac(v.x, v.y, x, ph);
                     s[delay + i - c0] = v;
                 }
         }
@@ -266,18 +273,65 @@ __device__ __forceinline__ float4 synth_pair(const SynthArgs& k, const float2* p
                 const float2 p = ph[t * ph_stride];
                 if ((unsigned)j < span) {
                     const float2 x = k.tx[j + k.tx_lo];
-                    z.x += x.x * p.x - x.y * p.y;
-                    z.y += x.x * p.y + x.y * p.x;
+                    synth_cmac(z.x, z.y, x, p);
                 }
                 if ((unsigned)(j + 1) < span) {
                     const float2 x = k.tx[j + 1 + k.tx_lo];
-                    z.z += x.x * p.x - x.y * p.y;
-                    z.w += x.x * p.y + x.y * p.x;
+                    synth_cmac(z.z, z.w, x, p);
                 }
             }
         }
     }
     return z;
+}
+// The same samples for the KS channels c = c0 + 4 s of one thread of dbf_synth_kernel at once: the hull test, the delay and the
+// two tx_pulse samples of a target do not depend on the channel, so they are fetched once per target and applied to every
+// channel with that channel's phasor (per channel: the statements of synth_pair in the same order, hence the same bits).
+// With 64 targets per frame the target loop is most of the fused kernel; this form runs a third fewer instructions in it.
+template <int KS>
+__device__ __forceinline__ void synth_pair_channels(const SynthArgs& k, const float2* ph /* phasor of channel c0 */, int ph_stride, const int* delay,
+                                                    int n0, size_t line0 /* pulse * C + c0 */, int c0, int C, unsigned act0, unsigned act1,
+                                                    float4 (&z)[KS]) {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        z[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k.noise_sigma > 0.f && c0 + 4 * s < C) {
+            const size_t line_id = line0 + 4 * s;
+            const uint4 r = philox4x32_10(make_uint4((unsigned)(n0 / 2), (unsigned)line_id, (unsigned)(line_id >> 32), 0u), k.round_key);
+            const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+            z[s] = make_float4(z0.x * k.noise_sigma, z0.y * k.noise_sigma, z1.x * k.noise_sigma, z1.y * k.noise_sigma);
+        }
+    }
+    const unsigned span = (unsigned)(k.tx_hi - k.tx_lo);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        unsigned m = h == 0 ? act0 : act1;
+        if (h == 0 ? k.n_targets < 32 : k.n_targets < 64) m &= (1u << (k.n_targets - 32 * h > 0 ? k.n_targets - 32 * h : 0)) - 1u;
+        while (m) {                                                         // ascending target index, like the plain loop
+            const int t = 32 * h + __ffs(m) - 1;
+            m &= m - 1;
+            const int j = n0 - delay[t] - k.tx_lo;                          // tx index of sample n0, relative to the hull
+            if ((unsigned)(j + 1) <= span) {                                // sample n0 or n0 + 1 is inside the delayed hull
+                const bool in0 = (unsigned)j < span, in1 = (unsigned)(j + 1) < span;
+                float2 x0 = make_float2(0.f, 0.f), x1 = x0;
+                if (in0) x0 = k.tx[j + k.tx_lo];
+                if (in1) x1 = k.tx[j + 1 + k.tx_lo];
+                const float2* pt = ph + t * ph_stride;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    if (c0 + 4 * s < C) {
+                        const float2 p = pt[4 * s];
+                        if (in0) {
+                            synth_cmac(z[s].x, z[s].y, x0, p);
+                        }
+                        if (in1) {
+                            synth_cmac(z[s].z, z[s].w, x1, p);
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 __global__ void __launch_bounds__(256) synth_gather_kernel(const __grid_constant__ SynthArgs k) {
     __shared__ float2 s_ph[RSP_SYNTH_GATHER_T];
@@ -310,13 +364,11 @@ __global__ void __launch_bounds__(256) synth_gather_kernel(const __grid_constant
                 const float2 ph = s_ph[t];
                 if ((unsigned)j < span) {
                     const float2 x = k.tx[j + k.tx_lo];
-                    z.x += x.x * ph.x - x.y * ph.y;
-                    z.y += x.x * ph.y + x.y * ph.x;
+                    synth_cmac(z.x, z.y, x, ph);
                 }
                 if ((unsigned)(j + 1) < span) {
                     const float2 x = k.tx[j + 1 + k.tx_lo];
-                    z.z += x.x * ph.x - x.y * ph.y;
-                    z.w += x.x * ph.y + x.y * ph.x;
+                    synth_cmac(z.z, z.w, x, ph);
                 }
             }
         }
@@ -668,14 +720,14 @@ __global__ void __launch_bounds__(RSP_DBF_MMA_THREADS) dbf_synth_kernel(const __
     }
     float4 x[KS][NQ];
 #pragma unroll
-    for (int s = 0; s < KS; ++s) {
-        const int c = 4 * s + t;
+    for (int q = 0; q < NQ; ++q) {
+        const int n0 = n_base + 16 * q + sg;
+        float4 z[KS];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int n0 = n_base + 16 * q + sg;
-            x[s][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < C && n0 < N) x[s][q] = synth_pair(k, s_ph + c, 4 * KS, s_delay, n0, (size_t)p * C + c, act[0], act[1]);
-        }
+        for (int s = 0; s < KS; ++s) z[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 < N) synth_pair_channels<KS>(k, s_ph + t, 4 * KS, s_delay, n0, (size_t)p * C + t, t, C, act[0], act[1], z);
+#pragma unroll
+        for (int s = 0; s < KS; ++s) x[s][q] = z[s];
     }
     float acc[MT][2 * NQ][4];
 #pragma unroll
