@@ -2224,9 +2224,10 @@ int rsp_process_frames(rsp_ctx* c, const rsp_target_in* targets, const int32_t* 
             // into a vector of the job's own
             CU(c, cudaEventSynchronize(c->slot_done[j % c->slots]));
             n = c->h_slot_count[j % c->slots];
-            if (n > c->prm.max_detections) { rc = fail(c, RSP_ERR_OVERFLOW, "frame %d: %d detections exceed max_detections=%d", j, n, c->prm.max_detections); ++fetched; break; }
+            // (errors before the fetch leave the slot to the drain loop below, which clears it)
+            if (n > c->prm.max_detections) { rc = fail(c, RSP_ERR_OVERFLOW, "frame %d: %d detections exceed max_detections=%d", j, n, c->prm.max_detections); break; }
             if (dets) {
-                if (off + n > det_cap_total) { rc = fail(c, RSP_ERR_OVERFLOW, "frame %d: detections exceed the caller's capacity %lld", j, (long long)det_cap_total); ++fetched; break; }
+                if (off + n > det_cap_total) { rc = fail(c, RSP_ERR_OVERFLOW, "frame %d: detections exceed the caller's capacity %lld", j, (long long)det_cap_total); break; }
                 job.d = dets + off;
             } else {
                 job.own.resize((size_t)std::max(n, 1));

@@ -552,6 +552,17 @@ def test_batched_frames_equal_one_at_a_time():
     assert chain._lib.rsp_process_frames(*args(1)) == -5 and n_fin[0] == 2          # RSP_ERR_OVERFLOW
     f3, d3 = chain.process_targets(lists[1], cluster_params, 1.0, seeds[1])
     assert np.array_equal(f3, one[1][0]) and np.array_equal(d3, one[1][1])
+    # a flat detection buffer that is too small for the block: overflow error as well, and exact fit works
+    nd1 = len(one[1][1])
+    assert nd1 > 1
+    fin8, offs = np.zeros(8, dtype=rsp.frame.TARGET_DTYPE), np.zeros(2, dtype=np.int64)
+    for cap_total, want in ((nd1 - 1, -5), (nd1, 0)):
+        dbuf = np.zeros(max(cap_total, 1), dtype=rsp.frame.DETECTION_DTYPE)
+        rc = chain._lib.rsp_process_frames(chain._ctx, C.c_void_p(tg.ctypes.data), C.c_void_p(n_tg.ctypes.data), 1, 1.0, C.c_void_p(sd.ctypes.data),
+                                           C.byref(cp), 0, 2, C.c_void_p(fin8.ctypes.data), 8, C.c_void_p(n_fin.ctypes.data),
+                                           C.c_void_p(dbuf.ctypes.data), cap_total, C.c_void_p(offs.ctypes.data))
+        assert rc == want, (cap_total, rc)
+    assert offs[1] == nd1 and np.array_equal(dbuf, one[1][1]) and np.array_equal(fin8[:n_fin[0]], one[1][0])
     chain.close()
 
 
