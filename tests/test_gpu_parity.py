@@ -566,6 +566,44 @@ def test_batched_frames_equal_one_at_a_time():
     chain.close()
 
 
+def test_frames_with_more_detections_than_the_prefetch_block():
+    """A pipelined frame brings its count and the first 2048 detection records to pinned memory behind its kernels; a frame
+    with more than that fetches the rest on a stream of its own (fetch_slot).  With a low CFAR threshold a config-1 frame has
+    several thousand detections: the pipelined paths (frame by frame and rsp_process_frames) must return exactly the list of
+    the synchronous call, in the reference's find order, and a frame above max_detections is an error on every path."""
+    config, cfar_params, cluster_params = rsp.named_config("cfg1")
+    pd = rsp.build_precomputed_data(config)
+    chain = rsp.RadarChain(config, cfar_params, pd, max_detections=65536)
+    chain.set_waveform(config, pd)
+    v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+    rng = np.random.default_rng(3)
+    dR = float(pd.deltaR)
+    tl = [dict(Range=float(rng.uniform(400 * dR, (chain.G - 40) * dR)), Velocity=float(rng.uniform(-0.3, 0.3) * v_max),
+               ElevationAngle=float(rng.uniform(-10.0, 50.0)), SNR_dB=30.0) for _ in range(64)]     # strong: seen in many cells and beam pairs
+    fin0, d0 = chain.process_targets(tl, cluster_params, 1.0, 7)
+    assert 2048 < len(d0) < 65536 and len(fin0) <= 512, (len(d0), len(fin0))
+    key = d0["pair_idx"].astype(np.int64) * (1 << 40) + d0["r_idx"].astype(np.int64) * (1 << 20) + d0["v_idx"]
+    assert np.all(np.diff(key) > 0)                                              # find order, no duplicates
+    chain.submit_targets(tl, 3, 1.0, 7)
+    fin1, d1 = chain.fetch_targets(3, cluster_params)
+    assert np.array_equal(d1, d0) and np.array_equal(fin1, fin0)
+    for ret in (True, False):
+        res = chain.process_targets_batch([tl, [], tl], cluster_params, 1.0, [7, 8, 7], return_detections=ret)
+        assert np.array_equal(res[0][0], fin0) and np.array_equal(res[2][0], fin0)
+        if ret:
+            assert np.array_equal(res[0][1], d0) and np.array_equal(res[2][1], d0) and len(res[1][1]) < len(d0)
+    chain.close()
+    small = rsp.RadarChain(config, cfar_params, pd, max_detections=2100)
+    small.set_waveform(config, pd)
+    assert len(d0) > 2100
+    for call in (lambda: small.process_targets(tl, cluster_params, 1.0, 7),
+                 lambda: small.process_targets_batch([tl], cluster_params, 1.0, [7])):
+        with pytest.raises(rsp.RspError) as ei:
+            call()
+        assert ei.value.code == -5
+    small.close()
+
+
 @pytest.mark.parametrize("name", ["cfg1", "cfg2"])
 def test_fused_synthesis_equals_the_two_kernel_path(name):
     """The pipelined frame path generates the echoes inside the DBF (dbf_synth_kernel, same Philox
