@@ -714,6 +714,32 @@ def test_dense_scene_64_targets_device_synthesis_then_chain():
     chain.close()
 
 
+@pytest.mark.parametrize("C,B,P,N", [(12, 5, 32, 4096), (6, 13, 36, 4112), (16, 16, 32, 4098), (3, 2, 64, 4096)])
+def test_fused_synthesis_on_ragged_shapes(C, B, P, N):
+    """The fused S4 + S5 kernel (dbf_synth_kernel / synth_pair_channels) where the channel count is not a multiple of the
+    four channels a thread covers per k-step, with one or two beam tiles and a sample count that ends inside a warp's group:
+    pipelined frames (fused) == the synchronous call (synthesis kernel into a cube, then the chain), for 1, 9 and 64 targets
+    and a noise-only frame, with and without noise."""
+    config, cfar_params, cluster_params = rsp.default_config(channel_num=C, beam_num=B, prtNum=P, point_PRT=N)
+    pd = rsp.build_precomputed_data(config)
+    chain = rsp.RadarChain(config, cfar_params, pd, max_detections=32768)
+    chain.set_waveform(config, pd)
+    v_max = config.Sig_Config.wavelength / (2 * config.Sig_Config.prt)
+    rng = np.random.default_rng(C * 100 + B)
+    dR = float(pd.deltaR)
+    mk = lambda n: [dict(Range=float(rng.uniform(300 * dR, (chain.G - 40) * dR)), Velocity=float(rng.uniform(-0.2, 0.2) * v_max),
+                         ElevationAngle=float(rng.uniform(-10.0, 40.0)), SNR_dB=float(rng.uniform(5.0, 25.0))) for _ in range(n)]
+    lists = [mk(1), mk(9), mk(64), []]
+    for noise in (1.0, 0.0):
+        seeds = [21, 22, 23, 24]
+        one = [chain.process_targets(tl, cluster_params, noise, sd) for tl, sd in zip(lists, seeds)]
+        many = chain.process_targets_batch(lists, cluster_params, noise, seeds)
+        for i, ((f1, d1), (f2, d2)) in enumerate(zip(one, many)):
+            assert np.array_equal(d1, d2) and np.array_equal(f1, f2), (noise, i, len(d1), len(d2))
+        assert any(len(d) > 0 for _, d in one)
+    chain.close()
+
+
 def test_fused_synthesis_of_64_targets_matches_the_oracle():
     """BASELINE config 4: 64 targets synthesised inside the DBF (dbf_synth_kernel, no raw cube) ahead of the chain, checked
     DIRECTLY against the oracle with the noise switched off: beam cube, range-Doppler map, detection cells, targets."""
