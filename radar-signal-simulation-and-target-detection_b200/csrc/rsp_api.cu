@@ -253,7 +253,7 @@ template <typename KernelT> static cudaError_t opt_in_smem(KernelT kern, size_t 
 static size_t smem_for_occupancy(size_t needed, int max_ctas_per_sm) {
     if (max_ctas_per_sm <= 0) return needed;
     // RSP_SMEM_RESERVE_KB: shared memory left free beside the capped CTAs (room for a co-resident kernel of another stream)
-    static const size_t reserve = [] { const char* e = getenv("RSP_SMEM_RESERVE_KB"); return (size_t)(e ? atoi(e) : 0) * 1024; }();
+    static const size_t reserve = (size_t)probe_env("RSP_SMEM_RESERVE_KB", 0) * 1024;
     const size_t per_sm = 227 * 1024 - reserve;
     size_t pad_to = per_sm / (size_t)(max_ctas_per_sm + 1) + 1024;               // max_ctas + 1 no longer fit
     pad_to = std::min(pad_to, per_sm / (size_t)max_ctas_per_sm - 2048);          // ... but max_ctas still do
@@ -267,7 +267,7 @@ template <class Cfg> static size_t pc_smem_bytes() {
     return ((size_t)Cfg::NG * Cfg::SMEM_ELEMS + (Cfg::R2 - 1) * Cfg::SPAN2) * sizeof(float2) + 256 * sizeof(float);
 }
 // RSP_OCC_PC caps the pulse-compression CTAs per SM (shared-memory padding), leaving registers for the kernels of other lanes
-static int pc_occ_cap() { static const int v = [] { const char* e = getenv("RSP_OCC_PC"); return e ? atoi(e) : 0; }(); return v; }
+static int pc_occ_cap() { static const int v = probe_env("RSP_OCC_PC", 0); return v; }
 template <class A, class B> static size_t pc_smem_pair() { return smem_for_occupancy(std::max(pc_smem_bytes<A>(), pc_smem_bytes<B>()), pc_occ_cap()); }
 // X(long plan, medium plan)
 #define RSP_FOR_EACH_PC_PAIR(X) X(Pc1024, Pc1024) X(Pc2048, Pc1024) X(Pc4096, Pc1024) X(Pc1024, Pc2048) X(Pc2048, Pc2048) \
@@ -515,7 +515,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
             CU(c, upload(&c->d_Wfrag_wa, make_dbf_fragments_wa(reinterpret_cast<const double*>(k->dbf_weights), B, C, (B + 7) / 8, c->dbf_ks)));
             c->dbf_wa = !(e && std::string(e) == "mma");
             c->dbf_tma2 = e && std::string(e) == "tma2";
-            { const char* et = getenv("RSP_DBF_TMA2_TILES"); c->dbf_tma2_tiles = et ? std::max(1, atoi(et)) : 8; }
+            c->dbf_tma2_tiles = std::max(1, probe_env("RSP_DBF_TMA2_TILES", 8));
         }
     }
     std::vector<float> fir(k->n_fir);
@@ -584,7 +584,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         CU(c, upload(&c->d_dop_perm, c->dop.iperm));
         c->mtd_tg = RSP_MTD_TG;
         c->mtd_smem = ((size_t)P * (RSP_MTD_TG + 1) + c->dop.tw.size() + 1) * sizeof(float2);
-        { const char* e = getenv("RSP_OCC_MTD"); c->mtd_smem = smem_for_occupancy(c->mtd_smem, e ? atoi(e) : 0); }
+        c->mtd_smem = smem_for_occupancy(c->mtd_smem, probe_env("RSP_OCC_MTD", 0));
         CU(c, mtd_opt_in(P, c->mtd_smem));
     } else {
         std::vector<float2> tw(P);
@@ -626,7 +626,7 @@ int rsp_upload_constants(rsp_ctx* c, const rsp_constants* k) {
         if (const char* e = getenv("RSP_CFAR_TG")) { const int v = atoi(e); if (v == 64 || v == 32 || v == 16) c->cfar_tg = v; }
         c->cfar_smem = smem_for(c->cfar_tg);
         if (c->cfar_smem > 200 * 1024) return fail(c, RSP_ERR_UNSUPPORTED, "CFAR tile does not fit shared memory");
-        { const char* e = getenv("RSP_OCC_CFAR"); c->cfar_smem = smem_for_occupancy(c->cfar_smem, e ? atoi(e) : 3); }
+        c->cfar_smem = smem_for_occupancy(c->cfar_smem, probe_env("RSP_OCC_CFAR", 3));
         const int rr = c->prm.ref_r, rv = c->prm.ref_v, gv = c->prm.guard_v;
         c->cfar_variant = (rr == 5 && rv == 5 && gv == 10) ? 1 : (rr == 5 && rv == 4 && gv == 2) ? 2 : 0;
 #define RSP_CFAR_DISPATCH(TGV, ACTION)                                                      \
@@ -942,7 +942,7 @@ static int plan_dbf_tc(rsp_ctx* c, const rsp_constants* k) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->prm.device);
     int per_sm = 1;
-    if (const char* ep = getenv("RSP_TC_CTAS_PER_SM")) per_sm = std::max(1, atoi(ep));
+    per_sm = std::max(1, probe_env("RSP_TC_CTAS_PER_SM", 1));
     c->dbf_tc_grid = std::min(nsm * per_sm, c->P * a.tiles_per_pulse);
     if (const char* ec = getenv("RSP_TC_CHUNK")) a.chunk = std::max(0, atoi(ec));
     if (a.chunk > 0) c->dbf_tc_grid = (c->P * a.tiles_per_pulse + a.chunk - 1) / a.chunk;
