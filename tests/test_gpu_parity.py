@@ -525,6 +525,13 @@ def test_batched_frames_equal_one_at_a_time():
         assert np.array_equal(one[i % 5][1], d2) and np.array_equal(one[i % 5][0], f2)
     with pytest.raises(rsp.RspError):
         chain.submit_targets([lists[0][0]] * 65, 0)
+    # more frames than ring slots and than one rsp_process_frames block (256): slots wrap, blocks chain, order is kept
+    n_long = 2 * chain.stream_slots() + 300
+    long_res = chain.process_targets_batch([lists[i % 5] for i in range(n_long)], cluster_params, 1.0, [seeds[i % 5] for i in range(n_long)],
+                                           host_threads=5)
+    assert len(long_res) == n_long
+    for i, (f2, d2) in enumerate(long_res):
+        assert np.array_equal(one[i % 5][1], d2) and np.array_equal(one[i % 5][0], f2), i
     # the native block call (rsp_process_frames: worker threads sort and cluster) against the frame-by-frame Python pipeline
     py = chain.process_targets_batch(lists2, cluster_params, 1.0, seeds2, depth=4, native=False)
     for (f1, d1), (f2, d2) in zip(py, many2):
