@@ -2196,10 +2196,15 @@ int rsp_process_frames(rsp_ctx* c, const rsp_target_in* targets, const int32_t* 
                 queue.pop_front();
             }
             rsp_detection* d = job.d ? job.d : job.own.data();
-            sort_detections_keyed(d, job.n, keys, tmp);
-            fin.resize((size_t)std::max(job.n, 1));
             int32_t nf = 0, n1 = 0;
-            int rc = rsp_cluster(d, job.n, cp, nullptr, &n1, fin.data(), &nf);
+            int rc = RSP_OK;
+            try {
+                sort_detections_keyed(d, job.n, keys, tmp);
+                fin.resize((size_t)std::max(job.n, 1));
+                rc = rsp_cluster(d, job.n, cp, nullptr, &n1, fin.data(), &nf);
+            } catch (...) {                           // out of host memory
+                rc = RSP_ERR_INVALID_ARG;
+            }
             n_final[job.frame] = nf;
             if (!rc && nf > cap) rc = RSP_ERR_OVERFLOW;
             if (!rc && nf > 0) std::memcpy(final_targets + (size_t)job.frame * cap, fin.data(), (size_t)nf * sizeof(rsp_target));
@@ -2209,8 +2214,13 @@ int rsp_process_frames(rsp_ctx* c, const rsp_target_in* targets, const int32_t* 
             }
         }
     };
+    // No exception may cross the C ABI: a thread that cannot be created just leaves fewer workers (none: the calling thread
+    // sorts and clusters after the last fetch).
     std::vector<std::thread> pool;
-    for (int w = 0; w < n_workers; ++w) pool.emplace_back(work);
+    try {
+        for (int w = 0; w < n_workers; ++w) pool.emplace_back(work);
+    } catch (...) {
+    }
     int rc = RSP_OK, submitted = 0, fetched = 0;
     int64_t off = 0;
     if (det_offsets) det_offsets[0] = 0;
@@ -2254,6 +2264,7 @@ int rsp_process_frames(rsp_ctx* c, const rsp_target_in* targets, const int32_t* 
         closed = true;
     }
     cv.notify_all();
+    if (pool.empty()) work();
     for (auto& t : pool) t.join();
     if (rc) {                                     // keep the submit / fetch pairing of the ring intact for the next caller
         const std::string msg = c->err;
